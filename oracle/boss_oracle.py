@@ -1,0 +1,610 @@
+"""CPU oracle for the BOSS.jl GP hot path  --  TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / ``--impl reference``
+legs may import this module.  The product path (``boss.jl_b200``) never does: it fails loudly when
+the CUDA library is missing.
+
+What this is
+------------
+A numpy/scipy (OpenBLAS/LAPACK ``dpotrf``/``dtrsm`` -- the same BLAS family Julia's LinearAlgebra
+uses) restatement of the arithmetic BOSS.jl v0.6.1 performs on its hot path.  Every function cites
+the reference ``file:line`` (relative to ``/root/reference``) it follows.  The innermost numerics
+are NOT in the reference tree: they live in un-vendored third-party Julia packages
+(AbstractGPs.jl compat 0.5.21, KernelFunctions.jl, Distances.jl, Distributions.jl compat 0.25.109 ->
+StatsFuns/SpecialFunctions; ``Project.toml:24-36``, no Manifest).  Their published algorithms are
+restated following SURVEY.md Appendix A, same operation order:
+
+  x * (1/l)  ->  GEMM-trick pairwise sq. distances, max(.,0)  ->  kappa  ->  a^2 * kappa + s^2 I
+  ->  upper Cholesky (dpotrf 'U')  ->  U' \\ .  (dtrsm)  ->  a^2 - colsum(V^2) + 1e-18
+
+PARITY STATUS
+-------------
+* Pinned by the reference's own known-answer tests (re-encoded in tests/test_oracle_golden.py):
+  ``_clip_var`` table, closed-form EI cases, ``feas_prob`` 1 / 0.5 / 0.25, ``make_safe``,
+  ``best_so_far``, ``is_feasible``, DiscreteKernel rounding equalities.
+* **Posterior mean / variance values and log-marginal-likelihood values: PARITY UNPINNED.**
+  The reference holds no golden numbers for them and Julia is not installed in this
+  image, so the reference cannot be run.  The restatement is cross-checked against scikit-learn's
+  independent GP implementation and against an extended-precision (mpmath) adjudicator
+  (tests/test_oracle_crosscheck.py); that is corroboration, not a pin.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import scipy.linalg as sl
+from scipy.special import erfc
+
+# src/models/gaussian_process.jl:5
+MIN_PARAM_VALUE = 1e-8
+# src/models/gaussian_process.jl:13
+MAX_NEG_VAR = 1e-8
+# AbstractGPs default observation jitter of `f(x)` == FiniteGP(f, x, 1e-18)  (Appendix A.7)
+DEFAULT_JITTER = 1e-18
+
+KERNEL_SE = 0        # KernelFunctions.SqExponentialKernel
+KERNEL_MATERN32 = 1  # KernelFunctions.Matern32Kernel
+KERNEL_MATERN52 = 2  # KernelFunctions.Matern52Kernel   (default, src/deprecated.jl:34)
+
+SQRT3 = math.sqrt(3.0)
+SQRT5 = math.sqrt(5.0)
+LOG2PI = math.log(2.0 * math.pi)
+INVSQRT2 = 1.0 / math.sqrt(2.0)
+INVSQRT2PI = 1.0 / math.sqrt(2.0 * math.pi)
+
+
+class DomainError(ValueError):
+    """Mirror of Julia's DomainError thrown by `_clip_var` (gaussian_process.jl:191)."""
+
+
+class PosDefException(ValueError):
+    """Mirror of LinearAlgebra.PosDefException thrown by `cholesky` on a non-PD matrix."""
+
+
+# --------------------------------------------------------------------------------------
+# a1  hyper-parameter conditioning + kernel matrices
+# --------------------------------------------------------------------------------------
+
+def condition_params(lengthscales, amplitude, noise_std):
+    """src/models/gaussian_process.jl:227-241 -- asserts >= 0, then *adds* 1e-8 (not max)."""
+    ls = np.asarray(lengthscales, dtype=np.float64)
+    if not (np.all(ls >= 0) and amplitude >= 0 and noise_std >= 0):
+        raise AssertionError("negative GP hyper-parameter (gaussian_process.jl:227-229)")
+    return ls + MIN_PARAM_VALUE, float(amplitude) + MIN_PARAM_VALUE, float(noise_std) + MIN_PARAM_VALUE
+
+
+def julia_round(x):
+    """Julia `round` default = RoundNearest ties-to-even == numpy.rint.  (src/utils/utils.jl:24-26)"""
+    return np.rint(x)
+
+
+def discrete_round(mask, X):
+    """src/utils/utils.jl:24-26 `discrete_round(dims, x)` applied column-wise to a d x N matrix."""
+    if mask is None:
+        return X
+    mask = np.asarray(mask, dtype=bool)
+    Xr = np.array(X, dtype=np.float64, copy=True)
+    Xr[mask, :] = julia_round(Xr[mask, :])
+    return Xr
+
+
+def _kappa(d2, kernel_id):
+    """KernelFunctions kappa on squared (SE) / plain (Matern) Euclidean distance.  Appendix A.4."""
+    if kernel_id == KERNEL_SE:
+        return np.exp(-d2 / 2.0)
+    r = np.sqrt(d2)
+    if kernel_id == KERNEL_MATERN32:
+        return (1.0 + SQRT3 * r) * np.exp(-SQRT3 * r)
+    if kernel_id == KERNEL_MATERN52:
+        return (1.0 + SQRT5 * r + 5.0 * d2 / 3.0) * np.exp(-SQRT5 * r)
+    raise ValueError(f"unknown kernel_id {kernel_id}")
+
+
+def _pairwise_sqdist_gemm(A, B, symmetric=False):
+    """Distances.jl `pairwise(SqEuclidean(), A, B; dims=2)` GEMM trick.  Appendix A.3."""
+    sa = np.sum(A * A, axis=0)
+    sb = sa if symmetric else np.sum(B * B, axis=0)
+    R = A.T @ B
+    D = np.maximum(sa[:, None] + sb[None, :] - 2.0 * R, 0.0)
+    if symmetric:
+        np.fill_diagonal(D, 0.0)
+        D = np.triu(D) + np.triu(D, 1).T      # one-argument form mirrors the upper triangle
+    return D
+
+
+def _pairwise_sqdist_direct(A, B):
+    """Element-wise evaluation used for generic (DiscreteKernel-wrapped) kernels.  Appendix A.3."""
+    D = np.zeros((A.shape[1], B.shape[1]))
+    for i in range(A.shape[0]):
+        diff = A[i][:, None] - B[i][None, :]
+        D += diff * diff
+    return D
+
+
+def kernel_matrix(X1, X2, ls, amp, kernel_id, discrete_mask=None):
+    """a^2 * (kappa o ARDTransform(1/l)) evaluated on all column pairs.
+
+    `ls`, `amp` are the *conditioned* values.  gaussian_process.jl:243 (`with_lengthscale`) and
+    models/utils/kernels.jl:56-64 (DiscreteKernel: round first, then scale).  X2=None -> symmetric.
+    """
+    inv = 1.0 / ls
+    sym = X2 is None
+    if discrete_mask is not None and np.any(discrete_mask):
+        A = discrete_round(discrete_mask, X1) * inv[:, None]
+        B = A if sym else discrete_round(discrete_mask, X2) * inv[:, None]
+        D = _pairwise_sqdist_direct(A, B)
+    else:
+        A = X1 * inv[:, None]
+        B = A if sym else X2 * inv[:, None]
+        D = _pairwise_sqdist_gemm(A, B, symmetric=sym)
+    return (amp * amp) * _kappa(D, kernel_id)
+
+
+# --------------------------------------------------------------------------------------
+# a2  posterior fit
+# --------------------------------------------------------------------------------------
+
+@dataclass
+class GPPosterior:
+    """What AbstractGPs.posterior stores: (alpha_w, C=cholesky, X, delta).  Appendix A.6."""
+    X: np.ndarray            # d x n
+    ls: np.ndarray           # conditioned length-scales
+    amp: float               # conditioned amplitude
+    noise: float             # conditioned noise std
+    kernel_id: int
+    discrete_mask: Optional[np.ndarray]
+    U: np.ndarray            # upper Cholesky factor, K = U'U
+    alpha_w: np.ndarray      # K^{-1} (y - m(X))
+    delta: np.ndarray        # y - m(X)
+
+
+def cholesky_upper(K):
+    """LinearAlgebra.cholesky(Symmetric(K)) -> LAPACK dpotrf('U').  Appendix A.5."""
+    try:
+        return sl.cholesky(K, lower=False, check_finite=False)
+    except sl.LinAlgError as e:
+        raise PosDefException(str(e)) from None
+
+
+def posterior_fit(X, y_minus_mean, lengthscales, amplitude, noise_std, kernel_id=KERNEL_MATERN52,
+                  discrete_mask=None) -> GPPosterior:
+    """`posterior_gp` (gaussian_process.jl:199-211) -> finite_gp (:216-248) -> AbstractGPs.posterior.
+
+    `y_minus_mean` = Y[slice,:] - m(X): the prior mean (nothing | constant | closure) is evaluated
+    by the caller, exactly like the C ABI boundary.
+    """
+    X = np.asarray(X, dtype=np.float64)
+    delta = np.asarray(y_minus_mean, dtype=np.float64)
+    ls, amp, noise = condition_params(lengthscales, amplitude, noise_std)
+    assert ls.shape[0] == X.shape[0], "gaussian_process.jl:233"
+    n = X.shape[1]
+    K = kernel_matrix(X, None, ls, amp, kernel_id, discrete_mask)
+    K[np.diag_indices(n)] += noise * noise
+    U = cholesky_upper(K)
+    alpha_w = sl.cho_solve((U, False), delta, check_finite=False)
+    return GPPosterior(X, ls, amp, noise, kernel_id,
+                       None if discrete_mask is None else np.asarray(discrete_mask, bool), U, alpha_w, delta)
+
+
+# --------------------------------------------------------------------------------------
+# a3 / a4  predict + clip
+# --------------------------------------------------------------------------------------
+
+def clip_var(v):
+    """`_clip_var` scalar semantics, gaussian_process.jl:186-194 (NaN -> DomainError)."""
+    if v >= 0.0:
+        return v
+    if v >= -MAX_NEG_VAR:
+        return 0.0
+    raise DomainError(f"The posterior GP predicted variance {v}")
+
+
+def clip_var_status(var):
+    """Vectorised `_clip_var`: returns (clipped, status) with status 2 where Julia would throw."""
+    var = np.asarray(var, dtype=np.float64)
+    ok_pos = var >= 0.0
+    ok_clip = (~ok_pos) & (var >= -MAX_NEG_VAR)
+    bad = ~(ok_pos | ok_clip)
+    out = np.where(ok_clip, 0.0, var)
+    return out, np.where(bad, 2, 0).astype(np.int32)
+
+
+def mean_and_var_raw(post: GPPosterior, Xs, prior_mean_s=None):
+    """AbstractGPs `mean_and_var(post_gp(Xs))` before BOSS's clip.  Appendix A.7."""
+    Xs = np.asarray(Xs, dtype=np.float64)
+    if Xs.ndim == 1:
+        Xs = Xs[:, None]
+    Ks = kernel_matrix(post.X, Xs, post.ls, post.amp, post.kernel_id, post.discrete_mask)  # n x M
+    mu = Ks.T @ post.alpha_w
+    if prior_mean_s is not None:
+        mu = np.asarray(prior_mean_s, dtype=np.float64) + mu
+    V = sl.solve_triangular(post.U, Ks, trans='T', lower=False, check_finite=False)
+    var = (post.amp * post.amp) - np.sum(V * V, axis=0) + DEFAULT_JITTER
+    return mu, var
+
+
+def mean_and_var(post: GPPosterior, Xs, prior_mean_s=None):
+    """`mean_and_var(::GaussianProcessPosterior, X)` gaussian_process.jl:169-178 -> (mu, var, status)."""
+    mu, var = mean_and_var_raw(post, Xs, prior_mean_s)
+    var, status = clip_var_status(var)
+    return mu, var, status
+
+
+def posterior_cov(post: GPPosterior, Xs):
+    """`cov(::GaussianProcessPosterior, X)` gaussian_process.jl:163-167 (diagonal clipped)."""
+    Xs = np.asarray(Xs, dtype=np.float64)
+    Ks = kernel_matrix(post.X, Xs, post.ls, post.amp, post.kernel_id, post.discrete_mask)
+    Kss = kernel_matrix(Xs, None, post.ls, post.amp, post.kernel_id, post.discrete_mask)
+    V = sl.solve_triangular(post.U, Ks, trans='T', lower=False, check_finite=False)
+    C = Kss - V.T @ V + DEFAULT_JITTER * np.eye(Xs.shape[1])
+    dg, status = clip_var_status(np.diag(C))
+    C[np.diag_indices_from(C)] = dg
+    return C, status
+
+
+# --------------------------------------------------------------------------------------
+# a8  log marginal likelihood
+# --------------------------------------------------------------------------------------
+
+def gp_loglik(X, y_minus_mean, lengthscales, amplitude, noise_std, kernel_id=KERNEL_MATERN52,
+              discrete_mask=None):
+    """`gp_data_loglike_slice` gaussian_process.jl:269-280 -> `logpdf(::FiniteGP, y)`.  Appendix A.8.
+
+    Non-PD -> -Inf (what `safe_data_loglike` turns the exception into, src/surrogate_model.jl:2-12).
+    """
+    X = np.asarray(X, dtype=np.float64)
+    delta = np.asarray(y_minus_mean, dtype=np.float64)
+    ls, amp, noise = condition_params(lengthscales, amplitude, noise_std)
+    n = X.shape[1]
+    K = kernel_matrix(X, None, ls, amp, kernel_id, discrete_mask)
+    K[np.diag_indices(n)] += noise * noise
+    try:
+        U = cholesky_upper(K)
+    except PosDefException:
+        return -math.inf
+    w = sl.solve_triangular(U, delta, trans='T', lower=False, check_finite=False)
+    logdet = 2.0 * np.sum(np.log(np.diag(U)))
+    return float(-(n * LOG2PI + logdet + np.dot(w, w)) / 2.0)
+
+
+def gp_loglik_batch(X, Y_minus_mean, lengthscales, amplitude, noise_std, kernel_id=KERNEL_MATERN52,
+                    discrete_mask=None):
+    """The batch the fitters build (model_fitters/sampling.jl:59-78): one loglik per sample.
+
+    Y_minus_mean: (n,) shared or (S, n); lengthscales (S, d); amplitude (S,); noise_std (S,).
+    """
+    lengthscales = np.asarray(lengthscales, dtype=np.float64)
+    S = lengthscales.shape[0]
+    Ym = np.asarray(Y_minus_mean, dtype=np.float64)
+    out = np.empty(S)
+    for s in range(S):
+        ym = Ym if Ym.ndim == 1 else Ym[s]
+        out[s] = gp_loglik(X, ym, lengthscales[s], amplitude[s], noise_std[s], kernel_id, discrete_mask)
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# a6  acquisition: closed-form EI, probability of feasibility, guards
+# --------------------------------------------------------------------------------------
+
+def normcdf(z):
+    """StatsFuns.normcdf(z) = erfc(-z/sqrt2)/2.  Appendix A.9."""
+    return erfc(-np.asarray(z, dtype=np.float64) * INVSQRT2) / 2.0
+
+
+def normpdf(z):
+    """StatsFuns.normpdf(z) = exp(-z^2/2)/sqrt(2pi).  Appendix A.9."""
+    z = np.asarray(z, dtype=np.float64)
+    return np.exp(-(z * z) / 2.0) * INVSQRT2PI
+
+
+def normal_cdf(mu, sigma, x):
+    """`cdf(Normal(mu, sigma), x)` incl. the StatsFuns sigma == 0 special case and
+    `cdf(., Infinity()) = 1.` (src/utils/inf.jl:13-15).  Appendix A.9."""
+    mu = np.asarray(mu, dtype=np.float64)
+    sigma = np.asarray(sigma, dtype=np.float64)
+    x = np.asarray(x, dtype=np.float64)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        z = (x - mu) / sigma
+    z = np.where((sigma == 0.0) & (x == mu), np.inf, z)    # StatsFuns: x == mu, sigma == 0 -> 1
+    c = normcdf(z)
+    return np.where(np.isposinf(x), 1.0, c)
+
+
+def expected_improvement(coefs, mean, var, best_yet):
+    """`expected_improvement(::LinFitness, mean, var, eps, best_yet)` expected_improvement.jl:93-101.
+
+    mean, var: (y_dim,) or (y_dim, M).  Returns scalar or (M,).
+    """
+    coefs = np.asarray(coefs, dtype=np.float64)
+    mean = np.asarray(mean, dtype=np.float64)
+    var = np.asarray(var, dtype=np.float64)
+    mu_f = coefs @ mean
+    sigma_f = np.sqrt((coefs ** 2) @ var)
+    diff = mu_f - best_yet
+    with np.errstate(divide='ignore', invalid='ignore'):
+        z = diff / sigma_f
+        ei = diff * normcdf(z) + sigma_f * normpdf(z)
+    return np.where((diff == 0.0) & (sigma_f == 0.0), 0.0, ei)
+
+
+def feas_prob(mean, var, y_max):
+    """`feas_prob(mean, var, constraints)` expected_improvement.jl:113-114 (2nd arg is a VARIANCE)."""
+    if y_max is None:
+        return 1.0
+    mean = np.asarray(mean, dtype=np.float64)
+    var = np.asarray(var, dtype=np.float64)
+    y_max = np.asarray(y_max, dtype=np.float64)
+    ym = y_max if mean.ndim == 1 else y_max[:, None]
+    return np.prod(normal_cdf(mean, np.sqrt(var), ym), axis=0)
+
+
+def is_feasible(y, y_max):
+    """src/utils/utils.jl:33"""
+    return bool(np.all(np.asarray(y) <= np.asarray(y_max)))
+
+
+def best_so_far(coefs, Y, y_max):
+    """`best_so_far(fitness, X, Y, y_max)` expected_improvement.jl:135-140 (raw observations)."""
+    Y = np.asarray(Y, dtype=np.float64)
+    if Y.size == 0:
+        return None
+    y_max = np.asarray(y_max, dtype=np.float64)
+    feas = np.all(Y <= y_max[:, None], axis=0)
+    if not np.any(feas):
+        return None
+    fit = np.asarray(coefs, dtype=np.float64) @ Y
+    return float(np.max(fit[feas]))
+
+
+def in_bounds(Xs, lb, ub):
+    """src/types/domain.jl:73-78 (inclusive) on the columns of a d x M matrix."""
+    Xs = np.asarray(Xs, dtype=np.float64)
+    lb = np.asarray(lb, dtype=np.float64)[:, None]
+    ub = np.asarray(ub, dtype=np.float64)[:, None]
+    return ~(np.any(Xs < lb, axis=0) | np.any(Xs > ub, axis=0))
+
+
+def ei_acquisition(posts: Sequence[Sequence[GPPosterior]], Xs, coefs, best_yet, y_max, lb=None, ub=None,
+                   cons_mask=None, prior_mean_s=None):
+    """The safe acquisition closure of `construct_safe_acquisition` evaluated on every column of Xs.
+
+    posts[s][i] = posterior of BI sample s, output slice i (one sample for MAP params).
+    Follows expected_improvement.jl:49-90 (+ make_safe :58-65) and acquisition.jl:21-25:
+      case split on (y_max is None, best_yet is None); average over samples; out-of-domain -> 0.;
+      `_clip_var` DomainError -> -Inf for that candidate.
+    y_max=None  <=> all constraints infinite (problem.jl:71-73 turns Inf into `Infinity()` whose cdf
+    is exactly 1, so the product is exactly 1 either way).
+    Returns (acq (M,), mu (S, y_dim, M), var (S, y_dim, M)).
+    """
+    Xs = np.asarray(Xs, dtype=np.float64)
+    M = Xs.shape[1]
+    S = len(posts)
+    y_dim = len(posts[0])
+    acc = np.zeros(M)
+    failed = np.zeros(M, dtype=bool)
+    mus = np.empty((S, y_dim, M))
+    vars_ = np.empty((S, y_dim, M))
+    for s in range(S):
+        for i in range(y_dim):
+            pm = None if prior_mean_s is None else np.asarray(prior_mean_s)[i]
+            mu, var, st = mean_and_var(posts[s][i], Xs, pm)
+            mus[s, i], vars_[s, i] = mu, var
+            failed |= st != 0
+        if best_yet is None and y_max is None:
+            a = np.zeros(M)
+        elif best_yet is None:
+            a = feas_prob(mus[s], vars_[s], y_max)
+        elif y_max is None:
+            a = expected_improvement(coefs, mus[s], vars_[s], best_yet)
+        else:
+            a = expected_improvement(coefs, mus[s], vars_[s], best_yet) * feas_prob(mus[s], vars_[s], y_max)
+        acc = acc + a
+    acq = acc / S
+    acq = np.where(failed, -np.inf, acq)
+    if lb is not None:
+        acq = np.where(in_bounds(Xs, lb, ub), acq, 0.0)
+    if cons_mask is not None:
+        acq = np.where(np.asarray(cons_mask, dtype=bool), acq, 0.0)
+    return acq, mus, vars_
+
+
+def julia_argmax(vals):
+    """Julia `argmax(vals)` / `argmax(f, itr)`: first maximal element under `isless`
+    (NaN is maximal, -0.0 < +0.0).  Appendix A.11.  Returns a 0-based index."""
+    vals = np.asarray(vals, dtype=np.float64)
+    best = 0
+    for i in range(1, vals.shape[0]):
+        if _isless(vals[best], vals[i]):
+            best = i
+    return best
+
+
+def _isless(a, b):
+    if math.isnan(a):
+        return False
+    if math.isnan(b):
+        return True
+    if a == 0.0 and b == 0.0:
+        return math.copysign(1.0, a) < math.copysign(1.0, b)
+    return a < b
+
+
+def julia_argmax_fast(vals):
+    """Vectorised equivalent of `julia_argmax` (used at large M)."""
+    vals = np.asarray(vals, dtype=np.float64)
+    nan = np.isnan(vals)
+    if nan.any():
+        return int(np.argmax(nan))
+    m = vals.max()
+    idx = np.flatnonzero(vals == m)
+    if m == 0.0:
+        pos = idx[~np.signbit(vals[idx])]
+        if pos.size:
+            return int(pos[0])
+    return int(idx[0])
+
+
+# --------------------------------------------------------------------------------------
+# analytic x-gradients (what ForwardDiff produces through the same stack; optimization.jl:36)
+# --------------------------------------------------------------------------------------
+
+def _kappa_dr_over_r(d2, kernel_id):
+    """(d kappa / d r) / r  as a function of squared distance (finite at r = 0 for all three)."""
+    if kernel_id == KERNEL_SE:
+        return -np.exp(-d2 / 2.0)
+    r = np.sqrt(d2)
+    if kernel_id == KERNEL_MATERN32:
+        return -3.0 * np.exp(-SQRT3 * r)
+    if kernel_id == KERNEL_MATERN52:
+        return -(5.0 / 3.0) * (1.0 + SQRT5 * r) * np.exp(-SQRT5 * r)
+    raise ValueError(kernel_id)
+
+
+def mean_var_grad(post: GPPosterior, Xs, prior_mean_s=None, prior_mean_grad_s=None):
+    """mu, var (clipped) and their gradients w.r.t. each candidate column.
+
+    d mu/dx = sum_k alpha_k dk(x,x_k)/dx ;  d var/dx = -2 sum_k (K^{-1}k*)_k dk(x,x_k)/dx.
+    Discrete (rounded) dims have zero derivative.  Returns mu (M,), var (M,), dmu (d,M), dvar (d,M), status.
+    """
+    Xs = np.asarray(Xs, dtype=np.float64)
+    d, M = Xs.shape
+    inv = 1.0 / post.ls
+    Xa = discrete_round(post.discrete_mask, post.X) * inv[:, None]
+    Xb = discrete_round(post.discrete_mask, Xs) * inv[:, None]
+    D2 = _pairwise_sqdist_direct(Xa, Xb)                       # n x M
+    a2 = post.amp * post.amp
+    Ks = a2 * _kappa(D2, post.kernel_id)
+    G = a2 * _kappa_dr_over_r(D2, post.kernel_id)              # n x M ; dk/dx_j = G * (xb_j - xa_j) * inv_j
+    mu = Ks.T @ post.alpha_w
+    V = sl.solve_triangular(post.U, Ks, trans='T', lower=False, check_finite=False)
+    Uk = sl.solve_triangular(post.U, V, trans='N', lower=False, check_finite=False)   # K^{-1} k*
+    var = a2 - np.sum(V * V, axis=0) + DEFAULT_JITTER
+    dmu = np.empty((d, M))
+    dvar = np.empty((d, M))
+    for j in range(d):
+        diff = (Xb[j][None, :] - Xa[j][:, None]) * inv[j]      # n x M
+        dk = G * diff
+        dmu[j] = post.alpha_w @ dk
+        dvar[j] = -2.0 * np.sum(Uk * dk, axis=0)
+    if post.discrete_mask is not None:
+        dmu[post.discrete_mask] = 0.0
+        dvar[post.discrete_mask] = 0.0
+    if prior_mean_s is not None:
+        mu = mu + prior_mean_s
+    if prior_mean_grad_s is not None:
+        dmu = dmu + prior_mean_grad_s
+    var_c, status = clip_var_status(var)
+    dvar = np.where(var >= 0.0, dvar, 0.0)                     # clipped branch returns a constant zero
+    return mu, var_c, dmu, dvar, status
+
+
+def ei_value_grad(posts: Sequence[GPPosterior], Xs, coefs, best_yet, y_max, prior_mean_s=None):
+    """EI x PoF value and x-gradient for ONE parameter sample (posts[i] = slice i), in-domain points.
+
+    d EI = Phi(z) d(mu_f) + phi(z) d(sigma_f)   (the Delta*phi*dz terms cancel).
+    """
+    Xs = np.asarray(Xs, dtype=np.float64)
+    d, M = Xs.shape
+    y_dim = len(posts)
+    coefs = np.asarray(coefs, dtype=np.float64)
+    mus = np.empty((y_dim, M)); vs = np.empty((y_dim, M))
+    dmus = np.empty((y_dim, d, M)); dvs = np.empty((y_dim, d, M))
+    failed = np.zeros(M, bool)
+    for i in range(y_dim):
+        pm = None if prior_mean_s is None else prior_mean_s[i]
+        mus[i], vs[i], dmus[i], dvs[i], st = mean_var_grad(posts[i], Xs, pm)
+        failed |= st != 0
+    val = np.ones(M)
+    grad = np.zeros((d, M))
+    if best_yet is not None:
+        mu_f = coefs @ mus
+        s2 = (coefs ** 2) @ vs
+        sf = np.sqrt(s2)
+        diff = mu_f - best_yet
+        with np.errstate(divide='ignore', invalid='ignore'):
+            z = diff / sf
+            ei = np.where((diff == 0) & (sf == 0), 0.0, diff * normcdf(z) + sf * normpdf(z))
+            dmu_f = np.einsum('i,idm->dm', coefs, dmus)
+            ds2 = np.einsum('i,idm->dm', coefs ** 2, dvs)
+            dsf = np.where(sf > 0, ds2 / (2.0 * sf), 0.0)
+            dei = normcdf(z) * dmu_f + normpdf(z) * dsf
+        dei = np.where(sf > 0, dei, np.where(diff > 0, dmu_f, 0.0))
+        val, grad = ei, dei
+    elif y_max is None:
+        return np.zeros(M), np.zeros((d, M))
+    if y_max is not None:
+        y_max = np.asarray(y_max, dtype=np.float64)
+        pof = np.ones(M)
+        dlog = np.zeros((d, M))      # accumulate via product rule on factors
+        facs, dfacs = [], []
+        for i in range(y_dim):
+            if np.isposinf(y_max[i]):
+                continue
+            s = np.sqrt(vs[i])
+            with np.errstate(divide='ignore', invalid='ignore'):
+                z = (y_max[i] - mus[i]) / s
+                c = normal_cdf(mus[i], s, y_max[i])
+                dz = (-dmus[i]) / s - (y_max[i] - mus[i]) * dvs[i] / (2.0 * s * vs[i])
+                dc = np.where(s > 0, normpdf(z) * dz, 0.0)
+            facs.append(c); dfacs.append(dc)
+        pof = np.prod(facs, axis=0) if facs else np.ones(M)
+        dpof = np.zeros((d, M))
+        for a in range(len(facs)):
+            others = np.ones(M)
+            for b in range(len(facs)):
+                if b != a:
+                    others = others * facs[b]
+            dpof += dfacs[a] * others
+        grad = grad * pof + val * dpof if best_yet is not None else dpof
+        val = val * pof if best_yet is not None else pof
+    val = np.where(failed, -np.inf, val)
+    return val, grad
+
+
+# --------------------------------------------------------------------------------------
+# extended-precision adjudicator (mpmath; small n only)
+# --------------------------------------------------------------------------------------
+
+def adjudicator_mean_var_loglik(X, y_minus_mean, lengthscales, amplitude, noise_std, kernel_id, Xs, dps=50):
+    """Same maths in `dps`-digit arithmetic with direct distances.  For n <~ 64.  Not a restatement of
+    any reference op order: it approximates the *exact* value both implementations aim at."""
+    import mpmath as mp
+    mp.mp.dps = dps
+    X = np.asarray(X, dtype=np.float64); Xs = np.asarray(Xs, dtype=np.float64)
+    d, n = X.shape
+    M = Xs.shape[1]
+    ls = [mp.mpf(float(v)) + mp.mpf('1e-8') for v in lengthscales]
+    a = mp.mpf(float(amplitude)) + mp.mpf('1e-8')
+    s = mp.mpf(float(noise_std)) + mp.mpf('1e-8')
+
+    def k(p, q):
+        d2 = sum(((mp.mpf(float(p[i])) - mp.mpf(float(q[i]))) / ls[i]) ** 2 for i in range(d))
+        if kernel_id == KERNEL_SE:
+            kap = mp.e ** (-d2 / 2)
+        elif kernel_id == KERNEL_MATERN32:
+            r = mp.sqrt(d2); kap = (1 + mp.sqrt(3) * r) * mp.e ** (-mp.sqrt(3) * r)
+        else:
+            r = mp.sqrt(d2); kap = (1 + mp.sqrt(5) * r + 5 * d2 / 3) * mp.e ** (-mp.sqrt(5) * r)
+        return a * a * kap
+
+    K = mp.matrix(n, n)
+    for i in range(n):
+        for j in range(n):
+            K[i, j] = k(X[:, i], X[:, j]) + (s * s if i == j else 0)
+    L = mp.cholesky(K)
+    delta = mp.matrix([mp.mpf(float(v)) for v in y_minus_mean])
+    w = mp.lu_solve(L, delta)
+    alpha = mp.lu_solve(L.T, w)
+    logdet = 2 * sum(mp.log(L[i, i]) for i in range(n))
+    ll = -(n * mp.log(2 * mp.pi) + logdet + sum(w[i] ** 2 for i in range(n))) / 2
+    mu = np.empty(M); var = np.empty(M)
+    for m in range(M):
+        ks = mp.matrix([k(X[:, i], Xs[:, m]) for i in range(n)])
+        v = mp.lu_solve(L, ks)
+        mu[m] = float(sum(ks[i] * alpha[i] for i in range(n)))
+        var[m] = float(a * a - sum(v[i] ** 2 for i in range(n)) + mp.mpf('1e-18'))
+    return mu, var, float(ll)

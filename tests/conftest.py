@@ -1,0 +1,21 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
+
+
+@pytest.fixture(scope="session")
+def lib():
+    """The ctypes-bound C-ABI library, initialised on cuda:0 (GPU tests only)."""
+    import boss_b200
+    from boss_b200 import _lib
+    _lib.init(0)
+    return _lib
