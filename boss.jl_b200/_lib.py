@@ -1,0 +1,258 @@
+"""ctypes binding of libboss_b200.so (include/boss_b200.h).  No CPU fallback: importing this module
+without the built CUDA library raises, and every call raises BossError on a CUDA / argument error."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libboss_b200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(nvcc -gencode arch=compute_100a,code=sm_100a).  boss_b200 has no CPU fallback.")
+
+lib = C.CDLL(LIB_PATH)
+
+BOSS_OK, BOSS_NOT_POSDEF, BOSS_NEG_VARIANCE = 0, 1, 2
+KERNEL_SE, KERNEL_MATERN32, KERNEL_MATERN52 = 0, 1, 2
+
+_dp = C.POINTER(C.c_double)
+_u8p = C.POINTER(C.c_uint8)
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+_vp = C.c_void_p
+
+EXPORTS = {
+    "boss_init": (C.c_int, [C.c_int]),
+    "boss_shutdown": (None, []),
+    "boss_last_error": (C.c_char_p, []),
+    "boss_version": (C.c_int, []),
+    "boss_device": (C.c_int, []),
+    "boss_gp_fit": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, C.c_double, C.c_double, C.c_int, _vp,
+                              C.POINTER(_vp), _dp]),
+    "boss_gp_free": (None, [_vp]),
+    "boss_gp_n": (C.c_int, [_vp]),
+    "boss_gp_d": (C.c_int, [_vp]),
+    "boss_gp_predict": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp, _vp]),
+    "boss_gp_predict_dev": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp, _vp]),
+    "boss_gp_cov": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp]),
+    "boss_ei_score": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                _dp, _i64p]),
+    "boss_ei_score_dev": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                    _vp, _dp, _i64p, _vp]),
+    "boss_gp_loglik_batch": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, _vp, C.c_int, _vp, C.c_int64,
+                                       _vp]),
+    "boss_gp_loglik_batch_dev": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, _vp, C.c_int, _vp,
+                                           C.c_int64, _vp, _vp]),
+    "boss_set_timing": (None, [C.c_int]),
+    "boss_last_kernel_ms": (C.c_double, [C.c_int]),
+    "boss_last_kernel_count": (C.c_int, [C.c_int]),
+    "boss_launch_count": (C.c_int64, []),
+    "boss_dbg_gemm_nt": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
+    "boss_dbg_factors": (C.c_int, [_vp, _vp, _vp, _vp]),
+}
+for _name, (_res, _args) in EXPORTS.items():
+    _f = getattr(lib, _name)          # AttributeError here = header and library disagree
+    _f.restype = _res
+    _f.argtypes = _args
+
+
+class BossError(RuntimeError):
+    pass
+
+
+def last_error() -> str:
+    return lib.boss_last_error().decode()
+
+
+def _check(rc: int, what: str) -> int:
+    if rc < 0:
+        raise BossError(f"{what} failed ({rc}): {last_error()}")
+    return rc
+
+
+def init(device: int = 0) -> None:
+    _check(lib.boss_init(int(device)), "boss_init")
+
+
+def shutdown() -> None:
+    lib.boss_shutdown()
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        assert a.shape == shape, (a.shape, shape)
+    return a
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(_vp)
+
+
+def _cols(X):
+    """d x M matrix (BOSS.jl orientation) -> M x d C-contiguous = column-major d x M in memory."""
+    X = np.asarray(X, dtype=np.float64)
+    if X.ndim == 1:
+        X = X[:, None]
+    return np.ascontiguousarray(X.T)
+
+
+class GP:
+    """Owner of one `boss_gp*` (one output slice, one hyper-parameter vector)."""
+
+    def __init__(self, handle, n, d, loglik):
+        self._h = handle
+        self.n, self.d, self.loglik = n, d, loglik
+
+    @property
+    def handle(self):
+        if not self._h:
+            raise BossError("GP handle already freed")
+        return self._h
+
+    def free(self):
+        if self._h:
+            lib.boss_gp_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def gp_fit(X, y_minus_mean, lengthscales, amplitude, noise_std, kernel_id=KERNEL_MATERN52, discrete_mask=None):
+    """-> GP, or None when K is not positive definite (BOSS_NOT_POSDEF)."""
+    Xc = _cols(X)
+    n, d = Xc.shape
+    y = _f64(y_minus_mean, (n,))
+    ls = _f64(lengthscales, (d,))
+    dm = None if discrete_mask is None else np.ascontiguousarray(discrete_mask, dtype=np.uint8)
+    out = _vp()
+    ll = C.c_double()
+    rc = _check(lib.boss_gp_fit(_ptr(Xc), d, n, _ptr(y), _ptr(ls), float(amplitude), float(noise_std), int(kernel_id),
+                                _ptr(dm), C.byref(out), C.byref(ll)), "boss_gp_fit")
+    if rc == BOSS_NOT_POSDEF:
+        return None
+    return GP(out, n, d, ll.value)
+
+
+def gp_predict(gp: GP, Xs, prior_mean_s=None):
+    """-> mu (M,), var (M,), status (M,) int32."""
+    Xc = _cols(Xs)
+    M = Xc.shape[0]
+    pm = None if prior_mean_s is None else _f64(prior_mean_s, (M,))
+    mu = np.empty(M)
+    var = np.empty(M)
+    st = np.empty(M, dtype=np.int32)
+    _check(lib.boss_gp_predict(gp.handle, _ptr(Xc), M, _ptr(pm), _ptr(mu), _ptr(var), _ptr(st)), "boss_gp_predict")
+    return mu, var, st
+
+
+def _slice_array(slices):
+    flat = [g.handle for g in slices]
+    arr = (_vp * len(flat))(*flat)
+    return arr
+
+
+def ei_score(slices, y_dim, n_samples, Xs, coefs, best, y_max, lb=None, ub=None, cons_mask=None, prior_mean_s=None,
+             want_acq=True):
+    """slices: flat list, sample-major (slices[s*y_dim+i]).  -> acq (M,) or None, best_val, best_idx."""
+    Xc = _cols(Xs)
+    M, d = Xc.shape
+    assert len(slices) == y_dim * n_samples
+    arr = _slice_array(slices)
+    co = _f64(coefs, (y_dim,))
+    b = None if best is None else np.array([best], dtype=np.float64)
+    ym = None if y_max is None else _f64(y_max, (y_dim,))
+    lbv = None if lb is None else _f64(lb, (d,))
+    ubv = None if ub is None else _f64(ub, (d,))
+    cm = None if cons_mask is None else np.ascontiguousarray(cons_mask, dtype=np.uint8)
+    pm = None if prior_mean_s is None else np.ascontiguousarray(np.asarray(prior_mean_s, dtype=np.float64).T)
+    acq = np.empty(M) if want_acq else None
+    bv = C.c_double()
+    bi = C.c_int64()
+    _check(lib.boss_ei_score(arr, y_dim, n_samples, _ptr(Xc), M, _ptr(pm), _ptr(co), _ptr(b), _ptr(ym), _ptr(lbv),
+                             _ptr(ubv), _ptr(cm), _ptr(acq), None, C.byref(bv), C.byref(bi)), "boss_ei_score")
+    return acq, bv.value, bi.value
+
+
+def ei_score_dev(slices, y_dim, n_samples, Xs_ptr, M, coefs, best, y_max, lb=None, ub=None, acq_ptr=None,
+                 prior_mean_ptr=None, cons_mask_ptr=None):
+    """Device-pointer variant: Xs_ptr etc. are raw CUDA addresses (e.g. torch.Tensor.data_ptr())."""
+    arr = _slice_array(slices)
+    co = _f64(coefs, (y_dim,))
+    b = None if best is None else np.array([best], dtype=np.float64)
+    ym = None if y_max is None else _f64(y_max, (y_dim,))
+    lbv = None if lb is None else _f64(lb)
+    ubv = None if ub is None else _f64(ub)
+    bv = C.c_double()
+    bi = C.c_int64()
+    _check(lib.boss_ei_score_dev(arr, y_dim, n_samples, _vp(Xs_ptr), int(M), _vp(prior_mean_ptr) if prior_mean_ptr else None,
+                                 _ptr(co), _ptr(b), _ptr(ym), _ptr(lbv), _ptr(ubv),
+                                 _vp(cons_mask_ptr) if cons_mask_ptr else None, _vp(acq_ptr) if acq_ptr else None, None,
+                                 C.byref(bv), C.byref(bi), None), "boss_ei_score_dev")
+    return bv.value, bi.value
+
+
+def loglik_batch(X, Y_minus_mean, lengthscales, amplitude, noise_std, kernel_id=KERNEL_MATERN52, discrete_mask=None):
+    """lengthscales (S, d), amplitude (S,), noise_std (S,), Y_minus_mean (n,) shared or (S, n) -> (S,)"""
+    Xc = _cols(X)
+    n, d = Xc.shape
+    ls = _f64(lengthscales)
+    S = ls.shape[0]
+    assert ls.shape == (S, d)
+    amp = _f64(amplitude, (S,))
+    ns = _f64(noise_std, (S,))
+    Y = _f64(Y_minus_mean)
+    ldy = 0 if Y.ndim == 1 else n
+    assert Y.shape == ((n,) if ldy == 0 else (S, n))
+    dm = None if discrete_mask is None else np.ascontiguousarray(discrete_mask, dtype=np.uint8)
+    out = np.empty(S)
+    _check(lib.boss_gp_loglik_batch(_ptr(Xc), d, n, _ptr(Y), ldy, _ptr(ls), _ptr(amp), _ptr(ns), int(kernel_id),
+                                    _ptr(dm), S, _ptr(out)), "boss_gp_loglik_batch")
+    return out
+
+
+def loglik_batch_dev(X_ptr, d, n, Y_ptr, ldy, ls_ptr, amp_ptr, noise_ptr, kernel_id, S, out_ptr, discrete_mask=None):
+    dm = None if discrete_mask is None else np.ascontiguousarray(discrete_mask, dtype=np.uint8)
+    _check(lib.boss_gp_loglik_batch_dev(_vp(X_ptr), d, n, _vp(Y_ptr), ldy, _vp(ls_ptr), _vp(amp_ptr), _vp(noise_ptr),
+                                        int(kernel_id), _ptr(dm), int(S), _vp(out_ptr), None),
+           "boss_gp_loglik_batch_dev")
+
+
+def set_timing(on: bool):
+    lib.boss_set_timing(1 if on else 0)
+
+
+def last_kernel_ms(which: int):
+    return lib.boss_last_kernel_ms(which), lib.boss_last_kernel_count(which)
+
+
+def launch_count() -> int:
+    return lib.boss_launch_count()
+
+
+def dbg_gemm_nt(A, B):
+    A = _f64(A)
+    B = _f64(B)
+    M, K = A.shape
+    N = B.shape[0]
+    Cm = np.empty((M, N))
+    _check(lib.boss_dbg_gemm_nt(_ptr(A), _ptr(B), M, N, K, _ptr(Cm)), "boss_dbg_gemm_nt")
+    return Cm
+
+
+def dbg_factors(gp: GP):
+    n = gp.n
+    L = np.empty((n, n))
+    W = np.empty((n, n))
+    al = np.empty(n)
+    _check(lib.boss_dbg_factors(gp.handle, _ptr(L), _ptr(W), _ptr(al)), "boss_dbg_factors")
+    return L, W, al

@@ -1,0 +1,981 @@
+// boss_b200.cu -- host runtime + C ABI of libboss_b200.so (see include/boss_b200.h).
+//
+// One process drives one B200.  All numerics run in the hand-written sm_100a kernels of
+// cholesky.cuh / score.cuh on the library's stream; this file owns device memory (grow-only
+// workspaces sized for 180 GB HBM3e), the fitted-GP handles (the factor cache) and the chunked
+// candidate pipeline.  There is no CPU fallback: every entry point fails with BOSS_ERR_STATE /
+// BOSS_ERR_CUDA if the device is not usable.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/boss_b200.h"
+#include "cholesky.cuh"
+#include "score.cuh"
+
+using namespace boss;
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      e = cudaMalloc(&p, bytes);
+      want = bytes;
+    }
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T *as() const {
+    return reinterpret_cast<T *>(p);
+  }
+};
+
+constexpr int N_TIMERS = 4;
+constexpr int EV_POOL = 512;
+
+struct Ctx {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
+  std::string err;
+  int64_t launches = 0;
+  bool timing = false;
+  // workspaces
+  DevBuf ks, muv, sumsq, xs_stage, pm_stage, cm_stage, acq_stage, mu_stage, var_stage, st_stage, grad_stage;
+  DevBuf blk_val, blk_idx, small, chol_L, chol_Winv, chol_misc, tt;
+  // event pool for per-kernel-class timing
+  cudaEvent_t ev_a[EV_POOL], ev_b[EV_POOL];
+  int ev_class[EV_POOL];
+  int ev_used = 0;
+  bool ev_ready = false;
+  double last_ms[N_TIMERS] = {0, 0, 0, 0};
+  int last_cnt[N_TIMERS] = {0, 0, 0, 0};
+  cudaEvent_t call_a = nullptr, call_b = nullptr;
+};
+
+Ctx g;
+
+int fail(int code, const std::string &msg) {
+  g.err = msg;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                                 \
+  do {                                                                                                 \
+    cudaError_t _e = (expr);                                                                           \
+    if (_e != cudaSuccess)                                                                             \
+      return fail(BOSS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" __FILE__ ":" + \
+                                     std::to_string(__LINE__) + ")");                                  \
+  } while (0)
+
+// timing helpers: bracket one launch with a pooled event pair
+struct Timed {
+  int slot = -1;
+  Timed(int cls) {
+    if (g.timing && g.ev_used < EV_POOL) {
+      slot = g.ev_used++;
+      g.ev_class[slot] = cls;
+      cudaEventRecord(g.ev_a[slot], g.stream);
+    }
+  }
+  ~Timed() {
+    if (slot >= 0) cudaEventRecord(g.ev_b[slot], g.stream);
+  }
+};
+
+void timing_begin() {
+  g.ev_used = 0;
+  if (g.timing) cudaEventRecord(g.call_a, g.stream);
+}
+void timing_end() {  // call after the stream has been synchronised
+  for (int c = 0; c < N_TIMERS; ++c) {
+    g.last_ms[c] = 0;
+    g.last_cnt[c] = 0;
+  }
+  if (!g.timing) return;
+  cudaEventRecord(g.call_b, g.stream);
+  cudaEventSynchronize(g.call_b);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, g.call_a, g.call_b);
+  g.last_ms[3] = ms;
+  g.last_cnt[3] = 1;
+  for (int i = 0; i < g.ev_used; ++i) {
+    cudaEventElapsedTime(&ms, g.ev_a[i], g.ev_b[i]);
+    g.last_ms[g.ev_class[i]] += ms;
+    g.last_cnt[g.ev_class[i]] += 1;
+  }
+}
+
+int pick_dp(int d) {
+  if (d <= 2) return 2;
+  if (d <= 4) return 4;
+  if (d <= 8) return 8;
+  if (d <= 16) return 16;
+  if (d <= 32) return 32;
+  return -1;
+}
+
+unsigned long long mask_bits(const uint8_t *mask, int d) {
+  unsigned long long b = 0;
+  if (mask)
+    for (int i = 0; i < d; ++i)
+      if (mask[i]) b |= (1ull << i);
+  return b;
+}
+
+// ---- kernel dispatch on (kernel_id, DP) ----
+template <int KID, int DP>
+void launch_build_k_t(const BuildKParams &p, dim3 grid) {
+  build_k_kernel<KID, DP><<<grid, 256, 0, g.stream>>>(p);
+}
+template <int KID, int DP>
+void launch_xcov_t(const XcovParams &p, int ncb) {
+  xcov_kernel<KID, DP><<<ncb, 256, 0, g.stream>>>(p);
+}
+#define DISPATCH_KID_DP(FN, kid, dp, ...)                  \
+  do {                                                     \
+    switch ((kid) * 100 + (dp)) {                          \
+      case 2: FN<0, 2>(__VA_ARGS__); break;                \
+      case 4: FN<0, 4>(__VA_ARGS__); break;                \
+      case 8: FN<0, 8>(__VA_ARGS__); break;                \
+      case 16: FN<0, 16>(__VA_ARGS__); break;              \
+      case 32: FN<0, 32>(__VA_ARGS__); break;              \
+      case 102: FN<1, 2>(__VA_ARGS__); break;              \
+      case 104: FN<1, 4>(__VA_ARGS__); break;              \
+      case 108: FN<1, 8>(__VA_ARGS__); break;              \
+      case 116: FN<1, 16>(__VA_ARGS__); break;             \
+      case 132: FN<1, 32>(__VA_ARGS__); break;             \
+      case 202: FN<2, 2>(__VA_ARGS__); break;              \
+      case 204: FN<2, 4>(__VA_ARGS__); break;              \
+      case 208: FN<2, 8>(__VA_ARGS__); break;              \
+      case 216: FN<2, 16>(__VA_ARGS__); break;             \
+      case 232: FN<2, 32>(__VA_ARGS__); break;             \
+      default: break;                                      \
+    }                                                      \
+  } while (0)
+
+bool g_attr_done = false;
+int set_kernel_attrs() {
+  if (g_attr_done) return 0;
+  CUDA_TRY(cudaFuncSetAttribute(chol_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(chol_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(trtri_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(trtri_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(dbg_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(score_trmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(fwd_solve_loglik_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  g_attr_done = true;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// batched blocked Cholesky driver (shared by fit and loglik)
+// ---------------------------------------------------------------------------------------------
+// On return L holds the factors, Winv the inverted diagonal blocks, logdet_blk / status are filled.
+// W / WT non-null (S must be 1): also form the full triangular inverse.
+int run_cholesky(double *L, size_t L_stride, double *Winv, size_t Winv_stride, int nblk, int ktiles, int S,
+                 double *logdet_blk, int *status, double *W, double *WT, double *TT) {
+  CholGemmParams gp{};
+  gp.L = L;
+  gp.L_stride = L_stride;
+  gp.Winv = Winv;
+  gp.Winv_stride = Winv_stride;
+  gp.nblk = nblk;
+  gp.ktiles = ktiles;
+  gp.W = W;
+  gp.WT = WT;
+  gp.TT = TT;
+  PotrfParams pp{};
+  pp.L = L;
+  pp.L_stride = L_stride;
+  pp.Winv = Winv;
+  pp.Winv_stride = Winv_stride;
+  pp.nblk = nblk;
+  pp.ktiles = ktiles;
+  pp.logdet_blk = logdet_blk;
+  pp.status = status;
+  pp.W = W;
+  pp.WT = WT;
+  for (int j = 0; j < nblk; ++j) {
+    gp.j = j;
+    pp.j = j;
+    if (j > 0) {
+      Timed t(2);
+      chol_update_kernel<<<dim3(nblk - j, S), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(gp);
+      ++g.launches;
+    }
+    potrf_diag_kernel<<<S, 256, POTRF_SMEM_BYTES, g.stream>>>(pp);
+    ++g.launches;
+    if (j < nblk - 1) {
+      Timed t(2);
+      chol_trsm_kernel<<<dim3(nblk - j - 1, S), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(gp);
+      ++g.launches;
+    }
+  }
+  if (W) {
+    for (int delta = 1; delta < nblk; ++delta) {
+      gp.j = delta;
+      Timed t(2);
+      trtri_t_kernel<<<nblk - delta, GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(gp);
+      trtri_w_kernel<<<nblk - delta, GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(gp);
+      g.launches += 2;
+    }
+  }
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------------
+struct boss_gp {
+  int n = 0, d = 0, n_pad = 0, nblk = 0, ktiles = 0, kernel_id = 0, dp = 0;
+  unsigned long long disc = 0;
+  double amp = 0, noise = 0, a2 = 0;
+  double loglik = 0;
+  double *W = nullptr, *WT = nullptr, *L = nullptr, *alpha = nullptr, *Xt = nullptr, *invl = nullptr;
+  void free_dev() {
+    for (double **q : {&W, &WT, &L, &alpha, &Xt, &invl}) {
+      if (*q) cudaFree(*q);
+      *q = nullptr;
+    }
+  }
+};
+
+extern "C" {
+
+int boss_version(void) { return 100; }
+int boss_device(void) { return g.device; }
+const char *boss_last_error(void) { return g.err.c_str(); }
+int64_t boss_launch_count(void) { return g.launches; }
+double boss_last_kernel_ms(int which) { return (which >= 0 && which < N_TIMERS) ? g.last_ms[which] : 0.0; }
+int boss_last_kernel_count(int which) { return (which >= 0 && which < N_TIMERS) ? g.last_cnt[which] : 0; }
+void boss_set_timing(int on) { g.timing = on != 0; }
+
+int boss_init(int device) {
+  std::lock_guard<std::mutex> lk(g.mu);
+  if (g.device == device && g.stream) return 0;
+  if (g.device >= 0 && g.device != device) return fail(BOSS_ERR_STATE, "boss_init: already initialised on another device");
+  int count = 0;
+  CUDA_TRY(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count) return fail(BOSS_ERR_ARG, "boss_init: no such CUDA device");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(BOSS_ERR_STATE, std::string("boss_init: built for sm_100a, device is ") + prop.name);
+  CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  for (int i = 0; i < EV_POOL; ++i) {
+    CUDA_TRY(cudaEventCreate(&g.ev_a[i]));
+    CUDA_TRY(cudaEventCreate(&g.ev_b[i]));
+  }
+  CUDA_TRY(cudaEventCreate(&g.call_a));
+  CUDA_TRY(cudaEventCreate(&g.call_b));
+  g.ev_ready = true;
+  g.device = device;
+  return set_kernel_attrs();
+}
+
+void boss_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g.mu);
+  if (g.device < 0) return;
+  cudaSetDevice(g.device);
+  cudaStreamSynchronize(g.stream);
+  for (DevBuf *b : {&g.ks, &g.muv, &g.sumsq, &g.xs_stage, &g.pm_stage, &g.cm_stage, &g.acq_stage, &g.mu_stage,
+                    &g.var_stage, &g.st_stage, &g.grad_stage, &g.blk_val, &g.blk_idx, &g.small, &g.chol_L,
+                    &g.chol_Winv, &g.chol_misc, &g.tt})
+    b->release();
+  if (g.ev_ready) {
+    for (int i = 0; i < EV_POOL; ++i) {
+      cudaEventDestroy(g.ev_a[i]);
+      cudaEventDestroy(g.ev_b[i]);
+    }
+    cudaEventDestroy(g.call_a);
+    cudaEventDestroy(g.call_b);
+    g.ev_ready = false;
+  }
+  cudaStreamDestroy(g.stream);
+  g.stream = nullptr;
+  g.device = -1;
+}
+
+#define REQUIRE_INIT()                                                                  \
+  if (g.device < 0) return fail(BOSS_ERR_STATE, "boss_init() has not been called");    \
+  CUDA_TRY(cudaSetDevice(g.device))
+
+// ---------------------------------------------------------------------------------------------
+// fit
+// ---------------------------------------------------------------------------------------------
+int boss_gp_fit(const double *X, int d, int n, const double *y_minus_mean, const double *lengthscales,
+                double amplitude, double noise_std, int kernel_id, const uint8_t *discrete_mask, boss_gp **out,
+                double *loglik_out) {
+  std::lock_guard<std::mutex> lk(g.mu);
+  REQUIRE_INIT();
+  if (!out) return fail(BOSS_ERR_ARG, "boss_gp_fit: out is NULL");
+  *out = nullptr;
+  if (!X || !y_minus_mean || !lengthscales || d < 1 || n < 1) return fail(BOSS_ERR_ARG, "boss_gp_fit: bad arguments");
+  if (kernel_id < 0 || kernel_id > 2) return fail(BOSS_ERR_ARG, "boss_gp_fit: unknown kernel_id");
+  const int dp = pick_dp(d);
+  if (dp < 0) return fail(BOSS_ERR_ARG, "boss_gp_fit: x_dim > 32 is not supported");
+  // reference asserts (src/models/gaussian_process.jl:227-229)
+  for (int i = 0; i < d; ++i)
+    if (!(lengthscales[i] >= 0)) return fail(BOSS_ERR_ARG, "boss_gp_fit: negative lengthscale");
+  if (!(amplitude >= 0) || !(noise_std >= 0)) return fail(BOSS_ERR_ARG, "boss_gp_fit: negative amplitude / noise_std");
+
+  boss_gp *h = new boss_gp();
+  h->n = n;
+  h->d = d;
+  h->n_pad = round_up(n, TM);
+  h->nblk = h->n_pad / TM;
+  h->ktiles = h->n_pad / TK;
+  h->kernel_id = kernel_id;
+  h->dp = dp;
+  h->disc = mask_bits(discrete_mask, d);
+  h->amp = amplitude + MIN_PARAM_VALUE;
+  h->noise = noise_std + MIN_PARAM_VALUE;
+  h->a2 = h->amp * h->amp;
+  const size_t npad = h->n_pad, mat = npad * npad;
+  const int nblk = h->nblk;
+
+  auto bail = [&](int code) {
+    h->free_dev();
+    delete h;
+    return code;
+  };
+#define FIT_TRY(expr)                                                                                         \
+  do {                                                                                                        \
+    cudaError_t _e = (expr);                                                                                  \
+    if (_e != cudaSuccess)                                                                                    \
+      return bail(fail(BOSS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + " (line " +       \
+                                          std::to_string(__LINE__) + ")"));                                   \
+  } while (0)
+
+  FIT_TRY(cudaMalloc(&h->L, mat * 8));
+  FIT_TRY(cudaMalloc(&h->W, mat * 8));
+  FIT_TRY(cudaMalloc(&h->WT, mat * 8));
+  FIT_TRY(cudaMalloc(&h->alpha, npad * 8));
+  FIT_TRY(cudaMalloc(&h->Xt, npad * dp * 8));
+  FIT_TRY(cudaMalloc(&h->invl, dp * 8));
+  FIT_TRY(cudaMemsetAsync(h->L, 0, mat * 8, g.stream));
+  FIT_TRY(cudaMemsetAsync(h->W, 0, mat * 8, g.stream));
+  FIT_TRY(cudaMemsetAsync(h->WT, 0, mat * 8, g.stream));
+
+  // misc device scratch: X | ymm_pad | ls | amp | noise | invl(host computed) | logdet_blk | w | status
+  const size_t off_X = 0, off_y = off_X + (size_t)n * d, off_ls = off_y + npad, off_amp = off_ls + d,
+               off_noise = off_amp + 1, off_ld = off_noise + 1, off_w = off_ld + nblk, off_st = off_w + npad,
+               total = off_st + 2;
+  FIT_TRY(g.chol_misc.ensure(total * 8));
+  double *misc = g.chol_misc.as<double>();
+  FIT_TRY(cudaMemsetAsync(misc, 0, total * 8, g.stream));
+  FIT_TRY(cudaMemcpyAsync(misc + off_X, X, (size_t)n * d * 8, cudaMemcpyHostToDevice, g.stream));
+  FIT_TRY(cudaMemcpyAsync(misc + off_y, y_minus_mean, (size_t)n * 8, cudaMemcpyHostToDevice, g.stream));
+  FIT_TRY(cudaMemcpyAsync(misc + off_ls, lengthscales, (size_t)d * 8, cudaMemcpyHostToDevice, g.stream));
+  FIT_TRY(cudaMemcpyAsync(misc + off_amp, &amplitude, 8, cudaMemcpyHostToDevice, g.stream));
+  FIT_TRY(cudaMemcpyAsync(misc + off_noise, &noise_std, 8, cudaMemcpyHostToDevice, g.stream));
+  std::vector<double> invl(dp, 0.0);
+  for (int i = 0; i < d; ++i) invl[i] = 1.0 / (lengthscales[i] + MIN_PARAM_VALUE);
+  FIT_TRY(cudaMemcpyAsync(h->invl, invl.data(), dp * 8, cudaMemcpyHostToDevice, g.stream));
+  int *status = reinterpret_cast<int *>(misc + off_st);
+
+  FIT_TRY(g.chol_Winv.ensure((size_t)nblk * TM * TM * 8));
+  FIT_TRY(g.tt.ensure((size_t)std::max(1, nblk - 1) * TM * TM * 8));
+
+  timing_begin();
+  BuildKParams bk{};
+  bk.X = misc + off_X;
+  bk.d = d;
+  bk.n = n;
+  bk.nblk = nblk;
+  bk.ktiles = h->ktiles;
+  bk.ls = misc + off_ls;
+  bk.amp = misc + off_amp;
+  bk.noise = misc + off_noise;
+  bk.disc_bits = h->disc;
+  bk.K = h->L;
+  bk.K_stride = mat;
+  bk.status = status;
+  {
+    Timed t(1);
+    DISPATCH_KID_DP(launch_build_k_t, kernel_id, dp, bk, dim3(nblk * (nblk + 1) / 2, 1));
+    ++g.launches;
+  }
+  int rc = run_cholesky(h->L, mat, g.chol_Winv.as<double>(), (size_t)nblk * TM * TM, nblk, h->ktiles, 1,
+                        misc + off_ld, status, h->W, h->WT, g.tt.as<double>());
+  if (rc) return bail(rc);
+  // w = W delta ; alpha = W^T w
+  matvec_p_kernel<<<h->n_pad / 64, 256, 0, g.stream>>>(h->W, misc + off_y, misc + off_w, h->ktiles);
+  matvec_p_kernel<<<h->n_pad / 64, 256, 0, g.stream>>>(h->WT, misc + off_w, h->alpha, h->ktiles);
+  {
+    const int tot = h->n_pad * dp;
+    scale_train_kernel<<<(tot + 255) / 256, 256, 0, g.stream>>>(misc + off_X, d, n, h->n_pad, dp, h->invl, h->disc, h->Xt);
+  }
+  g.launches += 3;
+  FIT_TRY(cudaGetLastError());
+  std::vector<double> host(nblk + npad + 2);
+  FIT_TRY(cudaMemcpyAsync(host.data(), misc + off_ld, (nblk + npad + 2) * 8, cudaMemcpyDeviceToHost, g.stream));
+  FIT_TRY(cudaStreamSynchronize(g.stream));
+  timing_end();
+  int st;
+  std::memcpy(&st, &host[nblk + npad], sizeof(int));
+  if (st != 0) {
+    bail(0);
+    if (loglik_out) *loglik_out = -std::numeric_limits<double>::infinity();
+    g.err = "boss_gp_fit: kernel matrix is not positive definite";
+    return BOSS_NOT_POSDEF;
+  }
+  double ld = 0.0, mahal = 0.0;
+  for (int b = 0; b < nblk; ++b) ld += host[b];
+  for (size_t k = 0; k < npad; ++k) mahal = std::fma(host[nblk + k], host[nblk + k], mahal);
+  h->loglik = -((double)n * 1.8378770664093453 + 2.0 * ld + mahal) * 0.5;
+  if (loglik_out) *loglik_out = h->loglik;
+  *out = h;
+  return 0;
+#undef FIT_TRY
+}
+
+void boss_gp_free(boss_gp *gp) {
+  if (!gp) return;
+  std::lock_guard<std::mutex> lk(g.mu);
+  if (g.device >= 0) cudaSetDevice(g.device);
+  gp->free_dev();
+  delete gp;
+}
+int boss_gp_n(const boss_gp *gp) { return gp ? gp->n : -1; }
+int boss_gp_d(const boss_gp *gp) { return gp ? gp->d : -1; }
+
+// ---------------------------------------------------------------------------------------------
+// scoring core (shared by predict / ei_score, host- and device-pointer variants)
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct ScoreArgs {
+  const boss_gp *const *slices;
+  int y_dim, n_samples;
+  const double *Xs;  // host or device
+  long long M;
+  const double *prior_mean;  // y_dim x M, host or device
+  const double *coefs, *best, *y_max, *lb, *ub;  // host
+  const uint8_t *cons_mask;                      // host or device
+  double *acq, *grad;                            // host or device
+  double *mu_out, *var_out;                      // predict mode (single slice), host or device
+  int32_t *status_out;
+  double *best_val;  // host
+  int64_t *best_idx; // host
+  bool dev;          // arrays are device pointers
+  bool want_argmax;
+  int any_fail;      // out
+};
+
+int score_core(ScoreArgs &a) {
+  const int nsl = a.y_dim * a.n_samples;
+  if (nsl < 1 || a.y_dim > MAX_YDIM) return fail(BOSS_ERR_ARG, "score: y_dim must be in 1..16");
+  const boss_gp *g0 = a.slices[0];
+  for (int q = 0; q < nsl; ++q) {
+    if (!a.slices[q]) return fail(BOSS_ERR_ARG, "score: NULL slice handle");
+    if (a.slices[q]->d != g0->d) return fail(BOSS_ERR_ARG, "score: slices disagree on x_dim");
+  }
+  const int d = g0->d;
+  int max_npad = 0;
+  for (int q = 0; q < nsl; ++q) max_npad = std::max(max_npad, a.slices[q]->n_pad);
+  a.any_fail = 0;
+  if (a.M <= 0) {
+    if (a.best_idx) *a.best_idx = -1;
+    return 0;
+  }
+  // chunk size: K*^T scratch budget 4 GiB, at most 4 waves of 148 CTAs
+  long long ncb_max = (4ll << 30) / (1024ll * max_npad);
+  ncb_max = std::min<long long>(ncb_max, 592);
+  if (ncb_max >= 148) ncb_max = ncb_max / 148 * 148;
+  if (ncb_max < 1) return fail(BOSS_ERR_ARG, "score: n too large for the scratch budget");
+  const long long need_cb = (a.M + 127) / 128;
+  const int ncb_cap = (int)std::min<long long>(ncb_max, need_cb);
+  const int CH = ncb_cap * 128;
+
+  CUDA_TRY(g.ks.ensure((size_t)CH * max_npad * 8));
+  CUDA_TRY(g.muv.ensure((size_t)nsl * CH * 8));
+  CUDA_TRY(g.sumsq.ensure((size_t)nsl * CH * 8));
+  const int nblk_acq_max = (CH + 255) / 256;
+  CUDA_TRY(g.blk_val.ensure((size_t)nblk_acq_max * 8));
+  CUDA_TRY(g.blk_idx.ensure((size_t)nblk_acq_max * 8));
+  // small: a2[nsl] | lb[d] | ub[d] | best(1) | bidx(1 as int64) | any_fail(int)
+  const size_t sm_n = (size_t)nsl + 2 * d + 4;
+  CUDA_TRY(g.small.ensure(sm_n * 8));
+  double *small = g.small.as<double>();
+  std::vector<double> hs(sm_n, 0.0);
+  for (int q = 0; q < nsl; ++q) hs[q] = a.slices[q]->a2;
+  if (a.lb && a.ub) {
+    for (int i = 0; i < d; ++i) {
+      hs[nsl + i] = a.lb[i];
+      hs[nsl + d + i] = a.ub[i];
+    }
+  }
+  long long neg1 = -1;
+  std::memcpy(&hs[nsl + 2 * d + 1], &neg1, 8);
+  CUDA_TRY(cudaMemcpyAsync(small, hs.data(), sm_n * 8, cudaMemcpyHostToDevice, g.stream));
+  double *d_best = small + nsl + 2 * d;
+  long long *d_bidx = reinterpret_cast<long long *>(small + nsl + 2 * d + 1);
+  int *d_anyfail = reinterpret_cast<int *>(small + nsl + 2 * d + 2);
+
+  if (!a.dev) {
+    CUDA_TRY(g.xs_stage.ensure((size_t)CH * d * 8));
+    if (a.prior_mean) CUDA_TRY(g.pm_stage.ensure((size_t)CH * a.y_dim * 8));
+    if (a.cons_mask) CUDA_TRY(g.cm_stage.ensure((size_t)CH));
+    if (a.acq) CUDA_TRY(g.acq_stage.ensure((size_t)CH * 8));
+    if (a.mu_out) CUDA_TRY(g.mu_stage.ensure((size_t)CH * 8));
+    if (a.var_out) CUDA_TRY(g.var_stage.ensure((size_t)CH * 8));
+    if (a.status_out) CUDA_TRY(g.st_stage.ensure((size_t)CH * 4));
+  }
+
+  timing_begin();
+  for (long long m0 = 0; m0 < a.M; m0 += CH) {
+    const int ch = (int)std::min<long long>(CH, a.M - m0);
+    const int ncb = (ch + 127) / 128;
+    const double *xs_dev;
+    const double *pm_dev = nullptr;
+    const unsigned char *cm_dev = nullptr;
+    long long in_off, out_off;
+    double *acq_dev = nullptr, *mu_dev = nullptr, *var_dev = nullptr;
+    int *st_dev = nullptr;
+    if (a.dev) {
+      xs_dev = a.Xs;
+      pm_dev = a.prior_mean;
+      cm_dev = a.cons_mask;
+      in_off = 0;
+      out_off = 0;
+      acq_dev = a.acq;
+      mu_dev = a.mu_out;
+      var_dev = a.var_out;
+      st_dev = a.status_out;
+    } else {
+      CUDA_TRY(cudaMemcpyAsync(g.xs_stage.p, a.Xs + (size_t)m0 * d, (size_t)ch * d * 8, cudaMemcpyHostToDevice, g.stream));
+      xs_dev = g.xs_stage.as<double>();
+      if (a.prior_mean) {
+        CUDA_TRY(cudaMemcpyAsync(g.pm_stage.p, a.prior_mean + (size_t)m0 * a.y_dim, (size_t)ch * a.y_dim * 8,
+                                 cudaMemcpyHostToDevice, g.stream));
+        pm_dev = g.pm_stage.as<double>();
+      }
+      if (a.cons_mask) {
+        CUDA_TRY(cudaMemcpyAsync(g.cm_stage.p, a.cons_mask + m0, (size_t)ch, cudaMemcpyHostToDevice, g.stream));
+        cm_dev = g.cm_stage.as<unsigned char>();
+      }
+      in_off = m0;
+      out_off = m0;
+      if (a.acq) acq_dev = g.acq_stage.as<double>();
+      if (a.mu_out) mu_dev = g.mu_stage.as<double>();
+      if (a.var_out) var_dev = g.var_stage.as<double>();
+      if (a.status_out) st_dev = g.st_stage.as<int>();
+    }
+    for (int q = 0; q < nsl; ++q) {
+      const boss_gp *h = a.slices[q];
+      XcovParams xp{};
+      xp.Xs = xs_dev;
+      xp.M = a.M;
+      xp.m0 = m0;
+      xp.in_off = in_off;
+      xp.d = d;
+      xp.n = h->n;
+      xp.n_pad = h->n_pad;
+      xp.ktiles = h->ktiles;
+      xp.Xt = h->Xt;
+      xp.invl = h->invl;
+      xp.disc_bits = h->disc;
+      xp.alpha = h->alpha;
+      xp.a2 = h->a2;
+      xp.Ks = g.ks.as<double>();
+      xp.mu = g.muv.as<double>() + (size_t)q * CH;
+      {
+        Timed t(1);
+        DISPATCH_KID_DP(launch_xcov_t, h->kernel_id, h->dp, xp, ncb);
+      }
+      ScoreParams sp{};
+      sp.W = h->W;
+      sp.Ks = g.ks.as<double>();
+      sp.nblk = h->nblk;
+      sp.ktiles = h->ktiles;
+      sp.sumsq = g.sumsq.as<double>() + (size_t)q * CH;
+      {
+        Timed t(0);
+        score_trmm_kernel<<<ncb, GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(sp);
+      }
+      g.launches += 2;
+    }
+    AcqParams ap{};
+    ap.y_dim = a.y_dim;
+    ap.n_samples = a.n_samples;
+    ap.d = d;
+    ap.M = a.M;
+    ap.m0 = m0;
+    ap.in_off = in_off;
+    ap.out_off = out_off;
+    ap.chunk = ch;
+    ap.chunk_ld = CH;
+    ap.mu = g.muv.as<double>();
+    ap.sumsq = g.sumsq.as<double>();
+    ap.a2 = small;
+    ap.prior_mean = pm_dev;
+    for (int i = 0; i < a.y_dim; ++i) {
+      ap.coefs[i] = a.coefs ? a.coefs[i] : (i == 0 ? 1.0 : 0.0);
+      ap.y_max[i] = a.y_max ? a.y_max[i] : INFINITY;
+    }
+    ap.has_best = a.best != nullptr;
+    ap.best = a.best ? *a.best : 0.0;
+    ap.has_ymax = a.y_max != nullptr;
+    ap.Xs = xs_dev;
+    ap.lb = (a.lb && a.ub) ? small + nsl : nullptr;
+    ap.ub = (a.lb && a.ub) ? small + nsl + d : nullptr;
+    ap.cons_mask = cm_dev;
+    ap.acq = acq_dev;
+    ap.mu_out = mu_dev;
+    ap.var_out = var_dev;
+    ap.status_out = st_dev;
+    ap.any_fail = d_anyfail;
+    ap.blk_val = a.want_argmax ? g.blk_val.as<double>() : nullptr;
+    ap.blk_idx = a.want_argmax ? g.blk_idx.as<long long>() : nullptr;
+    const int nb = (ch + 255) / 256;
+    acq_kernel<<<nb, 256, 0, g.stream>>>(ap);
+    ++g.launches;
+    if (a.want_argmax) {
+      argmax_final_kernel<<<1, 256, 0, g.stream>>>(g.blk_val.as<double>(), g.blk_idx.as<long long>(), nb, d_best, d_bidx);
+      ++g.launches;
+    }
+    if (!a.dev) {
+      if (a.acq) CUDA_TRY(cudaMemcpyAsync(a.acq + m0, acq_dev, (size_t)ch * 8, cudaMemcpyDeviceToHost, g.stream));
+      if (a.mu_out) CUDA_TRY(cudaMemcpyAsync(a.mu_out + m0, mu_dev, (size_t)ch * 8, cudaMemcpyDeviceToHost, g.stream));
+      if (a.var_out) CUDA_TRY(cudaMemcpyAsync(a.var_out + m0, var_dev, (size_t)ch * 8, cudaMemcpyDeviceToHost, g.stream));
+      if (a.status_out)
+        CUDA_TRY(cudaMemcpyAsync(a.status_out + m0, st_dev, (size_t)ch * 4, cudaMemcpyDeviceToHost, g.stream));
+    }
+  }
+  CUDA_TRY(cudaGetLastError());
+  double hres[3];
+  CUDA_TRY(cudaMemcpyAsync(hres, d_best, 24, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  timing_end();
+  long long bidx;
+  std::memcpy(&bidx, &hres[1], 8);
+  int af;
+  std::memcpy(&af, &hres[2], 4);
+  a.any_fail = af;
+  if (a.want_argmax) {
+    if (a.best_val) *a.best_val = hres[0];
+    if (a.best_idx) *a.best_idx = bidx;
+  }
+  return 0;
+}
+
+}  // namespace
+
+int boss_gp_predict(const boss_gp *gp, const double *Xs, int64_t M, const double *prior_mean_s, double *mu,
+                    double *var, int32_t *status) {
+  std::lock_guard<std::mutex> lk(g.mu);
+  REQUIRE_INIT();
+  if (!gp || (!Xs && M > 0)) return fail(BOSS_ERR_ARG, "boss_gp_predict: bad arguments");
+  const boss_gp *sl[1] = {gp};
+  ScoreArgs a{};
+  a.slices = sl;
+  a.y_dim = 1;
+  a.n_samples = 1;
+  a.Xs = Xs;
+  a.M = M;
+  a.prior_mean = prior_mean_s;
+  a.mu_out = mu;
+  a.var_out = var;
+  a.status_out = status;
+  a.dev = false;
+  a.want_argmax = false;
+  int rc = score_core(a);
+  if (rc) return rc;
+  return a.any_fail ? BOSS_NEG_VARIANCE : 0;
+}
+
+int boss_gp_predict_dev(const boss_gp *gp, const double *Xs_dev, int64_t M, const double *prior_mean_s_dev,
+                        double *mu_dev, double *var_dev, int32_t *status_dev) {
+  std::lock_guard<std::mutex> lk(g.mu);
+  REQUIRE_INIT();
+  if (!gp || (!Xs_dev && M > 0)) return fail(BOSS_ERR_ARG, "boss_gp_predict_dev: bad arguments");
+  const boss_gp *sl[1] = {gp};
+  ScoreArgs a{};
+  a.slices = sl;
+  a.y_dim = 1;
+  a.n_samples = 1;
+  a.Xs = Xs_dev;
+  a.M = M;
+  a.prior_mean = prior_mean_s_dev;
+  a.mu_out = mu_dev;
+  a.var_out = var_dev;
+  a.status_out = status_dev;
+  a.dev = true;
+  a.want_argmax = false;
+  int rc = score_core(a);
+  if (rc) return rc;
+  return a.any_fail ? BOSS_NEG_VARIANCE : 0;
+}
+
+static int ei_score_impl(const boss_gp *const *slices, int y_dim, int n_samples, const double *Xs, int64_t M,
+                         const double *prior_mean_s, const double *fit_coefs, const double *best,
+                         const double *y_max, const double *lb, const double *ub, const uint8_t *cons_mask,
+                         double *acq, double *grad, double *best_val, int64_t *best_idx, bool dev) {
+  std::lock_guard<std::mutex> lk(g.mu);
+  REQUIRE_INIT();
+  if (!slices || y_dim < 1 || n_samples < 1 || (!Xs && M > 0) || !fit_coefs)
+    return fail(BOSS_ERR_ARG, "boss_ei_score: bad arguments");
+  if (grad) return fail(BOSS_ERR_ARG, "boss_ei_score: gradients are not available in this build");
+  if ((lb == nullptr) != (ub == nullptr)) return fail(BOSS_ERR_ARG, "boss_ei_score: lb and ub must be given together");
+  ScoreArgs a{};
+  a.slices = slices;
+  a.y_dim = y_dim;
+  a.n_samples = n_samples;
+  a.Xs = Xs;
+  a.M = M;
+  a.prior_mean = prior_mean_s;
+  a.coefs = fit_coefs;
+  a.best = best;
+  a.y_max = y_max;
+  a.lb = lb;
+  a.ub = ub;
+  a.cons_mask = cons_mask;
+  a.acq = acq;
+  a.grad = grad;
+  a.best_val = best_val;
+  a.best_idx = best_idx;
+  a.dev = dev;
+  a.want_argmax = (best_val != nullptr) || (best_idx != nullptr);
+  return score_core(a);
+}
+
+int boss_ei_score(const boss_gp *const *slices, int y_dim, int n_samples, const double *Xs, int64_t M,
+                  const double *prior_mean_s, const double *fit_coefs, const double *best, const double *y_max,
+                  const double *lb, const double *ub, const uint8_t *cons_mask, double *acq, double *grad,
+                  double *best_val, int64_t *best_idx) {
+  return ei_score_impl(slices, y_dim, n_samples, Xs, M, prior_mean_s, fit_coefs, best, y_max, lb, ub, cons_mask, acq,
+                       grad, best_val, best_idx, false);
+}
+
+int boss_ei_score_dev(const boss_gp *const *slices, int y_dim, int n_samples, const double *Xs_dev, int64_t M,
+                      const double *prior_mean_s_dev, const double *fit_coefs, const double *best,
+                      const double *y_max, const double *lb, const double *ub, const uint8_t *cons_mask_dev,
+                      double *acq_dev, double *grad_dev, double *best_val, int64_t *best_idx, void *stream) {
+  (void)stream;  // work is ordered on the library stream and synchronised before return
+  return ei_score_impl(slices, y_dim, n_samples, Xs_dev, M, prior_mean_s_dev, fit_coefs, best, y_max, lb, ub,
+                       cons_mask_dev, acq_dev, grad_dev, best_val, best_idx, true);
+}
+
+int boss_gp_cov(const boss_gp *, const double *, int64_t, const double *, double *, double *) {
+  return fail(BOSS_ERR_ARG, "boss_gp_cov: not available in this build");
+}
+
+// ---------------------------------------------------------------------------------------------
+// batched log marginal likelihood
+// ---------------------------------------------------------------------------------------------
+static int loglik_impl(const double *X, int d, int n, const double *Ymm, int64_t ldy, const double *ls,
+                       const double *amp, const double *noise, int kernel_id, const uint8_t *discrete_mask, int64_t S,
+                       double *loglik, bool dev) {
+  std::lock_guard<std::mutex> lk(g.mu);
+  REQUIRE_INIT();
+  if (!X || !Ymm || !ls || !amp || !noise || !loglik || d < 1 || n < 1 || S < 0)
+    return fail(BOSS_ERR_ARG, "boss_gp_loglik_batch: bad arguments");
+  if (kernel_id < 0 || kernel_id > 2) return fail(BOSS_ERR_ARG, "boss_gp_loglik_batch: unknown kernel_id");
+  const int dp = pick_dp(d);
+  if (dp < 0) return fail(BOSS_ERR_ARG, "boss_gp_loglik_batch: x_dim > 32 is not supported");
+  if (S == 0) return 0;
+  const int n_pad = round_up(n, TM), nblk = n_pad / TM, ktiles = n_pad / TK;
+  const size_t mat = (size_t)n_pad * n_pad;
+  if ((size_t)(n_pad + 128) * 8 > 200 * 1024) return fail(BOSS_ERR_ARG, "boss_gp_loglik_batch: n too large");
+  const unsigned long long disc = mask_bits(discrete_mask, d);
+
+  // sub-batch so that L + Winv stay within a 32 GiB workspace
+  const size_t per = mat * 8 + (size_t)nblk * TM * TM * 8;
+  long long Sb = std::max<long long>(1, std::min<long long>(S, (32ll << 30) / (long long)per));
+  Sb = std::min<long long>(Sb, 32768);
+  CUDA_TRY(g.chol_L.ensure((size_t)Sb * mat * 8));
+  CUDA_TRY(g.chol_Winv.ensure((size_t)Sb * nblk * TM * TM * 8));
+
+  // device copies of the inputs when called with host pointers
+  const double *dX = X, *dY = Ymm, *dls = ls, *damp = amp, *dnoise = noise;
+  double *dll = loglik;
+  const size_t ycount = ldy ? (size_t)S * ldy : (size_t)n;
+  // misc: [X | Y | ls | amp | noise | ll] (host variant) then logdet_blk[Sb*nblk] | status[Sb]
+  size_t off = 0, oX = 0, oY = 0, ols = 0, oamp = 0, onoise = 0, oll = 0;
+  if (!dev) {
+    oX = off; off += (size_t)n * d;
+    oY = off; off += ycount;
+    ols = off; off += (size_t)S * d;
+    oamp = off; off += S;
+    onoise = off; off += S;
+    oll = off; off += S;
+  }
+  const size_t old_ = off;
+  off += (size_t)Sb * nblk;
+  const size_t ost = off;
+  off += (size_t)(Sb + 1) / 2 + 1;
+  CUDA_TRY(g.chol_misc.ensure(off * 8));
+  double *misc = g.chol_misc.as<double>();
+  if (!dev) {
+    CUDA_TRY(cudaMemcpyAsync(misc + oX, X, (size_t)n * d * 8, cudaMemcpyHostToDevice, g.stream));
+    CUDA_TRY(cudaMemcpyAsync(misc + oY, Ymm, ycount * 8, cudaMemcpyHostToDevice, g.stream));
+    CUDA_TRY(cudaMemcpyAsync(misc + ols, ls, (size_t)S * d * 8, cudaMemcpyHostToDevice, g.stream));
+    CUDA_TRY(cudaMemcpyAsync(misc + oamp, amp, (size_t)S * 8, cudaMemcpyHostToDevice, g.stream));
+    CUDA_TRY(cudaMemcpyAsync(misc + onoise, noise, (size_t)S * 8, cudaMemcpyHostToDevice, g.stream));
+    dX = misc + oX; dY = misc + oY; dls = misc + ols; damp = misc + oamp; dnoise = misc + onoise; dll = misc + oll;
+  }
+  double *logdet_blk = misc + old_;
+  int *status = reinterpret_cast<int *>(misc + ost);
+
+  timing_begin();
+  for (long long s0 = 0; s0 < S; s0 += Sb) {
+    const int sb = (int)std::min<long long>(Sb, S - s0);
+    CUDA_TRY(cudaMemsetAsync(status, 0, (size_t)sb * 4, g.stream));
+    BuildKParams bk{};
+    bk.X = dX;
+    bk.d = d;
+    bk.n = n;
+    bk.nblk = nblk;
+    bk.ktiles = ktiles;
+    bk.ls = dls + (size_t)s0 * d;
+    bk.amp = damp + s0;
+    bk.noise = dnoise + s0;
+    bk.disc_bits = disc;
+    bk.K = g.chol_L.as<double>();
+    bk.K_stride = mat;
+    bk.status = status;
+    {
+      Timed t(1);
+      DISPATCH_KID_DP(launch_build_k_t, kernel_id, dp, bk, dim3(nblk * (nblk + 1) / 2, sb));
+      ++g.launches;
+    }
+    int rc = run_cholesky(g.chol_L.as<double>(), mat, g.chol_Winv.as<double>(), (size_t)nblk * TM * TM, nblk, ktiles, sb,
+                          logdet_blk, status, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    FwdParams fp{};
+    fp.L = g.chol_L.as<double>();
+    fp.L_stride = mat;
+    fp.Winv = g.chol_Winv.as<double>();
+    fp.Winv_stride = (size_t)nblk * TM * TM;
+    fp.nblk = nblk;
+    fp.ktiles = ktiles;
+    fp.n = n;
+    fp.ymm = dY + (ldy ? (size_t)s0 * ldy : 0);
+    fp.ldy = ldy;
+    fp.logdet_blk = logdet_blk;
+    fp.status = status;
+    fp.loglik = dll + s0;
+    fp.w_out = nullptr;
+    fwd_solve_loglik_kernel<<<sb, 256, (size_t)(n_pad + 128) * 8, g.stream>>>(fp);
+    ++g.launches;
+  }
+  CUDA_TRY(cudaGetLastError());
+  if (!dev) CUDA_TRY(cudaMemcpyAsync(loglik, dll, (size_t)S * 8, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  timing_end();
+  if (!dev) {
+    int any = 0;
+    for (int64_t s = 0; s < S; ++s) {
+      if (std::isnan(loglik[s])) return fail(BOSS_ERR_ARG, "boss_gp_loglik_batch: negative hyper-parameter");
+      if (std::isinf(loglik[s])) any = 1;
+    }
+    return any ? BOSS_NOT_POSDEF : 0;
+  }
+  return 0;
+}
+
+int boss_gp_loglik_batch(const double *X, int d, int n, const double *Y_minus_mean, int64_t ldy,
+                         const double *lengthscales, const double *amplitude, const double *noise_std, int kernel_id,
+                         const uint8_t *discrete_mask, int64_t S, double *loglik) {
+  return loglik_impl(X, d, n, Y_minus_mean, ldy, lengthscales, amplitude, noise_std, kernel_id, discrete_mask, S,
+                     loglik, false);
+}
+int boss_gp_loglik_batch_dev(const double *X_dev, int d, int n, const double *Y_minus_mean_dev, int64_t ldy,
+                             const double *lengthscales_dev, const double *amplitude_dev, const double *noise_std_dev,
+                             int kernel_id, const uint8_t *discrete_mask, int64_t S, double *loglik_dev, void *stream) {
+  (void)stream;
+  return loglik_impl(X_dev, d, n, Y_minus_mean_dev, ldy, lengthscales_dev, amplitude_dev, noise_std_dev, kernel_id,
+                     discrete_mask, S, loglik_dev, true);
+}
+
+// ---------------------------------------------------------------------------------------------
+// debug hooks
+// ---------------------------------------------------------------------------------------------
+static void pack_host(const double *dense, int R, int C, int Rp, int Cp, std::vector<double> &out) {
+  out.assign((size_t)Rp * Cp, 0.0);
+  const int kt = Cp / TK;
+  for (int r = 0; r < R; ++r)
+    for (int c = 0; c < C; ++c) out[p_index(r, c, kt)] = dense[(size_t)r * C + c];
+}
+
+int boss_dbg_gemm_nt(const double *A, const double *B, int M, int N, int K, double *C) {
+  std::lock_guard<std::mutex> lk(g.mu);
+  REQUIRE_INIT();
+  const int Mp = round_up(M, TM), Np = round_up(N, TM), Kp = round_up(K, TK);
+  std::vector<double> pa, pb;
+  pack_host(A, M, K, Mp, Kp, pa);
+  pack_host(B, N, K, Np, Kp, pb);
+  double *dA, *dB, *dC;
+  CUDA_TRY(cudaMalloc(&dA, pa.size() * 8));
+  CUDA_TRY(cudaMalloc(&dB, pb.size() * 8));
+  CUDA_TRY(cudaMalloc(&dC, (size_t)Mp * Np * 8));
+  CUDA_TRY(cudaMemcpy(dA, pa.data(), pa.size() * 8, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(dB, pb.data(), pb.size() * 8, cudaMemcpyHostToDevice));
+  DbgGemmParams p{dA, dB, dC, Kp / TK, Np / TK};
+  dbg_gemm_kernel<<<dim3(Np / TM, Mp / TM), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(p);
+  ++g.launches;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  std::vector<double> pc((size_t)Mp * Np);
+  CUDA_TRY(cudaMemcpy(pc.data(), dC, pc.size() * 8, cudaMemcpyDeviceToHost));
+  for (int r = 0; r < M; ++r)
+    for (int c = 0; c < N; ++c) C[(size_t)r * N + c] = pc[p_index(r, c, Np / TK)];
+  cudaFree(dA);
+  cudaFree(dB);
+  cudaFree(dC);
+  return 0;
+}
+
+int boss_dbg_factors(const boss_gp *gp, double *L, double *W, double *alpha) {
+  std::lock_guard<std::mutex> lk(g.mu);
+  REQUIRE_INIT();
+  if (!gp) return fail(BOSS_ERR_ARG, "boss_dbg_factors: NULL handle");
+  const size_t mat = (size_t)gp->n_pad * gp->n_pad;
+  std::vector<double> buf(mat);
+  const int n = gp->n;
+  if (L) {
+    CUDA_TRY(cudaMemcpy(buf.data(), gp->L, mat * 8, cudaMemcpyDeviceToHost));
+    for (int r = 0; r < n; ++r)
+      for (int c = 0; c < n; ++c) L[(size_t)r * n + c] = (c <= r) ? buf[p_index(r, c, gp->ktiles)] : 0.0;
+  }
+  if (W) {
+    CUDA_TRY(cudaMemcpy(buf.data(), gp->W, mat * 8, cudaMemcpyDeviceToHost));
+    for (int r = 0; r < n; ++r)
+      for (int c = 0; c < n; ++c) W[(size_t)r * n + c] = buf[p_index(r, c, gp->ktiles)];
+  }
+  if (alpha) CUDA_TRY(cudaMemcpy(alpha, gp->alpha, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+}  // extern "C"

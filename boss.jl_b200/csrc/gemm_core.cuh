@@ -1,0 +1,170 @@
+// gemm_core.cuh -- the one FP64 tensor-core mainloop every O(n^3)/O(n^2 M) stage runs on.
+//
+//   C(128x128) += A(128 x K) * B(128 x K)^T          ("NT": both operands K-major, P-layout)
+//
+// * operands arrive by 1-D TMA bulk copies (cp.async.bulk, one 16 KB macro-tile per operand per
+//   stage) into a STAGES-deep shared-memory ring, completion on mbarriers;
+// * 8 warps, warp tile 64x32 = 8x4 DMMA.8x8x4 fragments, accumulators in registers (FP64 has no
+//   tcgen05/TMEM path on sm_100a; DMMA.8x8x4 is the native FP64 tensor instruction);
+// * fragments are read with conflict-free LDS.128 straight from the P-layout (see common.cuh);
+// * a CTA walks a *sequence* of output tiles (iterator `It`): the ring keeps streaming across tile
+//   boundaries, the epilogue functor runs when a tile's last k-stage has been consumed.
+//
+// Users: Cholesky trailing update / panel solve, triangular inverse (cholesky.cuh) and the fused
+// posterior-variance kernel (score.cuh).
+#pragma once
+#include "common.cuh"
+
+namespace boss {
+
+constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_STAGES = 5;
+constexpr int GEMM_STAGE_ELEMS = 2 * TILE_ELEMS;                  // A tile + B tile
+constexpr int GEMM_STAGE_BYTES = GEMM_STAGE_ELEMS * 8;            // 32 KB
+constexpr int GEMM_RING_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES;   // 160 KB
+constexpr int GEMM_SCRATCH_BYTES = 4096;                          // epilogue scratch (after the ring)
+constexpr int GEMM_SMEM_BYTES = GEMM_RING_BYTES + GEMM_SCRATCH_BYTES + 64;  // + mbarriers
+
+// Accumulator fragment coordinates of this lane inside the 128x128 CTA tile:
+//   row(fm)    = 64*wm + 8*fm + (lane>>2)
+//   col(fn, e) = 32*wn + 8*fn + 2*(lane&3) + e
+struct FragCoord {
+  int wm, wn, lane;
+  __device__ __forceinline__ int row(int fm) const { return 64 * wm + 8 * fm + (lane >> 2); }
+  __device__ __forceinline__ int col(int fn, int e) const { return 32 * wn + 8 * fn + 2 * (lane & 3) + e; }
+};
+
+// Offset (in doubles) of local element (r, c) of a 128x128 block inside the P-layout run that
+// starts at the block's first macro-tile (the 8 macro-tiles of a block are consecutive).
+__host__ __device__ __forceinline__ int block_offset(int r, int c) {
+  return (c >> 4) * TILE_ELEMS + ((((r >> 3) << 1) + ((c & 15) >> 3)) << 6) + ((((r & 7) << 2) + (c & 3)) << 1) +
+         ((c & 7) >> 2);
+}
+
+// It must provide:  bool valid(); const double* A(); const double* B(); bool tile_end(); int tile(); void next();
+template <class It, class Epi>
+__device__ __forceinline__ void gemm_pipeline(It issue_it, It cons_it, Epi &&epi) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  double *ring = reinterpret_cast<double *>(smem_raw);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + GEMM_RING_BYTES + GEMM_SCRATCH_BYTES);
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int wm = warp >> 2, wn = warp & 3;
+
+  if (tid == 0) {
+    for (int s = 0; s < GEMM_STAGES; ++s) mbar_init(smem_u32(&bars[s]), 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  auto issue = [&](int slot) {
+    uint32_t bar = smem_u32(&bars[slot]);
+    uint32_t dst = smem_u32(ring + (size_t)slot * GEMM_STAGE_ELEMS);
+    mbar_arrive_expect_tx(bar, GEMM_STAGE_BYTES);
+    bulk_g2s(dst, issue_it.A(), TILE_BYTES, bar);
+    bulk_g2s(dst + TILE_BYTES, issue_it.B(), TILE_BYTES, bar);
+    issue_it.next();
+  };
+
+  int issued = 0;
+  if (tid == 0) {
+    for (; issued < GEMM_STAGES - 1 && issue_it.valid(); ++issued) issue(issued);
+  }
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int fm = 0; fm < 8; ++fm)
+#pragma unroll
+    for (int fn = 0; fn < 4; ++fn) acc[fm][fn][0] = acc[fm][fn][1] = 0.0;
+
+  const int a_off = (wm * 8) * 128 + lane * 2;  // micro-row (wm*8+fm) -> +fm*128 ; micro-col mc -> +mc*64
+  const int b_off = (wn * 4) * 128 + lane * 2;
+
+  int g = 0;
+  while (cons_it.valid()) {
+    const int slot = g % GEMM_STAGES;
+    // refill the slot freed at the end of iteration g-1 (all warps passed that __syncthreads)
+    if (tid == 0 && issue_it.valid()) {
+      issue(issued % GEMM_STAGES);
+      ++issued;
+    }
+    mbar_wait(smem_u32(&bars[slot]), (uint32_t)((g / GEMM_STAGES) & 1));
+
+    const double *As = ring + (size_t)slot * GEMM_STAGE_ELEMS;
+    const double *Bs = As + TILE_ELEMS;
+#pragma unroll
+    for (int mc = 0; mc < 2; ++mc) {
+      double2 a[8], b[4];
+#pragma unroll
+      for (int fm = 0; fm < 8; ++fm) a[fm] = lds128(As + a_off + fm * 128 + mc * 64);
+#pragma unroll
+      for (int fn = 0; fn < 4; ++fn) b[fn] = lds128(Bs + b_off + fn * 128 + mc * 64);
+#pragma unroll
+      for (int fm = 0; fm < 8; ++fm)
+#pragma unroll
+        for (int fn = 0; fn < 4; ++fn) dmma884(acc[fm][fn][0], acc[fm][fn][1], a[fm].x, b[fn].x);
+#pragma unroll
+      for (int fm = 0; fm < 8; ++fm)
+#pragma unroll
+        for (int fn = 0; fn < 4; ++fn) dmma884(acc[fm][fn][0], acc[fm][fn][1], a[fm].y, b[fn].y);
+    }
+    __syncthreads();
+
+    const bool tile_end = cons_it.tile_end();
+    const int tile = cons_it.tile();
+    cons_it.next();
+    ++g;
+    if (tile_end) {
+      FragCoord fc{wm, wn, lane};
+      epi(tile, acc, fc);
+#pragma unroll
+      for (int fm = 0; fm < 8; ++fm)
+#pragma unroll
+        for (int fn = 0; fn < 4; ++fn) acc[fm][fn][0] = acc[fm][fn][1] = 0.0;
+    }
+  }
+}
+
+// Simple iterator: one output tile, `nk` consecutive macro-tiles of A and of B.
+struct LinearIt {
+  const double *a;
+  const double *b;
+  int left;
+  __device__ __forceinline__ bool valid() const { return left > 0; }
+  __device__ __forceinline__ const double *A() const { return a; }
+  __device__ __forceinline__ const double *B() const { return b; }
+  __device__ __forceinline__ bool tile_end() const { return left == 1; }
+  __device__ __forceinline__ int tile() const { return 0; }
+  __device__ __forceinline__ void next() {
+    a += TILE_ELEMS;
+    b += TILE_ELEMS;
+    --left;
+  }
+};
+
+// Epilogue helper: write (or read-modify-write) the 128x128 accumulator tile to a block in P-layout.
+//   dst      : pointer to the first macro-tile of the destination block
+//   transpose: element (r, c) is stored at local (c, r)
+//   out = (cin ? cin[...] : 0) + scale * acc
+__device__ __forceinline__ void store_block(double *dst, bool transpose, double scale, const double *cin,
+                                            const double (&acc)[8][4][2], const FragCoord &fc) {
+#pragma unroll
+  for (int fm = 0; fm < 8; ++fm) {
+    const int r = fc.row(fm);
+#pragma unroll
+    for (int fn = 0; fn < 4; ++fn) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = fc.col(fn, e);
+        const int off = transpose ? block_offset(c, r) : block_offset(r, c);
+        double v = scale * acc[fm][fn][e];
+        if (cin) v += cin[off];
+        dst[off] = v;
+      }
+    }
+  }
+}
+
+}  // namespace boss

@@ -1,0 +1,335 @@
+// score.cuh -- the acquisition-scoring path for one chunk of candidates:
+//
+//   xcov_kernel        K*^T tile-packed (cand x train) + mu = K*^T alpha        [FP64 pipe: exp/sqrt]
+//   score_trmm_kernel  q_m = | W k*_m |^2, V = W K* never leaves the SM          [DMMA, TMA-fed]
+//   acq_kernel         var = a^2 - q + 1e-18, _clip_var, EI x PoF, guards, per-block argmax  [HBM]
+//   argmax_final_kernel  deterministic reduction of the block winners
+//
+// Reference: mean_and_var(::GaussianProcessPosterior, X) src/models/gaussian_process.jl:174-178 ->
+// AbstractGPs mean_and_var(PosteriorGP) (k* , U'\k*, colsum of squares); expected_improvement.jl:58-114;
+// argmax loops grid.jl:52-65, sampling.jl:37-48.  W = L^-1 is formed once per fit, so the per-candidate
+// triangular solve of the reference becomes a triangular matrix product.
+#pragma once
+#include "gemm_core.cuh"
+#include "kernel_fn.cuh"
+
+namespace boss {
+
+// ---------------------------------------------------------------------------------------------
+// cross-covariance of a candidate chunk with the training set, + posterior mean
+// ---------------------------------------------------------------------------------------------
+struct XcovParams {
+  const double *Xs;        // d x . raw candidates (device), candidate m at column (m - in_off)
+  long long M, m0, in_off; // global count, first candidate of this chunk
+  int d, n, n_pad, ktiles;
+  const double *Xt;        // [n_pad][DP] scaled (and rounded) training inputs
+  const double *invl;      // [DP]
+  unsigned long long disc_bits;
+  const double *alpha;     // [n_pad] K^-1 (y - m), zero padded
+  double a2;
+  double *Ks;              // chunk scratch, P-layout: rows = candidates of the chunk, cols = training index
+  double *mu;              // [chunk] K*^T alpha (prior mean added later)
+};
+
+constexpr int XCOV_KC = 128;  // training points staged per shared-memory pass
+
+template <int KID, int DP>
+__global__ void __launch_bounds__(256) xcov_kernel(XcovParams p) {
+  __shared__ double xt[XCOV_KC * DP];
+  __shared__ double al[XCOV_KC];
+  __shared__ double mu_part[2][128];
+  const int tid = threadIdx.x, r = tid & 127, kh = tid >> 7;
+  const int cb = blockIdx.x;
+  const long long m = p.m0 + (long long)cb * 128 + r;
+  double xc[DP];
+  load_scaled_point<DP>(xc, p.Xs + (size_t)(m - p.in_off) * p.d, p.d, p.invl, p.disc_bits, m < p.M);
+
+  double mu_acc = 0.0;
+  double *rowbase = p.Ks + (size_t)cb * p.ktiles * TILE_ELEMS + (((r >> 3) << 1) << 6) + ((r & 7) << 3);
+  for (int k0 = 0; k0 < p.n_pad; k0 += XCOV_KC) {
+    __syncthreads();
+    for (int e = tid; e < XCOV_KC * DP; e += 256) xt[e] = p.Xt[(size_t)k0 * DP + e];
+    if (tid < XCOV_KC) al[tid] = p.alpha[k0 + tid];
+    __syncthreads();
+    for (int mcol = kh; mcol < XCOV_KC / 8; mcol += 2) {
+      double v[8];
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        const int kl = mcol * 8 + kk;
+        double d2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < DP; ++i) {
+          const double df = xc[i] - xt[kl * DP + i];
+          d2 = fma(df, df, d2);
+        }
+        const double val = (k0 + kl < p.n) ? p.a2 * kappa<KID>(d2) : 0.0;
+        v[kk] = val;
+        mu_acc = fma(val, al[kl], mu_acc);
+      }
+      const int kg = k0 + mcol * 8;  // global training index of v[0]
+      double *dst = rowbase + (size_t)(kg >> 4) * TILE_ELEMS + (((kg >> 3) & 1) << 6);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) *reinterpret_cast<double2 *>(dst + 2 * q) = make_double2(v[q], v[q + 4]);
+    }
+  }
+  mu_part[kh][r] = mu_acc;
+  __syncthreads();
+  if (tid < 128) p.mu[(size_t)cb * 128 + tid] = mu_part[0][tid] + mu_part[1][tid];
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused triangular product + column sum of squares:  q[m] = sum_r ( sum_{k<=r} W[r][k] K*[k][m] )^2
+// One CTA owns 128 candidates and walks all row blocks of W; the ring streams W (L2-resident) and the
+// CTA's K*^T block (re-read once per row block, triangular k-range).
+// ---------------------------------------------------------------------------------------------
+struct ScoreParams {
+  const double *W;    // P-layout n_pad x n_pad lower-triangular inverse factor
+  const double *Ks;   // chunk scratch
+  int nblk, ktiles;
+  double *sumsq;      // [chunk]
+};
+
+struct ScoreIt {
+  const double *w_row;   // first tile of the current W row block
+  const double *ks;      // first tile of this CTA's K*^T block
+  int i, kt, nblk, ktiles;
+  __device__ __forceinline__ bool valid() const { return i < nblk; }
+  __device__ __forceinline__ const double *A() const { return w_row + (size_t)kt * TILE_ELEMS; }
+  __device__ __forceinline__ const double *B() const { return ks + (size_t)kt * TILE_ELEMS; }
+  __device__ __forceinline__ bool tile_end() const { return kt == (i + 1) * KT_PER_BLOCK - 1; }
+  __device__ __forceinline__ int tile() const { return i; }
+  __device__ __forceinline__ void next() {
+    if (kt == (i + 1) * KT_PER_BLOCK - 1) {
+      ++i;
+      kt = 0;
+      w_row += (size_t)ktiles * TILE_ELEMS;
+    } else {
+      ++kt;
+    }
+  }
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) score_trmm_kernel(ScoreParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  double *scratch = reinterpret_cast<double *>(smem_raw + GEMM_RING_BYTES);  // [2][128]
+  const int cb = blockIdx.x;
+  ScoreIt it{p.W, p.Ks + (size_t)cb * p.ktiles * TILE_ELEMS, 0, 0, p.nblk, p.ktiles};
+  double cs[4][2];
+#pragma unroll
+  for (int fn = 0; fn < 4; ++fn) cs[fn][0] = cs[fn][1] = 0.0;
+
+  gemm_pipeline(it, it, [&](int, const double(&acc)[8][4][2], const FragCoord &) {
+#pragma unroll
+    for (int fn = 0; fn < 4; ++fn)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int fm = 0; fm < 8; ++fm) sacc = fma(acc[fm][fn][e], acc[fm][fn][e], sacc);
+        cs[fn][e] += sacc;
+      }
+  });
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wm = warp >> 2, wn = warp & 3;
+#pragma unroll
+  for (int fn = 0; fn < 4; ++fn)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      double v = cs[fn][e];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (lane < 4) scratch[wm * 128 + 32 * wn + 8 * fn + 2 * lane + e] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x < 128) p.sumsq[(size_t)cb * 128 + threadIdx.x] = scratch[threadIdx.x] + scratch[128 + threadIdx.x];
+}
+
+// ---------------------------------------------------------------------------------------------
+// elementwise acquisition stage + block argmax
+// ---------------------------------------------------------------------------------------------
+constexpr int MAX_YDIM = 16;
+
+struct AcqParams {
+  int y_dim, n_samples, d;
+  long long M, m0;       // global candidate count / chunk start
+  long long in_off;      // Xs / prior_mean / cons_mask are indexed by (m - in_off)
+  long long out_off;     // acq / mu_out / var_out / status_out are indexed by (m - out_off)
+  int chunk;             // candidates in this chunk
+  int chunk_ld;          // leading dimension of mu / sumsq ([n_samples*y_dim][chunk_ld])
+  const double *mu;      // K*^T alpha per (sample, slice)
+  const double *sumsq;   // |W k*|^2 per (sample, slice)
+  const double *a2;      // [n_samples*y_dim] prior variance a^2 (device)
+  const double *prior_mean;  // y_dim x M or null
+  double coefs[MAX_YDIM];
+  double y_max[MAX_YDIM];
+  int has_best, has_ymax;
+  double best;
+  const double *Xs;      // d x M for the bounds check (null if no bounds)
+  const double *lb, *ub; // device, d each (null if no bounds)
+  const unsigned char *cons_mask;  // or null
+  double *acq;           // or null
+  double *mu_out, *var_out;  // predict mode (single slice) or null
+  int *status_out;       // predict mode or null
+  int *any_fail;         // device flag
+  double *blk_val;       // per-block winners
+  long long *blk_idx;
+};
+
+__device__ __forceinline__ double norm_cdf(double z) { return 0.5 * erfc(-z * 0.7071067811865476); }
+__device__ __forceinline__ double norm_pdf(double z) { return exp(-0.5 * z * z) * 0.3989422804014327; }
+
+// _clip_var, src/models/gaussian_process.jl:186-194.  returns false where the reference throws.
+__device__ __forceinline__ bool clip_var(double &v) {
+  if (v >= 0.0) return true;
+  if (v >= -MAX_NEG_VAR) {
+    v = 0.0;
+    return true;
+  }
+  return false;
+}
+
+__global__ void __launch_bounds__(256) acq_kernel(AcqParams p) {
+  __shared__ double sv[256];
+  __shared__ long long si[256];
+  const int tid = threadIdx.x;
+  const int c = blockIdx.x * 256 + tid;
+  const long long m = p.m0 + c;
+  double result = -INFINITY;
+  bool active = (c < p.chunk) && (m < p.M);
+  if (active) {
+    double accum = 0.0;
+    bool failed = false;
+    for (int s = 0; s < p.n_samples; ++s) {
+      double mu_f = 0.0, s2 = 0.0, pof = 1.0;
+      for (int i = 0; i < p.y_dim; ++i) {
+        const size_t row = (size_t)(s * p.y_dim + i) * p.chunk_ld + c;
+        double mu = p.mu[row];
+        if (p.prior_mean) mu = p.prior_mean[(size_t)(m - p.in_off) * p.y_dim + i] + mu;
+        double var = p.a2[s * p.y_dim + i] - p.sumsq[row] + VAR_JITTER;
+        const bool ok = clip_var(var);
+        if (!ok) failed = true;
+        if (p.mu_out) p.mu_out[m - p.out_off] = mu;
+        if (p.var_out) p.var_out[m - p.out_off] = var;
+        if (p.status_out) p.status_out[m - p.out_off] = ok ? 0 : 2;
+        mu_f = fma(p.coefs[i], mu, mu_f);
+        s2 = fma(p.coefs[i] * p.coefs[i], var, s2);
+        if (p.has_ymax) {
+          const double ym = p.y_max[i];
+          if (!(ym == INFINITY)) {                 // cdf(., Infinity()) == 1 exactly (src/utils/inf.jl:13-15)
+            const double sd = sqrt(var);
+            double z = (ym - mu) / sd;
+            if (sd == 0.0 && ym == mu) z = INFINITY;   // StatsFuns: x == mu, sigma == 0 -> cdf 1
+            pof *= norm_cdf(z);
+          }
+        }
+      }
+      double a;
+      if (p.has_best) {
+        const double sf = sqrt(s2);
+        const double diff = mu_f - p.best;
+        double ei;
+        if (diff == 0.0 && sf == 0.0) {
+          ei = 0.0;
+        } else {
+          const double z = diff / sf;
+          ei = diff * norm_cdf(z) + sf * norm_pdf(z);
+        }
+        a = p.has_ymax ? ei * pof : ei;
+      } else {
+        a = p.has_ymax ? pof : 0.0;
+      }
+      accum += a;
+    }
+    result = accum / (double)p.n_samples;
+    if (failed) {
+      result = -INFINITY;
+      *p.any_fail = 1;
+    }
+    if (p.lb) {
+      bool inb = true;
+      for (int i = 0; i < p.d; ++i) {
+        const double x = p.Xs[(size_t)(m - p.in_off) * p.d + i];
+        if (x < p.lb[i] || x > p.ub[i]) inb = false;
+      }
+      if (!inb) result = 0.0;
+    }
+    if (p.cons_mask && p.cons_mask[m - p.in_off] == 0) result = 0.0;
+    if (p.acq) p.acq[m - p.out_off] = result;
+  }
+  if (p.blk_val == nullptr) return;
+  // block argmax with Julia semantics (first maximal, NaN maximal); inactive lanes carry idx = LLONG_MAX
+  sv[tid] = result;
+  si[tid] = active ? m : 0x7fffffffffffffffLL;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) {
+      const double v2 = sv[tid + o];
+      const long long i2 = si[tid + o];
+      const bool a1 = si[tid] != 0x7fffffffffffffffLL, a2 = i2 != 0x7fffffffffffffffLL;
+      if (a2 && (!a1 || acq_better(v2, i2, sv[tid], si[tid]))) {
+        sv[tid] = v2;
+        si[tid] = i2;
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    p.blk_val[blockIdx.x] = sv[0];
+    p.blk_idx[blockIdx.x] = si[0];
+  }
+}
+
+// Fold `nblk` block winners into the running (val, idx) pair held in best[0], bidx[0].
+__global__ void argmax_final_kernel(const double *blk_val, const long long *blk_idx, int nblk, double *best,
+                                    long long *bidx) {
+  __shared__ double sv[256];
+  __shared__ long long si[256];
+  const int tid = threadIdx.x;
+  double v = 0.0;
+  long long ix = 0x7fffffffffffffffLL;
+  for (int b = tid; b < nblk; b += 256) {
+    const long long i2 = blk_idx[b];
+    if (i2 != 0x7fffffffffffffffLL && (ix == 0x7fffffffffffffffLL || acq_better(blk_val[b], i2, v, ix))) {
+      v = blk_val[b];
+      ix = i2;
+    }
+  }
+  sv[tid] = v;
+  si[tid] = ix;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) {
+      const long long i2 = si[tid + o];
+      if (i2 != 0x7fffffffffffffffLL && (si[tid] == 0x7fffffffffffffffLL || acq_better(sv[tid + o], i2, sv[tid], si[tid]))) {
+        sv[tid] = sv[tid + o];
+        si[tid] = i2;
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0 && si[0] != 0x7fffffffffffffffLL) {
+    if (*bidx < 0 || acq_better(sv[0], si[0], *best, *bidx)) {
+      *best = sv[0];
+      *bidx = si[0];
+    }
+  }
+}
+
+// Scale + round training inputs once per fit: Xt[k][i] = round?(X[k*d+i]) * invl[i], zero padded.
+__global__ void scale_train_kernel(const double *X, int d, int n, int n_pad, int DP, const double *invl,
+                                   unsigned long long disc_bits, double *Xt) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_pad * DP) return;
+  const int k = e / DP, i = e % DP;
+  double v = 0.0;
+  if (k < n && i < d) {
+    v = X[(size_t)k * d + i];
+    if ((disc_bits >> i) & 1ull) v = rint(v);
+    v *= invl[i];
+  }
+  Xt[e] = v;
+}
+
+}  // namespace boss

@@ -1,0 +1,153 @@
+/* boss_b200.h -- C ABI of libboss_b200.so, the B200 (sm_100a) backend for BOSS.jl's GP hot path.
+ *
+ * This is the drop-in boundary.  BOSS.jl (pure Julia) has no FFI of its own; the backend module
+ * (julia/BossB200.jl) adds more specific methods for the reference's documented
+ * extension interfaces and `ccall`s the entry points below.  Each entry point cites the reference
+ * function(s) it replaces (paths relative to the BOSS.jl v0.6.1 source tree).
+ *
+ * Conventions
+ *   - All matrices are Float64, column-major with points as columns, exactly BOSS.jl's layout
+ *     (src/types/data.jl:19-22): X is d x n  => point k is the d contiguous doubles at X + k*d.
+ *   - Pointers are caller-owned HOST memory valid for the duration of the call, except in the
+ *     `_dev` variants where every array argument is a DEVICE pointer on the library's device and the
+ *     work is enqueued on the caller-supplied CUDA stream (0 = the library's own stream).
+ *   - Raw hyper-parameters are passed exactly as the reference passes them to `finite_gp`
+ *     (src/models/gaussian_process.jl:216-245): the library asserts >= 0 and adds MIN_PARAM_VALUE
+ *     = 1e-8 itself.
+ *   - Return value: 0 ok; > 0 a numerical condition that the reference reports by throwing and that
+ *     its SafeFunction wrappers map to -Inf (BOSS_NOT_POSDEF, BOSS_NEG_VARIANCE); < 0 argument /
+ *     CUDA errors with text in boss_last_error().  Nothing aborts, nothing throws across the ABI.
+ *   - One process drives one GPU (boss_init(device)); multi-GPU = one process per GPU, sharding
+ *     candidates / samples in the caller (see boss.jl_b200/parallel.py and DESIGN.md).
+ *   - Thread-safe: entry points serialise on an internal mutex (the reference may call from
+ *     Threads.@threads tasks when parallel=true, src/utils/optim_multistart.jl:62).
+ */
+#ifndef BOSS_B200_H
+#define BOSS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BOSS_OK 0
+#define BOSS_NOT_POSDEF 1      /* LinearAlgebra.PosDefException in cholesky()                     */
+#define BOSS_NEG_VARIANCE 2    /* DomainError of _clip_var, src/models/gaussian_process.jl:186-194 */
+#define BOSS_ERR_ARG (-1)
+#define BOSS_ERR_CUDA (-2)
+#define BOSS_ERR_STATE (-3)
+
+/* kernel_id : KernelFunctions kernels the reference's GaussianProcess accepts on this path */
+#define BOSS_KERNEL_SE 0        /* SqExponentialKernel                         */
+#define BOSS_KERNEL_MATERN32 1  /* Matern32Kernel (examples/example.jl:88)     */
+#define BOSS_KERNEL_MATERN52 2  /* Matern52Kernel (default, src/deprecated.jl:34) */
+
+typedef struct boss_gp boss_gp; /* opaque: one fitted GP = one output slice x one hyper-parameter vector */
+
+/* ---- runtime ---------------------------------------------------------------------------- */
+int boss_init(int device);            /* select device, create streams + workspace; idempotent      */
+void boss_shutdown(void);
+const char *boss_last_error(void);
+int boss_version(void);
+int boss_device(void);                /* device ordinal in use, -1 before boss_init                 */
+
+/* ---- a1 + a2 : fit -----------------------------------------------------------------------
+ * Replaces posterior_gp (src/models/gaussian_process.jl:199-211) -> finite_gp (:216-248) ->
+ * AbstractGPs.posterior: builds K = a^2 kappa(|(x-x')/l|) + s^2 I, factors it (FP64 blocked
+ * Cholesky), forms the triangular inverse and alpha = K^-1 (y - m(X)), and keeps them on the device
+ * (the "factor cache": the reference refactors on every model_posterior call).
+ *   X             d x n   training inputs
+ *   y_minus_mean  n       Y[slice,:] - m(X)  (prior mean evaluated by the caller: nothing / const / closure)
+ *   lengthscales  d       raw lambda[:,slice];  amplitude, noise_std raw alpha[slice], sigma[slice]
+ *   discrete_mask d bytes or NULL  (DiscreteKernel, src/models/utils/kernels.jl:43-69: round, then scale)
+ *   loglik_out    optional: log marginal likelihood of the same fit (gaussian_process.jl:269-280)
+ * Returns BOSS_NOT_POSDEF (and *out = NULL) when the factorisation meets a non-positive pivot. */
+int boss_gp_fit(const double *X, int d, int n, const double *y_minus_mean, const double *lengthscales,
+                double amplitude, double noise_std, int kernel_id, const uint8_t *discrete_mask,
+                boss_gp **out, double *loglik_out);
+void boss_gp_free(boss_gp *gp);
+int boss_gp_n(const boss_gp *gp);
+int boss_gp_d(const boss_gp *gp);
+
+/* ---- a3 + a4 : predict --------------------------------------------------------------------
+ * Replaces mean / var / mean_and_var(::GaussianProcessPosterior, x | X)
+ * (src/models/gaussian_process.jl:143-178) incl. _clip_var (:186-194).
+ *   Xs d x M candidates; prior_mean_s M values m(x*) or NULL (zero mean)
+ *   mu, var  M each (either may be NULL); status M int32 or NULL: 0 ok, BOSS_NEG_VARIANCE where the
+ *   reference would throw DomainError (var is then the raw unclipped value).
+ * Returns 0, or BOSS_NEG_VARIANCE if any status is non-zero. */
+int boss_gp_predict(const boss_gp *gp, const double *Xs, int64_t M, const double *prior_mean_s,
+                    double *mu, double *var, int32_t *status);
+
+/* Same with device pointers (Xs, prior mean and outputs already resident in HBM). */
+int boss_gp_predict_dev(const boss_gp *gp, const double *Xs_dev, int64_t M, const double *prior_mean_s_dev,
+                        double *mu_dev, double *var_dev, int32_t *status_dev);
+
+/* Replaces cov / mean_and_cov(::GaussianProcessPosterior, X) (gaussian_process.jl:163-167,180-184):
+ * full M x M posterior covariance (column-major), diagonal clipped.  Intended for small M. */
+int boss_gp_cov(const boss_gp *gp, const double *Xs, int64_t M, const double *prior_mean_s,
+                double *mu, double *cov);
+
+/* ---- a5 + a6 + a7 : acquisition scoring -----------------------------------------------------
+ * Replaces the closure built by construct_safe_acquisition (src/acquisition.jl:21-25) ->
+ * construct_acquisition(::ExpectedImprovement) (src/acquisitions/expected_improvement.jl:49-90) applied
+ * to every column of Xs, and the argmax loops of GridAM / SamplingAM
+ * (src/acquisition_maximizers/grid.jl:52-65, sampling.jl:37-48).
+ *   slices        n_samples x y_dim handles, sample-major: slices[s*y_dim + i]  (posterior.jl:15-19,38-41)
+ *   prior_mean_s  y_dim x M (column-major: y_dim contiguous per candidate) or NULL
+ *   fit_coefs     y_dim LinFitness coefficients
+ *   best          pointer to best-so-far fitness or NULL (= `nothing`, no feasible observation)
+ *   y_max         y_dim constraints (+Inf = unconstrained, cdf == 1 exactly) or NULL (no constraints)
+ *   lb, ub        d each or NULL: out-of-bounds candidates score 0. (make_safe, :58-65; inclusive)
+ *   cons_mask     M bytes or NULL: 0 => cons(x) violated => score 0.
+ *   acq           M scores or NULL;  grad d x M x-gradients or NULL
+ *   best_val / best_idx  Julia argmax semantics: first maximal, NaN maximal (may be NULL)
+ * Candidates whose variance fails _clip_var score -Inf (SafeFunction, src/utils/optim.jl:20-34). */
+int boss_ei_score(const boss_gp *const *slices, int y_dim, int n_samples, const double *Xs, int64_t M,
+                  const double *prior_mean_s, const double *fit_coefs, const double *best,
+                  const double *y_max, const double *lb, const double *ub, const uint8_t *cons_mask,
+                  double *acq, double *grad, double *best_val, int64_t *best_idx);
+
+/* Same, every array argument a device pointer (candidates already resident in HBM); enqueued on
+ * `stream` and synchronised before return.  best_val / best_idx are HOST pointers. */
+int boss_ei_score_dev(const boss_gp *const *slices, int y_dim, int n_samples, const double *Xs_dev,
+                      int64_t M, const double *prior_mean_s_dev, const double *fit_coefs, const double *best,
+                      const double *y_max, const double *lb, const double *ub, const uint8_t *cons_mask_dev,
+                      double *acq_dev, double *grad_dev, double *best_val, int64_t *best_idx, void *stream);
+
+/* ---- a8 + a9 : batched log marginal likelihood ------------------------------------------------
+ * Replaces data_loglike(::GaussianProcess) / gp_data_loglike_slice (gaussian_process.jl:250-280)
+ * -> logpdf(::FiniteGP, y) evaluated for S hyper-parameter vectors at once: the batches built by
+ * SamplingMAP (src/model_fitters/sampling.jl:59-78), OptimizationMAP multistart
+ * (optimization.jl:116-119) and the TuringBI model (ext/TuringExt.jl:78-86), for ONE output slice.
+ *   Y_minus_mean  n (ldy == 0: shared by all samples) or S x n with sample s at Y_minus_mean + s*ldy
+ *                 (Semiparametric: the mean depends on theta_s)
+ *   lengthscales  d x S (sample s = d contiguous doubles), amplitude S, noise_std S (raw values)
+ *   loglik        S results; -Inf where K is not positive definite (safe_data_loglike)
+ * Returns 0 or BOSS_NOT_POSDEF if any sample failed. */
+int boss_gp_loglik_batch(const double *X, int d, int n, const double *Y_minus_mean, int64_t ldy,
+                         const double *lengthscales, const double *amplitude, const double *noise_std,
+                         int kernel_id, const uint8_t *discrete_mask, int64_t S, double *loglik);
+
+int boss_gp_loglik_batch_dev(const double *X_dev, int d, int n, const double *Y_minus_mean_dev, int64_t ldy,
+                             const double *lengthscales_dev, const double *amplitude_dev,
+                             const double *noise_std_dev, int kernel_id, const uint8_t *discrete_mask,
+                             int64_t S, double *loglik_dev, void *stream);
+
+/* ---- instrumentation ---------------------------------------------------------------------
+ * CUDA-event time (ms) of the dominant kernel class inside the last scoring / loglik call, and the
+ * number of kernel launches the library has issued since boss_init (bench.py's gpu_launches). */
+void boss_set_timing(int on);          /* bracket kernel classes with CUDA events (default off)              */
+double boss_last_kernel_ms(int which); /* 0 = scoring TRMM, 1 = kernel-matrix / cross-covariance, 2 = Cholesky GEMMs, 3 = whole call */
+int boss_last_kernel_count(int which); /* launches summed into boss_last_kernel_ms(which)                     */
+int64_t boss_launch_count(void);
+
+/* ---- debug / test hooks (used by tests/ only) ------------------------------------------------ */
+int boss_dbg_gemm_nt(const double *A, const double *B, int M, int N, int K, double *C); /* C = A B^T, row-major dense */
+int boss_dbg_factors(const boss_gp *gp, double *L, double *W, double *alpha);          /* dense row-major n x n, n   */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BOSS_B200_H */

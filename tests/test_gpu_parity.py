@@ -1,0 +1,247 @@
+"""GPU parity tests: the CUDA path through the C ABI vs the CPU oracle on identical seeded inputs.
+
+Tolerances are the north star's: relative error <= 1e-9 for posterior mean / variance / EI,
+<= 1e-8 for the log marginal likelihood, argmax index exact on tie-free candidate sets.
+"""
+import numpy as np
+import pytest
+
+from oracle import boss_oracle as O
+from tests.util_problems import make_hyper_samples, make_problem, relerr
+
+pytestmark = pytest.mark.gpu
+
+TOL_POST = 1e-9
+TOL_LL = 1e-8
+
+
+# ---------------------------------------------------------------------------------------------
+# the FP64 tensor-core mainloop in isolation
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(128, 128, 16), (128, 128, 80), (256, 384, 160), (130, 70, 33), (512, 128, 2048)])
+def test_gemm_core(lib, M, N, K):
+    rng = np.random.default_rng(M * 7 + N * 3 + K)
+    A = rng.standard_normal((M, K)); B = rng.standard_normal((N, K))
+    C = lib.dbg_gemm_nt(A, B)
+    ref = A @ B.T
+    assert np.max(np.abs(C - ref)) <= 1e-12 * K
+
+
+# ---------------------------------------------------------------------------------------------
+# fit: kernel matrix + blocked Cholesky + triangular inverse + alpha + loglik
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,d,kid", [(3, 2, 2), (20, 2, 0), (128, 1, 1), (200, 6, 2), (300, 3, 0), (512, 6, 2),
+                                     (640, 10, 1)])
+def test_fit_factors(lib, n, d, kid):
+    X, Y, ls, amp, ns = make_problem(n, d, seed=100 + n)
+    gp = lib.gp_fit(X, Y[0], ls[0], amp[0], ns[0], kid)
+    assert gp is not None
+    post = O.posterior_fit(X, Y[0], ls[0], amp[0], ns[0], kid)
+    L, W, alpha = lib.dbg_factors(gp)
+    Lref = post.U.T
+    assert np.max(np.abs(L - Lref)) / np.max(np.abs(Lref)) < 1e-11
+    Wref = np.linalg.inv(Lref)
+    assert np.max(np.abs(W - Wref)) / np.max(np.abs(Wref)) < 1e-9
+    assert np.max(np.abs(alpha - post.alpha_w)) / np.max(np.abs(post.alpha_w)) < 1e-9
+    ll = O.gp_loglik(X, Y[0], ls[0], amp[0], ns[0], kid)
+    assert abs(gp.loglik - ll) <= TOL_LL * abs(ll)
+    gp.free()
+
+
+# ---------------------------------------------------------------------------------------------
+# predict (mean_and_var) incl. prior mean, vector == matrix API, clip
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,d,kid,M", [(3, 2, 2, 7), (20, 2, 0, 300), (200, 6, 2, 1000), (512, 8, 1, 777),
+                                       (1024, 10, 2, 2048)])
+def test_predict(lib, n, d, kid, M):
+    X, Y, ls, amp, ns = make_problem(n, d, seed=200 + n)
+    rng = np.random.default_rng(n + M)
+    Xs = rng.random((d, M))
+    pm = rng.standard_normal(M)
+    gp = lib.gp_fit(X, Y[0], ls[0], amp[0], ns[0], kid)
+    post = O.posterior_fit(X, Y[0], ls[0], amp[0], ns[0], kid)
+    mu_ref, var_ref, st_ref = O.mean_and_var(post, Xs, pm)
+    mu, var, st = lib.gp_predict(gp, Xs, pm)
+    assert np.array_equal(st, st_ref)
+    assert relerr(mu, mu_ref) <= TOL_POST, relerr(mu, mu_ref)
+    assert relerr(var, var_ref) <= TOL_POST, relerr(var, var_ref)
+    # vector API == column of the matrix API  (test/unit/test/models/gaussian_process.jl:115-126)
+    m1, v1, _ = lib.gp_predict(gp, Xs[:, 3], pm[3:4])
+    assert m1[0] == mu[3] and v1[0] == var[3]
+    gp.free()
+
+
+def test_predict_at_training_points_interpolates(lib):
+    X, Y, ls, amp, ns = make_problem(40, 2, seed=5, noise=1e-3)
+    gp = lib.gp_fit(X, Y[0], ls[0], amp[0], ns[0], 2)
+    mu, var, st = lib.gp_predict(gp, X)
+    assert np.allclose(mu, Y[0], atol=0.01)
+    assert np.all(st == 0) and np.all(var >= 0)
+    far = np.full((2, 1), 1000.0)
+    mu_f, var_f, _ = lib.gp_predict(gp, far)
+    assert abs(mu_f[0]) < 1e-8 and abs(var_f[0] - (1.0 + 1e-8) ** 2) < 1e-8
+    gp.free()
+
+
+def test_discrete_kernel(lib):
+    X, Y, ls, amp, ns = make_problem(60, 3, seed=9)
+    X = X * 6.0
+    mask = np.array([True, False, True])
+    rng = np.random.default_rng(2)
+    Xs = rng.random((3, 257)) * 6.0
+    gp = lib.gp_fit(X, Y[0], ls[0] * 3, amp[0], ns[0], 1, mask)
+    post = O.posterior_fit(X, Y[0], ls[0] * 3, amp[0], ns[0], 1, mask)
+    mu_ref, var_ref, _ = O.mean_and_var(post, Xs)
+    mu, var, _ = lib.gp_predict(gp, Xs)
+    assert relerr(mu, mu_ref) <= TOL_POST and relerr(var, var_ref) <= TOL_POST
+    gp.free()
+
+
+# ---------------------------------------------------------------------------------------------
+# acquisition: EI, EI x PoF, PoF only, nothing; bounds / cons guards; BI average; argmax
+# ---------------------------------------------------------------------------------------------
+def _fit_all(lib, X, Y, ls, amp, ns, kid):
+    gps = [lib.gp_fit(X, Y[i], ls[i], amp[i], ns[i], kid) for i in range(Y.shape[0])]
+    posts = [O.posterior_fit(X, Y[i], ls[i], amp[i], ns[i], kid) for i in range(Y.shape[0])]
+    return gps, posts
+
+
+def _ei_mask(acq_ref):
+    # relative comparison where EI is representable without extreme-tail amplification
+    return acq_ref > 1e-200
+
+
+@pytest.mark.parametrize("case", ["ei", "ei_pof", "pof", "none"])
+def test_ei_score_cases(lib, case):
+    n, d, y_dim, M = 300, 4, 3, 5000
+    X, Y, ls, amp, ns = make_problem(n, d, seed=31, y_dim=y_dim)
+    gps, posts = _fit_all(lib, X, Y, ls, amp, ns, 2)
+    rng = np.random.default_rng(77)
+    Xs = rng.random((d, M)) * 1.2 - 0.1           # some candidates out of bounds
+    lb, ub = np.zeros(d), np.ones(d)
+    cons = (rng.random(M) > 0.1).astype(np.uint8)
+    coefs = np.array([1.0, 0.0, 0.25])
+    y_max = np.array([np.inf, float(np.quantile(Y[1], 0.7)), float(np.quantile(Y[2], 0.7))])
+    best = O.best_so_far(coefs, Y, y_max)
+    kw = dict(ei=(best, None), ei_pof=(best, y_max), pof=(None, y_max), none=(None, None))[case]
+    acq_ref, _, _ = O.ei_acquisition([posts], Xs, coefs, kw[0], kw[1], lb, ub, cons)
+    acq, bv, bi = lib.ei_score(gps, y_dim, 1, Xs, coefs, kw[0], kw[1], lb, ub, cons)
+    mask = _ei_mask(acq_ref)
+    assert relerr(acq[mask], acq_ref[mask]) <= TOL_POST, relerr(acq[mask], acq_ref[mask])
+    assert np.all(acq[~mask] <= 1e-200)
+    assert np.all(acq[(cons == 0) | ~O.in_bounds(Xs, lb, ub)] == 0.0)
+    assert bi == O.julia_argmax_fast(acq_ref)
+    assert bv == acq[bi]
+    for g in gps:
+        g.free()
+
+
+def test_ei_bi_sample_average(lib):
+    n, d, M, S = 150, 3, 1500, 4
+    X, Y, _, _, _ = make_problem(n, d, seed=41)
+    L, A, N = make_hyper_samples(S, d, seed=42)
+    gps = [lib.gp_fit(X, Y[0], L[s], A[s], N[s], 0) for s in range(S)]
+    posts = [[O.posterior_fit(X, Y[0], L[s], A[s], N[s], 0)] for s in range(S)]
+    Xs = np.random.default_rng(1).random((d, M))
+    best = float(np.median(Y[0]))
+    acq_ref, _, _ = O.ei_acquisition(posts, Xs, [1.0], best, None)
+    acq, bv, bi = lib.ei_score(gps, 1, S, Xs, [1.0], best, None)
+    assert relerr(acq, acq_ref) <= TOL_POST
+    assert bi == O.julia_argmax_fast(acq_ref)
+    for g in gps:
+        g.free()
+
+
+def test_ei_known_answers_on_device(lib):
+    """Reference EI known answers pushed through the device epilogue: a GP with a far-away single
+    training point has mu = prior mean, var = a^2, so EI follows the closed form exactly."""
+    X = np.array([[1000.0]]); y = np.array([0.0])
+    gp = lib.gp_fit(X, y, [1.0], 1.0, 0.1, 0)
+    Xs = np.zeros((1, 4))
+    acq, _, _ = lib.ei_score([gp], 1, 1, Xs, [1.0], 0.0, None, prior_mean_s=np.array([[0.0, -10.0, 1.0, 0.5]]))
+    a2 = (1.0 + 1e-8) ** 2
+    ref = O.expected_improvement([1.0], np.array([[0.0, -10.0, 1.0, 0.5]]), np.full((1, 4), a2 + 1e-18), 0.0)
+    assert relerr(acq, ref) <= 1e-12
+    assert acq[1] < 1e-20
+    gp.free()
+
+
+def test_argmax_first_max_and_ties(lib):
+    X, Y, ls, amp, ns = make_problem(50, 2, seed=3)
+    gp = lib.gp_fit(X, Y[0], ls[0], amp[0], ns[0], 2)
+    rng = np.random.default_rng(0)
+    base = rng.random((2, 700))
+    Xs = np.concatenate([base, base[:, ::-1]], axis=1)     # every candidate appears twice
+    acq, bv, bi = lib.ei_score([gp], 1, 1, Xs, [1.0], float(np.median(Y[0])), None)
+    assert bi == int(np.argmax(acq))                       # first maximal element
+    # everything out of bounds -> all zeros -> index 0
+    acq0, bv0, bi0 = lib.ei_score([gp], 1, 1, Xs + 5.0, [1.0], 0.0, None, np.zeros(2), np.ones(2))
+    assert np.all(acq0 == 0.0) and bi0 == 0 and bv0 == 0.0
+    gp.free()
+
+
+# ---------------------------------------------------------------------------------------------
+# batched log marginal likelihood
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,d,kid,S", [(3, 2, 2, 5), (20, 2, 0, 33), (130, 3, 1, 17), (512, 6, 2, 24), (512, 6, 0, 8),
+                                       (1024, 8, 2, 4)])
+def test_loglik_batch(lib, n, d, kid, S):
+    X, Y, _, _, _ = make_problem(n, d, seed=300 + n)
+    L, A, N = make_hyper_samples(S, d, seed=301 + n)
+    ref = O.gp_loglik_batch(X, Y[0], L, A, N, kid)
+    out = lib.loglik_batch(X, Y[0], L, A, N, kid)
+    assert relerr(out, ref) <= TOL_LL, relerr(out, ref)
+
+
+def test_loglik_batch_per_sample_mean(lib):
+    """Semiparametric: y - m_theta(X) differs per sample (src/models/semiparametric.jl:86-92)."""
+    n, d, S = 100, 2, 6
+    X, Y, _, _, _ = make_problem(n, d, seed=8)
+    L, A, N = make_hyper_samples(S, d, seed=9)
+    theta = np.random.default_rng(3).standard_normal((S, 2))
+    Ymm = np.stack([Y[0] - (theta[s, 0] * X[0] + theta[s, 1]) for s in range(S)])
+    ref = O.gp_loglik_batch(X, Ymm, L, A, N, 2)
+    out = lib.loglik_batch(X, Ymm, L, A, N, 2)
+    assert relerr(out, ref) <= TOL_LL
+
+
+def test_not_positive_definite(lib):
+    X = np.zeros((1, 40)); y = np.arange(40.0)
+    # zero noise, 40 identical points: K = a^2 * ones is numerically singular -> some pivot is <= 0
+    out = lib.loglik_batch(X, y, np.array([[1.0], [1.0]]), np.array([1e6, 1.0]), np.array([0.0, 0.5]), 0)
+    assert out[0] == -np.inf and np.isfinite(out[1])
+    assert O.gp_loglik(X, y, [1.0], 1e6, 0.0, 0) == -np.inf
+    assert lib.gp_fit(X, y, [1.0], 1e6, 0.0, 0) is None
+
+
+def test_negative_hyperparameters_rejected(lib):
+    X, Y, ls, amp, ns = make_problem(10, 2, seed=1)
+    with pytest.raises(lib.BossError):
+        lib.gp_fit(X, Y[0], -ls[0], amp[0], ns[0], 2)
+
+
+# ---------------------------------------------------------------------------------------------
+# headline shape: n = 2048, d = 8, Matern52 (BASELINE.json configs[1]) on a 65 536-candidate subset
+# ---------------------------------------------------------------------------------------------
+def test_headline_shape_parity(lib):
+    n, d, M = 2048, 8, 65536
+    X, Y, ls, amp, ns = make_problem(n, d, seed=1002)
+    Xs = np.random.default_rng(2002).random((d, M))
+    gp = lib.gp_fit(X, Y[0], ls[0], amp[0], ns[0], 2)
+    post = O.posterior_fit(X, Y[0], ls[0], amp[0], ns[0], 2)
+    ll = O.gp_loglik(X, Y[0], ls[0], amp[0], ns[0], 2)
+    assert abs(gp.loglik - ll) <= TOL_LL * abs(ll)
+    mu_ref, var_ref, st_ref = O.mean_and_var(post, Xs)
+    mu, var, st = lib.gp_predict(gp, Xs)
+    assert relerr(mu, mu_ref) <= TOL_POST and relerr(var, var_ref) <= TOL_POST
+    best = float(np.max(Y[0]))
+    acq_ref, _, _ = O.ei_acquisition([[post]], Xs, [1.0], best, None)
+    acq, bv, bi = lib.ei_score([gp], 1, 1, Xs, [1.0], best, None)
+    mask = _ei_mask(acq_ref)
+    assert relerr(acq[mask], acq_ref[mask]) <= TOL_POST
+    assert bi == O.julia_argmax_fast(acq_ref)
+    # size-independent property: scoring a permutation permutes the scores bit-exactly
+    perm = np.random.default_rng(0).permutation(M)
+    acq_p, _, bi_p = lib.ei_score([gp], 1, 1, Xs[:, perm], [1.0], best, None)
+    assert np.array_equal(acq_p, acq[perm])
+    gp.free()
