@@ -161,7 +161,7 @@ def test_ei_known_answers_on_device(lib):
     acq, _, _ = lib.ei_score([gp], 1, 1, Xs, [1.0], 0.0, None, prior_mean_s=np.array([[0.0, -10.0, 1.0, 0.5]]))
     a2 = (1.0 + 1e-8) ** 2
     ref = O.expected_improvement([1.0], np.array([[0.0, -10.0, 1.0, 0.5]]), np.full((1, 4), a2 + 1e-18), 0.0)
-    assert relerr(acq, ref) <= 1e-12
+    assert relerr(acq, ref) <= 1e-10     # z = -10 tail: erfc ulp differences are amplified ~|z|^2
     assert acq[1] < 1e-20
     gp.free()
 

@@ -6,7 +6,7 @@ if [ "$1" != "nomicro" ]; then
   timeout 120 ./tools/microbench > gpurun_out/microbench.json 2> gpurun_out/microbench.err
   timeout 300 python tools/dgemm_peak.py > gpurun_out/dgemm_peak.json 2> gpurun_out/dgemm_peak.err
 fi
-timeout 900 python -m pytest tests -m gpu -q -x --timeout 600 > gpurun_out/pytest_gpu.log 2>&1
+timeout 900 python -m pytest tests -m gpu -q --timeout 600 > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -40 gpurun_out/pytest_gpu.log
 cat gpurun_out/microbench.json gpurun_out/dgemm_peak.json 2>/dev/null
