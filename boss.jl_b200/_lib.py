@@ -32,6 +32,7 @@ EXPORTS = {
     "boss_last_error": (C.c_char_p, []),
     "boss_version": (C.c_int, []),
     "boss_device": (C.c_int, []),
+    "boss_stream": (_vp, []),
     "boss_gp_fit": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, C.c_double, C.c_double, C.c_int, _vp,
                               C.POINTER(_vp), _dp]),
     "boss_gp_free": (None, [_vp]),
@@ -77,6 +78,10 @@ def _check(rc: int, what: str) -> int:
 
 def init(device: int = 0) -> None:
     _check(lib.boss_init(int(device)), "boss_init")
+
+
+def stream_ptr() -> int:
+    return int(lib.boss_stream() or 0)
 
 
 def shutdown() -> None:

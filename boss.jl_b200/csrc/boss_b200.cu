@@ -274,6 +274,7 @@ extern "C" {
 
 int boss_version(void) { return 100; }
 int boss_device(void) { return g.device; }
+void *boss_stream(void) { return (void *)g.stream; }
 const char *boss_last_error(void) { return g.err.c_str(); }
 int64_t boss_launch_count(void) { return g.launches; }
 double boss_last_kernel_ms(int which) { return (which >= 0 && which < N_TIMERS) ? g.last_ms[which] : 0.0; }

@@ -51,6 +51,7 @@ void boss_shutdown(void);
 const char *boss_last_error(void);
 int boss_version(void);
 int boss_device(void);                /* device ordinal in use, -1 before boss_init                 */
+void *boss_stream(void);              /* the cudaStream_t all library work is ordered on (for event timing) */
 
 /* ---- a1 + a2 : fit -----------------------------------------------------------------------
  * Replaces posterior_gp (src/models/gaussian_process.jl:199-211) -> finite_gp (:216-248) ->
