@@ -7,7 +7,7 @@ weak scaling, candidates sharded by contiguous block, (best value, index) pairs 
 A "step" = one scoring pass over the rank's candidates.  `value` = candidates/s with candidates resident
 in HBM; `e2e` = the same through the host-pointer C-ABI call (pinned host candidates, H2D inside the
 timed region, D2H of the argmax pair).  The second headline metric, batched GP log-likelihood evals/s at
-n = 2048, d = 8 (S = 32 hyper-parameter vectors per GPU per step), is reported under "loglik".
+n = 2048, d = 8 (S = 256 hyper-parameter vectors per GPU per step), is reported under "loglik".
 
 `--impl reference` times the CPU restatement of the reference path (oracle/, numpy + OpenBLAS with all host
 threads) on a bounded sample of the same workload; Julia is not installed, so the reference itself cannot run.
@@ -27,7 +27,7 @@ sys.path.insert(0, ROOT)
 
 N_TRAIN, X_DIM, KERNEL_ID = 2048, 8, 2
 M_PER_GPU = 1 << 21
-LOGLIK_S_PER_GPU = 32
+LOGLIK_S_PER_GPU = 256
 F_CAND = N_TRAIN * N_TRAIN + N_TRAIN * (3 * X_DIM + 12)                      # 4 268 032 flop / candidate
 F_LL = N_TRAIN * (N_TRAIN + 1) // 2 * (3 * X_DIM + 8) + N_TRAIN ** 3 / 3 + N_TRAIN ** 2 + 3 * N_TRAIN  # 2.9347e9
 CPU_SAMPLE_M = 8192
@@ -270,6 +270,12 @@ def run_gpu(args):
             ms = float(t.item())
         return ms / steps, launches, out
 
+    if args.only == "loglik":          # profiling aid: only the batched log-likelihood step
+        ms_ll, launches_ll, _ = timed(step_loglik, args.steps, args.warmup)
+        if rank == 0:
+            print(json.dumps({"only": "loglik", "ms_per_step": ms_ll, "evals_per_s": S * world / (ms_ll * 1e-3),
+                              "gpu_launches": int(launches_ll)}))
+        return
     sampler = ClockSampler(local) if rank == 0 else None
     _lib.set_timing(True)
     ms_step, launches, res = timed(step_resident, args.steps, args.warmup)
@@ -325,6 +331,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--only", default="all", choices=["all", "loglik"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -167,4 +167,21 @@ __device__ __forceinline__ void store_block(double *dst, bool transpose, double 
   }
 }
 
+// In-place trailing update C -= acc.  All 64 loads are issued before the first store (acc is reused as the
+// staging register file), so the tile's read-modify-write costs one memory round trip instead of 64.
+__device__ __forceinline__ void rmw_sub_block(double *dst, double (&acc)[8][4][2], const FragCoord &fc) {
+#pragma unroll
+  for (int fm = 0; fm < 8; ++fm)
+#pragma unroll
+    for (int fn = 0; fn < 4; ++fn)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) acc[fm][fn][e] = dst[block_offset(fc.row(fm), fc.col(fn, e))] - acc[fm][fn][e];
+#pragma unroll
+  for (int fm = 0; fm < 8; ++fm)
+#pragma unroll
+    for (int fn = 0; fn < 4; ++fn)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) dst[block_offset(fc.row(fm), fc.col(fn, e))] = acc[fm][fn][e];
+}
+
 }  // namespace boss
