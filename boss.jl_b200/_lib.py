@@ -45,6 +45,10 @@ EXPORTS = {
                                 _dp, _i64p]),
     "boss_ei_score_dev": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                     _vp, _dp, _i64p, _vp]),
+    "boss_ei_value_grad": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                     _vp]),
+    "boss_ei_value_grad_dev": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                         _vp, _vp]),
     "boss_gp_loglik_batch": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, _vp, C.c_int, _vp, C.c_int64,
                                        _vp]),
     "boss_gp_loglik_batch_dev": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, _vp, C.c_int, _vp,
@@ -186,6 +190,40 @@ def ei_score(slices, y_dim, n_samples, Xs, coefs, best, y_max, lb=None, ub=None,
     _check(lib.boss_ei_score(arr, y_dim, n_samples, _ptr(Xc), M, _ptr(pm), _ptr(co), _ptr(b), _ptr(ym), _ptr(lbv),
                              _ptr(ubv), _ptr(cm), _ptr(acq), None, C.byref(bv), C.byref(bi)), "boss_ei_score")
     return acq, bv.value, bi.value
+
+
+def ei_value_grad(slices, y_dim, n_samples, Xs, coefs, best, y_max, lb=None, ub=None, cons_mask=None,
+                  prior_mean_s=None, prior_mean_grad_s=None):
+    """-> acq (M,), grad (d, M).  prior_mean_grad_s: (y_dim, d, M)."""
+    Xc = _cols(Xs)
+    M, d = Xc.shape
+    arr = _slice_array(slices)
+    co = _f64(coefs, (y_dim,))
+    b = None if best is None else np.array([best], dtype=np.float64)
+    ym = None if y_max is None else _f64(y_max, (y_dim,))
+    lbv = None if lb is None else _f64(lb, (d,))
+    ubv = None if ub is None else _f64(ub, (d,))
+    cm = None if cons_mask is None else np.ascontiguousarray(cons_mask, dtype=np.uint8)
+    pm = None if prior_mean_s is None else np.ascontiguousarray(np.asarray(prior_mean_s, dtype=np.float64).T)
+    pmg = None if prior_mean_grad_s is None else np.ascontiguousarray(
+        np.transpose(np.asarray(prior_mean_grad_s, dtype=np.float64), (2, 1, 0)))   # (M, d, y_dim)
+    acq = np.empty(M)
+    grad = np.empty((M, d))
+    _check(lib.boss_ei_value_grad(arr, y_dim, n_samples, _ptr(Xc), M, _ptr(pm), _ptr(pmg), _ptr(co), _ptr(b), _ptr(ym),
+                                  _ptr(lbv), _ptr(ubv), _ptr(cm), _ptr(acq), _ptr(grad)), "boss_ei_value_grad")
+    return acq, grad.T
+
+
+def ei_value_grad_dev(slices, y_dim, n_samples, Xs_ptr, M, coefs, best, y_max, acq_ptr, grad_ptr, lb=None, ub=None):
+    arr = _slice_array(slices)
+    co = _f64(coefs, (y_dim,))
+    b = None if best is None else np.array([best], dtype=np.float64)
+    ym = None if y_max is None else _f64(y_max, (y_dim,))
+    lbv = None if lb is None else _f64(lb)
+    ubv = None if ub is None else _f64(ub)
+    _check(lib.boss_ei_value_grad_dev(arr, y_dim, n_samples, _vp(Xs_ptr), int(M), None, None, _ptr(co), _ptr(b),
+                                      _ptr(ym), _ptr(lbv), _ptr(ubv), None, _vp(acq_ptr) if acq_ptr else None,
+                                      _vp(grad_ptr)), "boss_ei_value_grad_dev")
 
 
 def ei_score_dev(slices, y_dim, n_samples, Xs_ptr, M, coefs, best, y_max, lb=None, ub=None, acq_ptr=None,

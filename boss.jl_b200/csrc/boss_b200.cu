@@ -19,6 +19,7 @@
 #include "../../include/boss_b200.h"
 #include "cholesky.cuh"
 #include "score.cuh"
+#include "grad.cuh"
 
 using namespace boss;
 
@@ -67,7 +68,7 @@ struct Ctx {
   bool timing = false;
   // workspaces
   DevBuf ks, muv, sumsq, xs_stage, pm_stage, cm_stage, acq_stage, mu_stage, var_stage, st_stage, grad_stage;
-  DevBuf blk_val, blk_idx, small, chol_L, chol_Winv, chol_misc, tt;
+  DevBuf blk_val, blk_idx, small, chol_L, chol_Winv, chol_misc, tt, vt, ut, dmu, dvar, pmg_stage;
   // event pool for per-kernel-class timing
   cudaEvent_t ev_a[EV_POOL], ev_b[EV_POOL];
   int ev_class[EV_POOL];
@@ -157,6 +158,10 @@ template <int KID, int DP>
 void launch_xcov_t(const XcovParams &p, int ncb) {
   xcov_kernel<KID, DP><<<ncb, 256, 0, g.stream>>>(p);
 }
+template <int KID, int DP>
+void launch_grad_t(const GradParams &p, int ncb) {
+  grad_kernel<KID, DP><<<ncb, 256, 0, g.stream>>>(p);
+}
 #define DISPATCH_KID_DP(FN, kid, dp, ...)                  \
   do {                                                     \
     switch ((kid) * 100 + (dp)) {                          \
@@ -188,6 +193,7 @@ int set_kernel_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(trtri_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(dbg_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(score_trmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(wtv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(fwd_solve_loglik_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   g_attr_done = true;
@@ -311,7 +317,7 @@ void boss_shutdown(void) {
   cudaStreamSynchronize(g.stream);
   for (DevBuf *b : {&g.ks, &g.muv, &g.sumsq, &g.xs_stage, &g.pm_stage, &g.cm_stage, &g.acq_stage, &g.mu_stage,
                     &g.var_stage, &g.st_stage, &g.grad_stage, &g.blk_val, &g.blk_idx, &g.small, &g.chol_L,
-                    &g.chol_Winv, &g.chol_misc, &g.tt})
+                    &g.chol_Winv, &g.chol_misc, &g.tt, &g.vt, &g.ut, &g.dmu, &g.dvar, &g.pmg_stage})
     b->release();
   if (g.ev_ready) {
     for (int i = 0; i < EV_POOL; ++i) {
@@ -485,6 +491,7 @@ struct ScoreArgs {
   const double *coefs, *best, *y_max, *lb, *ub;  // host
   const uint8_t *cons_mask;                      // host or device
   double *acq, *grad;                            // host or device
+  const double *prior_mean_grad;                 // y_dim x d x M (host or device) or null
   double *mu_out, *var_out;                      // predict mode (single slice), host or device
   int32_t *status_out;
   double *best_val;  // host
@@ -515,6 +522,7 @@ int score_core(ScoreArgs &a) {
   ncb_max = std::min<long long>(ncb_max, 592);
   if (ncb_max >= 148) ncb_max = ncb_max / 148 * 148;
   if (ncb_max < 1) return fail(BOSS_ERR_ARG, "score: n too large for the scratch budget");
+  if (a.grad) ncb_max = std::max<long long>(1, std::min<long long>(ncb_max, ncb_max >= 296 ? 296 : ncb_max));
   const long long need_cb = (a.M + 127) / 128;
   const int ncb_cap = (int)std::min<long long>(ncb_max, need_cb);
   const int CH = ncb_cap * 128;
@@ -522,6 +530,13 @@ int score_core(ScoreArgs &a) {
   CUDA_TRY(g.ks.ensure((size_t)CH * max_npad * 8));
   CUDA_TRY(g.muv.ensure((size_t)nsl * CH * 8));
   CUDA_TRY(g.sumsq.ensure((size_t)nsl * CH * 8));
+  if (a.grad) {
+    if (d > 32) return fail(BOSS_ERR_ARG, "score: gradients need x_dim <= 32");
+    CUDA_TRY(g.vt.ensure((size_t)CH * max_npad * 8));
+    CUDA_TRY(g.ut.ensure((size_t)CH * max_npad * 8));
+    CUDA_TRY(g.dmu.ensure((size_t)nsl * d * CH * 8));
+    CUDA_TRY(g.dvar.ensure((size_t)nsl * d * CH * 8));
+  }
   const int nblk_acq_max = (CH + 255) / 256;
   CUDA_TRY(g.blk_val.ensure((size_t)nblk_acq_max * 8));
   CUDA_TRY(g.blk_idx.ensure((size_t)nblk_acq_max * 8));
@@ -552,6 +567,8 @@ int score_core(ScoreArgs &a) {
     if (a.mu_out) CUDA_TRY(g.mu_stage.ensure((size_t)CH * 8));
     if (a.var_out) CUDA_TRY(g.var_stage.ensure((size_t)CH * 8));
     if (a.status_out) CUDA_TRY(g.st_stage.ensure((size_t)CH * 4));
+    if (a.grad) CUDA_TRY(g.grad_stage.ensure((size_t)CH * d * 8));
+    if (a.grad && a.prior_mean_grad) CUDA_TRY(g.pmg_stage.ensure((size_t)CH * d * a.y_dim * 8));
   }
 
   timing_begin();
@@ -562,7 +579,8 @@ int score_core(ScoreArgs &a) {
     const double *pm_dev = nullptr;
     const unsigned char *cm_dev = nullptr;
     long long in_off, out_off;
-    double *acq_dev = nullptr, *mu_dev = nullptr, *var_dev = nullptr;
+    double *acq_dev = nullptr, *mu_dev = nullptr, *var_dev = nullptr, *grad_dev = nullptr;
+    const double *pmg_dev = nullptr;
     int *st_dev = nullptr;
     if (a.dev) {
       xs_dev = a.Xs;
@@ -574,6 +592,8 @@ int score_core(ScoreArgs &a) {
       mu_dev = a.mu_out;
       var_dev = a.var_out;
       st_dev = a.status_out;
+      grad_dev = a.grad;
+      pmg_dev = a.prior_mean_grad;
     } else {
       CUDA_TRY(cudaMemcpyAsync(g.xs_stage.p, a.Xs + (size_t)m0 * d, (size_t)ch * d * 8, cudaMemcpyHostToDevice, g.stream));
       xs_dev = g.xs_stage.as<double>();
@@ -592,6 +612,12 @@ int score_core(ScoreArgs &a) {
       if (a.mu_out) mu_dev = g.mu_stage.as<double>();
       if (a.var_out) var_dev = g.var_stage.as<double>();
       if (a.status_out) st_dev = g.st_stage.as<int>();
+      if (a.grad) grad_dev = g.grad_stage.as<double>();
+      if (a.grad && a.prior_mean_grad) {
+        CUDA_TRY(cudaMemcpyAsync(g.pmg_stage.p, a.prior_mean_grad + (size_t)m0 * d * a.y_dim,
+                                 (size_t)ch * d * a.y_dim * 8, cudaMemcpyHostToDevice, g.stream));
+        pmg_dev = g.pmg_stage.as<double>();
+      }
     }
     for (int q = 0; q < nsl; ++q) {
       const boss_gp *h = a.slices[q];
@@ -621,11 +647,42 @@ int score_core(ScoreArgs &a) {
       sp.nblk = h->nblk;
       sp.ktiles = h->ktiles;
       sp.sumsq = g.sumsq.as<double>() + (size_t)q * CH;
+      sp.VT = a.grad ? g.vt.as<double>() : nullptr;
       {
         Timed t(0);
         score_trmm_kernel<<<ncb, GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(sp);
       }
       g.launches += 2;
+      if (a.grad) {
+        WtvParams wp{h->WT, g.vt.as<double>(), g.ut.as<double>(), h->nblk, h->ktiles};
+        {
+          Timed t(0);
+          wtv_kernel<<<ncb, GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(wp);
+        }
+        GradParams gq{};
+        gq.Xs = xs_dev;
+        gq.M = a.M;
+        gq.m0 = m0;
+        gq.in_off = in_off;
+        gq.d = d;
+        gq.n = h->n;
+        gq.n_pad = h->n_pad;
+        gq.ktiles = h->ktiles;
+        gq.chunk_ld = CH;
+        gq.Xt = h->Xt;
+        gq.invl = h->invl;
+        gq.alpha = h->alpha;
+        gq.disc_bits = h->disc;
+        gq.a2 = h->a2;
+        gq.UT = g.ut.as<double>();
+        gq.dmu = g.dmu.as<double>() + (size_t)q * d * CH;
+        gq.dvar = g.dvar.as<double>() + (size_t)q * d * CH;
+        {
+          Timed t(1);
+          DISPATCH_KID_DP(launch_grad_t, h->kernel_id, h->dp, gq, ncb);
+        }
+        g.launches += 2;
+      }
     }
     AcqParams ap{};
     ap.y_dim = a.y_dim;
@@ -665,6 +722,13 @@ int score_core(ScoreArgs &a) {
     if (a.want_argmax) {
       argmax_final_kernel<<<1, 256, 0, g.stream>>>(g.blk_val.as<double>(), g.blk_idx.as<long long>(), nb, d_best, d_bidx);
       ++g.launches;
+    }
+    if (a.grad) {
+      AcqGradParams gp2{ap, g.dmu.as<double>(), g.dvar.as<double>(), pmg_dev, grad_dev};
+      acq_grad_kernel<<<(ch + 127) / 128, 128, 0, g.stream>>>(gp2);
+      ++g.launches;
+      if (!a.dev)
+        CUDA_TRY(cudaMemcpyAsync(a.grad + (size_t)m0 * d, grad_dev, (size_t)ch * d * 8, cudaMemcpyDeviceToHost, g.stream));
     }
     if (!a.dev) {
       if (a.acq) CUDA_TRY(cudaMemcpyAsync(a.acq + m0, acq_dev, (size_t)ch * 8, cudaMemcpyDeviceToHost, g.stream));
@@ -742,12 +806,12 @@ int boss_gp_predict_dev(const boss_gp *gp, const double *Xs_dev, int64_t M, cons
 static int ei_score_impl(const boss_gp *const *slices, int y_dim, int n_samples, const double *Xs, int64_t M,
                          const double *prior_mean_s, const double *fit_coefs, const double *best,
                          const double *y_max, const double *lb, const double *ub, const uint8_t *cons_mask,
-                         double *acq, double *grad, double *best_val, int64_t *best_idx, bool dev) {
+                         double *acq, double *grad, double *best_val, int64_t *best_idx, bool dev,
+                         const double *prior_mean_grad = nullptr) {
   std::lock_guard<std::mutex> lk(g.mu);
   REQUIRE_INIT();
   if (!slices || y_dim < 1 || n_samples < 1 || (!Xs && M > 0) || !fit_coefs)
     return fail(BOSS_ERR_ARG, "boss_ei_score: bad arguments");
-  if (grad) return fail(BOSS_ERR_ARG, "boss_ei_score: gradients are not available in this build");
   if ((lb == nullptr) != (ub == nullptr)) return fail(BOSS_ERR_ARG, "boss_ei_score: lb and ub must be given together");
   ScoreArgs a{};
   a.slices = slices;
@@ -764,6 +828,7 @@ static int ei_score_impl(const boss_gp *const *slices, int y_dim, int n_samples,
   a.cons_mask = cons_mask;
   a.acq = acq;
   a.grad = grad;
+  a.prior_mean_grad = prior_mean_grad;
   a.best_val = best_val;
   a.best_idx = best_idx;
   a.dev = dev;
@@ -786,6 +851,24 @@ int boss_ei_score_dev(const boss_gp *const *slices, int y_dim, int n_samples, co
   (void)stream;  // work is ordered on the library stream and synchronised before return
   return ei_score_impl(slices, y_dim, n_samples, Xs_dev, M, prior_mean_s_dev, fit_coefs, best, y_max, lb, ub,
                        cons_mask_dev, acq_dev, grad_dev, best_val, best_idx, true);
+}
+
+int boss_ei_value_grad(const boss_gp *const *slices, int y_dim, int n_samples, const double *Xs, int64_t M,
+                       const double *prior_mean_s, const double *prior_mean_grad_s, const double *fit_coefs,
+                       const double *best, const double *y_max, const double *lb, const double *ub,
+                       const uint8_t *cons_mask, double *acq, double *grad) {
+  if (!grad) return fail(BOSS_ERR_ARG, "boss_ei_value_grad: grad is NULL");
+  return ei_score_impl(slices, y_dim, n_samples, Xs, M, prior_mean_s, fit_coefs, best, y_max, lb, ub, cons_mask, acq,
+                       grad, nullptr, nullptr, false, prior_mean_grad_s);
+}
+
+int boss_ei_value_grad_dev(const boss_gp *const *slices, int y_dim, int n_samples, const double *Xs_dev, int64_t M,
+                           const double *prior_mean_s_dev, const double *prior_mean_grad_s_dev,
+                           const double *fit_coefs, const double *best, const double *y_max, const double *lb,
+                           const double *ub, const uint8_t *cons_mask_dev, double *acq_dev, double *grad_dev) {
+  if (!grad_dev) return fail(BOSS_ERR_ARG, "boss_ei_value_grad_dev: grad is NULL");
+  return ei_score_impl(slices, y_dim, n_samples, Xs_dev, M, prior_mean_s_dev, fit_coefs, best, y_max, lb, ub,
+                       cons_mask_dev, acq_dev, grad_dev, nullptr, nullptr, true, prior_mean_grad_s_dev);
 }
 
 int boss_gp_cov(const boss_gp *, const double *, int64_t, const double *, double *, double *) {

@@ -1,0 +1,233 @@
+// grad.cuh -- analytic x-gradients of the acquisition for the multi-start optimiser
+// (reference: OptimizationAM pushes ForwardDiff.Dual candidates through the whole posterior stack,
+//  src/acquisition_maximizers/optimization.jl:36,100-113; here the same derivative in closed form).
+//
+//   mu(x)    = m(x) + sum_k alpha_k k(x, x_k)         d mu  = sum_k alpha_k dk_k
+//   var(x)   = a^2 - |W k*(x)|^2                       d var = -2 sum_k u_k dk_k ,  u = W^T (W k*) = K^-1 k*
+//   dk_k/dx_j = a^2 kappa'(r)/r * (x~_j - x~_kj) / l_j
+//
+// Pipeline per chunk and slice: xcov -> score_trmm (also stores V^T) -> wtv_kernel (U^T = (W^T V)^T, the
+// second triangular product, same DMMA mainloop) -> grad_kernel (kernel derivatives, FP64 pipe) ->
+// acq_grad_kernel (chain rule through EI x PoF).
+#pragma once
+#include "score.cuh"
+
+namespace boss {
+
+// U[k][c] = sum_{r >= k} WT[k][r] V[r][c] ;  A = WT row block i (tiles 8i .. ktiles-1), B = V^T block of the CTA
+struct WtvParams {
+  const double *WT;
+  const double *VT;   // chunk scratch: rows = candidates, cols = V row index
+  double *UT;         // chunk scratch: rows = candidates, cols = training index
+  int nblk, ktiles;
+};
+struct WtvIt {
+  const double *wt_row;
+  const double *vt;
+  int i, kt, nblk, ktiles;
+  __device__ __forceinline__ bool valid() const { return i < nblk; }
+  __device__ __forceinline__ const double *A() const { return wt_row + (size_t)kt * TILE_ELEMS; }
+  __device__ __forceinline__ const double *B() const { return vt + (size_t)kt * TILE_ELEMS; }
+  __device__ __forceinline__ bool tile_end() const { return kt == ktiles - 1; }
+  __device__ __forceinline__ int tile() const { return i; }
+  __device__ __forceinline__ void next() {
+    if (kt == ktiles - 1) {
+      ++i;
+      kt = i * KT_PER_BLOCK;
+      wt_row += (size_t)ktiles * TILE_ELEMS;
+    } else {
+      ++kt;
+    }
+  }
+};
+__global__ void __launch_bounds__(GEMM_THREADS, 1) wtv_kernel(WtvParams p) {
+  const int cb = blockIdx.x;
+  WtvIt it{p.WT, p.VT + (size_t)cb * p.ktiles * TILE_ELEMS, 0, 0, p.nblk, p.ktiles};
+  double *ut = p.UT + (size_t)cb * p.ktiles * TILE_ELEMS;
+  gemm_pipeline(it, it, [&](int tile, const double(&acc)[8][4][2], const FragCoord &fc) {
+    store_block(ut + (size_t)tile * KT_PER_BLOCK * TILE_ELEMS, true, 1.0, nullptr, acc, fc);
+  });
+}
+
+// d mu / dx and d var / dx for one slice and one chunk.
+struct GradParams {
+  const double *Xs;
+  long long M, m0, in_off;
+  int d, n, n_pad, ktiles, chunk_ld;
+  const double *Xt, *invl, *alpha;
+  unsigned long long disc_bits;
+  double a2;
+  const double *UT;    // chunk scratch (P-layout), u = K^-1 k*
+  double *dmu, *dvar;  // [d][chunk_ld] each (this slice's section)
+};
+
+template <int KID, int DP>
+__global__ void __launch_bounds__(256) grad_kernel(GradParams p) {
+  __shared__ double xt[XCOV_KC * DP];
+  __shared__ double al[XCOV_KC];
+  __shared__ double red[2][128];
+  const int tid = threadIdx.x, r = tid & 127, kh = tid >> 7;
+  const int cb = blockIdx.x;
+  const long long m = p.m0 + (long long)cb * 128 + r;
+  double xc[DP];
+  load_scaled_point<DP>(xc, p.Xs + (size_t)(m - p.in_off) * p.d, p.d, p.invl, p.disc_bits, m < p.M);
+  double gm[DP], gv[DP];
+#pragma unroll
+  for (int i = 0; i < DP; ++i) gm[i] = gv[i] = 0.0;
+  const double *rowbase = p.UT + (size_t)cb * p.ktiles * TILE_ELEMS + (((r >> 3) << 1) << 6) + ((r & 7) << 3);
+  for (int k0 = 0; k0 < p.n_pad; k0 += XCOV_KC) {
+    __syncthreads();
+    for (int e = tid; e < XCOV_KC * DP; e += 256) xt[e] = p.Xt[(size_t)k0 * DP + e];
+    if (tid < XCOV_KC) al[tid] = p.alpha[k0 + tid];
+    __syncthreads();
+    for (int mcol = kh; mcol < XCOV_KC / 8; mcol += 2) {
+      const int kg = k0 + mcol * 8;
+      const double *src = rowbase + (size_t)(kg >> 4) * TILE_ELEMS + (((kg >> 3) & 1) << 6);
+      double u[8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double2 v = *reinterpret_cast<const double2 *>(src + 2 * q);
+        u[q] = v.x;
+        u[q + 4] = v.y;
+      }
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        const int kl = mcol * 8 + kk;
+        if (k0 + kl < p.n) {
+          double df[DP];
+          double d2 = 0.0;
+#pragma unroll
+          for (int i = 0; i < DP; ++i) {
+            df[i] = xc[i] - xt[kl * DP + i];
+            d2 = fma(df[i], df[i], d2);
+          }
+          const double g = p.a2 * kappa_dr_over_r<KID>(d2);
+          const double t1 = g * al[kl], t2 = g * u[kk];
+#pragma unroll
+          for (int i = 0; i < DP; ++i) {
+            gm[i] = fma(t1, df[i], gm[i]);
+            gv[i] = fma(t2, df[i], gv[i]);
+          }
+        }
+      }
+    }
+  }
+  // combine the two k-halves per dimension (fixed order), apply 1/l_j, the -2 and the discrete mask
+#pragma unroll
+  for (int i = 0; i < DP; ++i) {
+    if (i >= p.d) break;
+    __syncthreads();
+    red[kh][r] = gm[i];
+    __syncthreads();
+    const bool disc = (p.disc_bits >> i) & 1ull;
+    if (kh == 0) p.dmu[(size_t)i * p.chunk_ld + cb * 128 + r] = disc ? 0.0 : (red[0][r] + red[1][r]) * p.invl[i];
+    __syncthreads();
+    red[kh][r] = gv[i];
+    __syncthreads();
+    if (kh == 0)
+      p.dvar[(size_t)i * p.chunk_ld + cb * 128 + r] = disc ? 0.0 : -2.0 * (red[0][r] + red[1][r]) * p.invl[i];
+  }
+}
+
+// Chain rule through EI x PoF.  dmu / dvar: [(sample*y_dim + slice)][d][chunk_ld].
+struct AcqGradParams {
+  AcqParams a;
+  const double *dmu, *dvar;
+  const double *prior_mean_grad;  // y_dim x d x M (column-major: index ((m)*d + j)*y_dim + i) or null
+  double *grad;                   // d x M, indexed by (m - out_off)
+};
+
+__global__ void __launch_bounds__(128) acq_grad_kernel(AcqGradParams q) {
+  const AcqParams &p = q.a;
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  const long long m = p.m0 + c;
+  if (c >= p.chunk || m >= p.M) return;
+  const int d = p.d;
+  double gacc[32];
+  for (int j = 0; j < d; ++j) gacc[j] = 0.0;
+  bool failed = false;
+  for (int s = 0; s < p.n_samples; ++s) {
+    // pass 1: scalars
+    double cdf_i[MAX_YDIM], wmu_i[MAX_YDIM], wvar_i[MAX_YDIM];
+    bool live_i[MAX_YDIM];
+    double mu_f = 0.0, s2 = 0.0, pof = 1.0;
+    for (int i = 0; i < p.y_dim; ++i) {
+      const size_t row = (size_t)(s * p.y_dim + i) * p.chunk_ld + c;
+      double mu = p.mu[row];
+      if (p.prior_mean) mu = p.prior_mean[(size_t)(m - p.in_off) * p.y_dim + i] + mu;
+      double var = p.a2[s * p.y_dim + i] - p.sumsq[row] + VAR_JITTER;
+      const bool unclipped = var >= 0.0;
+      if (!clip_var(var)) failed = true;
+      live_i[i] = unclipped;   // the clipped branch of _clip_var returns a constant zero -> zero derivative
+      mu_f = fma(p.coefs[i], mu, mu_f);
+      s2 = fma(p.coefs[i] * p.coefs[i], var, s2);
+      cdf_i[i] = 1.0;
+      wmu_i[i] = wvar_i[i] = 0.0;
+      if (p.has_ymax && !(p.y_max[i] == INFINITY)) {
+        const double sd = sqrt(var);
+        double z = (p.y_max[i] - mu) / sd;
+        if (sd == 0.0 && p.y_max[i] == mu) z = INFINITY;
+        cdf_i[i] = norm_cdf(z);
+        if (sd > 0.0) {   // d cdf = pdf(z) * ( -dmu/sd - (ymax-mu) dvar / (2 sd var) )
+          const double pz = norm_pdf(z);
+          wmu_i[i] = -pz / sd;
+          wvar_i[i] = -pz * (p.y_max[i] - mu) / (2.0 * sd * var);
+        }
+        pof *= cdf_i[i];
+      }
+    }
+    double ei = 0.0, cphi = 0.0, cpdf_over_2sf = 0.0;   // d ei = cphi * d mu_f + cpdf_over_2sf * d s2
+    if (p.has_best) {
+      const double sf = sqrt(s2), diff = mu_f - p.best;
+      if (diff == 0.0 && sf == 0.0) {
+        ei = 0.0;
+      } else {
+        const double z = diff / sf;
+        const double cz = norm_cdf(z), pz = norm_pdf(z);
+        ei = diff * cz + sf * pz;
+        if (sf > 0.0) {
+          cphi = cz;
+          cpdf_over_2sf = pz / (2.0 * sf);
+        } else {
+          cphi = diff > 0.0 ? 1.0 : 0.0;
+        }
+      }
+    }
+    // pass 2: per input dimension
+    for (int j = 0; j < d; ++j) {
+      double dmu_f = 0.0, ds2 = 0.0, dpof = 0.0;
+      for (int i = 0; i < p.y_dim; ++i) {
+        const size_t row = ((size_t)(s * p.y_dim + i) * d + j) * p.chunk_ld + c;
+        double dm = q.dmu[row];
+        if (q.prior_mean_grad) dm += q.prior_mean_grad[((size_t)(m - p.in_off) * d + j) * p.y_dim + i];
+        const double dv = live_i[i] ? q.dvar[row] : 0.0;
+        dmu_f = fma(p.coefs[i], dm, dmu_f);
+        ds2 = fma(p.coefs[i] * p.coefs[i], dv, ds2);
+        if (p.has_ymax && !(p.y_max[i] == INFINITY)) {
+          double others = 1.0;
+          for (int b = 0; b < p.y_dim; ++b)
+            if (b != i) others *= cdf_i[b];
+          dpof = fma(wmu_i[i] * dm + wvar_i[i] * dv, others, dpof);
+        }
+      }
+      const double dei = cphi * dmu_f + cpdf_over_2sf * ds2;
+      double g;
+      if (p.has_best)
+        g = p.has_ymax ? dei * pof + ei * dpof : dei;
+      else
+        g = p.has_ymax ? dpof : 0.0;
+      gacc[j] += g;
+    }
+  }
+  bool zero = failed;
+  if (p.lb) {
+    for (int i = 0; i < d; ++i) {
+      const double x = p.Xs[(size_t)(m - p.in_off) * d + i];
+      if (x < p.lb[i] || x > p.ub[i]) zero = true;
+    }
+  }
+  if (p.cons_mask && p.cons_mask[m - p.in_off] == 0) zero = true;
+  for (int j = 0; j < d; ++j) q.grad[(size_t)(m - p.out_off) * d + j] = zero ? 0.0 : gacc[j] / (double)p.n_samples;
+}
+
+}  // namespace boss

@@ -87,6 +87,7 @@ struct ScoreParams {
   const double *Ks;   // chunk scratch
   int nblk, ktiles;
   double *sumsq;      // [chunk]
+  double *VT;         // optional chunk scratch (P-layout, rows = candidates): V = W K* stored transposed (gradient mode)
 };
 
 struct ScoreIt {
@@ -118,7 +119,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) score_trmm_kernel(ScoreParams
 #pragma unroll
   for (int fn = 0; fn < 4; ++fn) cs[fn][0] = cs[fn][1] = 0.0;
 
-  gemm_pipeline(it, it, [&](int, const double(&acc)[8][4][2], const FragCoord &) {
+  double *vt = p.VT ? p.VT + (size_t)cb * p.ktiles * TILE_ELEMS : nullptr;
+  gemm_pipeline(it, it, [&](int tile, const double(&acc)[8][4][2], const FragCoord &fc) {
+    if (vt) store_block(vt + (size_t)tile * KT_PER_BLOCK * TILE_ELEMS, true, 1.0, nullptr, acc, fc);
 #pragma unroll
     for (int fn = 0; fn < 4; ++fn)
 #pragma unroll

@@ -117,6 +117,20 @@ int boss_ei_score_dev(const boss_gp *const *slices, int y_dim, int n_samples, co
                       const double *y_max, const double *lb, const double *ub, const uint8_t *cons_mask_dev,
                       double *acq_dev, double *grad_dev, double *best_val, int64_t *best_idx, void *stream);
 
+/* Value + analytic x-gradient of the same acquisition for a batch of points: what OptimizationAM's
+ * multi-start solver needs per iteration over all starts (src/acquisition_maximizers/optimization.jl:89-118;
+ * the reference obtains the gradient by pushing ForwardDiff.Dual numbers through the posterior).
+ *   prior_mean_grad_s  y_dim x d x M (index (m*d + j)*y_dim + i) gradient of the host-evaluated prior mean, or NULL
+ *   grad               d x M;  zero for out-of-domain / failed candidates; discrete (rounded) dims have zero derivative */
+int boss_ei_value_grad(const boss_gp *const *slices, int y_dim, int n_samples, const double *Xs, int64_t M,
+                       const double *prior_mean_s, const double *prior_mean_grad_s, const double *fit_coefs,
+                       const double *best, const double *y_max, const double *lb, const double *ub,
+                       const uint8_t *cons_mask, double *acq, double *grad);
+int boss_ei_value_grad_dev(const boss_gp *const *slices, int y_dim, int n_samples, const double *Xs_dev, int64_t M,
+                           const double *prior_mean_s_dev, const double *prior_mean_grad_s_dev,
+                           const double *fit_coefs, const double *best, const double *y_max, const double *lb,
+                           const double *ub, const uint8_t *cons_mask_dev, double *acq_dev, double *grad_dev);
+
 /* ---- a8 + a9 : batched log marginal likelihood ------------------------------------------------
  * Replaces data_loglike(::GaussianProcess) / gp_data_loglike_slice (gaussian_process.jl:250-280)
  * -> logpdf(::FiniteGP, y) evaluated for S hyper-parameter vectors at once: the batches built by

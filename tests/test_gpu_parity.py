@@ -245,3 +245,63 @@ def test_headline_shape_parity(lib):
     acq_p, _, bi_p = lib.ei_score([gp], 1, 1, Xs[:, perm], [1.0], best, None)
     assert np.array_equal(acq_p, acq[perm])
     gp.free()
+
+
+# ---------------------------------------------------------------------------------------------
+# analytic x-gradients (multi-start optimiser path, config C4 style)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kid,d,n", [(2, 4, 300), (0, 3, 130), (1, 2, 64)])
+def test_ei_value_grad_single_output(lib, kid, d, n):
+    X, Y, ls, amp, ns = make_problem(n, d, seed=500 + n)
+    gp = lib.gp_fit(X, Y[0], ls[0], amp[0], ns[0], kid)
+    post = O.posterior_fit(X, Y[0], ls[0], amp[0], ns[0], kid)
+    Xs = np.random.default_rng(4).random((d, 700))
+    best = float(np.quantile(Y[0], 0.8))
+    val_ref, grad_ref = O.ei_value_grad([post], Xs, [1.0], best, None)
+    val, grad = lib.ei_value_grad([gp], 1, 1, Xs, [1.0], best, None)
+    assert relerr(val, val_ref) <= TOL_POST
+    scale = np.max(np.abs(grad_ref), axis=1, keepdims=True)
+    assert np.max(np.abs(grad - grad_ref) / scale) <= 1e-8
+    # value path unchanged by gradient mode
+    acq, _, _ = lib.ei_score([gp], 1, 1, Xs, [1.0], best, None)
+    assert np.array_equal(acq, val)
+    gp.free()
+
+
+def test_ei_value_grad_multi_output_pof_and_prior_mean(lib):
+    n, d, y_dim, M = 200, 3, 2, 400
+    X, Y, ls, amp, ns = make_problem(n, d, seed=61, y_dim=y_dim)
+    theta = np.array([0.3, -0.2, 0.1])
+    mean_X = theta @ X                                  # Semiparametric: linear parametric mean on output 0
+    Ymm = Y.copy(); Ymm[0] -= mean_X
+    gps = [lib.gp_fit(X, Ymm[i], ls[i], amp[i], ns[i], 2) for i in range(y_dim)]
+    posts = [O.posterior_fit(X, Ymm[i], ls[i], amp[i], ns[i], 2) for i in range(y_dim)]
+    Xs = np.random.default_rng(5).random((d, M))
+    pm = np.stack([theta @ Xs, np.zeros(M)])
+    pmg = np.zeros((y_dim, d, M)); pmg[0] = theta[:, None]
+    coefs = [1.0, 0.2]; y_max = [np.inf, float(np.quantile(Y[1], 0.6))]
+    best = float(np.median(np.asarray(coefs) @ Y))
+    val, grad = lib.ei_value_grad(gps, y_dim, 1, Xs, coefs, best, y_max, prior_mean_s=pm, prior_mean_grad_s=pmg)
+    ref, _, _ = O.ei_acquisition([posts], Xs, coefs, best, y_max, prior_mean_s=pm)
+    assert relerr(val, ref) <= TOL_POST
+    # central finite differences of the oracle acquisition (prior mean moves with x)
+    h = 1e-6
+    for j in range(d):
+        Xp = Xs.copy(); Xp[j] += h
+        Xm = Xs.copy(); Xm[j] -= h
+        fp, _, _ = O.ei_acquisition([posts], Xp, coefs, best, y_max, prior_mean_s=np.stack([theta @ Xp, np.zeros(M)]))
+        fm, _, _ = O.ei_acquisition([posts], Xm, coefs, best, y_max, prior_mean_s=np.stack([theta @ Xm, np.zeros(M)]))
+        fd = (fp - fm) / (2 * h)
+        assert np.allclose(grad[j], fd, rtol=5e-5, atol=1e-8), j
+    for g in gps:
+        g.free()
+
+
+def test_ei_value_grad_guards(lib):
+    X, Y, ls, amp, ns = make_problem(80, 2, seed=71)
+    gp = lib.gp_fit(X, Y[0], ls[0], amp[0], ns[0], 2)
+    Xs = np.array([[0.5, 1.5, 0.2], [0.5, 0.5, -0.1]])
+    val, grad = lib.ei_value_grad([gp], 1, 1, Xs, [1.0], float(np.median(Y[0])), None, np.zeros(2), np.ones(2))
+    assert val[1] == 0.0 and val[2] == 0.0 and np.all(grad[:, 1:] == 0.0)
+    assert val[0] > 0.0 and np.any(grad[:, 0] != 0.0)
+    gp.free()
