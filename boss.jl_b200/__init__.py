@@ -7,5 +7,19 @@ Layout:
   meaning and error behaviour) on top of the C ABI.
 """
 from . import _lib  # noqa: F401  (raises loudly when the CUDA library has not been built)
+from .types import (BIParams, BossOptions, BossProblem, Dirac, Domain, ExperimentData, FixedParams, LinFitness,  # noqa: F401
+                    LogNormal, MAPParams, NonlinFitness, Product, Uniform, generate_LHC, in_bounds, in_domain,
+                    mvlognormal)
+from .gaussian_process import (DiscreteKernel, GaussianProcess, GaussianProcessParams, GaussianProcessPosterior,  # noqa: F401
+                               Matern32Kernel, Matern52Kernel, Parametric, Semiparametric, SemiparametricParams,
+                               SqExponentialKernel, data_loglike, model_posterior_slice)
+from .posterior import DefaultModelPosterior, average_mean, model_posterior  # noqa: F401
+from .acquisition import (Acquisition, ExpectedImprovement, best_so_far, construct_acquisition,  # noqa: F401
+                          construct_safe_acquisition)
+from .acquisition_maximizers import (GridAM, OptimizationAM, SampleOptAM, SamplingAM, batched_lbfgs_maximize,  # noqa: F401
+                                     maximize_acquisition)
+from .model_fitters import OptimizationMAP, SamplingMAP, estimate_parameters, model_loglike  # noqa: F401
+from .bo import IterLimit, bo  # noqa: F401
+from . import parallel  # noqa: F401
 
-__all__ = ["_lib"]
+Nonparametric = GaussianProcess

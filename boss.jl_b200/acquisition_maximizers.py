@@ -1,0 +1,166 @@
+"""Acquisition maximizers that build candidate batches (mirror of src/acquisition_maximizers/*.jl).
+Each one turns the reference's per-point loop into one batched scoring call."""
+from __future__ import annotations
+
+import itertools
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from .acquisition import construct_safe_acquisition
+from .types import BossOptions, BossProblem, Domain, discrete_round, generate_LHC, in_domain
+
+
+class GridAM:
+    """grid.jl:24-65.  `points` are generated once from the domain, filtered by in_domain."""
+
+    def __init__(self, problem: BossProblem, steps, shuffle: bool = True, seed: Optional[int] = None):
+        dom = problem.domain
+        lb, ub = dom.bounds
+        ranges = []
+        for lo, hi, st, disc in zip(lb, ub, steps, dom.discrete):
+            if disc:
+                st = float(np.ceil(st))
+                ranges.append(np.arange(np.ceil(lo), np.floor(hi) + 0.5 * st, st))
+            else:
+                cnt = int(np.floor((hi - lo) / st + 1e-12)) + 1
+                ranges.append(lo + st * np.arange(cnt))
+        # Iterators.product: first dimension varies fastest
+        pts = [np.array(p[::-1]) for p in itertools.product(*ranges[::-1])]
+        self.points = np.array([p for p in pts if in_domain(p, dom)]).T          # d x M
+        self.steps = steps
+        self.shuffle = shuffle
+        self.rng = np.random.default_rng(seed)
+
+
+class SamplingAM:
+    """sampling.jl:8-57: draw `samples` points from x_prior restricted to the domain, score, argmax."""
+
+    def __init__(self, x_prior, samples: int, max_attempts: int = 200, seed: Optional[int] = None):
+        self.x_prior = x_prior            # callable rng -> x (d,), or None = uniform over the bounds
+        self.samples = samples
+        self.max_attempts = max_attempts
+        self.rng = np.random.default_rng(seed)
+
+
+class OptimizationAM:
+    """optimization.jl:20-118: multi-start local optimisation.  Here all starts advance in lock-step: every
+    iteration is ONE batched value+gradient call (projected L-BFGS with backtracking)."""
+
+    def __init__(self, multistart=200, iters: int = 60, history: int = 8, seed: Optional[int] = None):
+        self.multistart = multistart
+        self.iters = iters
+        self.history = history
+        self.rng = np.random.default_rng(seed)
+
+
+class SampleOptAM:
+    """sample_opt.jl:41-52: SamplingAM (return_all) -> best `multistart` samples -> OptimizationAM from them."""
+
+    def __init__(self, x_prior, samples: int, multistart: int, iters: int = 60, seed: Optional[int] = None):
+        self.sampler = SamplingAM(x_prior, samples, seed=seed)
+        self.multistart = multistart
+        self.iters = iters
+
+
+def _rand_in_domain(am: SamplingAM, domain: Domain):
+    lb, ub = domain.bounds
+    for _ in range(am.max_attempts):
+        x = am.x_prior(am.rng) if am.x_prior is not None else am.rng.uniform(lb, ub)
+        x = discrete_round(domain.discrete, x)
+        if in_domain(x, domain):
+            return x
+    return None
+
+
+def batched_lbfgs_maximize(value_and_grad, starts, lb, ub, iters=60, history=8, discrete=None):
+    """Maximise f over the box [lb, ub] from every column of `starts` simultaneously.
+    value_and_grad(X: d x S) -> (f: S, g: d x S).  Returns X (d x S), f (S)."""
+    X = np.clip(np.array(starts, dtype=np.float64, copy=True), lb[:, None], ub[:, None])
+    d, S = X.shape
+    f, g = value_and_grad(X)
+    f = np.where(np.isfinite(f), f, -np.inf)
+    s_hist, y_hist = [], []
+    step0 = 0.1 * np.max(ub - lb)
+    for it in range(iters):
+        # two-loop recursion, vectorised over starts (ascent direction)
+        q = g.copy()
+        alphas = []
+        for s_k, y_k in zip(reversed(s_hist), reversed(y_hist)):
+            rho = 1.0 / np.maximum(np.sum(s_k * y_k, axis=0), 1e-300)
+            a = rho * np.sum(s_k * q, axis=0)
+            q = q - a * y_k
+            alphas.append((a, rho))
+        if s_hist:
+            gamma = np.sum(s_hist[-1] * y_hist[-1], axis=0) / np.maximum(np.sum(y_hist[-1] ** 2, axis=0), 1e-300)
+            q = q * np.where(np.isfinite(gamma) & (gamma > 0), gamma, 1.0)
+        else:
+            q = q * (step0 / np.maximum(np.linalg.norm(g, axis=0), 1e-300))
+        for (a, rho), s_k, y_k in zip(reversed(alphas), s_hist, y_hist):
+            b = rho * np.sum(y_k * q, axis=0)
+            q = q + s_k * (a - b)
+        dirn = q
+        bad = np.sum(dirn * g, axis=0) <= 0                  # not an ascent direction -> steepest ascent
+        dirn[:, bad] = g[:, bad] * (step0 / np.maximum(np.linalg.norm(g[:, bad], axis=0), 1e-300))
+        t = np.ones(S)
+        Xn, fn, gn = X, f, g
+        done = np.zeros(S, dtype=bool)
+        for _ in range(12):                                   # backtracking, all starts per trial in one call
+            Xt = np.clip(X + dirn * t, lb[:, None], ub[:, None])
+            ft, gt = value_and_grad(Xt)
+            ft = np.where(np.isfinite(ft), ft, -np.inf)
+            ok = (ft >= f + 1e-4 * np.sum(g * (Xt - X), axis=0)) & ~done
+            Xn = np.where(ok, Xt, Xn); fn = np.where(ok, ft, fn); gn = np.where(ok, gt, gn)
+            done |= ok
+            if done.all():
+                break
+            t = np.where(done, t, t * 0.5)
+        sk, yk = Xn - X, -(gn - g)                            # curvature pairs for maximisation (minimise -f)
+        valid = np.sum(sk * yk, axis=0) > 1e-16
+        sk[:, ~valid] = 0.0; yk[:, ~valid] = 0.0
+        if valid.any():
+            s_hist.append(sk); y_hist.append(yk)
+            if len(s_hist) > history:
+                s_hist.pop(0); y_hist.pop(0)
+        moved = np.max(np.abs(Xn - X)) if S else 0.0
+        X, f, g = Xn, fn, gn
+        if moved < 1e-10:
+            break
+    return X, f
+
+
+def maximize_acquisition(am, problem: BossProblem, options: BossOptions = BossOptions(), return_all: bool = False):
+    """-> (x, val).  src/types/acquisition_maximizer.jl:12-20"""
+    acq = construct_safe_acquisition(problem, options)
+    dom = problem.domain
+    if isinstance(am, GridAM):
+        pts = am.points[:, am.rng.permutation(am.points.shape[1])] if am.shuffle else am.points   # grid.jl:47
+        idx, val = acq.argmax(pts)
+        return pts[:, idx].copy(), val
+    if isinstance(am, SamplingAM):
+        xs = [x for x in (_rand_in_domain(am, dom) for _ in range(am.samples)) if x is not None]
+        if not xs:
+            raise RuntimeError("SamplingAM: No samples were successfully drawn!")
+        X = np.stack(xs, axis=1)
+        if return_all:
+            return X, acq(X)
+        idx, val = acq.argmax(X)
+        return X[:, idx].copy(), val
+    if isinstance(am, SampleOptAM):
+        X, vals = maximize_acquisition(am.sampler, problem, options, return_all=True)
+        top = np.argsort(-vals, kind="stable")[: am.multistart]
+        return maximize_acquisition(OptimizationAM(X[:, top], am.iters), problem, options)
+    if isinstance(am, OptimizationAM):
+        lb, ub = dom.bounds
+        if isinstance(am.multistart, int):
+            starts = (0.5 * (lb + ub))[:, None] if am.multistart == 1 else generate_LHC(dom.bounds, am.multistart, am.rng)
+        else:
+            starts = np.asarray(am.multistart, dtype=np.float64)
+        X, f = batched_lbfgs_maximize(acq.value_and_grad, starts, lb, ub, am.iters, am.history)
+        if np.all(np.isneginf(f)):
+            raise RuntimeError("All optimization runs failed!")                      # optim_multistart.jl:34
+        b = int(np.argmax(f))                                                         # first maximal
+        x = discrete_round(dom.discrete, X[:, b])                                     # optimization.jl:116
+        return x, acq(x)
+    raise TypeError(f"unsupported acquisition maximizer {type(am).__name__}")

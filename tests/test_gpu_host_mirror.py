@@ -1,0 +1,128 @@
+"""GPU tests of the reference-facing host mirror (boss_b200.*) -- they read like the reference's own tests
+(test/unit/test/models/gaussian_process.jl, test/unit/test/acquisitions/expected_improvement.jl)."""
+import numpy as np
+import pytest
+
+import boss_b200 as B
+from oracle import boss_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem(noise=0.1, y_max=None, discrete=None, cons=None, seed=0, n=20, f=None):
+    rng = np.random.default_rng(seed)
+    f = f or (lambda x: np.array([np.sin(x[0]) + 0.5 * np.cos(2 * x[1])]))
+    dom = B.Domain(([0.0, 0.0], [10.0, 10.0]), discrete=discrete, cons=cons)
+    X = B.generate_LHC(dom.bounds, n, rng)
+    if discrete is not None:
+        X = np.array([B.types.discrete_round(discrete, X[:, j]) for j in range(n)]).T
+    Y = np.stack([f(X[:, j]) for j in range(n)], axis=1)
+    model = B.GaussianProcess(
+        kernel=B.SqExponentialKernel(),
+        lengthscale_priors=[B.mvlognormal([0.5, 0.5], [0.5, 0.5])] * Y.shape[0],
+        amplitude_priors=[B.LogNormal(0.0, 0.5)] * Y.shape[0],
+        noise_std_priors=[B.Dirac(noise)] * Y.shape[0])
+    return B.BossProblem(f, dom, B.ExpectedImprovement(B.LinFitness([1.0] + [0.0] * (Y.shape[0] - 1))), model,
+                         B.ExperimentData(X, Y), y_max=y_max)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _init(lib):
+    return lib
+
+
+def test_gp_posterior_properties():
+    # test/unit/test/models/gaussian_process.jl:57-126: 3-point 2-D data
+    X = np.array([[1.0, 5.0, 9.0], [2.0, 5.0, 8.0]]); Y = np.array([[1.0, -1.0, 2.0]])
+    model = B.GaussianProcess(kernel=B.Matern52Kernel())
+    params = B.GaussianProcessParams(np.array([[2.0], [2.0]]), np.array([1.0]), np.array([1e-3]))
+    post = B.model_posterior(model, params, B.ExperimentData(X, Y))
+    Xs = np.array([[2.0, 4.0, 7.5], [3.0, 4.0, 1.0]])
+    mus, vs = post.mean_and_var(Xs)
+    assert mus.shape == (1, 3) and vs.shape == (1, 3)
+    for j in range(3):
+        m1, v1 = post.mean_and_var(Xs[:, j])
+        assert abs(m1[0] - mus[0, j]) <= 1e-8 and abs(v1[0] - vs[0, j]) <= 1e-8
+    assert np.allclose(post.mean(X)[0], Y[0], atol=0.01)
+    assert abs(post.mean(np.array([1000.0, 1000.0]))[0]) < 1e-8
+    v = post.var(np.array([[1.0, 1.5, 2.5], [2.0, 2.5, 3.5]]))[0]
+    assert v[0] < v[1] < v[2]
+
+
+def test_construct_acquisition_and_gridam_match_oracle():
+    prob = _problem(seed=3)
+    prob.params = B.estimate_parameters(B.SamplingMAP(64, seed=1), prob)
+    acq = B.construct_acquisition(prob)
+    assert isinstance(acq(np.array([1.0, 1.0])), float)
+    assert acq(np.array([11.0, 1.0])) == 0.0                         # out of bounds -> 0.
+    am = B.GridAM(prob, steps=[0.25, 0.25], shuffle=False)
+    x, val = B.maximize_acquisition(am, prob)
+    p = prob.params.params
+    post = O.posterior_fit(prob.data.X, prob.data.Y[0], p.lengthscales[:, 0], p.amplitudes[0], p.noise_std[0], O.KERNEL_SE)
+    ref, _, _ = O.ei_acquisition([[post]], am.points, [1.0], B.best_so_far(prob, prob.acquisition.fitness), None,
+                                 *prob.domain.bounds)
+    k = O.julia_argmax_fast(ref)
+    assert np.array_equal(x, am.points[:, k]) and abs(val - ref[k]) <= 1e-9 * abs(ref[k])
+
+
+def test_sampling_map_picks_first_best_of_the_batch():
+    prob = _problem(seed=4)
+    fit = B.SamplingMAP(50, seed=7)
+    res = B.estimate_parameters(fit, prob)
+    # replay the same prior draws through the oracle
+    sampler = prob.model.params_sampler(np.random.default_rng(7))
+    samples = [sampler() for _ in range(50)]
+    pll = prob.model.params_loglike()
+    vals = np.array([O.gp_loglik(prob.data.X, prob.data.Y[0], s.lengthscales[:, 0], s.amplitudes[0], s.noise_std[0],
+                                 O.KERNEL_SE) + pll(s) for s in samples])
+    b = int(np.argmax(vals))
+    assert np.array_equal(res.params.lengthscales, samples[b].lengthscales)
+    assert abs(res.loglike - vals[b]) <= 1e-8 * abs(vals[b])
+
+
+def test_optimization_am_beats_grid_and_respects_bounds():
+    prob = _problem(seed=5)
+    prob.params = B.estimate_parameters(B.SamplingMAP(64, seed=2), prob)
+    _, gval = B.maximize_acquisition(B.GridAM(prob, steps=[0.5, 0.5], shuffle=False), prob)
+    x, val = B.maximize_acquisition(B.OptimizationAM(multistart=64, iters=40, seed=0), prob)
+    assert B.in_bounds(x, prob.domain.bounds)
+    assert val >= gval * (1 - 1e-6)
+
+
+def test_constrained_discrete_multi_output_problem_runs():
+    f = lambda x: np.array([np.sin(x[0]) + 0.1 * x[1], np.cos(x[0]) - 0.05 * x[1]])
+    prob = _problem(y_max=[np.inf, 0.5], discrete=[True, False], cons=lambda x: [x[0] + x[1] - 1.0], seed=6, f=f)
+    prob.params = B.estimate_parameters(B.SamplingMAP(32, seed=3), prob)
+    acq = B.construct_acquisition(prob)
+    vals = acq(np.array([[0.2, 3.0, 3.4], [0.2, 3.0, 3.0]]))
+    assert vals[0] == 0.0                                            # cons violated
+    assert vals[1] == vals[2]                                        # DiscreteKernel: 3.4 rounds to 3.0
+    x, val = B.maximize_acquisition(B.SamplingAM(None, 500, seed=1), prob)
+    assert B.in_domain(x, prob.domain)
+
+
+def test_bo_loop_example_style():
+    """BASELINE configs[0] style: 2-D SE-ARD GP, 20 initial points, OptimizationMAP + OptimizationAM, EI."""
+    prob = _problem(seed=8)
+    n0 = len(prob.data)
+    B.bo(prob, B.OptimizationMAP(multistart=8, iters=10, seed=0), B.OptimizationAM(multistart=32, iters=20, seed=0),
+         B.IterLimit(3))
+    assert len(prob.data) == n0 + 3 and prob.consistent
+    assert np.isfinite(prob.params.loglike)
+
+
+def test_semiparametric_loglike_uses_per_sample_mean():
+    rng = np.random.default_rng(9)
+    X = rng.random((2, 40)) * 4; Y = (2.0 * X[0] + np.sin(X[1]))[None, :]
+    gp = B.GaussianProcess(kernel=B.Matern52Kernel(), lengthscale_priors=[B.mvlognormal([0, 0], [0.3, 0.3])],
+                           amplitude_priors=[B.LogNormal()], noise_std_priors=[B.Dirac(0.1)])
+    model = B.Semiparametric(B.Parametric(lambda x, th: np.array([th[0] * x[0] + th[1]]), [B.Uniform(-3, 3), B.Uniform(-1, 1)]), gp)
+    data = B.ExperimentData(X, Y)
+    ll = B.data_loglike(model, data)
+    mk = lambda th: B.SemiparametricParams(np.array(th), np.array([[1.0], [1.0]]), np.array([1.0]), np.array([0.1]))
+    good, bad = ll(mk([2.0, 0.0])), ll(mk([-2.0, 0.0]))
+    assert good > bad                                                # loglik ordering incl. theta (semiparametric tests)
+    both = ll([mk([2.0, 0.0]), mk([-2.0, 0.0])])
+    assert both[0] == good and both[1] == bad
+    ref = O.gp_loglik(X, Y[0] - 2.0 * X[0], [1.0, 1.0], 1.0, 0.1, O.KERNEL_MATERN52)
+    assert abs(good - ref) <= 1e-8 * abs(ref)

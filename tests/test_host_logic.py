@@ -1,0 +1,110 @@
+"""CPU tests of the host-side mirror (no GPU, no compute through the C ABI) and of the multi-rank plumbing
+(world_size 2, gloo)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import boss_b200 as B
+from boss_b200 import parallel
+
+
+def test_domain_guards_match_reference_semantics():
+    dom = B.Domain(([5.0, 5.0], [10.0, 10.0]))
+    # make_safe test, test/unit/test/acquisitions/expected_improvement.jl:26-40 (bounds inclusive)
+    assert not B.in_bounds(np.array([1.0, 7.0]), dom.bounds)
+    assert B.in_bounds(np.array([5.0, 10.0]), dom.bounds)
+    assert list(B.in_bounds(np.array([[4.9, 5.0, 10.0, 10.1], [7.0, 7.0, 7.0, 7.0]]), dom.bounds)) == [False, True, True, False]
+    dom2 = B.Domain(([0.0, 0.0], [10.0, 10.0]), discrete=[True, False], cons=lambda x: [x[0] - 2.0])
+    assert B.in_domain(np.array([3.0, 0.5]), dom2)
+    assert not B.in_domain(np.array([3.5, 0.5]), dom2)            # not integer in a discrete dim
+    assert not B.in_domain(np.array([1.0, 0.5]), dom2)            # cons < 0
+    assert dom2.cons(np.array([2.4, 0.0]))[0] == 0.0              # cons sees the rounded point (make_discrete)
+
+
+def test_lhc_one_point_per_stratum():
+    rng = np.random.default_rng(0)
+    lb, ub = np.array([0.0, -1.0, 2.0]), np.array([1.0, 1.0, 4.0])
+    X = B.generate_LHC((lb, ub), 16, rng)
+    assert X.shape == (3, 16)
+    for i in range(3):
+        strata = np.floor((X[i] - lb[i]) / (ub[i] - lb[i]) * 16).astype(int)
+        assert sorted(strata) == list(range(16))
+
+
+def test_gridam_points_follow_iterators_product_order():
+    class P:  # minimal stand-in: GridAM only reads problem.domain
+        domain = B.Domain(([0.0, 0.0], [1.0, 2.0]), cons=lambda x: [1.5 - x[1]])
+    am = B.GridAM(P, steps=[0.5, 1.0], shuffle=False)
+    assert am.points.T.tolist() == [[0.0, 0.0], [0.5, 0.0], [1.0, 0.0], [0.0, 1.0], [0.5, 1.0], [1.0, 1.0]]
+
+
+def test_batched_lbfgs_on_concave_quadratic_with_box():
+    rng = np.random.default_rng(1)
+    d, S = 4, 64
+    c = np.array([0.3, 0.8, 1.4, -0.5])       # unconstrained maximiser; box clips dims 2, 3
+    A = np.diag([1.0, 5.0, 2.0, 0.5])
+
+    def vg(X):
+        D = X - c[:, None]
+        return -0.5 * np.sum(D * (A @ D), axis=0), -(A @ D)
+    lb, ub = np.zeros(d), np.ones(d)
+    X, f = B.batched_lbfgs_maximize(vg, rng.random((d, S)), lb, ub, iters=80)
+    target = np.clip(c, lb, ub)
+    assert np.max(np.abs(X - target[:, None])) < 1e-6
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 16, 4096):
+        for w in (1, 2, 3, 8):
+            spans = [parallel.shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_reduce_pairs_julia_semantics():
+    assert parallel.reduce_pairs([(1.0, 5), (3.0, 9), (3.0, 2)]) == (3.0, 2)       # tie -> lowest index
+    v, i = parallel.reduce_pairs([(1.0, 5), (float("nan"), 9), (7.0, 2)])
+    assert np.isnan(v) and i == 9                                                    # NaN maximal
+    assert parallel.reduce_pairs([(-0.0, 1), (0.0, 4)]) == (0.0, 4)                  # isless(-0.0, 0.0)
+    assert parallel.reduce_pairs([(2.0, -1), (1.0, 3)]) == (1.0, 3)                  # empty shard ignored
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    M = 1001
+    scores = np.sin(np.arange(M) * 0.37) + np.arange(M) * 1e-4
+
+    def score_shard(lo, hi):
+        loc = scores[lo:hi]
+        return int(np.argmax(loc)), float(loc.max())
+    val, idx = parallel.sharded_argmax(score_shard, M)
+    S = 37
+    ll_all = np.cos(np.arange(S) * 0.11)
+    got = parallel.sharded_loglik(lambda lo, hi: ll_all[lo:hi], S)
+    q.put((rank, val, idx, got.tolist()))
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_argmax_and_loglik_gather():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    M = 1001
+    scores = np.sin(np.arange(M) * 0.37) + np.arange(M) * 1e-4
+    S = 37
+    for rank, val, idx, got in res:
+        assert idx == int(np.argmax(scores)) and val == float(scores.max())
+        assert np.array_equal(np.array(got), np.cos(np.arange(S) * 0.11))
