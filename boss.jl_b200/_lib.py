@@ -214,14 +214,17 @@ def ei_value_grad(slices, y_dim, n_samples, Xs, coefs, best, y_max, lb=None, ub=
     return acq, grad.T
 
 
-def ei_value_grad_dev(slices, y_dim, n_samples, Xs_ptr, M, coefs, best, y_max, acq_ptr, grad_ptr, lb=None, ub=None):
+def ei_value_grad_dev(slices, y_dim, n_samples, Xs_ptr, M, coefs, best, y_max, acq_ptr, grad_ptr, lb=None, ub=None,
+                      prior_mean_ptr=None, prior_mean_grad_ptr=None):
     arr = _slice_array(slices)
     co = _f64(coefs, (y_dim,))
     b = None if best is None else np.array([best], dtype=np.float64)
     ym = None if y_max is None else _f64(y_max, (y_dim,))
     lbv = None if lb is None else _f64(lb)
     ubv = None if ub is None else _f64(ub)
-    _check(lib.boss_ei_value_grad_dev(arr, y_dim, n_samples, _vp(Xs_ptr), int(M), None, None, _ptr(co), _ptr(b),
+    _check(lib.boss_ei_value_grad_dev(arr, y_dim, n_samples, _vp(Xs_ptr), int(M),
+                                      _vp(prior_mean_ptr) if prior_mean_ptr else None,
+                                      _vp(prior_mean_grad_ptr) if prior_mean_grad_ptr else None, _ptr(co), _ptr(b),
                                       _ptr(ym), _ptr(lbv), _ptr(ubv), None, _vp(acq_ptr) if acq_ptr else None,
                                       _vp(grad_ptr)), "boss_ei_value_grad_dev")
 

@@ -502,7 +502,7 @@ def mean_var_grad(post: GPPosterior, Xs, prior_mean_s=None, prior_mean_grad_s=No
     return mu, var_c, dmu, dvar, status
 
 
-def ei_value_grad(posts: Sequence[GPPosterior], Xs, coefs, best_yet, y_max, prior_mean_s=None):
+def ei_value_grad(posts: Sequence[GPPosterior], Xs, coefs, best_yet, y_max, prior_mean_s=None, prior_mean_grad_s=None):
     """EI x PoF value and x-gradient for ONE parameter sample (posts[i] = slice i), in-domain points.
 
     d EI = Phi(z) d(mu_f) + phi(z) d(sigma_f)   (the Delta*phi*dz terms cancel).
@@ -516,7 +516,8 @@ def ei_value_grad(posts: Sequence[GPPosterior], Xs, coefs, best_yet, y_max, prio
     failed = np.zeros(M, bool)
     for i in range(y_dim):
         pm = None if prior_mean_s is None else prior_mean_s[i]
-        mus[i], vs[i], dmus[i], dvs[i], st = mean_var_grad(posts[i], Xs, pm)
+        pmg = None if prior_mean_grad_s is None else prior_mean_grad_s[i]
+        mus[i], vs[i], dmus[i], dvs[i], st = mean_var_grad(posts[i], Xs, pm, pmg)
         failed |= st != 0
     val = np.ones(M)
     grad = np.zeros((d, M))
