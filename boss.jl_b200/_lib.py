@@ -164,6 +164,17 @@ def gp_predict(gp: GP, Xs, prior_mean_s=None):
     return mu, var, st
 
 
+def gp_cov(gp: GP, Xs, prior_mean_s=None):
+    """mean_and_cov(::GaussianProcessPosterior, X): -> mu (M,), cov (M, M) with the diagonal clipped, rc."""
+    Xc = _cols(Xs)
+    M = Xc.shape[0]
+    pm = None if prior_mean_s is None else _f64(prior_mean_s, (M,))
+    mu = np.empty(M)
+    cov = np.empty((M, M))
+    rc = _check(lib.boss_gp_cov(gp.handle, _ptr(Xc), M, _ptr(pm), _ptr(mu), _ptr(cov)), "boss_gp_cov")
+    return mu, cov, rc
+
+
 def _slice_array(slices):
     flat = [g.handle for g in slices]
     arr = (_vp * len(flat))(*flat)

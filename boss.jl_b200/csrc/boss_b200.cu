@@ -69,6 +69,7 @@ struct Ctx {
   // workspaces
   DevBuf ks, muv, sumsq, xs_stage, pm_stage, cm_stage, acq_stage, mu_stage, var_stage, st_stage, grad_stage;
   DevBuf blk_val, blk_idx, small, chol_L, chol_Winv, chol_misc, tt, vt, ut, dmu, dvar, pmg_stage;
+  DevBuf part_mu, part_ss, part_gm, part_gv, cov_p, cov_stage;   // split-invariant partial sums (score.cuh / grad.cuh)
   // event pool for per-kernel-class timing
   cudaEvent_t ev_a[EV_POOL], ev_b[EV_POOL];
   int ev_class[EV_POOL];
@@ -155,12 +156,16 @@ void launch_build_k_t(const BuildKParams &p, dim3 grid) {
   build_k_kernel<KID, DP><<<grid, 256, 0, g.stream>>>(p);
 }
 template <int KID, int DP>
-void launch_xcov_t(const XcovParams &p, int ncb) {
-  xcov_kernel<KID, DP><<<ncb, 256, 0, g.stream>>>(p);
+void launch_xcov_t(const XcovParams &p, dim3 grid) {
+  xcov_kernel<KID, DP><<<grid, 256, 0, g.stream>>>(p);
 }
 template <int KID, int DP>
-void launch_grad_t(const GradParams &p, int ncb) {
-  grad_kernel<KID, DP><<<ncb, 256, 0, g.stream>>>(p);
+void launch_cov_finish_t(const CovFinishParams &p, dim3 grid) {
+  cov_finish_kernel<KID, DP><<<grid, 256, 0, g.stream>>>(p);
+}
+template <int KID, int DP>
+void launch_grad_t(const GradParams &p, dim3 grid) {
+  grad_kernel<KID, DP><<<grid, 256, 0, g.stream>>>(p);
 }
 #define DISPATCH_KID_DP(FN, kid, dp, ...)                  \
   do {                                                     \
@@ -183,6 +188,33 @@ void launch_grad_t(const GradParams &p, int ncb) {
       default: break;                                      \
     }                                                      \
   } while (0)
+
+// Number of zig-zag row-block splits per candidate block for the triangular products (score_trmm / wtv):
+// minimise waves x (largest per-CTA share of the nblk(nblk+1)/2 block-steps + ~1 block-step of pipeline fill).
+int pick_row_splits(int ncb, int nblk) {
+  if (ncb >= 4 * 148 || nblk < 2) return 1;
+  double best_t = 1e300;
+  int best = 1;
+  for (int ns = 1; ns <= nblk; ++ns) {
+    int maxw = 0;
+    for (int y = 0; y < ns; ++y) {
+      int w = 0;
+      for (int j = 0;; ++j) {
+        const int i = (j >> 1) * 2 * ns + ((j & 1) ? 2 * ns - 1 - y : y);
+        if (i >= nblk) break;
+        w += i + 1;
+      }
+      maxw = std::max(maxw, w);
+    }
+    const long ctas = (long)ncb * ns, waves = (ctas + 147) / 148;
+    const double t = (double)waves * (maxw + 1.0);
+    if (t < best_t * (1.0 - 1e-9)) {
+      best_t = t;
+      best = ns;
+    }
+  }
+  return best;
+}
 
 bool g_attr_done = false;
 int set_kernel_attrs() {
@@ -317,7 +349,8 @@ void boss_shutdown(void) {
   cudaStreamSynchronize(g.stream);
   for (DevBuf *b : {&g.ks, &g.muv, &g.sumsq, &g.xs_stage, &g.pm_stage, &g.cm_stage, &g.acq_stage, &g.mu_stage,
                     &g.var_stage, &g.st_stage, &g.grad_stage, &g.blk_val, &g.blk_idx, &g.small, &g.chol_L,
-                    &g.chol_Winv, &g.chol_misc, &g.tt, &g.vt, &g.ut, &g.dmu, &g.dvar, &g.pmg_stage})
+                    &g.chol_Winv, &g.chol_misc, &g.tt, &g.vt, &g.ut, &g.dmu, &g.dvar, &g.pmg_stage, &g.part_mu,
+                    &g.part_ss, &g.part_gm, &g.part_gv, &g.cov_p, &g.cov_stage})
     b->release();
   if (g.ev_ready) {
     for (int i = 0; i < EV_POOL; ++i) {
@@ -530,12 +563,17 @@ int score_core(ScoreArgs &a) {
   CUDA_TRY(g.ks.ensure((size_t)CH * max_npad * 8));
   CUDA_TRY(g.muv.ensure((size_t)nsl * CH * 8));
   CUDA_TRY(g.sumsq.ensure((size_t)nsl * CH * 8));
+  const int max_nblk = max_npad / TM;
+  CUDA_TRY(g.part_mu.ensure((size_t)2 * max_nblk * CH * 8));
+  CUDA_TRY(g.part_ss.ensure((size_t)2 * max_nblk * CH * 8));
   if (a.grad) {
     if (d > 32) return fail(BOSS_ERR_ARG, "score: gradients need x_dim <= 32");
     CUDA_TRY(g.vt.ensure((size_t)CH * max_npad * 8));
     CUDA_TRY(g.ut.ensure((size_t)CH * max_npad * 8));
     CUDA_TRY(g.dmu.ensure((size_t)nsl * d * CH * 8));
     CUDA_TRY(g.dvar.ensure((size_t)nsl * d * CH * 8));
+    CUDA_TRY(g.part_gm.ensure((size_t)2 * max_nblk * d * CH * 8));
+    CUDA_TRY(g.part_gv.ensure((size_t)2 * max_nblk * d * CH * 8));
   }
   const int nblk_acq_max = (CH + 255) / 256;
   CUDA_TRY(g.blk_val.ensure((size_t)nblk_acq_max * 8));
@@ -621,6 +659,13 @@ int score_core(ScoreArgs &a) {
     }
     for (int q = 0; q < nsl; ++q) {
       const boss_gp *h = a.slices[q];
+      // Small candidate batches (multi-start optimiser iterations, single-point calls) cannot fill 148 SMs
+      // with one CTA per 128 candidates: deal the training chunks / W row blocks of a candidate block to
+      // several CTAs.  Partial sums are kept per chunk / per row block, so results do not depend on the split.
+      const int want = (2 * 148 + ncb - 1) / ncb;
+      const int nks = std::max(1, std::min(h->nblk, want));            // xcov / grad: splits over training chunks
+      const int nsp = pick_row_splits(ncb, h->nblk);                   // trmm / wtv: zig-zag row-block splits
+      const int cnt = ncb * 128;
       XcovParams xp{};
       xp.Xs = xs_dev;
       xp.M = a.M;
@@ -636,28 +681,34 @@ int score_core(ScoreArgs &a) {
       xp.alpha = h->alpha;
       xp.a2 = h->a2;
       xp.Ks = g.ks.as<double>();
-      xp.mu = g.muv.as<double>() + (size_t)q * CH;
+      xp.mu_part = g.part_mu.as<double>();
+      xp.ld = CH;
       {
         Timed t(1);
-        DISPATCH_KID_DP(launch_xcov_t, h->kernel_id, h->dp, xp, ncb);
+        DISPATCH_KID_DP(launch_xcov_t, h->kernel_id, h->dp, xp, dim3(ncb, nks));
       }
+      reduce_rows_kernel<<<(cnt + 255) / 256, 256, 0, g.stream>>>(g.part_mu.as<double>(), 2 * h->nblk, (size_t)CH,
+                                                                 g.muv.as<double>() + (size_t)q * CH, cnt);
       ScoreParams sp{};
       sp.W = h->W;
       sp.Ks = g.ks.as<double>();
       sp.nblk = h->nblk;
       sp.ktiles = h->ktiles;
-      sp.sumsq = g.sumsq.as<double>() + (size_t)q * CH;
+      sp.ss_part = g.part_ss.as<double>();
+      sp.ld = CH;
       sp.VT = a.grad ? g.vt.as<double>() : nullptr;
       {
         Timed t(0);
-        score_trmm_kernel<<<ncb, GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(sp);
+        score_trmm_kernel<<<dim3(ncb, nsp), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(sp);
       }
-      g.launches += 2;
+      reduce_rows_kernel<<<(cnt + 255) / 256, 256, 0, g.stream>>>(g.part_ss.as<double>(), 2 * h->nblk, (size_t)CH,
+                                                                 g.sumsq.as<double>() + (size_t)q * CH, cnt);
+      g.launches += 4;
       if (a.grad) {
         WtvParams wp{h->WT, g.vt.as<double>(), g.ut.as<double>(), h->nblk, h->ktiles};
         {
           Timed t(0);
-          wtv_kernel<<<ncb, GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(wp);
+          wtv_kernel<<<dim3(ncb, nsp), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(wp);
         }
         GradParams gq{};
         gq.Xs = xs_dev;
@@ -675,13 +726,16 @@ int score_core(ScoreArgs &a) {
         gq.disc_bits = h->disc;
         gq.a2 = h->a2;
         gq.UT = g.ut.as<double>();
-        gq.dmu = g.dmu.as<double>() + (size_t)q * d * CH;
-        gq.dvar = g.dvar.as<double>() + (size_t)q * d * CH;
+        gq.gm_part = g.part_gm.as<double>();
+        gq.gv_part = g.part_gv.as<double>();
         {
           Timed t(1);
-          DISPATCH_KID_DP(launch_grad_t, h->kernel_id, h->dp, gq, ncb);
+          DISPATCH_KID_DP(launch_grad_t, h->kernel_id, h->dp, gq, dim3(ncb, nks));
         }
-        g.launches += 2;
+        GradReduceParams gr{g.part_gm.as<double>(), g.part_gv.as<double>(), 2 * h->nblk, d, CH, cnt, h->invl, h->disc,
+                            g.dmu.as<double>() + (size_t)q * d * CH, g.dvar.as<double>() + (size_t)q * d * CH};
+        grad_reduce_kernel<<<dim3((cnt + 255) / 256, d), 256, 0, g.stream>>>(gr);
+        g.launches += 3;
       }
     }
     AcqParams ap{};
@@ -871,8 +925,84 @@ int boss_ei_value_grad_dev(const boss_gp *const *slices, int y_dim, int n_sample
                        cons_mask_dev, acq_dev, grad_dev, nullptr, nullptr, true, prior_mean_grad_s_dev);
 }
 
-int boss_gp_cov(const boss_gp *, const double *, int64_t, const double *, double *, double *) {
-  return fail(BOSS_ERR_ARG, "boss_gp_cov: not available in this build");
+int boss_gp_cov(const boss_gp *gp, const double *Xs, int64_t M, const double *prior_mean_s, double *mu, double *cov) {
+  std::lock_guard<std::mutex> lk(g.mu);
+  REQUIRE_INIT();
+  if (!gp || !Xs || !cov || M < 1) return fail(BOSS_ERR_ARG, "boss_gp_cov: bad arguments");
+  if (M > 8192) return fail(BOSS_ERR_ARG, "boss_gp_cov: M > 8192 (the full covariance is meant for small batches)");
+  const boss_gp *h = gp;
+  const int d = h->d, ncb = (int)((M + 127) / 128), Mp = ncb * 128, cnt = Mp;
+  const size_t blk_elems = (size_t)Mp * h->n_pad;
+  CUDA_TRY(g.ks.ensure(blk_elems * 8));
+  CUDA_TRY(g.vt.ensure(blk_elems * 8));
+  CUDA_TRY(g.part_mu.ensure((size_t)2 * h->nblk * Mp * 8));
+  CUDA_TRY(g.part_ss.ensure((size_t)2 * h->nblk * Mp * 8));
+  CUDA_TRY(g.muv.ensure((size_t)Mp * 8));
+  CUDA_TRY(g.cov_p.ensure((size_t)Mp * Mp * 8));
+  CUDA_TRY(g.cov_stage.ensure((size_t)M * M * 8));
+  CUDA_TRY(g.xs_stage.ensure((size_t)Mp * d * 8));
+  CUDA_TRY(g.mu_stage.ensure((size_t)Mp * 8));
+  CUDA_TRY(g.small.ensure(64));
+  if (prior_mean_s) CUDA_TRY(g.pm_stage.ensure((size_t)M * 8));
+  int *d_fail = g.small.as<int>();
+  CUDA_TRY(cudaMemsetAsync(d_fail, 0, 4, g.stream));
+  CUDA_TRY(cudaMemcpyAsync(g.xs_stage.p, Xs, (size_t)M * d * 8, cudaMemcpyHostToDevice, g.stream));
+  if (prior_mean_s) CUDA_TRY(cudaMemcpyAsync(g.pm_stage.p, prior_mean_s, (size_t)M * 8, cudaMemcpyHostToDevice, g.stream));
+  const int want = (2 * 148 + ncb - 1) / ncb;
+  const int nks = std::max(1, std::min(h->nblk, want));
+  const int nsp = pick_row_splits(ncb, h->nblk);
+  XcovParams xp{};
+  xp.Xs = g.xs_stage.as<double>();
+  xp.M = M;
+  xp.d = d;
+  xp.n = h->n;
+  xp.n_pad = h->n_pad;
+  xp.ktiles = h->ktiles;
+  xp.Xt = h->Xt;
+  xp.invl = h->invl;
+  xp.disc_bits = h->disc;
+  xp.alpha = h->alpha;
+  xp.a2 = h->a2;
+  xp.Ks = g.ks.as<double>();
+  xp.mu_part = g.part_mu.as<double>();
+  xp.ld = Mp;
+  DISPATCH_KID_DP(launch_xcov_t, h->kernel_id, h->dp, xp, dim3(ncb, nks));
+  reduce_rows_kernel<<<(cnt + 255) / 256, 256, 0, g.stream>>>(g.part_mu.as<double>(), 2 * h->nblk, (size_t)Mp,
+                                                             g.muv.as<double>(), cnt);
+  ScoreParams sp{};
+  sp.W = h->W;
+  sp.Ks = g.ks.as<double>();
+  sp.nblk = h->nblk;
+  sp.ktiles = h->ktiles;
+  sp.ss_part = g.part_ss.as<double>();
+  sp.ld = Mp;
+  sp.VT = g.vt.as<double>();
+  score_trmm_kernel<<<dim3(ncb, nsp), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(sp);
+  DbgGemmParams gm{g.vt.as<double>(), g.vt.as<double>(), g.cov_p.as<double>(), h->ktiles, Mp / TK, 1};
+  dbg_gemm_kernel<<<dim3(ncb, ncb), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(gm);
+  CovFinishParams cf{};
+  cf.Xs = g.xs_stage.as<double>();
+  cf.M = (int)M;
+  cf.d = d;
+  cf.ktilesC = Mp / TK;
+  cf.invl = h->invl;
+  cf.disc_bits = h->disc;
+  cf.a2 = h->a2;
+  cf.C = g.cov_p.as<double>();
+  cf.mu = g.muv.as<double>();
+  cf.prior_mean = prior_mean_s ? g.pm_stage.as<double>() : nullptr;
+  cf.mu_out = mu ? g.mu_stage.as<double>() : nullptr;
+  cf.cov = g.cov_stage.as<double>();
+  cf.any_fail = d_fail;
+  DISPATCH_KID_DP(launch_cov_finish_t, h->kernel_id, h->dp, cf, dim3((unsigned)((M + 15) / 16), (unsigned)((M + 15) / 16)));
+  g.launches += 5;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(cov, g.cov_stage.p, (size_t)M * M * 8, cudaMemcpyDeviceToHost, g.stream));
+  if (mu) CUDA_TRY(cudaMemcpyAsync(mu, g.mu_stage.p, (size_t)M * 8, cudaMemcpyDeviceToHost, g.stream));
+  int hfail = 0;
+  CUDA_TRY(cudaMemcpyAsync(&hfail, d_fail, 4, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  return hfail ? BOSS_NEG_VARIANCE : 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1026,7 +1156,7 @@ int boss_dbg_gemm_nt(const double *A, const double *B, int M, int N, int K, doub
   CUDA_TRY(cudaMalloc(&dC, (size_t)Mp * Np * 8));
   CUDA_TRY(cudaMemcpy(dA, pa.data(), pa.size() * 8, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(dB, pb.data(), pb.size() * 8, cudaMemcpyHostToDevice));
-  DbgGemmParams p{dA, dB, dC, Kp / TK, Np / TK};
+  DbgGemmParams p{dA, dB, dC, Kp / TK, Np / TK, 0};
   dbg_gemm_kernel<<<dim3(Np / TM, Mp / TM), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(p);
   ++g.launches;
   CUDA_TRY(cudaGetLastError());

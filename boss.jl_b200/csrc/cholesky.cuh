@@ -162,9 +162,11 @@ struct DbgGemmParams {
   double *C;
   int ktilesAB;  // K/16
   int ktilesC;   // N/16
+  int lower_only;  // skip tiles above the block diagonal (symmetric products: boss_gp_cov)
 };
 __global__ void __launch_bounds__(GEMM_THREADS, 1) dbg_gemm_kernel(DbgGemmParams p) {
   const int cb = blockIdx.x, rb = blockIdx.y;
+  if (p.lower_only && cb > rb) return;
   LinearIt it{p.A + (size_t)rb * p.ktilesAB * TILE_ELEMS, p.B + (size_t)cb * p.ktilesAB * TILE_ELEMS, p.ktilesAB};
   double *dst = p.C + ((size_t)rb * p.ktilesC + (size_t)cb * KT_PER_BLOCK) * TILE_ELEMS;
   gemm_pipeline(it, it, [&](int, const double(&acc)[8][4][2], const FragCoord &fc) {

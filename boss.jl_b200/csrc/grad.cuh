@@ -22,27 +22,29 @@ struct WtvParams {
   int nblk, ktiles;
 };
 struct WtvIt {
-  const double *wt_row;
+  const double *wt;      // W^T (upper triangular): row block i uses k-tiles 8i .. ktiles-1
   const double *vt;
-  int i, kt, nblk, ktiles;
+  int j, i, kt, nblk, ktiles, y, ns2;
   __device__ __forceinline__ bool valid() const { return i < nblk; }
-  __device__ __forceinline__ const double *A() const { return wt_row + (size_t)kt * TILE_ELEMS; }
+  __device__ __forceinline__ const double *A() const { return wt + ((size_t)i * ktiles + kt) * TILE_ELEMS; }
   __device__ __forceinline__ const double *B() const { return vt + (size_t)kt * TILE_ELEMS; }
   __device__ __forceinline__ bool tile_end() const { return kt == ktiles - 1; }
   __device__ __forceinline__ int tile() const { return i; }
   __device__ __forceinline__ void next() {
     if (kt == ktiles - 1) {
-      ++i;
+      ++j;
+      i = zigzag_row(j, y, ns2);
       kt = i * KT_PER_BLOCK;
-      wt_row += (size_t)ktiles * TILE_ELEMS;
     } else {
       ++kt;
     }
   }
 };
+// grid = (candidate blocks, ns row-block splits), same zig-zag deal as score_trmm_kernel
 __global__ void __launch_bounds__(GEMM_THREADS, 1) wtv_kernel(WtvParams p) {
-  const int cb = blockIdx.x;
-  WtvIt it{p.WT, p.VT + (size_t)cb * p.ktiles * TILE_ELEMS, 0, 0, p.nblk, p.ktiles};
+  const int cb = blockIdx.x, y = blockIdx.y, ns2 = 2 * gridDim.y;
+  const int i0 = zigzag_row(0, y, ns2);
+  WtvIt it{p.WT, p.VT + (size_t)cb * p.ktiles * TILE_ELEMS, 0, i0, i0 * KT_PER_BLOCK, p.nblk, p.ktiles, y, ns2};
   double *ut = p.UT + (size_t)cb * p.ktiles * TILE_ELEMS;
   gemm_pipeline(it, it, [&](int tile, const double(&acc)[8][4][2], const FragCoord &fc) {
     store_block(ut + (size_t)tile * KT_PER_BLOCK * TILE_ELEMS, true, 1.0, nullptr, acc, fc);
@@ -58,24 +60,23 @@ struct GradParams {
   unsigned long long disc_bits;
   double a2;
   const double *UT;    // chunk scratch (P-layout), u = K^-1 k*
-  double *dmu, *dvar;  // [d][chunk_ld] each (this slice's section)
+  double *gm_part, *gv_part;  // [2*nblk][d][chunk_ld] per-(training chunk, k-half) partial sums (unscaled)
 };
 
 template <int KID, int DP>
 __global__ void __launch_bounds__(256) grad_kernel(GradParams p) {
   __shared__ double xt[XCOV_KC * DP];
   __shared__ double al[XCOV_KC];
-  __shared__ double red[2][128];
   const int tid = threadIdx.x, r = tid & 127, kh = tid >> 7;
   const int cb = blockIdx.x;
   const long long m = p.m0 + (long long)cb * 128 + r;
   double xc[DP];
   load_scaled_point<DP>(xc, p.Xs + (size_t)(m - p.in_off) * p.d, p.d, p.invl, p.disc_bits, m < p.M);
-  double gm[DP], gv[DP];
-#pragma unroll
-  for (int i = 0; i < DP; ++i) gm[i] = gv[i] = 0.0;
   const double *rowbase = p.UT + (size_t)cb * p.ktiles * TILE_ELEMS + (((r >> 3) << 1) << 6) + ((r & 7) << 3);
-  for (int k0 = 0; k0 < p.n_pad; k0 += XCOV_KC) {
+  for (int k0 = blockIdx.y * XCOV_KC; k0 < p.n_pad; k0 += gridDim.y * XCOV_KC) {
+    double gm[DP], gv[DP];
+#pragma unroll
+    for (int i = 0; i < DP; ++i) gm[i] = gv[i] = 0.0;
     __syncthreads();
     for (int e = tid; e < XCOV_KC * DP; e += 256) xt[e] = p.Xt[(size_t)k0 * DP + e];
     if (tid < XCOV_KC) al[tid] = p.alpha[k0 + tid];
@@ -111,22 +112,39 @@ __global__ void __launch_bounds__(256) grad_kernel(GradParams p) {
         }
       }
     }
-  }
-  // combine the two k-halves per dimension (fixed order), apply 1/l_j, the -2 and the discrete mask
+    const size_t prow = (size_t)(2 * (k0 / XCOV_KC) + kh) * p.d;
 #pragma unroll
-  for (int i = 0; i < DP; ++i) {
-    if (i >= p.d) break;
-    __syncthreads();
-    red[kh][r] = gm[i];
-    __syncthreads();
-    const bool disc = (p.disc_bits >> i) & 1ull;
-    if (kh == 0) p.dmu[(size_t)i * p.chunk_ld + cb * 128 + r] = disc ? 0.0 : (red[0][r] + red[1][r]) * p.invl[i];
-    __syncthreads();
-    red[kh][r] = gv[i];
-    __syncthreads();
-    if (kh == 0)
-      p.dvar[(size_t)i * p.chunk_ld + cb * 128 + r] = disc ? 0.0 : -2.0 * (red[0][r] + red[1][r]) * p.invl[i];
+    for (int i = 0; i < DP; ++i) {
+      if (i < p.d) {
+        p.gm_part[(prow + i) * p.chunk_ld + cb * 128 + r] = gm[i];
+        p.gv_part[(prow + i) * p.chunk_ld + cb * 128 + r] = gv[i];
+      }
+    }
   }
+}
+
+// Fixed-order sum of the per-chunk partials, then 1/l_j, the -2 of d var and the discrete mask:
+//   dmu[j][c] = invl_j * sum_p gm_part[p][j][c] ;  dvar[j][c] = -2 invl_j * sum_p gv_part[p][j][c]
+struct GradReduceParams {
+  const double *gm_part, *gv_part;
+  int P, d, chunk_ld, count;
+  const double *invl;
+  unsigned long long disc_bits;
+  double *dmu, *dvar;  // [d][chunk_ld] each (this slice's section)
+};
+__global__ void __launch_bounds__(256) grad_reduce_kernel(GradReduceParams p) {
+  const int c = blockIdx.x * 256 + threadIdx.x, j = blockIdx.y;
+  if (c >= p.count) return;
+  double am = 0.0, av = 0.0;
+  for (int q = 0; q < p.P; ++q) {
+    const size_t o = ((size_t)q * p.d + j) * p.chunk_ld + c;
+    am += p.gm_part[o];
+    av += p.gv_part[o];
+  }
+  const bool disc = (p.disc_bits >> j) & 1ull;
+  const double il = p.invl[j];
+  p.dmu[(size_t)j * p.chunk_ld + c] = disc ? 0.0 : am * il;
+  p.dvar[(size_t)j * p.chunk_ld + c] = disc ? 0.0 : -2.0 * av * il;
 }
 
 // Chain rule through EI x PoF.  dmu / dvar: [(sample*y_dim + slice)][d][chunk_ld].

@@ -28,25 +28,27 @@ struct XcovParams {
   const double *alpha;     // [n_pad] K^-1 (y - m), zero padded
   double a2;
   double *Ks;              // chunk scratch, P-layout: rows = candidates of the chunk, cols = training index
-  double *mu;              // [chunk] K*^T alpha (prior mean added later)
+  double *mu_part;         // [2*nblk][ld] per-(128-chunk of training points, k-half) partials of K*^T alpha
+  int ld;                  // leading dimension of mu_part (= chunk capacity)
 };
 
 constexpr int XCOV_KC = 128;  // training points staged per shared-memory pass
 
+// grid = (candidate blocks, splits over the 128-point training chunks).  Every chunk's contribution to
+// mu is written as its own partial (fixed summation order downstream), so results do not depend on the split.
 template <int KID, int DP>
 __global__ void __launch_bounds__(256) xcov_kernel(XcovParams p) {
   __shared__ double xt[XCOV_KC * DP];
   __shared__ double al[XCOV_KC];
-  __shared__ double mu_part[2][128];
   const int tid = threadIdx.x, r = tid & 127, kh = tid >> 7;
   const int cb = blockIdx.x;
   const long long m = p.m0 + (long long)cb * 128 + r;
   double xc[DP];
   load_scaled_point<DP>(xc, p.Xs + (size_t)(m - p.in_off) * p.d, p.d, p.invl, p.disc_bits, m < p.M);
 
-  double mu_acc = 0.0;
   double *rowbase = p.Ks + (size_t)cb * p.ktiles * TILE_ELEMS + (((r >> 3) << 1) << 6) + ((r & 7) << 3);
-  for (int k0 = 0; k0 < p.n_pad; k0 += XCOV_KC) {
+  for (int k0 = blockIdx.y * XCOV_KC; k0 < p.n_pad; k0 += gridDim.y * XCOV_KC) {
+    double mu_acc = 0.0;
     __syncthreads();
     for (int e = tid; e < XCOV_KC * DP; e += 256) xt[e] = p.Xt[(size_t)k0 * DP + e];
     if (tid < XCOV_KC) al[tid] = p.alpha[k0 + tid];
@@ -71,10 +73,18 @@ __global__ void __launch_bounds__(256) xcov_kernel(XcovParams p) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) *reinterpret_cast<double2 *>(dst + 2 * q) = make_double2(v[q], v[q + 4]);
     }
+    p.mu_part[(size_t)(2 * (k0 / XCOV_KC) + kh) * p.ld + (size_t)cb * 128 + r] = mu_acc;
   }
-  mu_part[kh][r] = mu_acc;
-  __syncthreads();
-  if (tid < 128) p.mu[(size_t)cb * 128 + tid] = mu_part[0][tid] + mu_part[1][tid];
+}
+
+// out[c] = sum_{p = 0}^{P-1} in[p*ld + c]  (ascending p: the fixed order that makes results split-invariant)
+__global__ void __launch_bounds__(256) reduce_rows_kernel(const double *__restrict__ in, int P, size_t ld,
+                                                          double *__restrict__ out, int count) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= count) return;
+  double acc = 0.0;
+  for (int q = 0; q < P; ++q) acc += in[(size_t)q * ld + c];
+  out[c] = acc;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -86,67 +96,57 @@ struct ScoreParams {
   const double *W;    // P-layout n_pad x n_pad lower-triangular inverse factor
   const double *Ks;   // chunk scratch
   int nblk, ktiles;
-  double *sumsq;      // [chunk]
+  double *ss_part;    // [2*nblk][ld] per-(row block, warp-row half) partial sums of squares
+  int ld;
   double *VT;         // optional chunk scratch (P-layout, rows = candidates): V = W K* stored transposed (gradient mode)
 };
 
+// Row blocks of a triangular operand are dealt to the `ns` CTAs of a candidate block in zig-zag order
+// (split y gets y, 2ns-1-y, 2ns+y, 4ns-1-y, ...), which balances the triangular work; ns = 1 is the plain walk.
+__device__ __forceinline__ int zigzag_row(int j, int y, int ns2) { return (j >> 1) * ns2 + ((j & 1) ? ns2 - 1 - y : y); }
+
 struct ScoreIt {
-  const double *w_row;   // first tile of the current W row block
+  const double *w;       // W (lower triangular): row block i uses k-tiles 0 .. 8(i+1)-1
   const double *ks;      // first tile of this CTA's K*^T block
-  int i, kt, nblk, ktiles;
+  int j, i, kt, nblk, ktiles, y, ns2;
   __device__ __forceinline__ bool valid() const { return i < nblk; }
-  __device__ __forceinline__ const double *A() const { return w_row + (size_t)kt * TILE_ELEMS; }
+  __device__ __forceinline__ const double *A() const { return w + ((size_t)i * ktiles + kt) * TILE_ELEMS; }
   __device__ __forceinline__ const double *B() const { return ks + (size_t)kt * TILE_ELEMS; }
   __device__ __forceinline__ bool tile_end() const { return kt == (i + 1) * KT_PER_BLOCK - 1; }
   __device__ __forceinline__ int tile() const { return i; }
   __device__ __forceinline__ void next() {
     if (kt == (i + 1) * KT_PER_BLOCK - 1) {
-      ++i;
+      ++j;
+      i = zigzag_row(j, y, ns2);
       kt = 0;
-      w_row += (size_t)ktiles * TILE_ELEMS;
     } else {
       ++kt;
     }
   }
 };
 
+// grid = (candidate blocks, ns row-block splits).  Each finished 128x128 tile of V = W K* contributes one
+// partial column sum of squares per (row block, warp-row half); reduce_rows_kernel adds them in ascending order.
 __global__ void __launch_bounds__(GEMM_THREADS, 1) score_trmm_kernel(ScoreParams p) {
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  double *scratch = reinterpret_cast<double *>(smem_raw + GEMM_RING_BYTES);  // [2][128]
-  const int cb = blockIdx.x;
-  ScoreIt it{p.W, p.Ks + (size_t)cb * p.ktiles * TILE_ELEMS, 0, 0, p.nblk, p.ktiles};
-  double cs[4][2];
-#pragma unroll
-  for (int fn = 0; fn < 4; ++fn) cs[fn][0] = cs[fn][1] = 0.0;
-
+  const int cb = blockIdx.x, y = blockIdx.y, ns2 = 2 * gridDim.y;
+  ScoreIt it{p.W, p.Ks + (size_t)cb * p.ktiles * TILE_ELEMS, 0, zigzag_row(0, y, ns2), 0, p.nblk, p.ktiles, y, ns2};
   double *vt = p.VT ? p.VT + (size_t)cb * p.ktiles * TILE_ELEMS : nullptr;
   gemm_pipeline(it, it, [&](int tile, const double(&acc)[8][4][2], const FragCoord &fc) {
     if (vt) store_block(vt + (size_t)tile * KT_PER_BLOCK * TILE_ELEMS, true, 1.0, nullptr, acc, fc);
+    double *dst = p.ss_part + (size_t)(2 * tile + fc.wm) * p.ld + (size_t)cb * 128 + 32 * fc.wn;
 #pragma unroll
     for (int fn = 0; fn < 4; ++fn)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        double sacc = 0.0;
+        double v = 0.0;
 #pragma unroll
-        for (int fm = 0; fm < 8; ++fm) sacc = fma(acc[fm][fn][e], acc[fm][fn][e], sacc);
-        cs[fn][e] += sacc;
+        for (int fm = 0; fm < 8; ++fm) v = fma(acc[fm][fn][e], acc[fm][fn][e], v);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if (fc.lane < 4) dst[8 * fn + 2 * fc.lane + e] = v;
       }
   });
-
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int wm = warp >> 2, wn = warp & 3;
-#pragma unroll
-  for (int fn = 0; fn < 4; ++fn)
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      double v = cs[fn][e];
-      v += __shfl_xor_sync(0xffffffffu, v, 4);
-      v += __shfl_xor_sync(0xffffffffu, v, 8);
-      v += __shfl_xor_sync(0xffffffffu, v, 16);
-      if (lane < 4) scratch[wm * 128 + 32 * wn + 8 * fn + 2 * lane + e] = v;
-    }
-  __syncthreads();
-  if (threadIdx.x < 128) p.sumsq[(size_t)cb * 128 + threadIdx.x] = scratch[threadIdx.x] + scratch[128 + threadIdx.x];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -318,6 +318,48 @@ __global__ void argmax_final_kernel(const double *blk_val, const long long *blk_
       *bidx = si[0];
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// full posterior covariance of a small candidate batch (cov / mean_and_cov, gaussian_process.jl:163-167,180-184)
+//   cov[i][j] = k(x*_i, x*_j) - (V^T V)[i][j] + 1e-18 [i == j],   diagonal through _clip_var
+// C = V^T V arrives tile-packed (lower block triangle computed; mirrored here so the result is exactly symmetric).
+// ---------------------------------------------------------------------------------------------
+struct CovFinishParams {
+  const double *Xs;     // d x M raw candidates
+  int M, d, ktilesC;    // ktilesC = M_pad / 16
+  const double *invl;
+  unsigned long long disc_bits;
+  double a2;
+  const double *C;      // P-layout M_pad x M_pad
+  const double *mu;     // [M] K*^T alpha
+  const double *prior_mean;  // [M] or null
+  double *mu_out;       // [M] or null
+  double *cov;          // M x M column-major
+  int *any_fail;
+};
+
+template <int KID, int DP>
+__global__ void __launch_bounds__(256) cov_finish_kernel(CovFinishParams p) {
+  const int i = blockIdx.x * 16 + (threadIdx.x & 15), j = blockIdx.y * 16 + (threadIdx.x >> 4);
+  if (i >= p.M || j >= p.M) return;
+  double xi[DP], xj[DP];
+  load_scaled_point<DP>(xi, p.Xs + (size_t)i * p.d, p.d, p.invl, p.disc_bits, true);
+  load_scaled_point<DP>(xj, p.Xs + (size_t)j * p.d, p.d, p.invl, p.disc_bits, true);
+  double d2 = 0.0;
+#pragma unroll
+  for (int q = 0; q < DP; ++q) {
+    const double df = xi[q] - xj[q];
+    d2 = fma(df, df, d2);
+  }
+  const int hi = max(i, j), lo = min(i, j);
+  double v = p.a2 * kappa<KID>(d2) - p.C[p_index(hi, lo, p.ktilesC)];
+  if (i == j) {
+    v += VAR_JITTER;
+    if (!clip_var(v)) *p.any_fail = 1;
+    if (p.mu_out) p.mu_out[i] = p.prior_mean ? p.prior_mean[i] + p.mu[i] : p.mu[i];
+  }
+  p.cov[(size_t)j * p.M + i] = v;
 }
 
 // Scale + round training inputs once per fit: Xt[k][i] = round?(X[k*d+i]) * invl[i], zero padded.

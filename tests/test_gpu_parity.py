@@ -305,3 +305,55 @@ def test_ei_value_grad_guards(lib):
     assert val[1] == 0.0 and val[2] == 0.0 and np.all(grad[:, 1:] == 0.0)
     assert val[0] > 0.0 and np.any(grad[:, 0] != 0.0)
     gp.free()
+
+
+def test_small_batch_split_is_bitwise_invariant(lib):
+    """Small candidate batches are dealt to several CTAs per candidate block (row-block / training-chunk
+    splits).  Partial sums are kept per row block and added in a fixed order, so the same point scores
+    bit-identically whether it arrives alone, in a 1 000-start batch or inside a 40 000-candidate grid
+    (=> results do not depend on how a batch is sharded over GPUs)."""
+    n, d = 700, 4
+    X, Y, ls, amp, ns = make_problem(n, d, seed=91)
+    gp = lib.gp_fit(X, Y[0], ls[0], amp[0], ns[0], 2)
+    post = O.posterior_fit(X, Y[0], ls[0], amp[0], ns[0], 2)
+    rng = np.random.default_rng(92)
+    big = rng.random((d, 40000))                       # 313 candidate blocks: unsplit
+    best = float(np.quantile(Y[0], 0.9))
+    acq_big, _, _ = lib.ei_score([gp], 1, 1, big, [1.0], best, None)
+    for m in (1, 100, 1000):                           # 1 / 1 / 8 candidate blocks: split over CTAs
+        acq_s, _, bi = lib.ei_score([gp], 1, 1, big[:, :m], [1.0], best, None)
+        assert np.array_equal(acq_s, acq_big[:m])
+        assert bi == int(np.argmax(acq_big[:m]))
+        val, grad = lib.ei_value_grad([gp], 1, 1, big[:, :m], [1.0], best, None)
+        assert np.array_equal(val, acq_big[:m])
+    val_big, grad_big = lib.ei_value_grad([gp], 1, 1, big[:, :38000], [1.0], best, None)
+    val_s, grad_s = lib.ei_value_grad([gp], 1, 1, big[:, :1000], [1.0], best, None)
+    assert np.array_equal(grad_s, grad_big[:, :1000])
+    ref, gref = O.ei_value_grad([post], big[:, :1000], [1.0], best, None)
+    assert relerr(val_s, ref) <= TOL_POST
+    assert np.max(np.abs(grad_s - gref) / np.max(np.abs(gref), axis=1, keepdims=True)) <= 1e-8
+    gp.free()
+
+
+@pytest.mark.parametrize("n,d,kid,M", [(60, 2, 2, 5), (300, 4, 0, 200), (700, 3, 1, 333)])
+def test_posterior_cov(lib, n, d, kid, M):
+    """cov / mean_and_cov(::GaussianProcessPosterior, X) (gaussian_process.jl:163-167,180-184)."""
+    X, Y, ls, amp, ns = make_problem(n, d, seed=600 + n)
+    gp = lib.gp_fit(X, Y[0], ls[0], amp[0], ns[0], kid)
+    post = O.posterior_fit(X, Y[0], ls[0], amp[0], ns[0], kid)
+    Xs = np.random.default_rng(6).random((d, M))
+    pm = np.linspace(-1, 1, M)
+    mu, cov, rc = lib.gp_cov(gp, Xs, prior_mean_s=pm)
+    C_ref, st = O.posterior_cov(post, Xs)
+    mu_ref, var_ref, _ = O.mean_and_var(post, Xs, pm)
+    assert rc == 0 and not st.any()
+    assert relerr(mu, mu_ref) <= TOL_POST
+    assert relerr(np.diag(cov), var_ref) <= TOL_POST
+    # off-diagonal entries cancel to ~0 between distant points: compare relative to sqrt(var_i var_j)
+    scale = np.sqrt(np.outer(var_ref, var_ref))
+    assert np.max(np.abs(cov - C_ref) / scale) <= TOL_POST
+    assert np.array_equal(cov, cov.T)
+    # the diagonal agrees with the variance path (different summation order: V^T V tile product vs fused squares)
+    _, var, _ = lib.gp_predict(gp, Xs)
+    assert relerr(np.diag(cov), var) <= 1e-11
+    gp.free()
