@@ -20,6 +20,7 @@
 #include "cholesky.cuh"
 #include "score.cuh"
 #include "grad.cuh"
+#include "small.cuh"
 
 using namespace boss;
 
@@ -154,6 +155,10 @@ unsigned long long mask_bits(const uint8_t *mask, int d) {
 template <int KID, int DP>
 void launch_build_k_t(const BuildKParams &p, dim3 grid) {
   build_k_kernel<KID, DP><<<grid, 256, 0, g.stream>>>(p);
+}
+template <int KID, int DP>
+void launch_loglik_small_t(const SmallLoglikParams &p, int nblocks) {
+  loglik_small_kernel<KID, DP><<<nblocks, SMALL_WARPS * 32, 0, g.stream>>>(p);
 }
 template <int KID, int DP>
 void launch_xcov_t(const XcovParams &p, dim3 grid) {
@@ -1024,12 +1029,16 @@ static int loglik_impl(const double *X, int d, int n, const double *Ymm, int64_t
   if ((size_t)(n_pad + 128) * 8 > 200 * 1024) return fail(BOSS_ERR_ARG, "boss_gp_loglik_batch: n too large");
   const unsigned long long disc = mask_bits(discrete_mask, d);
 
+  const bool small = n <= SMALL_N;   // warp-register path (small.cuh): no workspace at all
   // sub-batch so that L + Winv stay within a 32 GiB workspace
   const size_t per = mat * 8 + (size_t)nblk * TM * TM * 8;
   long long Sb = std::max<long long>(1, std::min<long long>(S, (32ll << 30) / (long long)per));
   Sb = std::min<long long>(Sb, 32768);
-  CUDA_TRY(g.chol_L.ensure((size_t)Sb * mat * 8));
-  CUDA_TRY(g.chol_Winv.ensure((size_t)Sb * nblk * TM * TM * 8));
+  if (small) Sb = 1;
+  if (!small) {
+    CUDA_TRY(g.chol_L.ensure((size_t)Sb * mat * 8));
+    CUDA_TRY(g.chol_Winv.ensure((size_t)Sb * nblk * TM * TM * 8));
+  }
 
   // device copies of the inputs when called with host pointers
   const double *dX = X, *dY = Ymm, *dls = ls, *damp = amp, *dnoise = noise;
@@ -1063,7 +1072,24 @@ static int loglik_impl(const double *X, int d, int n, const double *Ymm, int64_t
   int *status = reinterpret_cast<int *>(misc + ost);
 
   timing_begin();
-  for (long long s0 = 0; s0 < S; s0 += Sb) {
+  if (small) {
+    SmallLoglikParams sp{};
+    sp.X = dX;
+    sp.d = d;
+    sp.n = n;
+    sp.ymm = dY;
+    sp.ldy = ldy;
+    sp.ls = dls;
+    sp.amp = damp;
+    sp.noise = dnoise;
+    sp.disc_bits = disc;
+    sp.S = S;
+    sp.loglik = dll;
+    Timed t(2);
+    DISPATCH_KID_DP(launch_loglik_small_t, kernel_id, dp, sp, (int)((S + SMALL_WARPS - 1) / SMALL_WARPS));
+    ++g.launches;
+  }
+  for (long long s0 = 0; s0 < S && !small; s0 += Sb) {
     const int sb = (int)std::min<long long>(Sb, S - s0);
     CUDA_TRY(cudaMemsetAsync(status, 0, (size_t)sb * 4, g.stream));
     BuildKParams bk{};

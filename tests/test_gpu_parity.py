@@ -357,3 +357,40 @@ def test_posterior_cov(lib, n, d, kid, M):
     _, var, _ = lib.gp_predict(gp, Xs)
     assert relerr(np.diag(cov), var) <= 1e-11
     gp.free()
+
+
+# ---------------------------------------------------------------------------------------------
+# warp-register small-n log-likelihood path (n <= 32, csrc/small.cuh)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,d,kid,S", [(1, 1, 2, 3), (2, 3, 0, 9), (17, 5, 1, 100), (30, 2, 0, 1000), (32, 9, 2, 257),
+                                       (33, 2, 2, 40)])
+def test_loglik_small_n_warp_path(lib, n, d, kid, S):
+    X, Y, _, _, _ = make_problem(n, d, seed=700 + n)
+    L, A, N = make_hyper_samples(S, d, seed=701 + n)
+    ref = O.gp_loglik_batch(X, Y[0], L, A, N, kid)
+    out = lib.loglik_batch(X, Y[0], L, A, N, kid)
+    assert relerr(out, ref) <= TOL_LL, relerr(out, ref)
+    # the blocked (128-padded) factorisation used by boss_gp_fit agrees with the warp path
+    for s in range(min(S, 3)):
+        gp = lib.gp_fit(X, Y[0], L[s], A[s], N[s], kid)
+        assert abs(gp.loglik - out[s]) <= 1e-11 * abs(out[s])
+        gp.free()
+
+
+def test_loglik_small_n_discrete_mean_and_failures(lib):
+    n, d, S = 24, 3, 12
+    X, Y, _, _, _ = make_problem(n, d, seed=801)
+    X = X * 4.0
+    mask = np.array([True, False, True])
+    L, A, N = make_hyper_samples(S, d, seed=802)
+    Ymm = Y[0][None, :] - np.linspace(-1, 1, S)[:, None]
+    ref = O.gp_loglik_batch(X, Ymm, L, A, N, 2, discrete_mask=mask)
+    out = lib.loglik_batch(X, Ymm, L, A, N, 2, discrete_mask=mask)
+    assert relerr(out, ref) <= TOL_LL
+    # 24 identical points, zero noise, huge amplitude: K = a^2 * ones is numerically singular -> -Inf for that sample only
+    Xz = np.zeros((1, 24)); yz = np.arange(24.0)
+    out = lib.loglik_batch(Xz, yz, np.array([[1.0], [1.0]]), np.array([1e6, 1.0]), np.array([0.0, 0.5]), 0)
+    assert out[0] == -np.inf and np.isfinite(out[1])
+    assert abs(out[1] - O.gp_loglik(Xz, yz, [1.0], 1.0, 0.5, 0)) <= TOL_LL * abs(out[1])
+    with pytest.raises(lib.BossError):
+        lib.loglik_batch(X, Y[0], -L, A, N, 2)
