@@ -11,6 +11,7 @@
 #pragma once
 #include "gemm_core.cuh"
 #include "kernel_fn.cuh"
+#include "potrf128.cuh"
 
 namespace boss {
 
@@ -177,16 +178,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dbg_gemm_kernel(DbgGemmParams
 // ---------------------------------------------------------------------------------------------
 // POTRF of one 128x128 diagonal block per matrix + its triangular inverse (shared memory)
 // ---------------------------------------------------------------------------------------------
-struct PotrfParams {
-  double *L;
-  size_t L_stride;
-  double *Winv;
-  size_t Winv_stride;
-  int nblk, ktiles, j;
-  double *logdet_blk;  // S x nblk : sum_k log L_kk of this block
-  int *status;         // S : BOSS_NOT_POSDEF on a non-positive / NaN pivot
-  double *W, *WT;      // optional (single matrix): also deposit Winv_jj into W(j,j), its transpose into WT(j,j)
-};
 constexpr int POTRF_LD = 129;
 constexpr int POTRF_SMEM_BYTES = (128 * POTRF_LD + 128 + 3 * 32 * 33) * 8;
 

@@ -65,6 +65,39 @@ __global__ void sqrt_kernel(double *out, int iters, double seed) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// Do DFMA (FP64 vector pipe) and DMMA (FP64 tensor path) share execution resources?  Even warps issue DMMA,
+// odd warps DFMA; if the combined rate exceeds either ceiling the two can overlap inside one SM.
+__global__ void __launch_bounds__(256, 2) mixed_kernel(double *out, int iters_dmma, int iters_dfma, double seed) {
+  const int warp = threadIdx.x >> 5;
+  double s = 0;
+  if (warp & 1) {
+    double a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = seed + i * 1e-3 + threadIdx.x * 1e-6;
+    const double b = 1.0000001, c = 1e-9;
+    for (int it = 0; it < iters_dfma; ++it) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a[i] = fma(a[i], b, c);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += a[i];
+  } else {
+    double c0[16], c1[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c0[i] = c1[i] = 0.0;
+    double a = seed + threadIdx.x * 1e-6, b = 1.0 - threadIdx.x * 1e-7;
+    for (int it = 0; it < iters_dmma; ++it) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c0[i]), "+d"(c1[i]) : "d"(a), "d"(b));
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += c0[i] + c1[i];
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <class F>
 float time_ms(F launch, int reps) {
   cudaEvent_t a, b;
@@ -120,6 +153,20 @@ int main() {
     printf(", \"exp_gops\": %.2f", 8.0 * 1024 * blocks * threads / ms * 1e-6);
     ms = time_ms([&] { sqrt_kernel<<<blocks, threads>>>(out, 1024, 1.0); }, 5);
     printf(", \"sqrt_gops\": %.2f", 8.0 * 1024 * blocks * threads / ms * 1e-6);
+  }
+  {
+    // 16 warps per SM: 8 DMMA warps + 8 DFMA warps; each side sized to ~the same solo duration
+    const int threads = 256, blocks = sms * 2;
+    const int it_mma = 4096, it_fma = 4096 * 8;   // per warp: 2*256*16*it_mma vs 2*16*32*it_fma flop (equal)
+    float ms_mma = time_ms([&] { mixed_kernel<<<blocks, threads>>>(out, it_mma, 0, 1.0); }, 5);
+    float ms_fma = time_ms([&] { mixed_kernel<<<blocks, threads>>>(out, 0, it_fma, 1.0); }, 5);
+    float ms_both = time_ms([&] { mixed_kernel<<<blocks, threads>>>(out, it_mma, it_fma, 1.0); }, 5);
+    const double fl_mma = 2.0 * 256 * 16 * it_mma * (double)blocks * 4, fl_fma = 2.0 * 16 * 32 * (double)it_fma * blocks * 4;
+    cudaError_t me = cudaGetLastError();
+    if (me != cudaSuccess) printf(", \"mixed_error\": \"%s\"", cudaGetErrorString(me));
+    printf(", \"mixed_dmma_only_tflops\": %.3f, \"mixed_dfma_only_tflops\": %.3f, \"mixed_both_tflops\": %.3f, "
+           "\"mixed_ms\": [%.4f, %.4f, %.4f]",
+           fl_mma / ms_mma * 1e-9, fl_fma / ms_fma * 1e-9, (fl_mma + fl_fma) / ms_both * 1e-9, ms_mma, ms_fma, ms_both);
   }
   printf("}\n");
   return 0;
