@@ -68,7 +68,6 @@ struct Ctx {
   std::string err;
   int64_t launches = 0;
   bool timing = false;
-  bool potrf_v1 = false;   // BOSS_POTRF_V1=1: previous scalar diagonal-block kernel (A/B comparison only)
   // workspaces
   DevBuf ks, muv, sumsq, xs_stage, pm_stage, cm_stage, acq_stage, mu_stage, var_stage, st_stage, grad_stage;
   DevBuf blk_val, blk_idx, small, chol_L, chol_Winv, chol_misc, tt, vt, ut, dmu, dvar, pmg_stage;
@@ -233,7 +232,6 @@ int set_kernel_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(dbg_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(score_trmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(wtv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  CUDA_TRY(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(fwd_solve_loglik_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   g_attr_done = true;
@@ -276,10 +274,7 @@ int run_cholesky(double *L, size_t L_stride, double *Winv, size_t Winv_stride, i
       chol_update_kernel<<<dim3(nblk - j, S), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(gp);
       ++g.launches;
     }
-    if (g.potrf_v1)
-      potrf_diag_kernel<<<S, 256, POTRF_SMEM_BYTES, g.stream>>>(pp);
-    else
-      potrf_tile_kernel<<<S, 256, PT_SMEM_BYTES, g.stream>>>(pp);
+    potrf_tile_kernel<<<S, 256, PT_SMEM_BYTES, g.stream>>>(pp);
     ++g.launches;
     if (j < nblk - 1) {
       Timed t(2);
@@ -350,7 +345,6 @@ int boss_init(int device) {
   CUDA_TRY(cudaEventCreate(&g.call_b));
   g.ev_ready = true;
   g.device = device;
-  g.potrf_v1 = getenv("BOSS_POTRF_V1") != nullptr;
   return set_kernel_attrs();
 }
 

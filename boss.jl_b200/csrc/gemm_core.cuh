@@ -184,4 +184,161 @@ __device__ __forceinline__ void rmw_sub_block(double *dst, double (&acc)[8][4][2
       for (int e = 0; e < 2; ++e) dst[block_offset(fc.row(fm), fc.col(fn, e))] = acc[fm][fn][e];
 }
 
+// ---------------------------------------------------------------------------------------------
+// Triangular variants of the mainloop for the two places where half of a 128x128 tile's work is
+// structurally zero:
+//   syrk_diag_pipeline  C = A B^T where only the lower triangle of C is wanted (diagonal tile of the
+//                       Cholesky trailing update):            micro-tile (R, C) is live iff R >= C
+//   trsm_tri_pipeline   C = A B^T with B lower triangular (panel solve L_ij = A_ij Winv_jj^T, K = 128):
+//                       k-micro-step kk contributes to column slab C iff kk <= C
+// Warp w owns the two 8-column slabs c0 = w and c1 = 15 - w, which deals the 136 live micro-tiles
+// (of 256) evenly: 17 per warp, 34 per SM sub-partition.  Same TMA ring, same P-layout fragment loads
+// (LDS.128); the live set is enumerated branch-free so loads and DMMAs schedule freely.
+// ---------------------------------------------------------------------------------------------
+struct TmaRing {
+  double *ring;
+  uint64_t *bars;
+  int issued;
+  __device__ __forceinline__ void init() {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    ring = reinterpret_cast<double *>(smem_raw);
+    bars = reinterpret_cast<uint64_t *>(smem_raw + GEMM_RING_BYTES + GEMM_SCRATCH_BYTES);
+    issued = 0;
+    if (threadIdx.x == 0) {
+      for (int s = 0; s < GEMM_STAGES; ++s) mbar_init(smem_u32(&bars[s]), 1);
+      mbar_fence_init();
+    }
+    __syncthreads();
+  }
+  template <class It>
+  __device__ __forceinline__ void issue(It &it) {   // thread 0 only
+    const int slot = issued % GEMM_STAGES;
+    const uint32_t bar = smem_u32(&bars[slot]);
+    const uint32_t dst = smem_u32(ring + (size_t)slot * GEMM_STAGE_ELEMS);
+    mbar_arrive_expect_tx(bar, GEMM_STAGE_BYTES);
+    bulk_g2s(dst, it.A(), TILE_BYTES, bar);
+    bulk_g2s(dst + TILE_BYTES, it.B(), TILE_BYTES, bar);
+    it.next();
+    ++issued;
+  }
+  __device__ __forceinline__ const double *wait(int g) const {
+    mbar_wait(smem_u32(&bars[g % GEMM_STAGES]), (uint32_t)((g / GEMM_STAGES) & 1));
+    return ring + (size_t)(g % GEMM_STAGES) * GEMM_STAGE_ELEMS;
+  }
+};
+
+// Live micro-tile t (0..16) of warp w in the lower-triangular output: t < 16 - w -> (row slab w + t, slab c0 = w),
+// else (row slab (15 - w) + (t - (16 - w)), slab c1 = 15 - w).
+struct SyrkCoord {
+  int w, lane;
+  __device__ __forceinline__ int rslab(int t) const { return t < 16 - w ? w + t : t - 1; }   // (15-w)+(t-(16-w)) = t-1
+  __device__ __forceinline__ int cslab(int t) const { return t < 16 - w ? w : 15 - w; }
+  __device__ __forceinline__ int row(int t) const { return 8 * rslab(t) + (lane >> 2); }
+  __device__ __forceinline__ int col(int t, int e) const { return 8 * cslab(t) + 2 * (lane & 3) + e; }
+};
+
+template <class Epi>
+__device__ __forceinline__ void syrk_diag_pipeline(LinearIt issue_it, LinearIt cons_it, Epi &&epi) {
+  TmaRing rg;
+  rg.init();
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid == 0)
+    while (rg.issued < GEMM_STAGES - 1 && issue_it.valid()) rg.issue(issue_it);
+  double acc[17][2];
+#pragma unroll
+  for (int t = 0; t < 17; ++t) acc[t][0] = acc[t][1] = 0.0;
+  const SyrkCoord sc{w, lane};
+  int aoff[17];
+#pragma unroll
+  for (int t = 0; t < 17; ++t) aoff[t] = sc.rslab(t) * 128 + 2 * lane;
+  const int b0off = TILE_ELEMS + w * 128 + 2 * lane, b1off = TILE_ELEMS + (15 - w) * 128 + 2 * lane;
+  const int n0 = 16 - w;
+  int g = 0;
+  while (cons_it.valid()) {
+    if (tid == 0 && issue_it.valid()) rg.issue(issue_it);
+    const double *st = rg.wait(g);
+#pragma unroll
+    for (int mc = 0; mc < 2; ++mc) {
+      const double2 b0 = lds128(st + b0off + mc * 64), b1 = lds128(st + b1off + mc * 64);
+      double2 a[17];
+#pragma unroll
+      for (int t = 0; t < 17; ++t) a[t] = lds128(st + aoff[t] + mc * 64);
+#pragma unroll
+      for (int t = 0; t < 17; ++t) dmma884(acc[t][0], acc[t][1], a[t].x, t < n0 ? b0.x : b1.x);
+#pragma unroll
+      for (int t = 0; t < 17; ++t) dmma884(acc[t][0], acc[t][1], a[t].y, t < n0 ? b0.y : b1.y);
+    }
+    __syncthreads();
+    cons_it.next();
+    ++g;
+  }
+  epi(acc, sc);
+}
+
+struct TrsmCoord {
+  int c0, c1, lane;
+  __device__ __forceinline__ int row(int R) const { return 8 * R + (lane >> 2); }
+  __device__ __forceinline__ int col(int h, int e) const { return 8 * (h ? c1 : c0) + 2 * (lane & 3) + e; }
+};
+
+// K = 128 exactly (8 stages): B = Winv_jj (lower triangular, K-major rows = output columns)
+template <class Epi>
+__device__ __forceinline__ void trsm_tri_pipeline(LinearIt issue_it, LinearIt cons_it, Epi &&epi) {
+  TmaRing rg;
+  rg.init();
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int c0 = w, c1 = 15 - w;   // c0 < c1
+  if (tid == 0)
+    while (rg.issued < GEMM_STAGES - 1 && issue_it.valid()) rg.issue(issue_it);
+  double acc[16][2][2];
+#pragma unroll
+  for (int R = 0; R < 16; ++R) acc[R][0][0] = acc[R][0][1] = acc[R][1][0] = acc[R][1][1] = 0.0;
+  int g = 0;
+  while (cons_it.valid()) {
+    if (tid == 0 && issue_it.valid()) rg.issue(issue_it);
+    const double *As = rg.wait(g) + 2 * lane;
+    const double *Bs = As + TILE_ELEMS;
+#pragma unroll
+    for (int mc = 0; mc < 2; ++mc) {
+      const int kk = 2 * g + mc;   // k micro-step 0..15
+      if (kk <= c0) {              // both column slabs live
+        const double2 b0 = lds128(Bs + (c0 * 2 + mc) * 64), b1 = lds128(Bs + (c1 * 2 + mc) * 64);
+#pragma unroll
+        for (int Rg = 0; Rg < 16; Rg += 8) {
+          double2 a[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) a[q] = lds128(As + ((Rg + q) * 2 + mc) * 64);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            dmma884(acc[Rg + q][0][0], acc[Rg + q][0][1], a[q].x, b0.x);
+            dmma884(acc[Rg + q][1][0], acc[Rg + q][1][1], a[q].x, b1.x);
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            dmma884(acc[Rg + q][0][0], acc[Rg + q][0][1], a[q].y, b0.y);
+            dmma884(acc[Rg + q][1][0], acc[Rg + q][1][1], a[q].y, b1.y);
+          }
+        }
+      } else if (kk <= c1) {       // only the far slab
+        const double2 b1 = lds128(Bs + (c1 * 2 + mc) * 64);
+#pragma unroll
+        for (int Rg = 0; Rg < 16; Rg += 8) {
+          double2 a[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) a[q] = lds128(As + ((Rg + q) * 2 + mc) * 64);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) dmma884(acc[Rg + q][1][0], acc[Rg + q][1][1], a[q].x, b1.x);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) dmma884(acc[Rg + q][1][0], acc[Rg + q][1][1], a[q].y, b1.y);
+        }
+      }
+    }
+    __syncthreads();
+    cons_it.next();
+    ++g;
+  }
+  TrsmCoord tc{c0, c1, lane};
+  epi(acc, tc);
+}
+
 }  // namespace boss

@@ -22,9 +22,12 @@ def peak():
         return float(json.load(f)["fp64_tflops_peak_used"])
 
 
-def timed(torch, stream, fn, steps, warmup=3):
-    for _ in range(warmup):
-        fn()
+def timed(torch, stream, fn, steps, warmup=3, warm_ms=150.0):
+    """>= `warmup` untimed calls and >= `warm_ms` of untimed work (SM clocks drop within milliseconds of idling --
+    e.g. while the CPU oracle computes the parity subset -- and a few short calls do not bring them back)."""
+    t0 = time.perf_counter(); k = 0
+    while k < warmup or (time.perf_counter() - t0) * 1e3 < warm_ms:
+        fn(); k += 1
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
