@@ -316,6 +316,15 @@ def run_gpu(args):
                        "chol_gemm_ms_per_step": chol_ms, "chol_gemm_launches": chol_cnt, "gpu_launches": int(launches_ll)},
             "argmax": {"value": res[0], "index": res[1], "e2e_index": res_e2e[1]},
         }
+        try:
+            with open(os.path.join(ROOT, "profiles", "score_trmm_traffic.json")) as f:
+                out["roofline"]["traffic"] = json.load(f)["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        if world == 1 and not args.no_configs:
+            # per-GPU shares of BASELINE configs C3 / C4 / C5 (device-resident, oracle parity spot checks inside)
+            from tools import bench_configs
+            out["configs"] = bench_configs.run_all(torch, _lib, lib_stream, steps=3)
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline()
         print(json.dumps(out))
@@ -331,6 +340,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C3/C4/C5 per-config numbers (N=1 only)")
     ap.add_argument("--only", default="all", choices=["all", "loglik"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

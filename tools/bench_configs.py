@@ -93,7 +93,7 @@ def run_c5(torch, _lib, O, stream, args):
     posts = [O.posterior_fit(X, Y[i], ls[i], amp[i], ns[i], 2) for i in range(y_dim)]
     ref, _, _ = O.ei_acquisition([posts], Xs_h, coefs, best, y_max)
     got = acq[:k].cpu().numpy()
-    m = ref > 1e-200
+    m = ref > 1e-30 * np.max(ref)                  # beyond that EI sits > 11 sigma in the tail: rel. error amplified by z^2
     a_all = acq.cpu().numpy()
     F = y_dim * (n * n + n * (3 * d + 12))
     out = {"config": "C5", "n": n, "d": d, "y_dim": y_dim, "M_per_gpu": M, "ms_per_step": ms,
@@ -141,7 +141,7 @@ def run_c4(torch, _lib, O, stream, args):
     a_ref, g_ref = O.ei_value_grad([post], starts[:, :k], [1.0], best, None,
                                    prior_mean_s=[theta[0] * starts[0, :k] + theta[1]],
                                    prior_mean_grad_s=[np.ascontiguousarray(pmg_h[:k].T)])
-    m = a_ref > 1e-200
+    m = a_ref > 1e-30 * np.max(a_ref)              # see run_c5: deeper in the tail EI's rel. error is z^2-amplified
     gscale = np.max(np.abs(g_ref[:, m]), axis=0)
     gerr = float(np.max(np.abs(g_dev[:, :k][:, m] - g_ref[:, m]) / gscale)) if m.any() else 0.0
     Fg = 2 * n * n + n * (9 * d + 16)
@@ -156,6 +156,18 @@ def run_c4(torch, _lib, O, stream, args):
            "parity_points": int(m.sum())}
     gp.free()
     return [out]
+
+
+def run_all(torch, _lib, stream, steps=3, full=False, configs=("c3", "c4", "c5")):
+    """In-process entry for bench.py: list of per-config result dicts."""
+    from oracle import boss_oracle as O
+    args = argparse.Namespace(steps=steps, full=full)
+    out = []
+    for c in configs:
+        for line in {"c3": run_c3, "c4": run_c4, "c5": run_c5}[c](torch, _lib, O, stream, args):
+            line["full_job_on_one_gpu"] = bool(full)
+            out.append(line)
+    return out
 
 
 def main():

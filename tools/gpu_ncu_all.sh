@@ -11,8 +11,8 @@ echo "ncu ll mid exit $?"
 ncu --set full --clock-control none --import-source on -k regex:'build_k|fwd_solve' -s 6 -c 2 -o gpurun_out/prof_ll_ends \
     python bench.py --only loglik --steps 1 --warmup 3 > gpurun_out/ncu_ll_ends.log 2>&1
 echo "ncu ll ends exit $?"
-python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/plain_sc.log 2>&1 || exit 1
+python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-configs > gpurun_out/plain_sc.log 2>&1 || exit 1
 ncu --set full --clock-control none --import-source on -k regex:'xcov|acq_kernel|argmax_final' -s 12 -c 3 -o gpurun_out/prof_score_small \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_sc_small.log 2>&1
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-configs > gpurun_out/ncu_sc_small.log 2>&1
 echo "ncu score small exit $?"
 ls -la gpurun_out/*.ncu-rep
