@@ -118,12 +118,12 @@ def run_reference(args):
     cb = {"value": val, "unit": "candidates/s", "cores": cpu_threads(), "kind": "port",
           "sample": f"each step = one {CPU_SAMPLE_M}-candidate batched tile (mode B, level-3 BLAS, all host threads) of the "
                     f"2 Mi-candidate per-GPU workload; oracle port - the Julia reference cannot run in this image"}
-    print(json.dumps({
+    print(file=args.out, flush=True, *[json.dumps({
         "impl": "reference", "metric": "EI candidate evals/sec (n=2048,d=8)", "value": val, "unit": "candidates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args.gpus), "cpu_baseline": cb,
-        "e2e": {"value": val, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        "e2e": {"value": val, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})])
 
 
 def workload_config(n_gpus):
@@ -219,6 +219,7 @@ def run_gpu(args):
     t_ll = torch.empty(S, dtype=torch.float64, device="cuda")
 
     gathered = [torch.zeros(2, dtype=torch.float64, device="cuda") for _ in range(world)]
+    last_pairs = []          # (best value, global index) of every rank in the last reduction
 
     def reduce_pairs(bv, bi):
         """(best value, global index) all-gather + deterministic local reduce (NCCL has no arg-max op)."""
@@ -227,6 +228,7 @@ def run_gpu(args):
         mine = torch.tensor([bv, float(rank * M + bi)], dtype=torch.float64, device="cuda")
         dist.all_gather(gathered, mine)
         vals = torch.stack(gathered).cpu().numpy()
+        last_pairs[:] = vals.tolist()
         k = 0
         for r in range(1, world):
             a, b = vals[k, 0], vals[r, 0]
@@ -274,7 +276,7 @@ def run_gpu(args):
         ms_ll, launches_ll, _ = timed(step_loglik, args.steps, args.warmup)
         if rank == 0:
             print(json.dumps({"only": "loglik", "ms_per_step": ms_ll, "evals_per_s": S * world / (ms_ll * 1e-3),
-                              "gpu_launches": int(launches_ll)}))
+                              "gpu_launches": int(launches_ll)}), file=args.out, flush=True)
         return
     sampler = ClockSampler(local) if rank == 0 else None
     _lib.set_timing(True)
@@ -314,7 +316,7 @@ def run_gpu(args):
                        "achieved_tflops_per_gpu": F_LL * S / (ms_ll * 1e-3) * 1e-12,
                        "frac_of_peak": F_LL * S / (ms_ll * 1e-3) * 1e-12 / peak,
                        "chol_gemm_ms_per_step": chol_ms, "chol_gemm_launches": chol_cnt, "gpu_launches": int(launches_ll)},
-            "argmax": {"value": res[0], "index": res[1], "e2e_index": res_e2e[1]},
+            "argmax": {"value": res[0], "index": res[1], "e2e_index": res_e2e[1], "per_rank_pairs": list(last_pairs)},
         }
         try:
             with open(os.path.join(ROOT, "profiles", "score_trmm_traffic.json")) as f:
@@ -327,10 +329,29 @@ def run_gpu(args):
             out["configs"] = bench_configs.run_all(torch, _lib, lib_stream, steps=3)
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(out))
+        print(json.dumps(out), file=args.out, flush=True)
     gp.free()
     if world > 1:
         dist.destroy_process_group()
+
+
+class StdoutToStderr:
+    """The contract is ONE JSON line on stdout.  NCCL (`NCCL version ...` with NCCL_DEBUG set) and other native
+    libraries write to file descriptor 1 directly; route fd 1 to stderr while the benchmark runs and hand the
+    real stdout back only to the final print."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        self.real = os.fdopen(self.saved, "w")
+        return self.real
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        self.real.flush()
+        os.dup2(self.real.fileno(), 1)
+        return False
 
 
 def main():
@@ -344,10 +365,12 @@ def main():
     ap.add_argument("--only", default="all", choices=["all", "loglik"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_gpu(args)
+    with StdoutToStderr() as real_stdout:
+        args.out = real_stdout
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_gpu(args)
 
 
 if __name__ == "__main__":

@@ -35,6 +35,7 @@ EXPORTS = {
     "boss_stream": (_vp, []),
     "boss_gp_fit": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, C.c_double, C.c_double, C.c_int, _vp,
                               C.POINTER(_vp), _dp]),
+    "boss_gp_append": (C.c_int, [_vp, _vp, C.c_double, _dp]),
     "boss_gp_free": (None, [_vp]),
     "boss_gp_n": (C.c_int, [_vp]),
     "boss_gp_d": (C.c_int, [_vp]),
@@ -150,6 +151,18 @@ def gp_fit(X, y_minus_mean, lengthscales, amplitude, noise_std, kernel_id=KERNEL
     if rc == BOSS_NOT_POSDEF:
         return None
     return GP(out, n, d, ll.value)
+
+
+def gp_append(gp: GP, x_new, y_minus_mean_new) -> bool:
+    """Rank-1 extension of the factor cache by one data point (same hyper-parameters).  False = not PD (unchanged)."""
+    x = _f64(np.asarray(x_new, dtype=np.float64).reshape(-1), (gp.d,))
+    ll = C.c_double()
+    rc = _check(lib.boss_gp_append(gp.handle, _ptr(x), float(y_minus_mean_new), C.byref(ll)), "boss_gp_append")
+    if rc == BOSS_NOT_POSDEF:
+        return False
+    gp.n += 1
+    gp.loglik = ll.value
+    return True
 
 
 def gp_predict(gp: GP, Xs, prior_mean_s=None):

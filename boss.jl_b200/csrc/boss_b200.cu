@@ -22,6 +22,7 @@
 #include "score.cuh"
 #include "grad.cuh"
 #include "small.cuh"
+#include "append.cuh"
 
 using namespace boss;
 
@@ -152,6 +153,14 @@ unsigned long long mask_bits(const uint8_t *mask, int d) {
   return b;
 }
 
+struct boss_gp_view {   // the fields append_kvec needs (boss_gp is defined after the anonymous namespace)
+  int d, n, n_pad;
+  const double *invl;
+  unsigned long long disc;
+  double a2;
+  double *Xt;
+};
+
 // ---- kernel dispatch on (kernel_id, DP) ----
 template <int KID, int DP>
 void launch_build_k_t(const BuildKParams &p, dim3 grid) {
@@ -160,6 +169,11 @@ void launch_build_k_t(const BuildKParams &p, dim3 grid) {
 template <int KID, int DP>
 void launch_loglik_small_t(const SmallLoglikParams &p, int nblocks) {
   loglik_small_kernel<KID, DP><<<nblocks, SMALL_WARPS * 32, 0, g.stream>>>(p);
+}
+template <int KID, int DP>
+void launch_append_kvec_t(const double *xnew, const boss_gp_view &v, double *kvec) {
+  append_kvec_kernel<KID, DP><<<(v.n_pad + 255) / 256, 256, 0, g.stream>>>(xnew, v.d, v.n, v.n_pad, v.invl, v.disc, v.a2,
+                                                                        v.Xt, kvec);
 }
 template <int KID, int DP>
 void launch_xcov_t(const XcovParams &p, dim3 grid) {
@@ -306,8 +320,9 @@ struct boss_gp {
   double amp = 0, noise = 0, a2 = 0;
   double loglik = 0;
   double *W = nullptr, *WT = nullptr, *L = nullptr, *alpha = nullptr, *Xt = nullptr, *invl = nullptr;
+  double *wvec = nullptr, *ymm = nullptr;   // w = L^-1 delta and delta = y - m(X), kept for boss_gp_append
   void free_dev() {
-    for (double **q : {&W, &WT, &L, &alpha, &Xt, &invl}) {
+    for (double **q : {&W, &WT, &L, &alpha, &Xt, &invl, &wvec, &ymm}) {
       if (*q) cudaFree(*q);
       *q = nullptr;
     }
@@ -429,6 +444,8 @@ int boss_gp_fit(const double *X, int d, int n, const double *y_minus_mean, const
   FIT_TRY(cudaMalloc(&h->alpha, npad * 8));
   FIT_TRY(cudaMalloc(&h->Xt, npad * dp * 8));
   FIT_TRY(cudaMalloc(&h->invl, dp * 8));
+  FIT_TRY(cudaMalloc(&h->wvec, npad * 8));
+  FIT_TRY(cudaMalloc(&h->ymm, npad * 8));
   FIT_TRY(cudaMemsetAsync(h->L, 0, mat * 8, g.stream));
   FIT_TRY(cudaMemsetAsync(h->W, 0, mat * 8, g.stream));
   FIT_TRY(cudaMemsetAsync(h->WT, 0, mat * 8, g.stream));
@@ -484,6 +501,8 @@ int boss_gp_fit(const double *X, int d, int n, const double *y_minus_mean, const
   }
   g.launches += 3;
   FIT_TRY(cudaGetLastError());
+  FIT_TRY(cudaMemcpyAsync(h->wvec, misc + off_w, npad * 8, cudaMemcpyDeviceToDevice, g.stream));
+  FIT_TRY(cudaMemcpyAsync(h->ymm, misc + off_y, npad * 8, cudaMemcpyDeviceToDevice, g.stream));
   std::vector<double> host(nblk + npad + 2);
   FIT_TRY(cudaMemcpyAsync(host.data(), misc + off_ld, (nblk + npad + 2) * 8, cudaMemcpyDeviceToHost, g.stream));
   FIT_TRY(cudaStreamSynchronize(g.stream));
@@ -513,6 +532,103 @@ void boss_gp_free(boss_gp *gp) {
   gp->free_dev();
   delete gp;
 }
+// Grow a handle's capacity by one 128-block (P-layout stride changes -> repack on the device).
+static int grow_handle(boss_gp *h) {
+  const int npad_new = h->n_pad + TM, kt_new = npad_new / TK;
+  const size_t mat_new = (size_t)npad_new * npad_new;
+  double *nL = nullptr, *nW = nullptr, *nWT = nullptr, *nal = nullptr, *nXt = nullptr, *nw = nullptr, *ny = nullptr;
+  auto cleanup = [&]() {
+    for (double *q : {nL, nW, nWT, nal, nXt, nw, ny})
+      if (q) cudaFree(q);
+  };
+#define GROW_TRY(expr)                                                                                       \
+  do {                                                                                                       \
+    cudaError_t _e = (expr);                                                                                 \
+    if (_e != cudaSuccess) {                                                                                 \
+      cleanup();                                                                                             \
+      return fail(BOSS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                        \
+    }                                                                                                        \
+  } while (0)
+  GROW_TRY(cudaMalloc(&nL, mat_new * 8));
+  GROW_TRY(cudaMalloc(&nW, mat_new * 8));
+  GROW_TRY(cudaMalloc(&nWT, mat_new * 8));
+  GROW_TRY(cudaMalloc(&nal, (size_t)npad_new * 8));
+  GROW_TRY(cudaMalloc(&nXt, (size_t)npad_new * h->dp * 8));
+  GROW_TRY(cudaMalloc(&nw, (size_t)npad_new * 8));
+  GROW_TRY(cudaMalloc(&ny, (size_t)npad_new * 8));
+  const unsigned nb = (unsigned)((mat_new + 255) / 256);
+  repack_grow_kernel<<<nb, 256, 0, g.stream>>>(h->L, h->ktiles, h->n_pad, nL, kt_new, npad_new);
+  repack_grow_kernel<<<nb, 256, 0, g.stream>>>(h->W, h->ktiles, h->n_pad, nW, kt_new, npad_new);
+  repack_grow_kernel<<<nb, 256, 0, g.stream>>>(h->WT, h->ktiles, h->n_pad, nWT, kt_new, npad_new);
+  g.launches += 3;
+  struct {
+    double *dst, *src;
+    size_t n_new, n_old;
+  } vecs[4] = {{nal, h->alpha, (size_t)npad_new, (size_t)h->n_pad},
+               {nXt, h->Xt, (size_t)npad_new * h->dp, (size_t)h->n_pad * h->dp},
+               {nw, h->wvec, (size_t)npad_new, (size_t)h->n_pad},
+               {ny, h->ymm, (size_t)npad_new, (size_t)h->n_pad}};
+  for (auto &v : vecs) {
+    GROW_TRY(cudaMemsetAsync(v.dst, 0, v.n_new * 8, g.stream));
+    GROW_TRY(cudaMemcpyAsync(v.dst, v.src, v.n_old * 8, cudaMemcpyDeviceToDevice, g.stream));
+  }
+  GROW_TRY(cudaGetLastError());
+  GROW_TRY(cudaStreamSynchronize(g.stream));
+#undef GROW_TRY
+  for (double *q : {h->L, h->W, h->WT, h->alpha, h->Xt, h->wvec, h->ymm}) cudaFree(q);
+  h->L = nL; h->W = nW; h->WT = nWT; h->alpha = nal; h->Xt = nXt; h->wvec = nw; h->ymm = ny;
+  h->n_pad = npad_new;
+  h->nblk = npad_new / TM;
+  h->ktiles = kt_new;
+  return 0;
+}
+
+int boss_gp_append(boss_gp *h, const double *x_new, double y_minus_mean_new, double *loglik_out) {
+  std::lock_guard<std::mutex> lk(g.mu);
+  REQUIRE_INIT();
+  if (!h || !x_new) return fail(BOSS_ERR_ARG, "boss_gp_append: bad arguments");
+  if (h->n == h->n_pad) {
+    int rc = grow_handle(h);
+    if (rc) return rc;
+  }
+  const int n = h->n, npad = h->n_pad, d = h->d;
+  // workspace: xnew[32] | kvec[npad] | l[npad] | u[npad] | sc[4] | status
+  const size_t o_k = 32, o_l = o_k + npad, o_u = o_l + npad, o_sc = o_u + npad, o_st = o_sc + 4, total = o_st + 1;
+  CUDA_TRY(g.chol_misc.ensure(total * 8));
+  double *ws = g.chol_misc.as<double>();
+  int *status = reinterpret_cast<int *>(ws + o_st);
+  CUDA_TRY(cudaMemsetAsync(status, 0, 8, g.stream));
+  CUDA_TRY(cudaMemcpyAsync(ws, x_new, (size_t)d * 8, cudaMemcpyHostToDevice, g.stream));
+  boss_gp_view v{d, n, npad, h->invl, h->disc, h->a2, h->Xt};
+  DISPATCH_KID_DP(launch_append_kvec_t, h->kernel_id, h->dp, ws, v, ws + o_k);
+  matvec_p_kernel<<<npad / 64, 256, 0, g.stream>>>(h->W, ws + o_k, ws + o_l, h->ktiles);
+  append_scalars_kernel<<<1, 256, 0, g.stream>>>(ws + o_l, h->wvec, n, h->a2 + h->noise * h->noise, y_minus_mean_new,
+                                                 ws + o_sc, status);
+  matvec_p_kernel<<<npad / 64, 256, 0, g.stream>>>(h->WT, ws + o_l, ws + o_u, h->ktiles);
+  append_scatter_kernel<<<(n + 256) / 256, 256, 0, g.stream>>>(h->L, h->W, h->WT, n, h->ktiles, ws + o_l, ws + o_u,
+                                                              ws + o_sc, status, h->wvec, h->ymm, y_minus_mean_new);
+  g.launches += 5;
+  CUDA_TRY(cudaGetLastError());
+  double hs[5];
+  CUDA_TRY(cudaMemcpyAsync(hs, ws + o_sc, 40, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  int st;
+  std::memcpy(&st, &hs[4], sizeof(int));
+  if (st != 0) {
+    if (loglik_out) *loglik_out = -std::numeric_limits<double>::infinity();
+    g.err = "boss_gp_append: the extended kernel matrix is not positive definite (handle left unchanged)";
+    return BOSS_NOT_POSDEF;
+  }
+  h->n = n + 1;
+  matvec_p_kernel<<<npad / 64, 256, 0, g.stream>>>(h->WT, h->wvec, h->alpha, h->ktiles);   // alpha = W^T w
+  ++g.launches;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  h->loglik += -0.5 * 1.8378770664093453 - std::log(hs[0]) - 0.5 * hs[1] * hs[1];
+  if (loglik_out) *loglik_out = h->loglik;
+  return 0;
+}
+
 int boss_gp_n(const boss_gp *gp) { return gp ? gp->n : -1; }
 int boss_gp_d(const boss_gp *gp) { return gp ? gp->d : -1; }
 

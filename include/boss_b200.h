@@ -67,6 +67,13 @@ void *boss_stream(void);              /* the cudaStream_t all library work is or
 int boss_gp_fit(const double *X, int d, int n, const double *y_minus_mean, const double *lengthscales,
                 double amplitude, double noise_std, int kernel_id, const uint8_t *discrete_mask,
                 boss_gp **out, double *loglik_out);
+/* Incremental factor cache: add ONE training point to a fitted GP with unchanged hyper-parameters in O(n^2)
+ * (new row of L and of W = L^-1, alpha and the log-likelihood updated in place) instead of the O(n^3)
+ * refactorisation the reference performs for every speculative point of SequentialBatchAM
+ * (src/acquisition_maximizers/batch.jl:26-38 -> augment_dataset!, src/types/problem.jl:191-198) and for
+ * every BO iteration (src/bo.jl:40-45).   x_new d coordinates; y_minus_mean_new = y - m(x_new).
+ * Returns BOSS_NOT_POSDEF (handle unchanged) when the extended matrix is not positive definite. */
+int boss_gp_append(boss_gp *gp, const double *x_new, double y_minus_mean_new, double *loglik_out);
 void boss_gp_free(boss_gp *gp);
 int boss_gp_n(const boss_gp *gp);
 int boss_gp_d(const boss_gp *gp);

@@ -394,3 +394,46 @@ def test_loglik_small_n_discrete_mean_and_failures(lib):
     assert abs(out[1] - O.gp_loglik(Xz, yz, [1.0], 1.0, 0.5, 0)) <= TOL_LL * abs(out[1])
     with pytest.raises(lib.BossError):
         lib.loglik_batch(X, Y[0], -L, A, N, 2)
+
+
+# ---------------------------------------------------------------------------------------------
+# incremental factor cache: boss_gp_append (SequentialBatchAM speculative points, BO iterations)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n0,m,d,kid", [(5, 40, 2, 2), (120, 20, 3, 0), (250, 10, 4, 1)])
+def test_append_matches_full_refit(lib, n0, m, d, kid):
+    """Appending points one at a time == fitting all of them at once (crosses the 128-block capacity boundary:
+    the handle is repacked to a larger P-layout)."""
+    n = n0 + m
+    X, Y, ls, amp, ns = make_problem(n, d, seed=900 + n0)
+    gp = lib.gp_fit(X[:, :n0], Y[0, :n0], ls[0], amp[0], ns[0], kid)
+    for k in range(n0, n):
+        assert lib.gp_append(gp, X[:, k], Y[0, k])
+    assert gp.n == n
+    post = O.posterior_fit(X, Y[0], ls[0], amp[0], ns[0], kid)
+    ll = O.gp_loglik(X, Y[0], ls[0], amp[0], ns[0], kid)
+    assert abs(gp.loglik - ll) <= TOL_LL * abs(ll)
+    L, W, al = lib.dbg_factors(gp)
+    assert np.max(np.abs(L - post.U.T)) <= 1e-10 * np.max(np.abs(post.U))
+    assert relerr(al, post.alpha_w) <= 1e-8
+    Xs = np.random.default_rng(3).random((d, 500))
+    mu, var, st = lib.gp_predict(gp, Xs)
+    mu_r, var_r, _ = O.mean_and_var(post, Xs)
+    assert relerr(mu, mu_r) <= TOL_POST and relerr(var, var_r) <= TOL_POST
+    best = float(np.quantile(Y[0], 0.8))
+    acq, _, bi = lib.ei_score([gp], 1, 1, Xs, [1.0], best, None)
+    ref, _, _ = O.ei_acquisition([[post]], Xs, [1.0], best, None)
+    mask = _ei_mask(ref)
+    assert relerr(acq[mask], ref[mask]) <= TOL_POST and bi == O.julia_argmax_fast(ref)
+    gp.free()
+
+
+def test_append_duplicate_point_without_noise_is_rejected(lib):
+    X, Y, ls, amp, ns = make_problem(30, 2, seed=5)
+    gp = lib.gp_fit(X, Y[0], ls[0], 1e6, 0.0, 0)       # huge amplitude, zero noise: a repeated point is singular
+    ll0 = gp.loglik
+    ok = lib.gp_append(gp, X[:, 3], Y[0, 3])
+    if not ok:                                          # rejected: handle unchanged
+        assert gp.n == 30 and gp.loglik == ll0
+        mu, var, _ = lib.gp_predict(gp, X[:, :5])
+        assert np.all(np.isfinite(mu))
+    gp.free()
