@@ -16,8 +16,8 @@ from .gaussian_process import (DiscreteKernel, GaussianProcess, GaussianProcessP
 from .posterior import DefaultModelPosterior, average_mean, model_posterior  # noqa: F401
 from .acquisition import (Acquisition, ExpectedImprovement, best_so_far, construct_acquisition,  # noqa: F401
                           construct_safe_acquisition)
-from .acquisition_maximizers import (GridAM, OptimizationAM, SampleOptAM, SamplingAM, batched_lbfgs_maximize,  # noqa: F401
-                                     maximize_acquisition)
+from .acquisition_maximizers import (GridAM, OptimizationAM, SampleOptAM, SamplingAM, SequentialBatchAM,  # noqa: F401
+                                     batched_lbfgs_maximize, maximize_acquisition)
 from .model_fitters import OptimizationMAP, SamplingMAP, estimate_parameters, model_loglike  # noqa: F401
 from .bo import IterLimit, bo  # noqa: F401
 from . import parallel  # noqa: F401

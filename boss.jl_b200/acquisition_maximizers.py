@@ -8,8 +8,12 @@ from typing import Optional
 
 import numpy as np
 
-from .acquisition import construct_safe_acquisition
-from .types import BossOptions, BossProblem, Domain, discrete_round, generate_LHC, in_domain
+import copy
+
+from . import _lib
+from .acquisition import Acquisition, best_so_far, construct_safe_acquisition
+from .posterior import average_mean, model_posterior
+from .types import BossOptions, BossProblem, Domain, ExperimentData, discrete_round, generate_LHC, in_domain
 
 
 class GridAM:
@@ -62,6 +66,17 @@ class SampleOptAM:
         self.sampler = SamplingAM(x_prior, samples, seed=seed)
         self.multistart = multistart
         self.iters = iters
+
+
+class SequentialBatchAM:
+    """batch.jl:1-38: pick `batch_size` candidates sequentially, extending the data set after each pick with the
+    speculative point (x, posterior mean at x).  The reference refits every GP from scratch per pick
+    (`model_posterior(problem)` in speculative_evaluation!); here the fitted factor caches are extended in place
+    with one O(n^2) boss_gp_append per slice (hyper-parameters do not change between picks)."""
+
+    def __init__(self, am, batch_size: int):
+        self.am = am
+        self.batch_size = batch_size
 
 
 def _rand_in_domain(am: SamplingAM, domain: Domain):
@@ -130,9 +145,33 @@ def batched_lbfgs_maximize(value_and_grad, starts, lb, ub, iters=60, history=8, 
     return X, f
 
 
-def maximize_acquisition(am, problem: BossProblem, options: BossOptions = BossOptions(), return_all: bool = False):
-    """-> (x, val).  src/types/acquisition_maximizer.jl:12-20"""
-    acq = construct_safe_acquisition(problem, options)
+def _sequential_batch(sb: SequentialBatchAM, problem: BossProblem, options: BossOptions):
+    prob = copy.copy(problem)                                       # deepcopy(problem) of batch.jl:27 (data only)
+    prob.data = ExperimentData(problem.data.X.copy(), problem.data.Y.copy())
+    posts = model_posterior(prob)                                   # ONE fit; extended in place below
+    post_list = posts if isinstance(posts, list) else [posts]
+    picks = []
+    for _ in range(sb.batch_size):
+        acq = Acquisition(prob, posts, prob.acquisition, best_so_far(prob, prob.acquisition.fitness))
+        x, _ = maximize_acquisition(sb.am, prob, options, acq=acq)
+        y = average_mean(post_list, x) if len(post_list) > 1 else post_list[0].mean(x)     # batch.jl:35
+        prob.data.augment(x, y)
+        for p in post_list:
+            for i, sl in enumerate(p.slices):
+                m = sl.model.mean_at(i, x[:, None])
+                if not _lib.gp_append(sl.gp, x, y[i] - (0.0 if m is None else float(m[0]))):
+                    raise ValueError("PosDefException: kernel matrix is not positive definite")
+        picks.append(x)
+    return np.stack(picks, axis=1), None
+
+
+def maximize_acquisition(am, problem: BossProblem, options: BossOptions = BossOptions(), return_all: bool = False,
+                         acq=None):
+    """-> (x, val).  src/types/acquisition_maximizer.jl:12-20.  `acq`: reuse an already constructed acquisition."""
+    if isinstance(am, SequentialBatchAM):
+        return _sequential_batch(am, problem, options)
+    if acq is None:
+        acq = construct_safe_acquisition(problem, options)
     dom = problem.domain
     if isinstance(am, GridAM):
         pts = am.points[:, am.rng.permutation(am.points.shape[1])] if am.shuffle else am.points   # grid.jl:47
@@ -148,9 +187,9 @@ def maximize_acquisition(am, problem: BossProblem, options: BossOptions = BossOp
         idx, val = acq.argmax(X)
         return X[:, idx].copy(), val
     if isinstance(am, SampleOptAM):
-        X, vals = maximize_acquisition(am.sampler, problem, options, return_all=True)
+        X, vals = maximize_acquisition(am.sampler, problem, options, return_all=True, acq=acq)
         top = np.argsort(-vals, kind="stable")[: am.multistart]
-        return maximize_acquisition(OptimizationAM(X[:, top], am.iters), problem, options)
+        return maximize_acquisition(OptimizationAM(X[:, top], am.iters), problem, options, acq=acq)
     if isinstance(am, OptimizationAM):
         lb, ub = dom.bounds
         if isinstance(am.multistart, int):

@@ -126,3 +126,23 @@ def test_semiparametric_loglike_uses_per_sample_mean():
     assert both[0] == good and both[1] == bad
     ref = O.gp_loglik(X, Y[0] - 2.0 * X[0], [1.0, 1.0], 1.0, 0.1, O.KERNEL_MATERN52)
     assert abs(good - ref) <= 1e-8 * abs(ref)
+
+
+def test_sequential_batch_am_matches_refit_per_pick():
+    """SequentialBatchAM (batch.jl:26-38) with the appended factor cache == the reference's refit-per-pick loop."""
+    prob = _problem(seed=11, n=25)
+    prob.params = B.estimate_parameters(B.SamplingMAP(48, seed=2), prob)
+    inner = B.GridAM(prob, steps=[0.5, 0.5], shuffle=False)
+    Xb, _ = B.maximize_acquisition(B.SequentialBatchAM(inner, 4), prob)
+    assert Xb.shape == (2, 4) and len(prob.data) == 25                 # the caller's problem is not modified
+    # reference loop: refit from scratch after every speculative point
+    ref = B.BossProblem(prob.f, prob.domain, prob.acquisition, prob.model,
+                        B.ExperimentData(prob.data.X.copy(), prob.data.Y.copy()), params=prob.params)
+    picks = []
+    for _ in range(4):
+        post = B.model_posterior(ref)
+        x, _ = B.maximize_acquisition(inner, ref)
+        ref.data.augment(x, post.mean(x))
+        picks.append(x)
+    assert np.array_equal(Xb, np.stack(picks, axis=1))
+    assert len({tuple(c) for c in Xb.T}) == 4                          # speculative points push the picks apart
