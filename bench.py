@@ -30,6 +30,8 @@ M_PER_GPU = 1 << 21
 LOGLIK_S_PER_GPU = 256
 F_CAND = N_TRAIN * N_TRAIN + N_TRAIN * (3 * X_DIM + 12)                      # 4 268 032 flop / candidate
 F_LL = N_TRAIN * (N_TRAIN + 1) // 2 * (3 * X_DIM + 8) + N_TRAIN ** 3 / 3 + N_TRAIN ** 2 + 3 * N_TRAIN  # 2.9347e9
+# value + gradient: Cholesky n^3/3, W = L^-1 n^3/3, K^-1 = W^T W n^3/3, kernel + derivative evaluations (6d + 14 each)
+F_LLG = N_TRAIN ** 3 + N_TRAIN * (N_TRAIN + 1) // 2 * (6 * X_DIM + 14) + 3 * N_TRAIN ** 2
 CPU_SAMPLE_M = 8192
 
 
@@ -217,6 +219,7 @@ def run_gpu(args):
     t_X = torch.tensor(np.ascontiguousarray(X.T), device="cuda"); t_y = torch.tensor(y, device="cuda")
     t_L = torch.tensor(Lh, device="cuda"); t_A = torch.tensor(Ah, device="cuda"); t_N = torch.tensor(Nh, device="cuda")
     t_ll = torch.empty(S, dtype=torch.float64, device="cuda")
+    t_gr = torch.empty((S, X_DIM + 2), dtype=torch.float64, device="cuda")
 
     gathered = [torch.zeros(2, dtype=torch.float64, device="cuda") for _ in range(world)]
     last_pairs = []          # (best value, global index) of every rank in the last reduction
@@ -247,6 +250,10 @@ def run_gpu(args):
     def step_loglik():
         _lib.loglik_batch_dev(t_X.data_ptr(), X_DIM, N_TRAIN, t_y.data_ptr(), 0, t_L.data_ptr(), t_A.data_ptr(),
                               t_N.data_ptr(), KERNEL_ID, S, t_ll.data_ptr())
+
+    def step_loglik_grad():
+        _lib.loglik_grad_batch_dev(t_X.data_ptr(), X_DIM, N_TRAIN, t_y.data_ptr(), 0, t_L.data_ptr(), t_A.data_ptr(),
+                                   t_N.data_ptr(), KERNEL_ID, S, t_ll.data_ptr(), t_gr.data_ptr())
 
     def barrier():
         if world > 1:
@@ -289,6 +296,7 @@ def run_gpu(args):
     ms_ll, launches_ll, _ = timed(step_loglik, max(2, args.steps // 2), 3)
     chol_ms, chol_cnt = _lib.last_kernel_ms(2)
     _lib.set_timing(False)
+    ms_llg, launches_llg, _ = timed(step_loglik_grad, max(2, args.steps // 2), 3)
     clocks = sampler.stop() if sampler else None
 
     if rank == 0:
@@ -316,6 +324,10 @@ def run_gpu(args):
                        "achieved_tflops_per_gpu": F_LL * S / (ms_ll * 1e-3) * 1e-12,
                        "frac_of_peak": F_LL * S / (ms_ll * 1e-3) * 1e-12 / peak,
                        "chol_gemm_ms_per_step": chol_ms, "chol_gemm_launches": chol_cnt, "gpu_launches": int(launches_ll)},
+            "loglik_grad": {"metric": "GP loglik + hyper-parameter gradient evals/sec (n=2048,d=8)",
+                            "value": S * world / (ms_llg * 1e-3), "unit": "evals/s", "ms_per_step": ms_llg,
+                            "flop_per_eval": F_LLG, "achieved_tflops_per_gpu": F_LLG * S / (ms_llg * 1e-3) * 1e-12,
+                            "frac_of_peak": F_LLG * S / (ms_llg * 1e-3) * 1e-12 / peak, "gpu_launches": int(launches_llg)},
             "argmax": {"value": res[0], "index": res[1], "e2e_index": res_e2e[1], "per_rank_pairs": list(last_pairs)},
         }
         try:

@@ -54,6 +54,10 @@ EXPORTS = {
                                        _vp]),
     "boss_gp_loglik_batch_dev": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, _vp, C.c_int, _vp,
                                            C.c_int64, _vp, _vp]),
+    "boss_gp_loglik_grad_batch": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, _vp, C.c_int, _vp, C.c_int64,
+                                            _vp, _vp]),
+    "boss_gp_loglik_grad_batch_dev": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, _vp, C.c_int, _vp,
+                                                C.c_int64, _vp, _vp]),
     "boss_set_timing": (None, [C.c_int]),
     "boss_last_kernel_ms": (C.c_double, [C.c_int]),
     "boss_last_kernel_count": (C.c_int, [C.c_int]),
@@ -288,6 +292,31 @@ def loglik_batch(X, Y_minus_mean, lengthscales, amplitude, noise_std, kernel_id=
     _check(lib.boss_gp_loglik_batch(_ptr(Xc), d, n, _ptr(Y), ldy, _ptr(ls), _ptr(amp), _ptr(ns), int(kernel_id),
                                     _ptr(dm), S, _ptr(out)), "boss_gp_loglik_batch")
     return out
+
+
+def loglik_grad_batch(X, Y_minus_mean, lengthscales, amplitude, noise_std, kernel_id=KERNEL_MATERN52, discrete_mask=None):
+    """-> loglik (S,), grad (S, d + 2) ordered [d lengthscales, amplitude, noise_std]."""
+    Xc = _cols(X)
+    n, d = Xc.shape
+    ls = _f64(lengthscales)
+    S = ls.shape[0]
+    assert ls.shape == (S, d)
+    amp = _f64(amplitude, (S,))
+    ns = _f64(noise_std, (S,))
+    Y = _f64(Y_minus_mean)
+    ldy = 0 if Y.ndim == 1 else n
+    dm = None if discrete_mask is None else np.ascontiguousarray(discrete_mask, dtype=np.uint8)
+    out = np.empty(S)
+    grad = np.empty((S, d + 2))
+    _check(lib.boss_gp_loglik_grad_batch(_ptr(Xc), d, n, _ptr(Y), ldy, _ptr(ls), _ptr(amp), _ptr(ns), int(kernel_id),
+                                         _ptr(dm), S, _ptr(out), _ptr(grad)), "boss_gp_loglik_grad_batch")
+    return out, grad
+
+
+def loglik_grad_batch_dev(X_ptr, d, n, Y_ptr, ldy, ls_ptr, amp_ptr, noise_ptr, kernel_id, S, out_ptr, grad_ptr):
+    _check(lib.boss_gp_loglik_grad_batch_dev(_vp(X_ptr), d, n, _vp(Y_ptr), ldy, _vp(ls_ptr), _vp(amp_ptr), _vp(noise_ptr),
+                                             int(kernel_id), None, int(S), _vp(out_ptr), _vp(grad_ptr)),
+           "boss_gp_loglik_grad_batch_dev")
 
 
 def loglik_batch_dev(X_ptr, d, n, Y_ptr, ldy, ls_ptr, amp_ptr, noise_ptr, kernel_id, S, out_ptr, discrete_mask=None):

@@ -72,7 +72,7 @@ struct Ctx {
   // workspaces
   DevBuf ks, muv, sumsq, xs_stage, pm_stage, cm_stage, acq_stage, mu_stage, var_stage, st_stage, grad_stage;
   DevBuf blk_val, blk_idx, small, chol_L, chol_Winv, chol_misc, tt, vt, ut, dmu, dvar, pmg_stage;
-  DevBuf part_mu, part_ss, part_gm, part_gv, cov_p, cov_stage;   // split-invariant partial sums (score.cuh / grad.cuh)
+  DevBuf part_mu, part_ss, part_gm, part_gv, cov_p, cov_stage, chol_W, chol_WT, ll_vec, ll_part;   // split-invariant partial sums (score.cuh / grad.cuh)
   // event pool for per-kernel-class timing
   cudaEvent_t ev_a[EV_POOL], ev_b[EV_POOL];
   int ev_class[EV_POOL];
@@ -176,6 +176,10 @@ void launch_append_kvec_t(const double *xnew, const boss_gp_view &v, double *kve
                                                                         v.Xt, kvec);
 }
 template <int KID, int DP>
+void launch_llgrad_tile_t(const LlGradParams &p, dim3 grid) {
+  loglik_grad_tile_kernel<KID, DP><<<grid, 256, 0, g.stream>>>(p);
+}
+template <int KID, int DP>
 void launch_xcov_t(const XcovParams &p, dim3 grid) {
   xcov_kernel<KID, DP><<<grid, 256, 0, g.stream>>>(p);
 }
@@ -244,6 +248,7 @@ int set_kernel_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(trtri_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(trtri_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(dbg_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(kinv_wtw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(score_trmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(wtv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM_BYTES));
@@ -258,7 +263,8 @@ int set_kernel_attrs() {
 // On return L holds the factors, Winv the inverted diagonal blocks, logdet_blk / status are filled.
 // W / WT non-null (S must be 1): also form the full triangular inverse.
 int run_cholesky(double *L, size_t L_stride, double *Winv, size_t Winv_stride, int nblk, int ktiles, int S,
-                 double *logdet_blk, int *status, double *W, double *WT, double *TT) {
+                 double *logdet_blk, int *status, double *W, double *WT, double *TT, size_t W_stride = 0,
+                 size_t TT_stride = 0) {
   CholGemmParams gp{};
   gp.L = L;
   gp.L_stride = L_stride;
@@ -269,6 +275,8 @@ int run_cholesky(double *L, size_t L_stride, double *Winv, size_t Winv_stride, i
   gp.W = W;
   gp.WT = WT;
   gp.TT = TT;
+  gp.W_stride = W_stride;
+  gp.TT_stride = TT_stride;
   PotrfParams pp{};
   pp.L = L;
   pp.L_stride = L_stride;
@@ -280,6 +288,7 @@ int run_cholesky(double *L, size_t L_stride, double *Winv, size_t Winv_stride, i
   pp.status = status;
   pp.W = W;
   pp.WT = WT;
+  pp.W_stride = W_stride;
   for (int j = 0; j < nblk; ++j) {
     gp.j = j;
     pp.j = j;
@@ -300,8 +309,8 @@ int run_cholesky(double *L, size_t L_stride, double *Winv, size_t Winv_stride, i
     for (int delta = 1; delta < nblk; ++delta) {
       gp.j = delta;
       Timed t(2);
-      trtri_t_kernel<<<nblk - delta, GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(gp);
-      trtri_w_kernel<<<nblk - delta, GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(gp);
+      trtri_t_kernel<<<dim3(nblk - delta, S), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(gp);
+      trtri_w_kernel<<<dim3(nblk - delta, S), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(gp);
       g.launches += 2;
     }
   }
@@ -371,7 +380,8 @@ void boss_shutdown(void) {
   for (DevBuf *b : {&g.ks, &g.muv, &g.sumsq, &g.xs_stage, &g.pm_stage, &g.cm_stage, &g.acq_stage, &g.mu_stage,
                     &g.var_stage, &g.st_stage, &g.grad_stage, &g.blk_val, &g.blk_idx, &g.small, &g.chol_L,
                     &g.chol_Winv, &g.chol_misc, &g.tt, &g.vt, &g.ut, &g.dmu, &g.dvar, &g.pmg_stage, &g.part_mu,
-                    &g.part_ss, &g.part_gm, &g.part_gv, &g.cov_p, &g.cov_stage})
+                    &g.part_ss, &g.part_gm, &g.part_gv, &g.cov_p, &g.cov_stage, &g.chol_W, &g.chol_WT, &g.ll_vec,
+                    &g.ll_part})
     b->release();
   if (g.ev_ready) {
     for (int i = 0; i < EV_POOL; ++i) {
@@ -1132,7 +1142,7 @@ int boss_gp_cov(const boss_gp *gp, const double *Xs, int64_t M, const double *pr
 // ---------------------------------------------------------------------------------------------
 static int loglik_impl(const double *X, int d, int n, const double *Ymm, int64_t ldy, const double *ls,
                        const double *amp, const double *noise, int kernel_id, const uint8_t *discrete_mask, int64_t S,
-                       double *loglik, bool dev) {
+                       double *loglik, bool dev, double *grad = nullptr) {
   std::lock_guard<std::mutex> lk(g.mu);
   REQUIRE_INIT();
   if (!X || !Ymm || !ls || !amp || !noise || !loglik || d < 1 || n < 1 || S < 0)
@@ -1146,15 +1156,24 @@ static int loglik_impl(const double *X, int d, int n, const double *Ymm, int64_t
   if ((size_t)(n_pad + 128) * 8 > 200 * 1024) return fail(BOSS_ERR_ARG, "boss_gp_loglik_batch: n too large");
   const unsigned long long disc = mask_bits(discrete_mask, d);
 
-  const bool small = n <= SMALL_N;   // warp-register path (small.cuh): no workspace at all
-  // sub-batch so that L + Winv stay within a 32 GiB workspace
-  const size_t per = mat * 8 + (size_t)nblk * TM * TM * 8;
+  const bool small = n <= SMALL_N && !grad;   // warp-register path (small.cuh): no workspace at all
+  // sub-batch so that L + Winv (+ W, W^T and the trtri scratch in gradient mode) stay within a 32 GiB workspace
+  const size_t per = (grad ? 3 : 1) * mat * 8 + (size_t)(grad ? 2 * nblk : nblk) * TM * TM * 8;
   long long Sb = std::max<long long>(1, std::min<long long>(S, (32ll << 30) / (long long)per));
   Sb = std::min<long long>(Sb, 32768);
   if (small) Sb = 1;
   if (!small) {
     CUDA_TRY(g.chol_L.ensure((size_t)Sb * mat * 8));
     CUDA_TRY(g.chol_Winv.ensure((size_t)Sb * nblk * TM * TM * 8));
+  }
+  const int ntiles = nblk * (nblk + 1) / 2;
+  const size_t tt_stride = (size_t)std::max(1, nblk - 1) * TM * TM;
+  if (grad) {
+    CUDA_TRY(g.chol_W.ensure((size_t)Sb * mat * 8));
+    CUDA_TRY(g.chol_WT.ensure((size_t)Sb * mat * 8));
+    CUDA_TRY(g.tt.ensure((size_t)Sb * tt_stride * 8));
+    CUDA_TRY(g.ll_vec.ensure((size_t)Sb * n_pad * 3 * 8));                 // delta_pad | w | alpha
+    CUDA_TRY(g.ll_part.ensure((size_t)Sb * ntiles * (dp + 2) * 8));
   }
 
   // device copies of the inputs when called with host pointers
@@ -1171,6 +1190,10 @@ static int loglik_impl(const double *X, int d, int n, const double *Ymm, int64_t
     onoise = off; off += S;
     oll = off; off += S;
   }
+  size_t ogr = 0;
+  if (!dev && grad) {
+    ogr = off; off += (size_t)S * (d + 2);
+  }
   const size_t old_ = off;
   off += (size_t)Sb * nblk;
   const size_t ost = off;
@@ -1185,6 +1208,7 @@ static int loglik_impl(const double *X, int d, int n, const double *Ymm, int64_t
     CUDA_TRY(cudaMemcpyAsync(misc + onoise, noise, (size_t)S * 8, cudaMemcpyHostToDevice, g.stream));
     dX = misc + oX; dY = misc + oY; dls = misc + ols; damp = misc + oamp; dnoise = misc + onoise; dll = misc + oll;
   }
+  double *dgrad = (grad && !dev) ? misc + ogr : grad;
   double *logdet_blk = misc + old_;
   int *status = reinterpret_cast<int *>(misc + ost);
 
@@ -1227,8 +1251,13 @@ static int loglik_impl(const double *X, int d, int n, const double *Ymm, int64_t
       DISPATCH_KID_DP(launch_build_k_t, kernel_id, dp, bk, dim3(nblk * (nblk + 1) / 2, sb));
       ++g.launches;
     }
+    if (grad) {   // identity / zero initial state of W and W^T (strictly-upper resp. strictly-lower blocks are never written)
+      CUDA_TRY(cudaMemsetAsync(g.chol_W.p, 0, (size_t)sb * mat * 8, g.stream));
+      CUDA_TRY(cudaMemsetAsync(g.chol_WT.p, 0, (size_t)sb * mat * 8, g.stream));
+    }
     int rc = run_cholesky(g.chol_L.as<double>(), mat, g.chol_Winv.as<double>(), (size_t)nblk * TM * TM, nblk, ktiles, sb,
-                          logdet_blk, status, nullptr, nullptr, nullptr);
+                          logdet_blk, status, grad ? g.chol_W.as<double>() : nullptr,
+                          grad ? g.chol_WT.as<double>() : nullptr, grad ? g.tt.as<double>() : nullptr, mat, tt_stride);
     if (rc) return rc;
     FwdParams fp{};
     fp.L = g.chol_L.as<double>();
@@ -1246,9 +1275,43 @@ static int loglik_impl(const double *X, int d, int n, const double *Ymm, int64_t
     fp.w_out = nullptr;
     fwd_solve_loglik_kernel<<<sb, 256, (size_t)(n_pad + 128) * 8, g.stream>>>(fp);
     ++g.launches;
+    if (grad) {
+      // alpha = W^T (W delta);  K^-1 = W^T W over the factor's storage;  tile partial sums;  final scaling
+      double *dpad = g.ll_vec.as<double>(), *wv = dpad + (size_t)sb * n_pad, *al = wv + (size_t)sb * n_pad;
+      pad_delta_kernel<<<dim3((n_pad + 255) / 256, sb), 256, 0, g.stream>>>(dY + (ldy ? (size_t)s0 * ldy : 0), ldy, n, n_pad, dpad);
+      matvec_p_kernel<<<dim3(n_pad / 64, sb), 256, 0, g.stream>>>(g.chol_W.as<double>(), dpad, wv, ktiles, mat, n_pad, n_pad);
+      matvec_p_kernel<<<dim3(n_pad / 64, sb), 256, 0, g.stream>>>(g.chol_WT.as<double>(), wv, al, ktiles, mat, n_pad, n_pad);
+      KinvParams kp{g.chol_WT.as<double>(), mat, g.chol_L.as<double>(), mat, nblk, ktiles};
+      {
+        Timed t(2);
+        kinv_wtw_kernel<<<dim3(ntiles, sb), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(kp);
+      }
+      LlGradParams lg{};
+      lg.X = dX;
+      lg.d = d;
+      lg.n = n;
+      lg.nblk = nblk;
+      lg.ktiles = ktiles;
+      lg.ls = dls + (size_t)s0 * d;
+      lg.amp = damp + s0;
+      lg.noise = dnoise + s0;
+      lg.disc_bits = disc;
+      lg.Kinv = g.chol_L.as<double>();
+      lg.K_stride = mat;
+      lg.alpha = al;
+      lg.part = g.ll_part.as<double>();
+      {
+        Timed t(1);
+        DISPATCH_KID_DP(launch_llgrad_tile_t, kernel_id, dp, lg, dim3(ntiles, sb));
+      }
+      loglik_grad_final_kernel<<<(sb + 127) / 128, 128, 0, g.stream>>>(g.ll_part.as<double>(), ntiles, dp, d, lg.ls, lg.amp,
+                                                                      lg.noise, status, dgrad + (size_t)s0 * (d + 2), sb);
+      g.launches += 6;
+    }
   }
   CUDA_TRY(cudaGetLastError());
   if (!dev) CUDA_TRY(cudaMemcpyAsync(loglik, dll, (size_t)S * 8, cudaMemcpyDeviceToHost, g.stream));
+  if (!dev && grad) CUDA_TRY(cudaMemcpyAsync(grad, dgrad, (size_t)S * (d + 2) * 8, cudaMemcpyDeviceToHost, g.stream));
   CUDA_TRY(cudaStreamSynchronize(g.stream));
   timing_end();
   if (!dev) {
@@ -1274,6 +1337,22 @@ int boss_gp_loglik_batch_dev(const double *X_dev, int d, int n, const double *Y_
   (void)stream;
   return loglik_impl(X_dev, d, n, Y_minus_mean_dev, ldy, lengthscales_dev, amplitude_dev, noise_std_dev, kernel_id,
                      discrete_mask, S, loglik_dev, true);
+}
+
+int boss_gp_loglik_grad_batch(const double *X, int d, int n, const double *Y_minus_mean, int64_t ldy,
+                              const double *lengthscales, const double *amplitude, const double *noise_std, int kernel_id,
+                              const uint8_t *discrete_mask, int64_t S, double *loglik, double *grad) {
+  if (!grad) return fail(BOSS_ERR_ARG, "boss_gp_loglik_grad_batch: grad is NULL");
+  return loglik_impl(X, d, n, Y_minus_mean, ldy, lengthscales, amplitude, noise_std, kernel_id, discrete_mask, S, loglik,
+                     false, grad);
+}
+int boss_gp_loglik_grad_batch_dev(const double *X_dev, int d, int n, const double *Y_minus_mean_dev, int64_t ldy,
+                                  const double *lengthscales_dev, const double *amplitude_dev, const double *noise_std_dev,
+                                  int kernel_id, const uint8_t *discrete_mask, int64_t S, double *loglik_dev,
+                                  double *grad_dev) {
+  if (!grad_dev) return fail(BOSS_ERR_ARG, "boss_gp_loglik_grad_batch_dev: grad is NULL");
+  return loglik_impl(X_dev, d, n, Y_minus_mean_dev, ldy, lengthscales_dev, amplitude_dev, noise_std_dev, kernel_id,
+                     discrete_mask, S, loglik_dev, true, grad_dev);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -113,7 +113,8 @@ struct CholGemmParams {
   size_t Winv_stride;
   int nblk, ktiles;
   int j;                 // block column (UPDATE / TRSM) or block distance delta (TRTRI)
-  double *W, *WT, *TT;   // full inverse, its transpose, per-task scratch (TRTRI; single matrix)
+  double *W, *WT, *TT;   // full inverse, its transpose, per-task scratch (TRTRI), one per matrix of the batch
+  size_t W_stride, TT_stride;
 };
 
 // A_ij -= L_i,0:j * L_j,0:j^T   for i = j + blockIdx.x.  The diagonal tile (i == j) is a SYRK: only its lower
@@ -158,13 +159,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) chol_trsm_kernel(CholGemmPara
   });
 }
 
-// Triangular inverse, block distance delta = i - j (single matrix):
+// Triangular inverse, block distance delta = i - j (blockIdx.y = matrix of the batch):
 //   T_ij = sum_{k=j}^{i-1} L_ik W_kj   -> stored transposed in TT[task]
 __global__ void __launch_bounds__(GEMM_THREADS, 1) trtri_t_kernel(CholGemmParams p) {
   const int jb = blockIdx.x, i = jb + p.j;
-  LinearIt it{p.L + ((size_t)i * p.ktiles + (size_t)jb * KT_PER_BLOCK) * TILE_ELEMS,
-              p.WT + ((size_t)jb * p.ktiles + (size_t)jb * KT_PER_BLOCK) * TILE_ELEMS, p.j * KT_PER_BLOCK};
-  double *dst = p.TT + (size_t)blockIdx.x * (TM * TM);
+  const double *Lm = p.L + (size_t)blockIdx.y * p.L_stride;
+  const double *WTm = p.WT + (size_t)blockIdx.y * p.W_stride;
+  LinearIt it{Lm + ((size_t)i * p.ktiles + (size_t)jb * KT_PER_BLOCK) * TILE_ELEMS,
+              WTm + ((size_t)jb * p.ktiles + (size_t)jb * KT_PER_BLOCK) * TILE_ELEMS, p.j * KT_PER_BLOCK};
+  double *dst = p.TT + (size_t)blockIdx.y * p.TT_stride + (size_t)blockIdx.x * (TM * TM);
   gemm_pipeline(it, it, [&](int, const double(&acc)[8][4][2], const FragCoord &fc) {
     store_block(dst, true, 1.0, nullptr, acc, fc);
   });
@@ -172,9 +175,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) trtri_t_kernel(CholGemmParams
 //   W_ij = -Winv_ii T_ij   -> W (normal) and WT (transposed)
 __global__ void __launch_bounds__(GEMM_THREADS, 1) trtri_w_kernel(CholGemmParams p) {
   const int jb = blockIdx.x, i = jb + p.j;
-  LinearIt it{p.Winv + (size_t)i * (TM * TM), p.TT + (size_t)blockIdx.x * (TM * TM), KT_PER_BLOCK};
-  double *dW = p.W + ((size_t)i * p.ktiles + (size_t)jb * KT_PER_BLOCK) * TILE_ELEMS;
-  double *dWT = p.WT + ((size_t)jb * p.ktiles + (size_t)i * KT_PER_BLOCK) * TILE_ELEMS;
+  LinearIt it{p.Winv + (size_t)blockIdx.y * p.Winv_stride + (size_t)i * (TM * TM),
+              p.TT + (size_t)blockIdx.y * p.TT_stride + (size_t)blockIdx.x * (TM * TM), KT_PER_BLOCK};
+  double *dW = p.W + (size_t)blockIdx.y * p.W_stride + ((size_t)i * p.ktiles + (size_t)jb * KT_PER_BLOCK) * TILE_ELEMS;
+  double *dWT = p.WT + (size_t)blockIdx.y * p.W_stride + ((size_t)jb * p.ktiles + (size_t)i * KT_PER_BLOCK) * TILE_ELEMS;
   gemm_pipeline(it, it, [&](int, const double(&acc)[8][4][2], const FragCoord &fc) {
     store_block(dW, false, -1.0, nullptr, acc, fc);
     store_block(dWT, true, -1.0, nullptr, acc, fc);
@@ -204,7 +208,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dbg_gemm_kernel(DbgGemmParams
 // w = W delta and alpha = W^T w in the posterior fit.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) matvec_p_kernel(const double *__restrict__ Mx, const double *__restrict__ x,
-                                                       double *__restrict__ y, int ktiles) {
+                                                       double *__restrict__ y, int ktiles, size_t m_stride = 0,
+                                                       size_t x_stride = 0, size_t y_stride = 0) {
+  Mx += (size_t)blockIdx.y * m_stride;   // blockIdx.y = matrix of the batch
+  x += (size_t)blockIdx.y * x_stride;
+  y += (size_t)blockIdx.y * y_stride;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int mrow = blockIdx.x * 8 + warp;      // global micro-row
   const int rb = mrow >> 4, mr = mrow & 15;
@@ -316,6 +324,162 @@ __global__ void __launch_bounds__(256) fwd_solve_loglik_kernel(FwdParams p) {
     if (st < 0) ll = NAN;
     p.loglik[s] = ll;
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Hyper-parameter gradient of the log marginal likelihood:
+//   d LML / d theta = 1/2 sum_ij G_ij dK_ij/dtheta,   G = alpha alpha^T - K^-1,  K^-1 = W^T W
+// (what ForwardDiff yields through logpdf(::FiniteGP), src/model_fitters/optimization.jl:41,153)
+// ---------------------------------------------------------------------------------------------
+// zero-padded copy of delta = y - m(X): dst[s][n_pad]
+__global__ void pad_delta_kernel(const double *ymm, long long ldy, int n, int n_pad, double *dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pad) return;
+  dst[(size_t)blockIdx.y * n_pad + i] = (i < n) ? ymm[(size_t)blockIdx.y * ldy + i] : 0.0;
+}
+
+// K^-1 lower block triangle: Kinv_ij = sum_{k >= i} WT_ik WT_jk^T  (i >= j), written over the factor's storage.
+struct KinvParams {
+  const double *WT;
+  size_t W_stride;
+  double *Kinv;
+  size_t K_stride;
+  int nblk, ktiles;
+};
+__global__ void __launch_bounds__(GEMM_THREADS, 1) kinv_wtw_kernel(KinvParams p) {
+  int t = blockIdx.x, i = 0;
+  while (t >= i + 1) {
+    t -= i + 1;
+    ++i;
+  }
+  const int j = t;
+  // longest k-ranges first would balance better; the grid is large (S x tiles) so dynamic scheduling suffices
+  const double *WTm = p.WT + (size_t)blockIdx.y * p.W_stride;
+  LinearIt it{WTm + ((size_t)i * p.ktiles + (size_t)i * KT_PER_BLOCK) * TILE_ELEMS,
+              WTm + ((size_t)j * p.ktiles + (size_t)i * KT_PER_BLOCK) * TILE_ELEMS, (p.nblk - i) * KT_PER_BLOCK};
+  double *dst = p.Kinv + (size_t)blockIdx.y * p.K_stride + ((size_t)i * p.ktiles + (size_t)j * KT_PER_BLOCK) * TILE_ELEMS;
+  gemm_pipeline(it, it, [&](int, const double(&acc)[8][4][2], const FragCoord &fc) {
+    store_block(dst, false, 1.0, nullptr, acc, fc);
+  });
+}
+
+// Per (lower tile, sample): partial sums  A1 = sum_{i>j} G_ij kappa_ij,  A2 = sum_i G_ii,  B_q = sum_{i>j} G_ij g_ij dq_ij^2
+// with g = kappa'(r)/r and dq the scaled coordinate difference.  part[s][tile][DP + 2].
+struct LlGradParams {
+  const double *X;
+  int d, n, nblk, ktiles;
+  const double *ls, *amp, *noise;   // raw hyper-parameters of the sub-batch
+  unsigned long long disc_bits;
+  const double *Kinv;
+  size_t K_stride;
+  const double *alpha;   // [S][n_pad]
+  double *part;          // [S][ntiles][DP + 2]
+};
+
+template <int KID, int DP>
+__global__ void __launch_bounds__(256) loglik_grad_tile_kernel(LlGradParams p) {
+  __shared__ double xcol[128 * DP];
+  __shared__ double acol[128];
+  __shared__ double invl[DP];
+  __shared__ double red[256];
+  const int s = blockIdx.y, tid = threadIdx.x;
+  int t = blockIdx.x, rb = 0;
+  while (t >= rb + 1) {
+    t -= rb + 1;
+    ++rb;
+  }
+  const int cb = t;
+  if (tid < DP) invl[tid] = (tid < p.d) ? 1.0 / (p.ls[(size_t)s * p.d + tid] + MIN_PARAM_VALUE) : 0.0;
+  __syncthreads();
+  const int n_pad = p.nblk * 128;
+  const double *al = p.alpha + (size_t)s * n_pad;
+  for (int e = tid; e < 128 * DP; e += 256) {
+    const int jj = e / DP, i = e % DP, j = cb * 128 + jj;
+    double v = 0.0;
+    if (j < p.n && i < p.d) {
+      v = p.X[(size_t)j * p.d + i];
+      if ((p.disc_bits >> i) & 1ull) v = rint(v);
+      v *= invl[i];
+    }
+    xcol[e] = v;
+  }
+  if (tid < 128) acol[tid] = al[cb * 128 + tid];
+  const int r = tid & 127, kh = tid >> 7, gi = rb * 128 + r;
+  double xr[DP];
+  load_scaled_point<DP>(xr, p.X + (size_t)gi * p.d, p.d, invl, p.disc_bits, gi < p.n);
+  const double ai = al[gi];
+  __syncthreads();
+  const double *blk = p.Kinv + (size_t)s * p.K_stride + ((size_t)rb * p.ktiles + (size_t)cb * KT_PER_BLOCK) * TILE_ELEMS;
+  double a1 = 0.0, a2 = 0.0, bq[DP];
+#pragma unroll
+  for (int q = 0; q < DP; ++q) bq[q] = 0.0;
+  for (int mcol = kh; mcol < 16; mcol += 2) {
+    if (rb == cb && mcol * 8 > r) continue;
+    const double *src = blk + (mcol >> 1) * TILE_ELEMS + ((((r >> 3) << 1) + (mcol & 1)) << 6) + ((r & 7) << 3);
+    double kv[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const double2 v = *reinterpret_cast<const double2 *>(src + 2 * q);
+      kv[q] = v.x;
+      kv[q + 4] = v.y;
+    }
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      const int jj = mcol * 8 + kk, gj = cb * 128 + jj;
+      if (gi >= p.n || gj > gi) continue;
+      const double G = ai * acol[jj] - kv[kk];
+      if (gj == gi) {
+        a2 += G;
+      } else {
+        double df[DP], d2 = 0.0;
+#pragma unroll
+        for (int q = 0; q < DP; ++q) {
+          df[q] = xr[q] - xcol[jj * DP + q];
+          d2 = fma(df[q], df[q], d2);
+        }
+        a1 = fma(G, kappa<KID>(d2), a1);
+        const double w = G * kappa_dr_over_r<KID>(d2);
+#pragma unroll
+        for (int q = 0; q < DP; ++q) bq[q] = fma(w * df[q], df[q], bq[q]);
+      }
+    }
+  }
+  // block reductions in a fixed order, one quantity at a time
+  double *out = p.part + ((size_t)s * gridDim.x + blockIdx.x) * (DP + 2);
+#pragma unroll
+  for (int q = 0; q < DP + 2; ++q) {
+    const double v = (q < DP) ? bq[q < DP ? q : 0] : (q == DP ? a1 : a2);
+    __syncthreads();
+    red[tid] = v;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (tid < o) red[tid] += red[tid + o];
+      __syncthreads();
+    }
+    if (tid == 0) out[q] = red[0];
+  }
+}
+
+// grad[s][0..d-1] = -(a^2 / l_q) sum_t B_q ;  grad[s][d] = a (2 sum A1 + sum A2) ;  grad[s][d+1] = s sum A2
+__global__ void loglik_grad_final_kernel(const double *part, int ntiles, int DP, int d, const double *ls, const double *amp,
+                                         const double *noise, const int *status, double *grad, long long S) {
+  const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const double a = amp[s] + MIN_PARAM_VALUE, sn = noise[s] + MIN_PARAM_VALUE;
+  double a1 = 0.0, a2 = 0.0;
+  const double *ps = part + (size_t)s * ntiles * (DP + 2);
+  const bool ok = status[s] == 0;
+  for (int t = 0; t < ntiles; ++t) {
+    a1 += ps[(size_t)t * (DP + 2) + DP];
+    a2 += ps[(size_t)t * (DP + 2) + DP + 1];
+  }
+  for (int q = 0; q < d; ++q) {
+    double b = 0.0;
+    for (int t = 0; t < ntiles; ++t) b += ps[(size_t)t * (DP + 2) + q];
+    grad[(size_t)s * (d + 2) + q] = ok ? -(a * a) * b / (ls[(size_t)s * d + q] + MIN_PARAM_VALUE) : 0.0;
+  }
+  grad[(size_t)s * (d + 2) + d] = ok ? a * (2.0 * a1 + a2) : 0.0;
+  grad[(size_t)s * (d + 2) + d + 1] = ok ? sn * a2 : 0.0;
 }
 
 }  // namespace boss

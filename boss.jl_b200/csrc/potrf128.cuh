@@ -29,7 +29,8 @@ struct PotrfParams {
   int nblk, ktiles, j;
   double *logdet_blk;  // S x nblk : sum_k log L_kk of this block
   int *status;         // S : BOSS_NOT_POSDEF on a non-positive / NaN pivot
-  double *W, *WT;      // optional (single matrix): also deposit Winv_jj into W(j,j), its transpose into WT(j,j)
+  double *W, *WT;      // optional: also deposit Winv_jj into W(j,j), its transpose into WT(j,j)
+  size_t W_stride;     // per matrix of the batch
 };
 
 constexpr int PT_TILES = 136;                        // 16*17/2 lower micro-tiles
@@ -283,8 +284,8 @@ __global__ void __launch_bounds__(256, 2) potrf_tile_kernel(PotrfParams p) {
 
   // ---- Winv_jj -> global (and, for a posterior fit, into W(j,j) and transposed into WT(j,j)) ----
   double *wi = p.Winv + (size_t)s_mat * p.Winv_stride + (size_t)p.j * (TM * TM);
-  double *wfull = p.W ? p.W + ((size_t)p.j * p.ktiles + (size_t)p.j * KT_PER_BLOCK) * TILE_ELEMS : nullptr;
-  double *wtfull = p.WT ? p.WT + ((size_t)p.j * p.ktiles + (size_t)p.j * KT_PER_BLOCK) * TILE_ELEMS : nullptr;
+  double *wfull = p.W ? p.W + (size_t)s_mat * p.W_stride + ((size_t)p.j * p.ktiles + (size_t)p.j * KT_PER_BLOCK) * TILE_ELEMS : nullptr;
+  double *wtfull = p.WT ? p.WT + (size_t)s_mat * p.W_stride + ((size_t)p.j * p.ktiles + (size_t)p.j * KT_PER_BLOCK) * TILE_ELEMS : nullptr;
   for (int e = tid; e < TM * TM; e += 256) {
     const int kt = e >> 11, micro = (e >> 6) & 31, w = e & 63;
     const int I = micro >> 1, J = (kt << 1) + (micro & 1);

@@ -157,6 +157,20 @@ int boss_gp_loglik_batch_dev(const double *X_dev, int d, int n, const double *Y_
                              const double *noise_std_dev, int kernel_id, const uint8_t *discrete_mask,
                              int64_t S, double *loglik_dev, void *stream);
 
+/* Same batch, plus the gradient of each log-likelihood w.r.t. the raw hyper-parameters, ordered like the
+ * reference's vectorizer [vec(lambda); alpha; sigma] (src/models/gaussian_process.jl:300-328):
+ *   d LML / d theta = 1/2 tr((alpha alpha^T - K^-1) dK/dtheta),  K^-1 = W^T W formed on the tensor cores.
+ * Replaces the ForwardDiff.Dual sweep through logpdf(::FiniteGP) that OptimizationMAP's gradient algorithms
+ * and NUTS (TuringBI) perform (src/model_fitters/optimization.jl:41,153; docs/src/example.md:155-163).
+ *   grad  S x (d + 2), sample s at grad + s*(d+2); zeros where the sample is not positive definite. */
+int boss_gp_loglik_grad_batch(const double *X, int d, int n, const double *Y_minus_mean, int64_t ldy,
+                              const double *lengthscales, const double *amplitude, const double *noise_std,
+                              int kernel_id, const uint8_t *discrete_mask, int64_t S, double *loglik, double *grad);
+int boss_gp_loglik_grad_batch_dev(const double *X_dev, int d, int n, const double *Y_minus_mean_dev, int64_t ldy,
+                                  const double *lengthscales_dev, const double *amplitude_dev,
+                                  const double *noise_std_dev, int kernel_id, const uint8_t *discrete_mask,
+                                  int64_t S, double *loglik_dev, double *grad_dev);
+
 /* ---- instrumentation ---------------------------------------------------------------------
  * CUDA-event time (ms) of the dominant kernel class inside the last scoring / loglik call, and the
  * number of kernel launches the library has issued since boss_init (bench.py's gpu_launches). */

@@ -286,6 +286,58 @@ def gp_loglik_batch(X, Y_minus_mean, lengthscales, amplitude, noise_std, kernel_
     return out
 
 
+def gp_loglik_grad(X, y_minus_mean, lengthscales, amplitude, noise_std, kernel_id=KERNEL_MATERN52,
+                   discrete_mask=None):
+    """Log marginal likelihood and its gradient w.r.t. the raw hyper-parameters, ordered like the reference's
+    vectorizer `[vec(lambda); alpha; sigma]` (gaussian_process.jl:300-328):
+
+        d LML / d theta = 1/2 tr((alpha alpha^T - K^-1) dK/dtheta),   alpha = K^-1 (y - m)
+
+    This is what ForwardDiff produces when OptimizationMAP / NUTS push Dual numbers through logpdf(::FiniteGP)
+    (src/model_fitters/optimization.jl:41,153).  Returns (ll, grad[d + 2]); (-inf, zeros)
+    when K is not positive definite.
+    """
+    X = np.asarray(X, dtype=np.float64)
+    delta = np.asarray(y_minus_mean, dtype=np.float64)
+    ls, amp, noise = condition_params(lengthscales, amplitude, noise_std)
+    d, n = X.shape
+    Xa = discrete_round(discrete_mask, X) / ls[:, None]
+    D2 = _pairwise_sqdist_direct(Xa, Xa)
+    a2 = amp * amp
+    Kc = _kappa(D2, kernel_id)
+    K = a2 * Kc
+    K[np.diag_indices(n)] += noise * noise
+    try:
+        U = cholesky_upper(K)
+    except PosDefException:
+        return -math.inf, np.zeros(d + 2)
+    w = sl.solve_triangular(U, delta, trans='T', lower=False, check_finite=False)
+    alpha = sl.solve_triangular(U, w, trans='N', lower=False, check_finite=False)
+    ll = float(-(n * LOG2PI + 2.0 * np.sum(np.log(np.diag(U))) + np.dot(w, w)) / 2.0)
+    Kinv = sl.cho_solve((U, False), np.eye(n), check_finite=False)
+    G = np.outer(alpha, alpha) - Kinv
+    g = _kappa_dr_over_r(D2, kernel_id)
+    grad = np.empty(d + 2)
+    for q in range(d):
+        dq2 = (Xa[q][:, None] - Xa[q][None, :]) ** 2
+        grad[q] = 0.5 * np.sum(G * (-a2 * g * dq2 / ls[q]))
+    grad[d] = 0.5 * np.sum(G * (2.0 * amp * Kc))
+    grad[d + 1] = 0.5 * np.trace(G) * 2.0 * noise
+    return ll, grad
+
+
+def gp_loglik_grad_batch(X, Y_minus_mean, lengthscales, amplitude, noise_std, kernel_id=KERNEL_MATERN52,
+                         discrete_mask=None):
+    lengthscales = np.asarray(lengthscales, dtype=np.float64)
+    S, d = lengthscales.shape
+    Ym = np.asarray(Y_minus_mean, dtype=np.float64)
+    ll = np.empty(S); gr = np.empty((S, d + 2))
+    for s in range(S):
+        ym = Ym if Ym.ndim == 1 else Ym[s]
+        ll[s], gr[s] = gp_loglik_grad(X, ym, lengthscales[s], amplitude[s], noise_std[s], kernel_id, discrete_mask)
+    return ll, gr
+
+
 # --------------------------------------------------------------------------------------
 # a6  acquisition: closed-form EI, probability of feasibility, guards
 # --------------------------------------------------------------------------------------

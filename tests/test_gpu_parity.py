@@ -437,3 +437,31 @@ def test_append_duplicate_point_without_noise_is_rejected(lib):
         mu, var, _ = lib.gp_predict(gp, X[:, :5])
         assert np.all(np.isfinite(mu))
     gp.free()
+
+
+# ---------------------------------------------------------------------------------------------
+# hyper-parameter gradient of the log marginal likelihood
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,d,kid,S", [(3, 2, 2, 4), (20, 2, 0, 9), (130, 3, 1, 7), (300, 5, 2, 6), (512, 6, 0, 5)])
+def test_loglik_grad_batch(lib, n, d, kid, S):
+    X, Y, _, _, _ = make_problem(n, d, seed=1300 + n)
+    L, A, N = make_hyper_samples(S, d, seed=1301 + n)
+    ll_ref, g_ref = O.gp_loglik_grad_batch(X, Y[0], L, A, N, kid)
+    ll, g = lib.loglik_grad_batch(X, Y[0], L, A, N, kid)
+    assert relerr(ll, ll_ref) <= TOL_LL
+    assert np.array_equal(ll, lib.loglik_batch(X, Y[0], L, A, N, kid)) or n <= 32      # same factorisation (n > 32)
+    scale = np.maximum(np.max(np.abs(g_ref), axis=1, keepdims=True), 1e-300)
+    assert np.max(np.abs(g - g_ref) / scale) <= 1e-8, np.max(np.abs(g - g_ref) / scale)
+
+
+def test_loglik_grad_discrete_and_per_sample_mean(lib):
+    n, d, S = 90, 3, 5
+    X, Y, _, _, _ = make_problem(n, d, seed=1401)
+    X = X * 5.0
+    mask = np.array([False, True, False])
+    L, A, N = make_hyper_samples(S, d, seed=1402)
+    Ymm = Y[0][None, :] - np.linspace(-0.5, 0.5, S)[:, None]
+    ll_ref, g_ref = O.gp_loglik_grad_batch(X, Ymm, L * 3, A, N, 2, discrete_mask=mask)
+    ll, g = lib.loglik_grad_batch(X, Ymm, L * 3, A, N, 2, discrete_mask=mask)
+    assert relerr(ll, ll_ref) <= TOL_LL
+    assert np.max(np.abs(g - g_ref) / np.max(np.abs(g_ref), axis=1, keepdims=True)) <= 1e-8
