@@ -12,7 +12,7 @@ from .types import (BIParams, BossOptions, BossProblem, Dirac, Domain, Experimen
                     mvlognormal)
 from .gaussian_process import (DiscreteKernel, GaussianProcess, GaussianProcessParams, GaussianProcessPosterior,  # noqa: F401
                                Matern32Kernel, Matern52Kernel, Parametric, Semiparametric, SemiparametricParams,
-                               SqExponentialKernel, data_loglike, model_posterior_slice)
+                               SqExponentialKernel, data_loglike, data_loglike_and_grad, model_posterior_slice)
 from .posterior import DefaultModelPosterior, average_mean, model_posterior  # noqa: F401
 from .acquisition import (Acquisition, ExpectedImprovement, best_so_far, construct_acquisition,  # noqa: F401
                           construct_safe_acquisition)

@@ -46,6 +46,10 @@ EXPORTS = {
                                 _dp, _i64p]),
     "boss_ei_score_dev": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                     _vp, _dp, _i64p, _vp]),
+    "boss_ei_score_grid": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp,
+                                     _vp, _vp, _vp, _vp, _dp, _i64p, _vp]),
+    "boss_ei_score_uniform": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int64, C.c_int64, _vp, _vp, _vp,
+                                        _vp, _vp, _vp, _vp, _vp, _dp, _i64p, _vp]),
     "boss_ei_value_grad": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                      _vp]),
     "boss_ei_value_grad_dev": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
@@ -218,6 +222,65 @@ def ei_score(slices, y_dim, n_samples, Xs, coefs, best, y_max, lb=None, ub=None,
     _check(lib.boss_ei_score(arr, y_dim, n_samples, _ptr(Xc), M, _ptr(pm), _ptr(co), _ptr(b), _ptr(ym), _ptr(lbv),
                              _ptr(ubv), _ptr(cm), _ptr(acq), None, C.byref(bv), C.byref(bi)), "boss_ei_score")
     return acq, bv.value, bi.value
+
+
+def _opt(a, dtype=np.float64):
+    return None if a is None else np.ascontiguousarray(a, dtype=dtype)
+
+
+def ei_score_grid(slices, y_dim, n_samples, grid_lo, grid_step, grid_count, coefs, best, y_max, lb=None, ub=None,
+                  first=0, M=-1, cons_mask=None, prior_mean_s=None, want_acq=False):
+    """Grid candidates generated on the device.  -> acq (or None), best_val, best_idx (global), best_x (d,)."""
+    lo, st = _f64(grid_lo), _f64(grid_step)
+    d = lo.shape[0]
+    cnt = np.ascontiguousarray(grid_count, dtype=np.int64)
+    total = int(np.prod(cnt))
+    m = total - first if M < 0 else M
+    arr = _slice_array(slices)
+    co = _f64(coefs, (y_dim,))
+    b = None if best is None else np.array([best], dtype=np.float64)
+    ym, lbv, ubv = _opt(y_max), _opt(lb), _opt(ub)
+    cm = _opt(cons_mask, np.uint8)
+    pm = None if prior_mean_s is None else np.ascontiguousarray(np.asarray(prior_mean_s, dtype=np.float64).T)
+    acq = np.empty(m) if want_acq else None
+    bv, bi, bx = C.c_double(), C.c_int64(), np.empty(d)
+    _check(lib.boss_ei_score_grid(arr, y_dim, n_samples, d, _ptr(lo), _ptr(st), _ptr(cnt), int(first), int(M), _ptr(pm),
+                                  _ptr(co), _ptr(b), _ptr(ym), _ptr(lbv), _ptr(ubv), _ptr(cm), _ptr(acq), C.byref(bv),
+                                  C.byref(bi), _ptr(bx)), "boss_ei_score_grid")
+    return acq, bv.value, bi.value, bx
+
+
+def ei_score_uniform(slices, y_dim, n_samples, seed, M, box_lb, box_ub, coefs, best, y_max, first=0, cons_mask=None,
+                     prior_mean_s=None, want_acq=False):
+    """Uniform-box candidates generated on the device (stateless counter hash).  -> acq, best_val, best_idx, best_x."""
+    lbv, ubv = _f64(box_lb), _f64(box_ub)
+    d = lbv.shape[0]
+    arr = _slice_array(slices)
+    co = _f64(coefs, (y_dim,))
+    b = None if best is None else np.array([best], dtype=np.float64)
+    ym = _opt(y_max)
+    cm = _opt(cons_mask, np.uint8)
+    pm = None if prior_mean_s is None else np.ascontiguousarray(np.asarray(prior_mean_s, dtype=np.float64).T)
+    acq = np.empty(M) if want_acq else None
+    bv, bi, bx = C.c_double(), C.c_int64(), np.empty(d)
+    _check(lib.boss_ei_score_uniform(arr, y_dim, n_samples, d, int(seed), int(first), int(M), _ptr(lbv), _ptr(ubv),
+                                     _ptr(pm), _ptr(co), _ptr(b), _ptr(ym), _ptr(cm), _ptr(acq), C.byref(bv), C.byref(bi),
+                                     _ptr(bx)), "boss_ei_score_uniform")
+    return acq, bv.value, bi.value, bx
+
+
+def uniform_candidates(seed, first, M, box_lb, box_ub):
+    """Host reproduction of the device generator (tests, and callers that want the coordinates of an index)."""
+    lbv, ubv = _f64(box_lb), _f64(box_ub)
+    d = lbv.shape[0]
+    ctr = (np.arange(first, first + M, dtype=np.uint64)[:, None] * np.uint64(d) + np.arange(d, dtype=np.uint64)[None, :])
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed) + (ctr + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    u = (z >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+    return (lbv[None, :] + u * (ubv - lbv)[None, :]).T          # d x M  (lb + u*w is one rounding apart from fma at most)
 
 
 def ei_value_grad(slices, y_dim, n_samples, Xs, coefs, best, y_max, lb=None, ub=None, cons_mask=None,

@@ -664,6 +664,7 @@ struct ScoreArgs {
   bool dev;          // arrays are device pointers
   bool want_argmax;
   int any_fail;      // out
+  const CandGen *gen = nullptr;   // candidates generated on the device (Xs == NULL); other arrays are host pointers
 };
 
 int score_core(ScoreArgs &a) {
@@ -765,7 +766,12 @@ int score_core(ScoreArgs &a) {
       grad_dev = a.grad;
       pmg_dev = a.prior_mean_grad;
     } else {
-      CUDA_TRY(cudaMemcpyAsync(g.xs_stage.p, a.Xs + (size_t)m0 * d, (size_t)ch * d * 8, cudaMemcpyHostToDevice, g.stream));
+      if (a.gen) {
+        gen_candidates_kernel<<<(ch * d + 255) / 256, 256, 0, g.stream>>>(*a.gen, m0, ch, g.xs_stage.as<double>());
+        ++g.launches;
+      } else {
+        CUDA_TRY(cudaMemcpyAsync(g.xs_stage.p, a.Xs + (size_t)m0 * d, (size_t)ch * d * 8, cudaMemcpyHostToDevice, g.stream));
+      }
       xs_dev = g.xs_stage.as<double>();
       if (a.prior_mean) {
         CUDA_TRY(cudaMemcpyAsync(g.pm_stage.p, a.prior_mean + (size_t)m0 * a.y_dim, (size_t)ch * a.y_dim * 8,
@@ -1037,6 +1043,90 @@ int boss_ei_score_dev(const boss_gp *const *slices, int y_dim, int n_samples, co
   (void)stream;  // work is ordered on the library stream and synchronised before return
   return ei_score_impl(slices, y_dim, n_samples, Xs_dev, M, prior_mean_s_dev, fit_coefs, best, y_max, lb, ub,
                        cons_mask_dev, acq_dev, grad_dev, best_val, best_idx, true);
+}
+
+static int ei_score_generated(const CandGen &gen, int64_t M, const boss_gp *const *slices, int y_dim, int n_samples,
+                              const double *prior_mean_s, const double *fit_coefs, const double *best, const double *y_max,
+                              const double *lb, const double *ub, const uint8_t *cons_mask, double *acq, double *best_val,
+                              int64_t *best_idx, double *best_x) {
+  std::lock_guard<std::mutex> lk(g.mu);
+  REQUIRE_INIT();
+  if (!slices || y_dim < 1 || n_samples < 1 || !fit_coefs || !slices[0]) return fail(BOSS_ERR_ARG, "boss_ei_score_*: bad arguments");
+  if ((lb == nullptr) != (ub == nullptr)) return fail(BOSS_ERR_ARG, "boss_ei_score_*: lb and ub must be given together");
+  if (gen.d != slices[0]->d) return fail(BOSS_ERR_ARG, "boss_ei_score_*: x_dim mismatch");
+  ScoreArgs a{};
+  a.slices = slices;
+  a.y_dim = y_dim;
+  a.n_samples = n_samples;
+  a.Xs = nullptr;
+  a.M = M;
+  a.prior_mean = prior_mean_s;
+  a.coefs = fit_coefs;
+  a.best = best;
+  a.y_max = y_max;
+  a.lb = lb;
+  a.ub = ub;
+  a.cons_mask = cons_mask;
+  a.acq = acq;
+  int64_t bi = -1;
+  double bv = 0.0;
+  a.best_val = &bv;
+  a.best_idx = &bi;
+  a.dev = false;
+  a.want_argmax = true;
+  a.gen = &gen;
+  int rc = score_core(a);
+  if (rc) return rc;
+  if (best_val) *best_val = bv;
+  if (best_idx) *best_idx = bi < 0 ? bi : gen.first + bi;                  // global index
+  if (best_x && bi >= 0)
+    for (int j = 0; j < gen.d; ++j) best_x[j] = cand_coord(gen, gen.first + bi, j);   // same arithmetic as the device generator
+  return 0;
+}
+
+int boss_ei_score_grid(const boss_gp *const *slices, int y_dim, int n_samples, int d, const double *grid_lo,
+                       const double *grid_step, const int64_t *grid_count, int64_t first, int64_t M,
+                       const double *prior_mean_s, const double *fit_coefs, const double *best, const double *y_max,
+                       const double *lb, const double *ub, const uint8_t *cons_mask, double *acq, double *best_val,
+                       int64_t *best_idx, double *best_x) {
+  if (d < 1 || d > 32 || !grid_lo || !grid_step || !grid_count || first < 0)
+    return fail(BOSS_ERR_ARG, "boss_ei_score_grid: bad grid");
+  CandGen gen{};
+  gen.mode = 1;
+  gen.d = d;
+  gen.first = first;
+  int64_t total = 1;
+  for (int j = 0; j < d; ++j) {
+    if (grid_count[j] < 1) return fail(BOSS_ERR_ARG, "boss_ei_score_grid: grid_count must be >= 1");
+    gen.lo[j] = grid_lo[j];
+    gen.step[j] = grid_step[j];
+    gen.count[j] = grid_count[j];
+    if (total > ((int64_t)1 << 40)) return fail(BOSS_ERR_ARG, "boss_ei_score_grid: grid too large");
+    total *= grid_count[j];
+  }
+  if (M < 0) M = total - first;
+  if (first + M > total) return fail(BOSS_ERR_ARG, "boss_ei_score_grid: shard exceeds the grid");
+  return ei_score_generated(gen, M, slices, y_dim, n_samples, prior_mean_s, fit_coefs, best, y_max, lb, ub, cons_mask, acq,
+                            best_val, best_idx, best_x);
+}
+
+int boss_ei_score_uniform(const boss_gp *const *slices, int y_dim, int n_samples, int d, uint64_t seed, int64_t first,
+                          int64_t M, const double *box_lb, const double *box_ub, const double *prior_mean_s,
+                          const double *fit_coefs, const double *best, const double *y_max, const uint8_t *cons_mask,
+                          double *acq, double *best_val, int64_t *best_idx, double *best_x) {
+  if (d < 1 || d > 32 || !box_lb || !box_ub || M < 0 || first < 0)
+    return fail(BOSS_ERR_ARG, "boss_ei_score_uniform: bad arguments");
+  CandGen gen{};
+  gen.mode = 2;
+  gen.d = d;
+  gen.seed = seed;
+  gen.first = first;
+  for (int j = 0; j < d; ++j) {
+    gen.lo[j] = box_lb[j];
+    gen.step[j] = box_ub[j] - box_lb[j];
+  }
+  return ei_score_generated(gen, M, slices, y_dim, n_samples, prior_mean_s, fit_coefs, best, y_max, box_lb, box_ub,
+                            cons_mask, acq, best_val, best_idx, best_x);
 }
 
 int boss_ei_value_grad(const boss_gp *const *slices, int y_dim, int n_samples, const double *Xs, int64_t M,

@@ -362,6 +362,52 @@ __global__ void __launch_bounds__(256) cov_finish_kernel(CovFinishParams p) {
   p.cov[(size_t)j * p.M + i] = v;
 }
 
+// ---------------------------------------------------------------------------------------------
+// device-side candidate generation: the batch never exists in host memory
+//   grid     GridAM's Iterators.product of per-dimension ranges, first dimension fastest (grid.jl:30-43):
+//            x_j = lo_j + step_j * ((m / prod_{i<j} count_i) mod count_j)
+//   uniform  SamplingAM with a uniform prior over the box (sampling.jl:59-75): counter-based generator,
+//            x_j = lb_j + u(seed, m, j) (ub_j - lb_j),  u = splitmix64(seed + (m*d + j) * golden) >> 11 * 2^-53
+//            (stateless, so any shard of [0, M) reproduces the same points on any number of GPUs)
+// ---------------------------------------------------------------------------------------------
+struct CandGen {
+  int mode;   // 0 = candidates supplied by the caller, 1 = grid, 2 = uniform box
+  int d;
+  double lo[32], step[32];      // grid origin / step, or box lower bound / width
+  long long count[32];          // grid points per dimension
+  unsigned long long seed;
+  long long first;              // global index of the shard's first candidate (multi-GPU: contiguous index blocks)
+};
+
+__host__ __device__ __forceinline__ double splitmix_unit(unsigned long long seed, unsigned long long ctr) {
+  unsigned long long z = seed + (ctr + 1ull) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+
+__host__ __device__ __forceinline__ double cand_coord(const CandGen &gq, long long m, int j) {
+  if (gq.mode == 1) {
+    long long r = m;
+    for (int i = 0; i < j; ++i) r /= gq.count[i];
+    return fma((double)(r % gq.count[j]), gq.step[j], gq.lo[j]);
+  }
+  // plain multiply-then-add (two roundings) so that any host language reproduces the points bit for bit
+#ifdef __CUDA_ARCH__
+  return __dadd_rn(gq.lo[j], __dmul_rn(splitmix_unit(gq.seed, (unsigned long long)m * gq.d + j), gq.step[j]));
+#else
+  volatile double t = splitmix_unit(gq.seed, (unsigned long long)m * gq.d + j) * gq.step[j];
+  return gq.lo[j] + t;
+#endif
+}
+
+__global__ void gen_candidates_kernel(CandGen gq, long long m0, int ch, double *xs) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ch * gq.d) return;
+  xs[e] = cand_coord(gq, gq.first + m0 + e / gq.d, e % gq.d);
+}
+
 // Scale + round training inputs once per fit: Xt[k][i] = round?(X[k*d+i]) * invl[i], zero padded.
 __global__ void scale_train_kernel(const double *X, int d, int n, int n_pad, int DP, const double *invl,
                                    unsigned long long disc_bits, double *Xt) {

@@ -169,6 +169,39 @@ def data_loglike(model, data: ExperimentData):
     return ll
 
 
+def data_loglike_and_grad(model, data: ExperimentData):
+    """(params | list of params) -> (loglik, grad): the data log-likelihood and its gradient w.r.t. the GP
+    hyper-parameters as GaussianProcessParams-shaped arrays (d lengthscales x y_dim, amplitudes, noise_std).
+    What `AutoForwardDiff` gives OptimizationMAP / NUTS in the reference (src/model_fitters/optimization.jl:41,153),
+    evaluated as one batched device call per output slice.  GaussianProcess models only (a Semiparametric
+    model's theta-gradient would need the user's predict closure differentiated on the host)."""
+    if isinstance(model, Semiparametric):
+        raise NotImplementedError("data_loglike_and_grad: GaussianProcess models only")
+
+    def llg(params):
+        single = not isinstance(params, (list, tuple))
+        plist = [params] if single else list(params)
+        S, d = len(plist), data.x_dim
+        total = np.zeros(S)
+        grads = [GaussianProcessParams(np.zeros((d, data.y_dim)), np.zeros(data.y_dim), np.zeros(data.y_dim))
+                 for _ in range(S)]
+        kid, mask = _kernel_parts(model.kernel)
+        for i in range(data.y_dim):
+            m = model.mean_at(i, data.X)
+            Ymm = data.Y[i] if m is None else data.Y[i] - m
+            L = np.stack([p.lengthscales[:, i] for p in plist])
+            A = np.array([p.amplitudes[i] for p in plist])
+            N = np.array([p.noise_std[i] for p in plist])
+            ll, g = _lib.loglik_grad_batch(data.X, Ymm, L, A, N, kid, mask)
+            total += ll
+            for s in range(S):
+                grads[s].lengthscales[:, i] = g[s, :d]
+                grads[s].amplitudes[i] = g[s, d]
+                grads[s].noise_std[i] = g[s, d + 1]
+        return (float(total[0]), grads[0]) if single else (total, grads)
+    return llg
+
+
 # ---- Semiparametric (src/models/semiparametric.jl) ---------------------------------------------------
 @dataclass
 class SemiparametricParams:

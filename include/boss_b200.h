@@ -124,6 +124,25 @@ int boss_ei_score_dev(const boss_gp *const *slices, int y_dim, int n_samples, co
                       const double *y_max, const double *lb, const double *ub, const uint8_t *cons_mask_dev,
                       double *acq_dev, double *grad_dev, double *best_val, int64_t *best_idx, void *stream);
 
+/* Same scoring with the candidates GENERATED ON THE DEVICE -- the batch never exists in host memory
+ * (16 Mi x 8 candidates = 1 GiB in BASELINE config C2).  Indices are global; a shard [first, first + M) of the
+ * index range reproduces exactly the points of the unsharded call, so multi-GPU sharding is by index block.
+ *   grid     GridAM's Iterators.product over per-dimension ranges, first dimension fastest
+ *            (src/acquisition_maximizers/grid.jl:30-43): x_j = lo_j + step_j * ((m / prod_{i<j} count_i) mod count_j);
+ *            M = -1 scores to the end of the grid
+ *   uniform  SamplingAM with a uniform prior over the box (src/acquisition_maximizers/sampling.jl:59-75):
+ *            x_j = lb_j + u(seed, m*d + j) (ub_j - lb_j), u a stateless splitmix64 counter hash in [0, 1)
+ *   prior_mean_s / cons_mask / acq  optional HOST arrays indexed by (m - first);  best_x d coordinates of the winner */
+int boss_ei_score_grid(const boss_gp *const *slices, int y_dim, int n_samples, int d, const double *grid_lo,
+                       const double *grid_step, const int64_t *grid_count, int64_t first, int64_t M,
+                       const double *prior_mean_s, const double *fit_coefs, const double *best, const double *y_max,
+                       const double *lb, const double *ub, const uint8_t *cons_mask, double *acq, double *best_val,
+                       int64_t *best_idx, double *best_x);
+int boss_ei_score_uniform(const boss_gp *const *slices, int y_dim, int n_samples, int d, uint64_t seed, int64_t first,
+                          int64_t M, const double *box_lb, const double *box_ub, const double *prior_mean_s,
+                          const double *fit_coefs, const double *best, const double *y_max, const uint8_t *cons_mask,
+                          double *acq, double *best_val, int64_t *best_idx, double *best_x);
+
 /* Value + analytic x-gradient of the same acquisition for a batch of points: what OptimizationAM's
  * multi-start solver needs per iteration over all starts (src/acquisition_maximizers/optimization.jl:89-118;
  * the reference obtains the gradient by pushing ForwardDiff.Dual numbers through the posterior).

@@ -146,3 +146,25 @@ def test_sequential_batch_am_matches_refit_per_pick():
         picks.append(x)
     assert np.array_equal(Xb, np.stack(picks, axis=1))
     assert len({tuple(c) for c in Xb.T}) == 4                          # speculative points push the picks apart
+
+
+def test_data_loglike_and_grad_matches_finite_differences():
+    prob = _problem(seed=5, n=18, f=lambda x: np.array([np.sin(x[0]), np.cos(x[1]) + 0.1 * x[0]]))
+    rng = np.random.default_rng(0)
+    p = B.GaussianProcessParams(rng.uniform(1.0, 3.0, (2, 2)), rng.uniform(0.5, 1.5, 2), rng.uniform(0.05, 0.2, 2))
+    ll = B.data_loglike(prob.model, prob.data)
+    llg = B.data_loglike_and_grad(prob.model, prob.data)
+    v, g = llg(p)
+    assert abs(v - ll(p)) <= 1e-9 * abs(v)
+    h = 1e-6
+    for name in ("lengthscales", "amplitudes", "noise_std"):
+        arr = getattr(p, name)
+        for idx in np.ndindex(arr.shape):
+            pp = B.GaussianProcessParams(p.lengthscales.copy(), p.amplitudes.copy(), p.noise_std.copy())
+            pm = B.GaussianProcessParams(p.lengthscales.copy(), p.amplitudes.copy(), p.noise_std.copy())
+            getattr(pp, name)[idx] += h
+            getattr(pm, name)[idx] -= h
+            fd = (ll(pp) - ll(pm)) / (2 * h)
+            assert abs(getattr(g, name)[idx] - fd) <= 1e-5 * max(1.0, abs(fd)), (name, idx)
+    vals, grads = llg([p, p])
+    assert vals[0] == vals[1] == v and np.array_equal(grads[1].lengthscales, g.lengthscales)

@@ -465,3 +465,47 @@ def test_loglik_grad_discrete_and_per_sample_mean(lib):
     ll, g = lib.loglik_grad_batch(X, Ymm, L * 3, A, N, 2, discrete_mask=mask)
     assert relerr(ll, ll_ref) <= TOL_LL
     assert np.max(np.abs(g - g_ref) / np.max(np.abs(g_ref), axis=1, keepdims=True)) <= 1e-8
+
+
+# ---------------------------------------------------------------------------------------------
+# device-side candidate generation: grid and uniform box
+# ---------------------------------------------------------------------------------------------
+def test_ei_score_grid_generated_on_device(lib):
+    n, d = 150, 3
+    X, Y, ls, amp, ns = make_problem(n, d, seed=1500)
+    gp = lib.gp_fit(X, Y[0], ls[0], amp[0], ns[0], 2)
+    lo, step, cnt = np.array([0.0, 0.125, -0.25]), np.array([0.0625, 0.125, 0.25]), np.array([17, 8, 7])
+    # Iterators.product order: first dimension fastest (exact dyadic arithmetic -> host grid == device grid)
+    idx = np.arange(int(np.prod(cnt)))
+    pts = np.stack([lo[0] + step[0] * (idx % cnt[0]), lo[1] + step[1] * ((idx // cnt[0]) % cnt[1]),
+                    lo[2] + step[2] * (idx // (cnt[0] * cnt[1]))])
+    best = float(np.quantile(Y[0], 0.7))
+    lb, ub = np.zeros(d), np.ones(d)                                   # third dimension partly out of bounds -> 0.
+    ref, bv_ref, bi_ref = lib.ei_score([gp], 1, 1, pts, [1.0], best, None, lb, ub)
+    acq, bv, bi, bx = lib.ei_score_grid([gp], 1, 1, lo, step, cnt, [1.0], best, None, lb, ub, want_acq=True)
+    assert np.array_equal(acq, ref) and bi == bi_ref and bv == bv_ref and np.array_equal(bx, pts[:, bi])
+    # shards of the index range reproduce the unsharded call (multi-GPU sharding by index block)
+    cut = 431
+    a0, v0, i0, _ = lib.ei_score_grid([gp], 1, 1, lo, step, cnt, [1.0], best, None, lb, ub, first=0, M=cut, want_acq=True)
+    a1, v1, i1, x1 = lib.ei_score_grid([gp], 1, 1, lo, step, cnt, [1.0], best, None, lb, ub, first=cut, want_acq=True)
+    assert np.array_equal(np.concatenate([a0, a1]), ref)
+    assert (i0 if v0 >= v1 else i1) == bi_ref
+    assert np.array_equal(x1, pts[:, i1])
+    gp.free()
+
+
+def test_ei_score_uniform_generated_on_device(lib):
+    n, d, M = 200, 5, 20000
+    X, Y, ls, amp, ns = make_problem(n, d, seed=1600)
+    gp = lib.gp_fit(X, Y[0], ls[0], amp[0], ns[0], 0)
+    lb, ub = np.full(d, 0.1), np.array([0.9, 1.0, 0.7, 0.95, 0.8])
+    pts = lib.uniform_candidates(1234, 0, M, lb, ub)                    # host reproduction of the counter hash
+    assert pts.min() >= 0.1 and np.all(pts.max(axis=1) <= ub)
+    assert abs(pts.mean() - 0.5 * (lb + ub).mean()) < 0.01
+    best = float(np.quantile(Y[0], 0.8))
+    ref, bv_ref, bi_ref = lib.ei_score([gp], 1, 1, pts, [1.0], best, None, lb, ub)
+    acq, bv, bi, bx = lib.ei_score_uniform([gp], 1, 1, 1234, M, lb, ub, [1.0], best, None, want_acq=True)
+    assert np.array_equal(acq, ref) and bi == bi_ref and bv == bv_ref and np.array_equal(bx, pts[:, bi])
+    a1, v1, i1, x1 = lib.ei_score_uniform([gp], 1, 1, 1234, 5000, lb, ub, [1.0], best, None, first=15000, want_acq=True)
+    assert np.array_equal(a1, ref[15000:]) and i1 == 15000 + int(np.argmax(ref[15000:]))
+    gp.free()
