@@ -50,6 +50,8 @@ EXPORTS = {
                                      _vp, _vp, _vp, _vp, _dp, _i64p, _vp]),
     "boss_ei_score_uniform": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int64, C.c_int64, _vp, _vp, _vp,
                                         _vp, _vp, _vp, _vp, _vp, _dp, _i64p, _vp]),
+    "boss_ei_maximize_multistart": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp,
+                                              _vp, _vp, _vp, _vp, _vp, _dp, _i64p, C.POINTER(C.c_int)]),
     "boss_ei_value_grad": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                      _vp]),
     "boss_ei_value_grad_dev": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
@@ -267,6 +269,27 @@ def ei_score_uniform(slices, y_dim, n_samples, seed, M, box_lb, box_ub, coefs, b
                                      _ptr(pm), _ptr(co), _ptr(b), _ptr(ym), _ptr(cm), _ptr(acq), C.byref(bv), C.byref(bi),
                                      _ptr(bx)), "boss_ei_score_uniform")
     return acq, bv.value, bi.value, bx
+
+
+def ei_maximize_multistart(slices, y_dim, n_samples, starts, coefs, best, y_max, lb, ub, iters=60, history=8,
+                           discrete_mask=None, prior_mean_affine=None):
+    """Device-resident lock-step multi-start L-BFGS.  -> X (d, M), f (M,), best_x (d,), best_val, best_idx, evals."""
+    Xc = _cols(starts)
+    M, d = Xc.shape
+    arr = _slice_array(slices)
+    co = _f64(coefs, (y_dim,))
+    b = None if best is None else np.array([best], dtype=np.float64)
+    ym = _opt(y_max)
+    lbv, ubv = _f64(lb, (d,)), _f64(ub, (d,))
+    dm = _opt(discrete_mask, np.uint8)
+    xo = np.empty((M, d)); fo = np.empty(M); bx = np.empty(d)
+    bv, bi, ev = C.c_double(), C.c_int64(), C.c_int()
+    aff = None if prior_mean_affine is None else _f64(prior_mean_affine, (y_dim, d + 1))
+    _check(lib.boss_ei_maximize_multistart(arr, y_dim, n_samples, _ptr(Xc), M, int(iters), int(history), _ptr(aff),
+                                           _ptr(co), _ptr(b),
+                                           _ptr(ym), _ptr(lbv), _ptr(ubv), _ptr(dm), _ptr(xo), _ptr(fo), _ptr(bx),
+                                           C.byref(bv), C.byref(bi), C.byref(ev)), "boss_ei_maximize_multistart")
+    return xo.T, fo, bx, bv.value, bi.value, ev.value
 
 
 def uniform_candidates(seed, first, M, box_lb, box_ub):

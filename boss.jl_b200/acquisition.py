@@ -47,6 +47,13 @@ class Acquisition:
         self.y_max = None if np.all(np.isinf(problem.y_max)) else problem.y_max
         self.cons_safe = ei.cons_safe
 
+    def device_resident_ok(self):
+        """True when nothing on the scoring path is a host closure (prior means, `cons`), i.e. the device-resident
+        multi-start driver can run the whole solve."""
+        probe = np.zeros((self.problem.data.x_dim, 1))
+        no_mean = all(m.mean_at(i, probe) is None for i, m in enumerate(self.models))
+        return no_mean and self.problem.domain.cons is None and self.cons_safe
+
     def _prior_mean(self, X):
         ms = [m.mean_at(i, X) for i, m in enumerate(self.models)]
         if all(v is None for v in ms):

@@ -196,6 +196,14 @@ def maximize_acquisition(am, problem: BossProblem, options: BossOptions = BossOp
             starts = (0.5 * (lb + ub))[:, None] if am.multistart == 1 else generate_LHC(dom.bounds, am.multistart, am.rng)
         else:
             starts = np.asarray(am.multistart, dtype=np.float64)
+        if acq.device_resident_ok():
+            # no host closures on the path (prior mean, cons): the whole multi-start solve stays on the device
+            _, f, bx, bv, _, _ = _lib.ei_maximize_multistart(acq.slices, acq.y_dim, len(acq.posts), starts, acq.coefs,
+                                                             acq.best, acq.y_max, lb, ub, am.iters, am.history,
+                                                             discrete_mask=dom.discrete if dom.discrete.any() else None)
+            if np.isneginf(bv):
+                raise RuntimeError("All optimization runs failed!")                  # optim_multistart.jl:34
+            return bx, bv
         X, f = batched_lbfgs_maximize(acq.value_and_grad, starts, lb, ub, am.iters, am.history)
         if np.all(np.isneginf(f)):
             raise RuntimeError("All optimization runs failed!")                      # optim_multistart.jl:34

@@ -23,6 +23,7 @@
 #include "grad.cuh"
 #include "small.cuh"
 #include "append.cuh"
+#include "multistart.cuh"
 
 using namespace boss;
 
@@ -72,7 +73,7 @@ struct Ctx {
   // workspaces
   DevBuf ks, muv, sumsq, xs_stage, pm_stage, cm_stage, acq_stage, mu_stage, var_stage, st_stage, grad_stage;
   DevBuf blk_val, blk_idx, small, chol_L, chol_Winv, chol_misc, tt, vt, ut, dmu, dvar, pmg_stage;
-  DevBuf part_mu, part_ss, part_gm, part_gv, cov_p, cov_stage, chol_W, chol_WT, ll_vec, ll_part;   // split-invariant partial sums (score.cuh / grad.cuh)
+  DevBuf part_mu, part_ss, part_gm, part_gv, cov_p, cov_stage, chol_W, chol_WT, ll_vec, ll_part, ms_buf;   // split-invariant partial sums (score.cuh / grad.cuh)
   // event pool for per-kernel-class timing
   cudaEvent_t ev_a[EV_POOL], ev_b[EV_POOL];
   int ev_class[EV_POOL];
@@ -381,7 +382,7 @@ void boss_shutdown(void) {
                     &g.var_stage, &g.st_stage, &g.grad_stage, &g.blk_val, &g.blk_idx, &g.small, &g.chol_L,
                     &g.chol_Winv, &g.chol_misc, &g.tt, &g.vt, &g.ut, &g.dmu, &g.dvar, &g.pmg_stage, &g.part_mu,
                     &g.part_ss, &g.part_gm, &g.part_gv, &g.cov_p, &g.cov_stage, &g.chol_W, &g.chol_WT, &g.ll_vec,
-                    &g.ll_part})
+                    &g.ll_part, &g.ms_buf})
     b->release();
   if (g.ev_ready) {
     for (int i = 0; i < EV_POOL; ++i) {
@@ -1127,6 +1128,163 @@ int boss_ei_score_uniform(const boss_gp *const *slices, int y_dim, int n_samples
   }
   return ei_score_generated(gen, M, slices, y_dim, n_samples, prior_mean_s, fit_coefs, best, y_max, box_lb, box_ub,
                             cons_mask, acq, best_val, best_idx, best_x);
+}
+
+// Device-resident lock-step multi-start maximisation of the acquisition (multistart.cuh).
+int boss_ei_maximize_multistart(const boss_gp *const *slices, int y_dim, int n_samples, const double *starts, int64_t M,
+                                int iters, int history, const double *prior_mean_affine, const double *fit_coefs,
+                                const double *best, const double *y_max, const double *lb, const double *ub,
+                                const uint8_t *discrete_mask, double *x_out, double *f_out, double *best_x,
+                                double *best_val, int64_t *best_idx, int *evals_out) {
+  std::lock_guard<std::mutex> lk(g.mu);
+  REQUIRE_INIT();
+  if (!slices || !slices[0] || y_dim < 1 || n_samples < 1 || !starts || M < 1 || !fit_coefs || !lb || !ub)
+    return fail(BOSS_ERR_ARG, "boss_ei_maximize_multistart: bad arguments (the box lb/ub is required)");
+  const int d = slices[0]->d;
+  if (d > MS_MAXD) return fail(BOSS_ERR_ARG, "boss_ei_maximize_multistart: x_dim > 32");
+  const int H = std::max(1, std::min(history, MS_MAXH - 1));
+  const int RC = H + 1;   // ring capacity: H live pairs + one free slot for the pair being formed
+  if (iters < 0) iters = 0;
+  const size_t Md = (size_t)M * d;
+  // carve one workspace: X Xt Xn | g gt gn | dirn | Sh Yh | f ft fn t | done | moved, counters
+  const size_t FANCAP = 4;   // compact trial buffers hold up to 4 M points (fan of MS_FAN steps for <= 0.4 M stragglers)
+  const size_t n_aff = prior_mean_affine ? (size_t)y_dim * (d + 1) + FANCAP * ((size_t)M * y_dim + Md * y_dim) : 0;
+  const size_t n_dbl = 3 * Md + 3 * Md + Md + 2 * (size_t)RC * Md + 4 * (size_t)M + n_aff + FANCAP * (2 * Md + M);
+  CUDA_TRY(g.ms_buf.ensure(n_dbl * 8 + (size_t)M * 12 + 64));
+  double *base = g.ms_buf.as<double>();
+  MsState st{};
+  st.d = d;
+  st.H = RC;
+  st.M = M;
+  st.X = base;
+  st.Xt = st.X + Md;
+  st.Xn = st.Xt + Md;
+  st.g = st.Xn + Md;
+  st.gt = st.g + Md;
+  st.gn = st.gt + Md;
+  st.dirn = st.gn + Md;
+  st.Sh = st.dirn + Md;
+  st.Yh = st.Sh + (size_t)RC * Md;
+  st.f = st.Yh + (size_t)RC * Md;
+  st.ft = st.f + M;
+  st.fn = st.ft + M;
+  st.t = st.fn + M;
+  double *aff = st.t + M, *pm = aff + (size_t)y_dim * (d + 1), *pmg = pm + FANCAP * (size_t)M * y_dim;
+  if (prior_mean_affine)
+    CUDA_TRY(cudaMemcpyAsync(aff, prior_mean_affine, (size_t)y_dim * (d + 1) * 8, cudaMemcpyHostToDevice, g.stream));
+  st.Xc = st.t + M + n_aff;
+  st.gc = st.Xc + FANCAP * Md;
+  st.fc = st.gc + FANCAP * Md;
+  st.moved_bits = reinterpret_cast<unsigned long long *>(st.fc + FANCAP * M);
+  st.counters = reinterpret_cast<int *>(st.moved_bits + 1);
+  st.done = st.counters + 4;
+  st.frozen = st.done + M;
+  st.idx = st.frozen + M;
+  CUDA_TRY(cudaMemsetAsync(st.frozen, 0, (size_t)M * 4, g.stream));
+  double span = 0.0;
+  for (int j = 0; j < d; ++j) {
+    st.lb[j] = lb[j];
+    st.ub[j] = ub[j];
+    span = std::max(span, ub[j] - lb[j]);
+  }
+  st.step0 = 0.1 * span;
+  const unsigned nbm = (unsigned)((M + 127) / 128);
+
+  long long evaluated = 0;
+  auto eval = [&](const double *Xp, long long Mp, double *fp, double *gp, bool want_best, double *bv, int64_t *bi) -> int {
+    ScoreArgs a{};
+    a.slices = slices;
+    a.y_dim = y_dim;
+    a.n_samples = n_samples;
+    a.Xs = Xp;
+    a.M = Mp;
+    evaluated += Mp;
+    if (prior_mean_affine) {
+      ms_affine_mean_kernel<<<(unsigned)((Mp + 127) / 128), 128, 0, g.stream>>>(Xp, Mp, d, y_dim, aff, pm, pmg);
+      ++g.launches;
+      a.prior_mean = pm;
+      a.prior_mean_grad = gp ? pmg : nullptr;
+    }
+    a.coefs = fit_coefs;
+    a.best = best;
+    a.y_max = y_max;
+    a.lb = lb;
+    a.ub = ub;
+    a.acq = fp;
+    a.grad = gp;
+    a.best_val = bv;
+    a.best_idx = bi;
+    a.dev = true;
+    a.want_argmax = want_best;
+    return score_core(a);
+  };
+
+  CUDA_TRY(cudaMemcpyAsync(st.Xt, starts, Md * 8, cudaMemcpyHostToDevice, g.stream));
+  ms_init_kernel<<<nbm, 128, 0, g.stream>>>(st, st.Xt);
+  int rc = eval(st.X, M, st.f, st.g, false, nullptr, nullptr);
+  if (rc) return rc;
+  ms_sanitize_kernel<<<nbm, 128, 0, g.stream>>>(st.f, M);
+  int hist_len = 0, hist_start = 0;
+  for (int it = 0; it < iters; ++it) {
+    ms_direction_kernel<<<nbm, 128, 0, g.stream>>>(st, hist_len, hist_start);
+    for (int trial = 0; trial < 12; ++trial) {
+      // only the starts that have not yet accepted a step are evaluated again (compacted batch)
+      CUDA_TRY(cudaMemsetAsync(st.counters, 0, 16, g.stream));
+      ms_compact_kernel<<<nbm, 128, 0, g.stream>>>(st);
+      int count = 0;
+      CUDA_TRY(cudaMemcpyAsync(&count, st.counters, 4, cudaMemcpyDeviceToHost, g.stream));
+      CUDA_TRY(cudaStreamSynchronize(g.stream));
+      ++g.launches;
+      if (count == 0) break;
+      if (trial >= 2 && (size_t)count * MS_FAN <= FANCAP * (size_t)M) {
+        // few stragglers left: all remaining step sizes in one batch instead of up to 10 tiny sequential ones
+        ms_fan_kernel<<<(count * MS_FAN + 127) / 128, 128, 0, g.stream>>>(st, count);
+        rc = eval(st.Xc, (long long)count * MS_FAN, st.fc, st.gc, false, nullptr, nullptr);
+        if (rc) return rc;
+        ms_accept_fan_kernel<<<(count + 127) / 128, 128, 0, g.stream>>>(st, count);
+        g.launches += 2;
+        break;
+      }
+      rc = eval(st.Xc, count, st.fc, st.gc, false, nullptr, nullptr);
+      if (rc) return rc;
+      ms_accept_kernel<<<(count + 127) / 128, 128, 0, g.stream>>>(st, count);
+      ++g.launches;
+    }
+    ms_freeze_kernel<<<nbm, 128, 0, g.stream>>>(st);
+    CUDA_TRY(cudaMemsetAsync(st.moved_bits, 0, 8 + 16, g.stream));
+    ms_update_kernel<<<nbm, 128, 0, g.stream>>>(st, (hist_start + hist_len) % RC);   // always a free slot
+    g.launches += 3;
+    struct {
+      unsigned long long moved;
+      int cnt[4];
+    } hs;
+    CUDA_TRY(cudaMemcpyAsync(&hs, st.moved_bits, 24, cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    if (hs.cnt[1]) {   // at least one start produced a valid pair: commit the slot
+      if (hist_len == H)
+        hist_start = (hist_start + 1) % RC;   // drop the oldest pair
+      else
+        ++hist_len;
+    }
+    double moved;
+    std::memcpy(&moved, &hs.moved, 8);
+    if (moved < 1e-10) break;
+  }
+  // final rounding of discrete dimensions and re-evaluation (optimization.jl:116-117), argmax over the starts
+  const unsigned long long disc = mask_bits(discrete_mask, d);
+  if (disc) ms_round_kernel<<<(unsigned)((Md + 255) / 256), 256, 0, g.stream>>>(st.X, M, d, disc);
+  double bv = 0.0;
+  int64_t bi = -1;
+  rc = eval(st.X, M, st.f, nullptr, true, &bv, &bi);
+  if (rc) return rc;
+  if (x_out) CUDA_TRY(cudaMemcpyAsync(x_out, st.X, Md * 8, cudaMemcpyDeviceToHost, g.stream));
+  if (f_out) CUDA_TRY(cudaMemcpyAsync(f_out, st.f, (size_t)M * 8, cudaMemcpyDeviceToHost, g.stream));
+  if (best_x && bi >= 0) CUDA_TRY(cudaMemcpyAsync(best_x, st.X + (size_t)bi * d, (size_t)d * 8, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  if (best_val) *best_val = bv;
+  if (best_idx) *best_idx = bi;
+  if (evals_out) *evals_out = (int)((evaluated + M - 1) / M);   // work in units of full-batch evaluations
+  return 0;
 }
 
 int boss_ei_value_grad(const boss_gp *const *slices, int y_dim, int n_samples, const double *Xs, int64_t M,

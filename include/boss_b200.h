@@ -157,6 +157,25 @@ int boss_ei_value_grad_dev(const boss_gp *const *slices, int y_dim, int n_sample
                            const double *fit_coefs, const double *best, const double *y_max, const double *lb,
                            const double *ub, const uint8_t *cons_mask_dev, double *acq_dev, double *grad_dev);
 
+/* Device-resident multi-start maximisation: OptimizationAM (src/acquisition_maximizers/optimization.jl:55-118)
+ * with all `multistart` local solves advancing in lock-step as projected L-BFGS with Armijo backtracking; every
+ * value + gradient evaluation of all starts is one batched pass on the device, the points never leave HBM
+ * between iterations.  Ends with the reference's discrete rounding + re-evaluation (optimization.jl:116-117) and
+ * the argmax over the starts (first maximal; failed starts = -Inf, optim_multistart.jl:28-42).
+ *   starts d x M; lb / ub the box (required); discrete_mask d bytes or NULL
+ *   prior_mean_affine  y_dim x (d + 1) or NULL: slice i has prior mean c_i + b_i . x with [c_i, b_i1..b_id] at
+ *                      prior_mean_affine + i*(d+1) (constant means, linear parametric part of a Semiparametric model)
+ *   x_out d x M final points, f_out M final values (either may be NULL); best_val == -Inf <=> all runs failed
+ *   evals_out  evaluated points / M (backtracking trials only re-evaluate the starts that have not accepted a step)
+ * General prior-mean closures and `cons` constraints are host code and are not supported here: use
+ * boss_ei_value_grad per iteration for those. */
+int boss_ei_maximize_multistart(const boss_gp *const *slices, int y_dim, int n_samples, const double *starts, int64_t M,
+                                int iters, int history, const double *prior_mean_affine, const double *fit_coefs,
+                                const double *best,
+                                const double *y_max, const double *lb, const double *ub, const uint8_t *discrete_mask,
+                                double *x_out, double *f_out, double *best_x, double *best_val, int64_t *best_idx,
+                                int *evals_out);
+
 /* ---- a8 + a9 : batched log marginal likelihood ------------------------------------------------
  * Replaces data_loglike(::GaussianProcess) / gp_data_loglike_slice (gaussian_process.jl:250-280)
  * -> logpdf(::FiniteGP, y) evaluated for S hyper-parameter vectors at once: the batches built by

@@ -13,15 +13,20 @@
 #   BOSS.data_loglike(::GaussianProcess, ::ExperimentData)
 #       replaces src/models/gaussian_process.jl:250-280                           -> boss_gp_loglik_batch
 #   BOSS.maximize_acquisition(::GridAM | ::SamplingAM, ::BossProblem, ::BossOptions)
-#       replaces src/acquisition_maximizers/grid.jl:45-65, sampling.jl:20-57      -> boss_ei_score
+#       replaces src/acquisition_maximizers/grid.jl:45-65, sampling.jl:20-57      -> boss_ei_score / boss_ei_score_grid
+#   cov / mean_and_cov(::B200Posterior, X)          gaussian_process.jl:163-167,180-184  -> boss_gp_cov
+#   BOSS.maximize_acquisition(::SequentialBatchAM, ...)  batch.jl:26-38                   -> boss_gp_append
+#   data_loglike_and_grad(model, data, params)      optimization.jl:41,153 (ForwardDiff)  -> boss_gp_loglik_grad_batch
 module BossB200
 
 using BOSS
 using BOSS: GaussianProcess, GaussianProcessParams, ExperimentData, ModelPosteriorSlice, BossProblem, BossOptions,
             GridAM, SamplingAM, ExpectedImprovement, LinFitness, mean_getindex, best_so_far, get_params, y_dim
 using KernelFunctions: SqExponentialKernel, Matern32Kernel, Matern52Kernel
-import Statistics: mean, var
-import StatsBase: mean_and_var
+import Statistics: mean, var, cov
+import Base: append!
+using LinearAlgebra: diag
+import StatsBase: mean_and_var, mean_and_cov
 
 const LIB = get(ENV, "BOSS_B200_LIB", joinpath(@__DIR__, "..", "boss.jl_b200", "lib", "libboss_b200.so"))
 
@@ -93,6 +98,33 @@ mean_and_var(post::B200Posterior, x::AbstractVector{<:Real}) = first.(mean_and_v
 mean(post::B200Posterior, x) = mean_and_var(post, x)[1]
 var(post::B200Posterior, x) = mean_and_var(post, x)[2]
 
+# cov / mean_and_cov(::GaussianProcessPosterior, X)  (gaussian_process.jl:163-167,180-184) -> boss_gp_cov
+function mean_and_cov(post::B200Posterior, X::AbstractMatrix{<:Real})
+    Xs = Matrix{Float64}(X)
+    M = size(Xs, 2)
+    pm = isnothing(post.mean) ? C_NULL : eval_mean(post.mean, Xs)
+    μ = Vector{Float64}(undef, M); Σ = Matrix{Float64}(undef, M, M)
+    rc = check(ccall((:boss_gp_cov, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Cdouble}, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}), post.handle, Xs, M, pm, μ, Σ))
+    rc == 2 && throw(DomainError(minimum(diag(Σ)), "The posterior GP predicted a variance below -1e-8."))
+    return μ, Σ
+end
+cov(post::B200Posterior, X::AbstractMatrix{<:Real}) = mean_and_cov(post, X)[2]
+
+# Incremental factor cache: one more data point, same hyper-parameters (O(n^2) instead of a refit).
+# Used by the SequentialBatchAM override below in place of `model_posterior(problem)` per speculative point
+# (src/acquisition_maximizers/batch.jl:26-38).
+function append!(post::B200Posterior, x::AbstractVector{<:Real}, y::Real)
+    xv = Vector{Float64}(x)
+    δ = Float64(y) - first(eval_mean(post.mean, hcat(xv)))
+    ll = Ref{Cdouble}(0.0)
+    rc = check(ccall((:boss_gp_append, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Cdouble, Ref{Cdouble}),
+        post.handle, xv, δ, ll))
+    rc == 1 && throw(BOSS.LinearAlgebra.PosDefException(1))
+    post.loglik = ll[]
+    return post
+end
+
 # ---- batched log-likelihood --------------------------------------------------------------------
 # data_loglike keeps the reference's closure signature (params -> Real) and additionally accepts a
 # vector of params (one library call for the whole batch; used by the batched SamplingMAP below).
@@ -121,6 +153,30 @@ function BOSS.data_loglike(model::GaussianProcess, data::ExperimentData)
     ll_data(p::GaussianProcessParams) = ll_batch([p])[1]
     ll_data(ps::AbstractVector{<:GaussianProcessParams}) = ll_batch(ps)
     return ll_data
+end
+
+# Value + gradient w.r.t. [vec(λ); α; σ] per output slice (the vectorizer order, gaussian_process.jl:300-328):
+# replaces the ForwardDiff.Dual sweep of OptimizationMAP's gradient algorithms / NUTS
+# (src/model_fitters/optimization.jl:41,153).  Returns (ll::Vector (S), grad::Array (d+2, S, y_dim)).
+function data_loglike_and_grad(model::GaussianProcess, data::ExperimentData, ps::AbstractVector{<:GaussianProcessParams})
+    X = Matrix{Float64}(data.X)
+    d, n = size(X)
+    kid = kernel_id(model.kernel); mask = discrete_mask(model.kernel)
+    ydim = size(data.Y, 1); S = length(ps)
+    total = zeros(S); grads = zeros(d + 2, S, ydim)
+    out = Vector{Float64}(undef, S); g = Matrix{Float64}(undef, d + 2, S)
+    for i in 1:ydim
+        δ = Vector{Float64}(data.Y[i, :]) .- eval_mean(mean_getindex(model.mean, i), X)
+        λ = reduce(hcat, [Vector{Float64}(p.λ[:, i]) for p in ps])
+        α = Float64[p.α[i] for p in ps]; σ = Float64[p.σ[i] for p in ps]
+        check(ccall((:boss_gp_loglik_grad_batch, LIB), Cint,
+            (Ptr{Cdouble}, Cint, Cint, Ptr{Cdouble}, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Ptr{UInt8}, Int64,
+             Ptr{Cdouble}, Ptr{Cdouble}),
+            X, d, n, δ, 0, λ, α, σ, kid, isnothing(mask) ? C_NULL : mask, S, out, g))
+        total .+= out
+        grads[:, :, i] .= g
+    end
+    return total, grads
 end
 
 # ---- batched acquisition maximisation -------------------------------------------------------------
@@ -155,6 +211,46 @@ function BOSS.maximize_acquisition(opt::GridAM, problem::BossProblem, options::B
     Xs = reduce(hcat, points)
     _, val, idx = score_batch(problem, Matrix{Float64}(Xs))
     return points[idx], val
+end
+
+# Full product grids without a `cons` filter need no host-side point list at all: the candidates are generated
+# on the device from (lo, step, count) (boss_ei_score_grid; grid.jl:30-43 builds the same Iterators.product).
+function maximize_grid_on_device(problem::BossProblem, lo::Vector{Float64}, step::Vector{Float64}, count::Vector{Int64})
+    ei = problem.acquisition::ExpectedImprovement
+    ps = get_params(problem); samples = ps isa AbstractVector ? ps : [ps]
+    ydim = y_dim(problem)
+    posts = [BOSS.model_posterior_slice(problem.model, p, problem.data, i) for p in samples for i in 1:ydim]
+    all(p -> isnothing(p.mean), posts) || error("BossB200: on-device grids need a zero prior mean (closures run on the host)")
+    handles = Ptr{Cvoid}[p.handle for p in posts]
+    b = best_so_far(problem, ei.fitness)
+    lb, ub = Vector{Float64}.(problem.domain.bounds)
+    bv = Ref{Cdouble}(0.0); bi = Ref{Int64}(-1); bx = Vector{Float64}(undef, length(lo))
+    GC.@preserve posts check(ccall((:boss_ei_score_grid, LIB), Cint,
+        (Ptr{Ptr{Cvoid}}, Cint, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Int64}, Int64, Int64, Ptr{Cdouble}, Ptr{Cdouble},
+         Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{UInt8}, Ptr{Cdouble}, Ref{Cdouble}, Ref{Int64}, Ptr{Cdouble}),
+        handles, ydim, length(samples), length(lo), lo, step, count, 0, -1, C_NULL, Vector{Float64}(ei.fitness.coefs),
+        isnothing(b) ? C_NULL : Ref(Float64(b)), Float64[isinf(c) ? Inf : c for c in problem.y_max], lb, ub, C_NULL, C_NULL,
+        bv, bi, bx))
+    return bx, bv[]
+end
+
+# SequentialBatchAM (batch.jl:26-38) on the appended factor cache: one fit, then O(n^2) per speculative point.
+function BOSS.maximize_acquisition(sb::BOSS.SequentialBatchAM, problem::BossProblem, options::BossOptions)
+    problem_ = deepcopy(problem)
+    ps = get_params(problem_)
+    ps isa AbstractVector && return invoke(BOSS.maximize_acquisition, Tuple{BOSS.SequentialBatchAM, BossProblem, BossOptions},
+                                           sb, problem, options)   # BI samples: stock path
+    ydim = y_dim(problem_)
+    posts = [BOSS.model_posterior_slice(problem_.model, ps, problem_.data, i) for i in 1:ydim]
+    xs = Vector{Vector{Float64}}()
+    for _ in 1:sb.batch_size
+        x, _ = BOSS.maximize_acquisition(sb.am, problem_, options)
+        y = [mean(p, x) for p in posts]
+        BOSS.augment_dataset!(problem_, x, y)
+        foreach(i -> append!(posts[i], x, y[i]), 1:ydim)
+        push!(xs, x)
+    end
+    return reduce(hcat, xs), nothing
 end
 
 end # module

@@ -509,3 +509,61 @@ def test_ei_score_uniform_generated_on_device(lib):
     a1, v1, i1, x1 = lib.ei_score_uniform([gp], 1, 1, 1234, 5000, lb, ub, [1.0], best, None, first=15000, want_acq=True)
     assert np.array_equal(a1, ref[15000:]) and i1 == 15000 + int(np.argmax(ref[15000:]))
     gp.free()
+
+
+# ---------------------------------------------------------------------------------------------
+# device-resident lock-step multi-start optimiser
+# ---------------------------------------------------------------------------------------------
+def test_multistart_on_device_matches_host_driver(lib):
+    """Same algorithm as the host-side batched L-BFGS of the mirror (boss_b200.batched_lbfgs_maximize), which
+    calls boss_ei_value_grad per evaluation: the device-resident driver must land on the same optima."""
+    import boss_b200 as B
+    n, d, M = 120, 3, 96
+    X, Y, ls, amp, ns = make_problem(n, d, seed=1700)
+    gp = lib.gp_fit(X, Y[0], ls[0], amp[0], ns[0], 2)
+    post = O.posterior_fit(X, Y[0], ls[0], amp[0], ns[0], 2)
+    best = float(np.quantile(Y[0], 0.7))
+    lb, ub = np.zeros(d), np.ones(d)
+    starts = B.generate_LHC((lb, ub), M, np.random.default_rng(1))
+    Xd, fd, bx, bv, bi, evals = lib.ei_maximize_multistart([gp], 1, 1, starts, [1.0], best, None, lb, ub, iters=40)
+    vg = lambda Z: lib.ei_value_grad([gp], 1, 1, Z, [1.0], best, None, lb, ub)
+    Xh, fh = B.batched_lbfgs_maximize(vg, starts, lb, ub, iters=40)
+    assert np.all(Xd >= lb[:, None]) and np.all(Xd <= ub[:, None])
+    f0, _, _ = lib.ei_score([gp], 1, 1, starts, [1.0], best, None, lb, ub)
+    assert np.all(fd >= f0 - 1e-15)                                   # monotone: never worse than the start
+    assert np.max(fd) >= np.max(f0) and bi == int(np.argmax(fd)) and bv == fd[bi] and np.array_equal(bx, Xd[:, bi])
+    assert abs(np.max(fd) - np.max(fh)) <= 1e-6 * np.max(fh)           # same best optimum as the host driver
+    close = np.abs(fd - fh) <= 1e-6 * np.maximum(np.abs(fh), 1e-12)
+    assert close.mean() >= 0.9                                        # start by start, up to line-search round-off
+    ref, _, _ = O.ei_acquisition([[post]], Xd, [1.0], best, None, lb, ub)
+    m = ref > 1e-30 * ref.max()
+    assert relerr(fd[m], ref[m]) <= TOL_POST                           # reported values are the acquisition at x_out
+    assert 3 <= evals < 41 * 12          # compaction: only starts still backtracking are re-evaluated
+    # affine prior mean evaluated on the device == the same mean passed as host arrays to boss_ei_value_grad
+    aff = np.array([[0.2, 0.5, -0.3, 0.1]])
+    pm = lambda Z: (aff[0, 0] + aff[0, 1:] @ Z)[None, :]
+    pmg = lambda Z: np.broadcast_to(aff[0, 1:][None, :, None], (1, d, Z.shape[1]))
+    vg2 = lambda Z: lib.ei_value_grad([gp], 1, 1, Z, [1.0], best, None, lb, ub, prior_mean_s=pm(Z), prior_mean_grad_s=pmg(Z))
+    Xa, fa, _, bva, _, _ = lib.ei_maximize_multistart([gp], 1, 1, starts, [1.0], best, None, lb, ub, iters=30,
+                                                      prior_mean_affine=aff)
+    Xh2, fh2 = B.batched_lbfgs_maximize(vg2, starts, lb, ub, iters=30)
+    assert abs(bva - np.max(fh2)) <= 1e-6 * np.max(fh2)
+    chk, _ = vg2(Xa)
+    assert relerr(fa, chk) <= 1e-11      # device fma chain vs numpy for the affine mean: last-bit differences only
+    gp.free()
+
+
+def test_multistart_discrete_rounding_and_failure(lib):
+    n, d = 60, 2
+    X, Y, ls, amp, ns = make_problem(n, d, seed=1800)
+    X = X * 6.0
+    mask = np.array([True, False])
+    gp = lib.gp_fit(X, Y[0], ls[0] * 4, amp[0], ns[0], 2, discrete_mask=mask)
+    lb, ub = np.zeros(d), np.full(d, 6.0)
+    starts = np.random.default_rng(3).random((d, 40)) * 6.0
+    Xd, fd, bx, bv, bi, _ = lib.ei_maximize_multistart([gp], 1, 1, starts, [1.0], float(np.median(Y[0])), None, lb, ub,
+                                                       iters=25, discrete_mask=mask)
+    assert np.array_equal(Xd[0], np.round(Xd[0]))                      # rounded like optimization.jl:116
+    chk, _, _ = lib.ei_score([gp], 1, 1, Xd, [1.0], float(np.median(Y[0])), None, lb, ub)
+    assert np.array_equal(chk, fd)                                     # re-evaluated after rounding
+    gp.free()
