@@ -61,6 +61,7 @@ struct DevBuf {
 };
 
 constexpr int N_TIMERS = 4;
+constexpr int LL_GROUPS = 16;  // max concurrent sub-batches of a log-likelihood window (separate streams)
 constexpr int EV_POOL = 512;
 
 struct Ctx {
@@ -82,6 +83,8 @@ struct Ctx {
   double last_ms[N_TIMERS] = {0, 0, 0, 0};
   int last_cnt[N_TIMERS] = {0, 0, 0, 0};
   cudaEvent_t call_a = nullptr, call_b = nullptr;
+  cudaStream_t ll_stream[LL_GROUPS] = {};
+  cudaEvent_t ll_fork = nullptr, ll_join[LL_GROUPS] = {};
 };
 
 Ctx g;
@@ -368,6 +371,11 @@ int boss_init(int device) {
   }
   CUDA_TRY(cudaEventCreate(&g.call_a));
   CUDA_TRY(cudaEventCreate(&g.call_b));
+  CUDA_TRY(cudaEventCreateWithFlags(&g.ll_fork, cudaEventDisableTiming));
+  for (int i = 0; i < LL_GROUPS; ++i) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&g.ll_stream[i], cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&g.ll_join[i], cudaEventDisableTiming));
+  }
   g.ev_ready = true;
   g.device = device;
   return set_kernel_attrs();
@@ -391,6 +399,11 @@ void boss_shutdown(void) {
     }
     cudaEventDestroy(g.call_a);
     cudaEventDestroy(g.call_b);
+    cudaEventDestroy(g.ll_fork);
+    for (int i = 0; i < LL_GROUPS; ++i) {
+      cudaStreamDestroy(g.ll_stream[i]);
+      cudaEventDestroy(g.ll_join[i]);
+    }
     g.ev_ready = false;
   }
   cudaStreamDestroy(g.stream);
@@ -1478,84 +1491,119 @@ static int loglik_impl(const double *X, int d, int n, const double *Ymm, int64_t
     DISPATCH_KID_DP(launch_loglik_small_t, kernel_id, dp, sp, (int)((S + SMALL_WARPS - 1) / SMALL_WARPS));
     ++g.launches;
   }
+  // A window of up to Sb matrices is live at a time.  Inside a window the matrices are processed as up to
+  // LL_GROUPS independent groups on separate streams: one group's latency-bound steps (diagonal-block
+  // factorisation, forward solve) and partially filled last waves overlap with another group's GEMM launches.
+  cudaStream_t main_stream = g.stream;
+  const size_t winv_stride = (size_t)nblk * TM * TM;
   for (long long s0 = 0; s0 < S && !small; s0 += Sb) {
     const int sb = (int)std::min<long long>(Sb, S - s0);
-    CUDA_TRY(cudaMemsetAsync(status, 0, (size_t)sb * 4, g.stream));
-    BuildKParams bk{};
-    bk.X = dX;
-    bk.d = d;
-    bk.n = n;
-    bk.nblk = nblk;
-    bk.ktiles = ktiles;
-    bk.ls = dls + (size_t)s0 * d;
-    bk.amp = damp + s0;
-    bk.noise = dnoise + s0;
-    bk.disc_bits = disc;
-    bk.K = g.chol_L.as<double>();
-    bk.K_stride = mat;
-    bk.status = status;
-    {
-      Timed t(1);
-      DISPATCH_KID_DP(launch_build_k_t, kernel_id, dp, bk, dim3(nblk * (nblk + 1) / 2, sb));
-      ++g.launches;
-    }
-    if (grad) {   // identity / zero initial state of W and W^T (strictly-upper resp. strictly-lower blocks are never written)
-      CUDA_TRY(cudaMemsetAsync(g.chol_W.p, 0, (size_t)sb * mat * 8, g.stream));
-      CUDA_TRY(cudaMemsetAsync(g.chol_WT.p, 0, (size_t)sb * mat * 8, g.stream));
-    }
-    int rc = run_cholesky(g.chol_L.as<double>(), mat, g.chol_Winv.as<double>(), (size_t)nblk * TM * TM, nblk, ktiles, sb,
-                          logdet_blk, status, grad ? g.chol_W.as<double>() : nullptr,
-                          grad ? g.chol_WT.as<double>() : nullptr, grad ? g.tt.as<double>() : nullptr, mat, tt_stride);
-    if (rc) return rc;
-    FwdParams fp{};
-    fp.L = g.chol_L.as<double>();
-    fp.L_stride = mat;
-    fp.Winv = g.chol_Winv.as<double>();
-    fp.Winv_stride = (size_t)nblk * TM * TM;
-    fp.nblk = nblk;
-    fp.ktiles = ktiles;
-    fp.n = n;
-    fp.ymm = dY + (ldy ? (size_t)s0 * ldy : 0);
-    fp.ldy = ldy;
-    fp.logdet_blk = logdet_blk;
-    fp.status = status;
-    fp.loglik = dll + s0;
-    fp.w_out = nullptr;
-    fwd_solve_loglik_kernel<<<sb, 256, (size_t)(n_pad + 128) * 8, g.stream>>>(fp);
-    ++g.launches;
-    if (grad) {
-      // alpha = W^T (W delta);  K^-1 = W^T W over the factor's storage;  tile partial sums;  final scaling
-      double *dpad = g.ll_vec.as<double>(), *wv = dpad + (size_t)sb * n_pad, *al = wv + (size_t)sb * n_pad;
-      pad_delta_kernel<<<dim3((n_pad + 255) / 256, sb), 256, 0, g.stream>>>(dY + (ldy ? (size_t)s0 * ldy : 0), ldy, n, n_pad, dpad);
-      matvec_p_kernel<<<dim3(n_pad / 64, sb), 256, 0, g.stream>>>(g.chol_W.as<double>(), dpad, wv, ktiles, mat, n_pad, n_pad);
-      matvec_p_kernel<<<dim3(n_pad / 64, sb), 256, 0, g.stream>>>(g.chol_WT.as<double>(), wv, al, ktiles, mat, n_pad, n_pad);
-      KinvParams kp{g.chol_WT.as<double>(), mat, g.chol_L.as<double>(), mat, nblk, ktiles};
-      {
-        Timed t(2);
-        kinv_wtw_kernel<<<dim3(ntiles, sb), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(kp);
+    int want_groups = 4;
+    if (const char *e = getenv("BOSS_LL_GROUPS")) want_groups = std::max(1, std::min(LL_GROUPS, atoi(e)));
+    const int ngroups = (g.timing || sb < 2 * want_groups) ? 1 : want_groups;   // per-kernel-class timing needs one stream
+    const int gsz = (sb + ngroups - 1) / ngroups;
+    if (ngroups > 1) CUDA_TRY(cudaEventRecord(g.ll_fork, main_stream));
+    int rc_all = 0;
+    for (int gi = 0; gi < ngroups; ++gi) {
+      const int wo = gi * gsz;                           // offset of the group inside the window
+      const int gs = std::min(gsz, sb - wo);
+      if (gs <= 0) break;
+      const long long so = s0 + wo;                      // offset of the group inside the batch
+      if (ngroups > 1) {
+        g.stream = g.ll_stream[gi];
+        CUDA_TRY(cudaStreamWaitEvent(g.stream, g.ll_fork, 0));
       }
-      LlGradParams lg{};
-      lg.X = dX;
-      lg.d = d;
-      lg.n = n;
-      lg.nblk = nblk;
-      lg.ktiles = ktiles;
-      lg.ls = dls + (size_t)s0 * d;
-      lg.amp = damp + s0;
-      lg.noise = dnoise + s0;
-      lg.disc_bits = disc;
-      lg.Kinv = g.chol_L.as<double>();
-      lg.K_stride = mat;
-      lg.alpha = al;
-      lg.part = g.ll_part.as<double>();
+      double *Lg = g.chol_L.as<double>() + (size_t)wo * mat;
+      double *Wig = g.chol_Winv.as<double>() + (size_t)wo * winv_stride;
+      double *ldg = logdet_blk + (size_t)wo * nblk;
+      int *stg = status + wo;
+      double *Wg = grad ? g.chol_W.as<double>() + (size_t)wo * mat : nullptr;
+      double *WTg = grad ? g.chol_WT.as<double>() + (size_t)wo * mat : nullptr;
+      double *TTg = grad ? g.tt.as<double>() + (size_t)wo * tt_stride : nullptr;
+      cudaMemsetAsync(stg, 0, (size_t)gs * 4, g.stream);
+      BuildKParams bk{};
+      bk.X = dX;
+      bk.d = d;
+      bk.n = n;
+      bk.nblk = nblk;
+      bk.ktiles = ktiles;
+      bk.ls = dls + (size_t)so * d;
+      bk.amp = damp + so;
+      bk.noise = dnoise + so;
+      bk.disc_bits = disc;
+      bk.K = Lg;
+      bk.K_stride = mat;
+      bk.status = stg;
       {
         Timed t(1);
-        DISPATCH_KID_DP(launch_llgrad_tile_t, kernel_id, dp, lg, dim3(ntiles, sb));
+        DISPATCH_KID_DP(launch_build_k_t, kernel_id, dp, bk, dim3(nblk * (nblk + 1) / 2, gs));
+        ++g.launches;
       }
-      loglik_grad_final_kernel<<<(sb + 127) / 128, 128, 0, g.stream>>>(g.ll_part.as<double>(), ntiles, dp, d, lg.ls, lg.amp,
-                                                                      lg.noise, status, dgrad + (size_t)s0 * (d + 2), sb);
-      g.launches += 6;
+      if (grad) {   // zero initial state of W and W^T (strictly-upper resp. strictly-lower blocks are never written)
+        cudaMemsetAsync(Wg, 0, (size_t)gs * mat * 8, g.stream);
+        cudaMemsetAsync(WTg, 0, (size_t)gs * mat * 8, g.stream);
+      }
+      int rc = run_cholesky(Lg, mat, Wig, winv_stride, nblk, ktiles, gs, ldg, stg, Wg, WTg, TTg, mat, tt_stride);
+      if (rc) rc_all = rc;
+      FwdParams fp{};
+      fp.L = Lg;
+      fp.L_stride = mat;
+      fp.Winv = Wig;
+      fp.Winv_stride = winv_stride;
+      fp.nblk = nblk;
+      fp.ktiles = ktiles;
+      fp.n = n;
+      fp.ymm = dY + (ldy ? (size_t)so * ldy : 0);
+      fp.ldy = ldy;
+      fp.logdet_blk = ldg;
+      fp.status = stg;
+      fp.loglik = dll + so;
+      fp.w_out = nullptr;
+      fwd_solve_loglik_kernel<<<gs, 256, (size_t)(n_pad + 128) * 8, g.stream>>>(fp);
+      ++g.launches;
+      if (grad) {
+        // alpha = W^T (W delta);  K^-1 = W^T W over the factor's storage;  tile partial sums;  final scaling
+        double *vec = g.ll_vec.as<double>();
+        double *dpad = vec + (size_t)wo * n_pad, *wv = vec + ((size_t)Sb + wo) * n_pad, *al = vec + ((size_t)2 * Sb + wo) * n_pad;
+        double *partg = g.ll_part.as<double>() + (size_t)wo * ntiles * (dp + 2);
+        pad_delta_kernel<<<dim3((n_pad + 255) / 256, gs), 256, 0, g.stream>>>(dY + (ldy ? (size_t)so * ldy : 0), ldy, n, n_pad, dpad);
+        matvec_p_kernel<<<dim3(n_pad / 64, gs), 256, 0, g.stream>>>(Wg, dpad, wv, ktiles, mat, n_pad, n_pad);
+        matvec_p_kernel<<<dim3(n_pad / 64, gs), 256, 0, g.stream>>>(WTg, wv, al, ktiles, mat, n_pad, n_pad);
+        KinvParams kp{WTg, mat, Lg, mat, nblk, ktiles};
+        {
+          Timed t(2);
+          kinv_wtw_kernel<<<dim3(ntiles, gs), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(kp);
+        }
+        LlGradParams lg{};
+        lg.X = dX;
+        lg.d = d;
+        lg.n = n;
+        lg.nblk = nblk;
+        lg.ktiles = ktiles;
+        lg.ls = dls + (size_t)so * d;
+        lg.amp = damp + so;
+        lg.noise = dnoise + so;
+        lg.disc_bits = disc;
+        lg.Kinv = Lg;
+        lg.K_stride = mat;
+        lg.alpha = al;
+        lg.part = partg;
+        {
+          Timed t(1);
+          DISPATCH_KID_DP(launch_llgrad_tile_t, kernel_id, dp, lg, dim3(ntiles, gs));
+        }
+        loglik_grad_final_kernel<<<(gs + 127) / 128, 128, 0, g.stream>>>(partg, ntiles, dp, d, lg.ls, lg.amp, lg.noise, stg,
+                                                                        dgrad + (size_t)so * (d + 2), gs);
+        g.launches += 6;
+      }
+      if (ngroups > 1) {
+        cudaEventRecord(g.ll_join[gi], g.stream);
+        g.stream = main_stream;
+        cudaStreamWaitEvent(main_stream, g.ll_join[gi], 0);
+      }
     }
+    g.stream = main_stream;
+    if (rc_all) return rc_all;
   }
   CUDA_TRY(cudaGetLastError());
   if (!dev) CUDA_TRY(cudaMemcpyAsync(loglik, dll, (size_t)S * 8, cudaMemcpyDeviceToHost, g.stream));
