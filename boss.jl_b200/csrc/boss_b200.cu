@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -83,11 +84,62 @@ struct Ctx {
   double last_ms[N_TIMERS] = {0, 0, 0, 0};
   int last_cnt[N_TIMERS] = {0, 0, 0, 0};
   cudaEvent_t call_a = nullptr, call_b = nullptr;
+  // handle-buffer pool: a BO loop refits GPs of the same size every iteration; cudaMalloc / cudaFree of the three
+  // n_pad^2 factors cost more than the factorisation itself.  Freed buffers are kept (up to POOL_CAP bytes) by size.
+  std::multimap<size_t, void *> pool;
+  std::map<void *, size_t> pool_sizes;
+  size_t pool_bytes = 0;
   cudaStream_t ll_stream[LL_GROUPS] = {};
   cudaEvent_t ll_fork = nullptr, ll_join[LL_GROUPS] = {};
 };
 
 Ctx g;
+
+constexpr size_t POOL_CAP = (size_t)16 << 30;
+
+cudaError_t pool_alloc(double **out, size_t bytes) {
+  auto it = g.pool.find(bytes);
+  if (it != g.pool.end()) {
+    *out = reinterpret_cast<double *>(it->second);
+    g.pool_bytes -= bytes;
+    g.pool.erase(it);
+    return cudaSuccess;
+  }
+  void *p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess && !g.pool.empty()) {   // out of memory: drop the pooled buffers and retry
+    for (auto &kv : g.pool) {
+      cudaFree(kv.second);
+      g.pool_sizes.erase(kv.second);
+    }
+    g.pool.clear();
+    g.pool_bytes = 0;
+    cudaGetLastError();
+    e = cudaMalloc(&p, bytes);
+  }
+  if (e == cudaSuccess) {
+    g.pool_sizes[p] = bytes;
+    *out = reinterpret_cast<double *>(p);
+  }
+  return e;
+}
+void pool_free(void *p) {
+  if (!p) return;
+  auto it = g.pool_sizes.find(p);
+  if (it == g.pool_sizes.end() || g.pool_bytes + it->second > POOL_CAP || g.device < 0) {
+    if (it != g.pool_sizes.end()) g.pool_sizes.erase(it);
+    cudaFree(p);
+    return;
+  }
+  g.pool.emplace(it->second, p);
+  g.pool_bytes += it->second;
+}
+void pool_release_all() {
+  for (auto &kv : g.pool) cudaFree(kv.second);
+  g.pool.clear();
+  g.pool_sizes.clear();
+  g.pool_bytes = 0;
+}
 
 int fail(int code, const std::string &msg) {
   g.err = msg;
@@ -253,6 +305,9 @@ int set_kernel_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(trtri_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(dbg_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(kinv_wtw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(chol_update_rl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(trtri_acc_rl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(trtri_row_rl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(score_trmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(wtv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM_BYTES));
@@ -268,7 +323,7 @@ int set_kernel_attrs() {
 // W / WT non-null (S must be 1): also form the full triangular inverse.
 int run_cholesky(double *L, size_t L_stride, double *Winv, size_t Winv_stride, int nblk, int ktiles, int S,
                  double *logdet_blk, int *status, double *W, double *WT, double *TT, size_t W_stride = 0,
-                 size_t TT_stride = 0) {
+                 size_t TT_stride = 0, bool single_fit = false) {
   CholGemmParams gp{};
   gp.L = L;
   gp.L_stride = L_stride;
@@ -293,10 +348,15 @@ int run_cholesky(double *L, size_t L_stride, double *Winv, size_t Winv_stride, i
   pp.W = W;
   pp.WT = WT;
   pp.W_stride = W_stride;
+  // Left-looking keeps accumulators in registers over the whole k-range (best when S x nblk CTAs fill the GPU);
+  // a small batch (a single posterior fit) cannot fill 148 SMs that way -> right-looking steps of K = 128 tiles.
+  // Only the posterior fit takes this path: batched log-likelihoods always run left-looking, so a sample's value
+  // never depends on how the batch was split (over sub-batches, streams or GPUs).
+  const bool right_looking = single_fit && (long long)S * nblk <= 148;
   for (int j = 0; j < nblk; ++j) {
     gp.j = j;
     pp.j = j;
-    if (j > 0) {
+    if (j > 0 && !right_looking) {
       Timed t(2);
       chol_update_kernel<<<dim3(nblk - j, S), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(gp);
       ++g.launches;
@@ -307,9 +367,23 @@ int run_cholesky(double *L, size_t L_stride, double *Winv, size_t Winv_stride, i
       Timed t(2);
       chol_trsm_kernel<<<dim3(nblk - j - 1, S), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(gp);
       ++g.launches;
+      if (right_looking) {
+        const int m = nblk - j - 1;
+        chol_update_rl_kernel<<<dim3(m * (m + 1) / 2, S), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(gp);
+        ++g.launches;
+      }
     }
   }
-  if (W) {
+  if (W && right_looking) {
+    for (int k = 0; k + 1 < nblk; ++k) {
+      Timed t(2);
+      gp.j = k;
+      trtri_acc_rl_kernel<<<dim3((nblk - k - 1) * (k + 1), S), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(gp);
+      gp.j = k + 1;
+      trtri_row_rl_kernel<<<dim3(k + 1, S), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(gp);
+      g.launches += 2;
+    }
+  } else if (W) {
     for (int delta = 1; delta < nblk; ++delta) {
       gp.j = delta;
       Timed t(2);
@@ -336,7 +410,7 @@ struct boss_gp {
   double *wvec = nullptr, *ymm = nullptr;   // w = L^-1 delta and delta = y - m(X), kept for boss_gp_append
   void free_dev() {
     for (double **q : {&W, &WT, &L, &alpha, &Xt, &invl, &wvec, &ymm}) {
-      if (*q) cudaFree(*q);
+      if (*q) pool_free(*q);
       *q = nullptr;
     }
   }
@@ -392,6 +466,7 @@ void boss_shutdown(void) {
                     &g.part_ss, &g.part_gm, &g.part_gv, &g.cov_p, &g.cov_stage, &g.chol_W, &g.chol_WT, &g.ll_vec,
                     &g.ll_part, &g.ms_buf})
     b->release();
+  pool_release_all();
   if (g.ev_ready) {
     for (int i = 0; i < EV_POOL; ++i) {
       cudaEventDestroy(g.ev_a[i]);
@@ -462,14 +537,14 @@ int boss_gp_fit(const double *X, int d, int n, const double *y_minus_mean, const
                                           std::to_string(__LINE__) + ")"));                                   \
   } while (0)
 
-  FIT_TRY(cudaMalloc(&h->L, mat * 8));
-  FIT_TRY(cudaMalloc(&h->W, mat * 8));
-  FIT_TRY(cudaMalloc(&h->WT, mat * 8));
-  FIT_TRY(cudaMalloc(&h->alpha, npad * 8));
-  FIT_TRY(cudaMalloc(&h->Xt, npad * dp * 8));
-  FIT_TRY(cudaMalloc(&h->invl, dp * 8));
-  FIT_TRY(cudaMalloc(&h->wvec, npad * 8));
-  FIT_TRY(cudaMalloc(&h->ymm, npad * 8));
+  FIT_TRY(pool_alloc(&h->L, mat * 8));
+  FIT_TRY(pool_alloc(&h->W, mat * 8));
+  FIT_TRY(pool_alloc(&h->WT, mat * 8));
+  FIT_TRY(pool_alloc(&h->alpha, npad * 8));
+  FIT_TRY(pool_alloc(&h->Xt, npad * dp * 8));
+  FIT_TRY(pool_alloc(&h->invl, dp * 8));
+  FIT_TRY(pool_alloc(&h->wvec, npad * 8));
+  FIT_TRY(pool_alloc(&h->ymm, npad * 8));
   FIT_TRY(cudaMemsetAsync(h->L, 0, mat * 8, g.stream));
   FIT_TRY(cudaMemsetAsync(h->W, 0, mat * 8, g.stream));
   FIT_TRY(cudaMemsetAsync(h->WT, 0, mat * 8, g.stream));
@@ -514,7 +589,7 @@ int boss_gp_fit(const double *X, int d, int n, const double *y_minus_mean, const
     ++g.launches;
   }
   int rc = run_cholesky(h->L, mat, g.chol_Winv.as<double>(), (size_t)nblk * TM * TM, nblk, h->ktiles, 1,
-                        misc + off_ld, status, h->W, h->WT, g.tt.as<double>());
+                        misc + off_ld, status, h->W, h->WT, g.tt.as<double>(), 0, 0, true);
   if (rc) return bail(rc);
   // w = W delta ; alpha = W^T w
   matvec_p_kernel<<<h->n_pad / 64, 256, 0, g.stream>>>(h->W, misc + off_y, misc + off_w, h->ktiles);
@@ -563,7 +638,7 @@ static int grow_handle(boss_gp *h) {
   double *nL = nullptr, *nW = nullptr, *nWT = nullptr, *nal = nullptr, *nXt = nullptr, *nw = nullptr, *ny = nullptr;
   auto cleanup = [&]() {
     for (double *q : {nL, nW, nWT, nal, nXt, nw, ny})
-      if (q) cudaFree(q);
+      if (q) pool_free(q);
   };
 #define GROW_TRY(expr)                                                                                       \
   do {                                                                                                       \
@@ -573,13 +648,13 @@ static int grow_handle(boss_gp *h) {
       return fail(BOSS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                        \
     }                                                                                                        \
   } while (0)
-  GROW_TRY(cudaMalloc(&nL, mat_new * 8));
-  GROW_TRY(cudaMalloc(&nW, mat_new * 8));
-  GROW_TRY(cudaMalloc(&nWT, mat_new * 8));
-  GROW_TRY(cudaMalloc(&nal, (size_t)npad_new * 8));
-  GROW_TRY(cudaMalloc(&nXt, (size_t)npad_new * h->dp * 8));
-  GROW_TRY(cudaMalloc(&nw, (size_t)npad_new * 8));
-  GROW_TRY(cudaMalloc(&ny, (size_t)npad_new * 8));
+  GROW_TRY(pool_alloc(&nL, mat_new * 8));
+  GROW_TRY(pool_alloc(&nW, mat_new * 8));
+  GROW_TRY(pool_alloc(&nWT, mat_new * 8));
+  GROW_TRY(pool_alloc(&nal, (size_t)npad_new * 8));
+  GROW_TRY(pool_alloc(&nXt, (size_t)npad_new * h->dp * 8));
+  GROW_TRY(pool_alloc(&nw, (size_t)npad_new * 8));
+  GROW_TRY(pool_alloc(&ny, (size_t)npad_new * 8));
   const unsigned nb = (unsigned)((mat_new + 255) / 256);
   repack_grow_kernel<<<nb, 256, 0, g.stream>>>(h->L, h->ktiles, h->n_pad, nL, kt_new, npad_new);
   repack_grow_kernel<<<nb, 256, 0, g.stream>>>(h->W, h->ktiles, h->n_pad, nW, kt_new, npad_new);
@@ -599,7 +674,7 @@ static int grow_handle(boss_gp *h) {
   GROW_TRY(cudaGetLastError());
   GROW_TRY(cudaStreamSynchronize(g.stream));
 #undef GROW_TRY
-  for (double *q : {h->L, h->W, h->WT, h->alpha, h->Xt, h->wvec, h->ymm}) cudaFree(q);
+  for (double *q : {h->L, h->W, h->WT, h->alpha, h->Xt, h->wvec, h->ymm}) pool_free(q);
   h->L = nL; h->W = nW; h->WT = nWT; h->alpha = nal; h->Xt = nXt; h->wvec = nw; h->ymm = ny;
   h->n_pad = npad_new;
   h->nblk = npad_new / TM;

@@ -159,6 +159,73 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) chol_trsm_kernel(CholGemmPara
   });
 }
 
+// ---- right-looking variants for small batches (a single posterior fit): every step exposes all tiles of the
+// trailing matrix as independent K = 128 products instead of a few CTAs with a long k-range ----
+// A_ik -= L_ij L_kj^T for j < k <= i  (after block column j has been solved)
+__global__ void __launch_bounds__(GEMM_THREADS, 1) chol_update_rl_kernel(CholGemmParams p) {
+  int t = blockIdx.x, ii = 0;
+  while (t >= ii + 1) {
+    t -= ii + 1;
+    ++ii;
+  }
+  const int i = p.j + 1 + ii, k = p.j + 1 + t;
+  double *Lm = p.L + (size_t)blockIdx.y * p.L_stride;
+  LinearIt it{Lm + ((size_t)i * p.ktiles + (size_t)p.j * KT_PER_BLOCK) * TILE_ELEMS,
+              Lm + ((size_t)k * p.ktiles + (size_t)p.j * KT_PER_BLOCK) * TILE_ELEMS, KT_PER_BLOCK};
+  double *dst = Lm + ((size_t)i * p.ktiles + (size_t)k * KT_PER_BLOCK) * TILE_ELEMS;
+  if (i == k) {
+    syrk_diag_pipeline(it, it, [&](double(&acc)[17][2], const SyrkCoord &sc) {
+#pragma unroll
+      for (int q = 0; q < 17; ++q)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) acc[q][e] = dst[block_offset(sc.row(q), sc.col(q, e))] - acc[q][e];
+#pragma unroll
+      for (int q = 0; q < 17; ++q)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) dst[block_offset(sc.row(q), sc.col(q, e))] = acc[q][e];
+    });
+  } else {
+    gemm_pipeline(it, it, [&](int, double(&acc)[8][4][2], const FragCoord &fc) { rmw_sub_block(dst, acc, fc); });
+  }
+}
+
+// Triangular inverse, right-looking step k = p.j:  T_ij^T += W_kj^T L_ik^T for i > k >= j, accumulated in the
+// (still unused) block WT(j, i);  blockIdx.x enumerates (i - k - 1, j)
+__global__ void __launch_bounds__(GEMM_THREADS, 1) trtri_acc_rl_kernel(CholGemmParams p) {
+  const int k = p.j, jb = blockIdx.x % (k + 1), i = k + 1 + blockIdx.x / (k + 1);
+  const double *Lm = p.L + (size_t)blockIdx.y * p.L_stride;
+  double *WTm = p.WT + (size_t)blockIdx.y * p.W_stride;
+  LinearIt it{WTm + ((size_t)jb * p.ktiles + (size_t)k * KT_PER_BLOCK) * TILE_ELEMS,
+              Lm + ((size_t)i * p.ktiles + (size_t)k * KT_PER_BLOCK) * TILE_ELEMS, KT_PER_BLOCK};
+  double *dst = WTm + ((size_t)jb * p.ktiles + (size_t)i * KT_PER_BLOCK) * TILE_ELEMS;
+  gemm_pipeline(it, it, [&](int, double(&acc)[8][4][2], const FragCoord &fc) {
+#pragma unroll
+    for (int fm = 0; fm < 8; ++fm)
+#pragma unroll
+      for (int fn = 0; fn < 4; ++fn)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) acc[fm][fn][e] += dst[block_offset(fc.row(fm), fc.col(fn, e))];
+#pragma unroll
+    for (int fm = 0; fm < 8; ++fm)
+#pragma unroll
+      for (int fn = 0; fn < 4; ++fn)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) dst[block_offset(fc.row(fm), fc.col(fn, e))] = acc[fm][fn][e];
+  });
+}
+//   W_ij = -Winv_ii T_ij for row i = p.j, j = blockIdx.x < i, T_ij^T read from WT(j, i) and overwritten by W_ij^T
+__global__ void __launch_bounds__(GEMM_THREADS, 1) trtri_row_rl_kernel(CholGemmParams p) {
+  const int i = p.j, jb = blockIdx.x;
+  double *WTm = p.WT + (size_t)blockIdx.y * p.W_stride;
+  double *dWT = WTm + ((size_t)jb * p.ktiles + (size_t)i * KT_PER_BLOCK) * TILE_ELEMS;
+  LinearIt it{p.Winv + (size_t)blockIdx.y * p.Winv_stride + (size_t)i * (TM * TM), dWT, KT_PER_BLOCK};
+  double *dW = p.W + (size_t)blockIdx.y * p.W_stride + ((size_t)i * p.ktiles + (size_t)jb * KT_PER_BLOCK) * TILE_ELEMS;
+  gemm_pipeline(it, it, [&](int, const double(&acc)[8][4][2], const FragCoord &fc) {
+    store_block(dW, false, -1.0, nullptr, acc, fc);
+    store_block(dWT, true, -1.0, nullptr, acc, fc);
+  });
+}
+
 // Triangular inverse, block distance delta = i - j (blockIdx.y = matrix of the batch):
 //   T_ij = sum_{k=j}^{i-1} L_ik W_kj   -> stored transposed in TT[task]
 __global__ void __launch_bounds__(GEMM_THREADS, 1) trtri_t_kernel(CholGemmParams p) {
