@@ -35,6 +35,8 @@ EXPORTS = {
     "boss_stream": (_vp, []),
     "boss_gp_fit": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, C.c_double, C.c_double, C.c_int, _vp,
                               C.POINTER(_vp), _dp]),
+    "boss_gp_fit_batch": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, _vp, C.c_int, _vp, C.c_int64,
+                                    C.POINTER(_vp), _vp]),
     "boss_gp_append": (C.c_int, [_vp, _vp, C.c_double, _dp]),
     "boss_gp_free": (None, [_vp]),
     "boss_gp_n": (C.c_int, [_vp]),
@@ -161,6 +163,27 @@ def gp_fit(X, y_minus_mean, lengthscales, amplitude, noise_std, kernel_id=KERNEL
     if rc == BOSS_NOT_POSDEF:
         return None
     return GP(out, n, d, ll.value)
+
+
+def gp_fit_batch(X, Y_minus_mean, lengthscales, amplitude, noise_std, kernel_id=KERNEL_MATERN52, discrete_mask=None):
+    """S fits in one call.  lengthscales (S, d), amplitude (S,), noise_std (S,), Y_minus_mean (n,) or (S, n).
+    -> list of GP (None where not positive definite)."""
+    Xc = _cols(X)
+    n, d = Xc.shape
+    ls = _f64(lengthscales)
+    S = ls.shape[0]
+    assert ls.shape == (S, d)
+    amp = _f64(amplitude, (S,))
+    ns = _f64(noise_std, (S,))
+    Y = _f64(Y_minus_mean)
+    ldy = 0 if Y.ndim == 1 else n
+    assert Y.shape == ((n,) if ldy == 0 else (S, n))
+    dm = None if discrete_mask is None else np.ascontiguousarray(discrete_mask, dtype=np.uint8)
+    out = (_vp * S)()
+    ll = np.empty(S)
+    _check(lib.boss_gp_fit_batch(_ptr(Xc), d, n, _ptr(Y), ldy, _ptr(ls), _ptr(amp), _ptr(ns), int(kernel_id), _ptr(dm), S,
+                                 out, _ptr(ll)), "boss_gp_fit_batch")
+    return [GP(_vp(out[s]), n, d, float(ll[s])) if out[s] else None for s in range(S)]
 
 
 def gp_append(gp: GP, x_new, y_minus_mean_new) -> bool:

@@ -1478,7 +1478,7 @@ int boss_gp_cov(const boss_gp *gp, const double *Xs, int64_t M, const double *pr
 // ---------------------------------------------------------------------------------------------
 static int loglik_impl(const double *X, int d, int n, const double *Ymm, int64_t ldy, const double *ls,
                        const double *amp, const double *noise, int kernel_id, const uint8_t *discrete_mask, int64_t S,
-                       double *loglik, bool dev, double *grad = nullptr) {
+                       double *loglik, bool dev, double *grad = nullptr, boss_gp **fit_out = nullptr) {
   std::lock_guard<std::mutex> lk(g.mu);
   REQUIRE_INIT();
   if (!X || !Ymm || !ls || !amp || !noise || !loglik || d < 1 || n < 1 || S < 0)
@@ -1492,9 +1492,10 @@ static int loglik_impl(const double *X, int d, int n, const double *Ymm, int64_t
   if ((size_t)(n_pad + 128) * 8 > 200 * 1024) return fail(BOSS_ERR_ARG, "boss_gp_loglik_batch: n too large");
   const unsigned long long disc = mask_bits(discrete_mask, d);
 
-  const bool small = n <= SMALL_N && !grad;   // warp-register path (small.cuh): no workspace at all
-  // sub-batch so that L + Winv (+ W, W^T and the trtri scratch in gradient mode) stay within a 32 GiB workspace
-  const size_t per = (grad ? 3 : 1) * mat * 8 + (size_t)(grad ? 2 * nblk : nblk) * TM * TM * 8;
+  const bool need_w = grad || fit_out;        // gradient and batched-fit modes also form W = L^-1, W^T and alpha
+  const bool small = n <= SMALL_N && !need_w; // warp-register path (small.cuh): no workspace at all
+  // sub-batch so that L + Winv (+ W, W^T and the trtri scratch) stay within a 32 GiB workspace
+  const size_t per = (need_w ? 3 : 1) * mat * 8 + (size_t)(need_w ? 2 * nblk : nblk) * TM * TM * 8;
   long long Sb = std::max<long long>(1, std::min<long long>(S, (32ll << 30) / (long long)per));
   Sb = std::min<long long>(Sb, 32768);
   if (small) Sb = 1;
@@ -1504,12 +1505,12 @@ static int loglik_impl(const double *X, int d, int n, const double *Ymm, int64_t
   }
   const int ntiles = nblk * (nblk + 1) / 2;
   const size_t tt_stride = (size_t)std::max(1, nblk - 1) * TM * TM;
-  if (grad) {
+  if (need_w) {
     CUDA_TRY(g.chol_W.ensure((size_t)Sb * mat * 8));
     CUDA_TRY(g.chol_WT.ensure((size_t)Sb * mat * 8));
     CUDA_TRY(g.tt.ensure((size_t)Sb * tt_stride * 8));
     CUDA_TRY(g.ll_vec.ensure((size_t)Sb * n_pad * 3 * 8));                 // delta_pad | w | alpha
-    CUDA_TRY(g.ll_part.ensure((size_t)Sb * ntiles * (dp + 2) * 8));
+    if (grad) CUDA_TRY(g.ll_part.ensure((size_t)Sb * ntiles * (dp + 2) * 8));
   }
 
   // device copies of the inputs when called with host pointers
@@ -1592,9 +1593,9 @@ static int loglik_impl(const double *X, int d, int n, const double *Ymm, int64_t
       double *Wig = g.chol_Winv.as<double>() + (size_t)wo * winv_stride;
       double *ldg = logdet_blk + (size_t)wo * nblk;
       int *stg = status + wo;
-      double *Wg = grad ? g.chol_W.as<double>() + (size_t)wo * mat : nullptr;
-      double *WTg = grad ? g.chol_WT.as<double>() + (size_t)wo * mat : nullptr;
-      double *TTg = grad ? g.tt.as<double>() + (size_t)wo * tt_stride : nullptr;
+      double *Wg = need_w ? g.chol_W.as<double>() + (size_t)wo * mat : nullptr;
+      double *WTg = need_w ? g.chol_WT.as<double>() + (size_t)wo * mat : nullptr;
+      double *TTg = need_w ? g.tt.as<double>() + (size_t)wo * tt_stride : nullptr;
       cudaMemsetAsync(stg, 0, (size_t)gs * 4, g.stream);
       BuildKParams bk{};
       bk.X = dX;
@@ -1614,7 +1615,7 @@ static int loglik_impl(const double *X, int d, int n, const double *Ymm, int64_t
         DISPATCH_KID_DP(launch_build_k_t, kernel_id, dp, bk, dim3(nblk * (nblk + 1) / 2, gs));
         ++g.launches;
       }
-      if (grad) {   // zero initial state of W and W^T (strictly-upper resp. strictly-lower blocks are never written)
+      if (need_w) {   // zero initial state of W and W^T (strictly-upper resp. strictly-lower blocks are never written)
         cudaMemsetAsync(Wg, 0, (size_t)gs * mat * 8, g.stream);
         cudaMemsetAsync(WTg, 0, (size_t)gs * mat * 8, g.stream);
       }
@@ -1636,14 +1637,17 @@ static int loglik_impl(const double *X, int d, int n, const double *Ymm, int64_t
       fp.w_out = nullptr;
       fwd_solve_loglik_kernel<<<gs, 256, (size_t)(n_pad + 128) * 8, g.stream>>>(fp);
       ++g.launches;
-      if (grad) {
-        // alpha = W^T (W delta);  K^-1 = W^T W over the factor's storage;  tile partial sums;  final scaling
-        double *vec = g.ll_vec.as<double>();
-        double *dpad = vec + (size_t)wo * n_pad, *wv = vec + ((size_t)Sb + wo) * n_pad, *al = vec + ((size_t)2 * Sb + wo) * n_pad;
-        double *partg = g.ll_part.as<double>() + (size_t)wo * ntiles * (dp + 2);
+      double *vec = g.ll_vec.as<double>();
+      double *dpad = vec + (size_t)wo * n_pad, *wv = vec + ((size_t)Sb + wo) * n_pad, *al = vec + ((size_t)2 * Sb + wo) * n_pad;
+      if (need_w) {   // alpha = W^T (W delta)
         pad_delta_kernel<<<dim3((n_pad + 255) / 256, gs), 256, 0, g.stream>>>(dY + (ldy ? (size_t)so * ldy : 0), ldy, n, n_pad, dpad);
         matvec_p_kernel<<<dim3(n_pad / 64, gs), 256, 0, g.stream>>>(Wg, dpad, wv, ktiles, mat, n_pad, n_pad);
         matvec_p_kernel<<<dim3(n_pad / 64, gs), 256, 0, g.stream>>>(WTg, wv, al, ktiles, mat, n_pad, n_pad);
+        g.launches += 3;
+      }
+      if (grad) {
+        // K^-1 = W^T W over the factor's storage;  tile partial sums;  final scaling
+        double *partg = g.ll_part.as<double>() + (size_t)wo * ntiles * (dp + 2);
         KinvParams kp{WTg, mat, Lg, mat, nblk, ktiles};
         {
           Timed t(2);
@@ -1669,7 +1673,7 @@ static int loglik_impl(const double *X, int d, int n, const double *Ymm, int64_t
         }
         loglik_grad_final_kernel<<<(gs + 127) / 128, 128, 0, g.stream>>>(partg, ntiles, dp, d, lg.ls, lg.amp, lg.noise, stg,
                                                                         dgrad + (size_t)so * (d + 2), gs);
-        g.launches += 6;
+        g.launches += 3;
       }
       if (ngroups > 1) {
         cudaEventRecord(g.ll_join[gi], g.stream);
@@ -1679,6 +1683,53 @@ static int loglik_impl(const double *X, int d, int n, const double *Ymm, int64_t
     }
     g.stream = main_stream;
     if (rc_all) return rc_all;
+    if (fit_out) {
+      // batched posterior fit: detach every factorisation of the window into its own handle
+      std::vector<int> hst(sb);
+      std::vector<double> hll(sb);
+      CUDA_TRY(cudaMemcpyAsync(hst.data(), status, (size_t)sb * 4, cudaMemcpyDeviceToHost, g.stream));
+      CUDA_TRY(cudaMemcpyAsync(hll.data(), dll + s0, (size_t)sb * 8, cudaMemcpyDeviceToHost, g.stream));
+      CUDA_TRY(cudaStreamSynchronize(g.stream));
+      double *vec = g.ll_vec.as<double>();
+      for (int q = 0; q < sb; ++q) {
+        const long long sidx = s0 + q;
+        fit_out[sidx] = nullptr;
+        if (hst[q] != 0) continue;
+        boss_gp *h = new boss_gp();
+        h->n = n; h->d = d; h->n_pad = n_pad; h->nblk = nblk; h->ktiles = ktiles; h->kernel_id = kernel_id; h->dp = dp;
+        h->disc = disc;
+        h->amp = amp[sidx] + MIN_PARAM_VALUE;
+        h->noise = noise[sidx] + MIN_PARAM_VALUE;
+        h->a2 = h->amp * h->amp;
+        h->loglik = hll[q];
+        cudaError_t e = cudaSuccess;
+        for (auto pr : {std::make_pair(&h->L, mat * 8), std::make_pair(&h->W, mat * 8), std::make_pair(&h->WT, mat * 8),
+                        std::make_pair(&h->alpha, (size_t)n_pad * 8), std::make_pair(&h->Xt, (size_t)n_pad * dp * 8),
+                        std::make_pair(&h->invl, (size_t)dp * 8), std::make_pair(&h->wvec, (size_t)n_pad * 8),
+                        std::make_pair(&h->ymm, (size_t)n_pad * 8)})
+          if (e == cudaSuccess) e = pool_alloc(pr.first, pr.second);
+        if (e != cudaSuccess) {
+          h->free_dev();
+          delete h;
+          return fail(BOSS_ERR_CUDA, std::string("boss_gp_fit_batch: ") + cudaGetErrorString(e));
+        }
+        std::vector<double> invl(dp, 0.0);
+        for (int i = 0; i < d; ++i) invl[i] = 1.0 / (ls[(size_t)sidx * d + i] + MIN_PARAM_VALUE);
+        cudaMemcpyAsync(h->invl, invl.data(), (size_t)dp * 8, cudaMemcpyHostToDevice, g.stream);
+        cudaStreamSynchronize(g.stream);   // invl is a stack temporary
+        cudaMemcpyAsync(h->L, g.chol_L.as<double>() + (size_t)q * mat, mat * 8, cudaMemcpyDeviceToDevice, g.stream);
+        cudaMemcpyAsync(h->W, g.chol_W.as<double>() + (size_t)q * mat, mat * 8, cudaMemcpyDeviceToDevice, g.stream);
+        cudaMemcpyAsync(h->WT, g.chol_WT.as<double>() + (size_t)q * mat, mat * 8, cudaMemcpyDeviceToDevice, g.stream);
+        cudaMemcpyAsync(h->ymm, vec + (size_t)q * n_pad, (size_t)n_pad * 8, cudaMemcpyDeviceToDevice, g.stream);
+        cudaMemcpyAsync(h->wvec, vec + ((size_t)Sb + q) * n_pad, (size_t)n_pad * 8, cudaMemcpyDeviceToDevice, g.stream);
+        cudaMemcpyAsync(h->alpha, vec + ((size_t)2 * Sb + q) * n_pad, (size_t)n_pad * 8, cudaMemcpyDeviceToDevice, g.stream);
+        scale_train_kernel<<<(n_pad * dp + 255) / 256, 256, 0, g.stream>>>(dX, d, n, n_pad, dp, h->invl, disc, h->Xt);
+        ++g.launches;
+        fit_out[sidx] = h;
+      }
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaStreamSynchronize(g.stream));
+    }
   }
   CUDA_TRY(cudaGetLastError());
   if (!dev) CUDA_TRY(cudaMemcpyAsync(loglik, dll, (size_t)S * 8, cudaMemcpyDeviceToHost, g.stream));
@@ -1708,6 +1759,25 @@ int boss_gp_loglik_batch_dev(const double *X_dev, int d, int n, const double *Y_
   (void)stream;
   return loglik_impl(X_dev, d, n, Y_minus_mean_dev, ldy, lengthscales_dev, amplitude_dev, noise_std_dev, kernel_id,
                      discrete_mask, S, loglik_dev, true);
+}
+
+int boss_gp_fit_batch(const double *X, int d, int n, const double *Y_minus_mean, int64_t ldy, const double *lengthscales,
+                      const double *amplitude, const double *noise_std, int kernel_id, const uint8_t *discrete_mask,
+                      int64_t S, boss_gp **out, double *loglik_out) {
+  if (!out) return fail(BOSS_ERR_ARG, "boss_gp_fit_batch: out is NULL");
+  for (int64_t s = 0; s < S; ++s) out[s] = nullptr;
+  std::vector<double> ll((size_t)std::max<int64_t>(S, 1));
+  int rc = loglik_impl(X, d, n, Y_minus_mean, ldy, lengthscales, amplitude, noise_std, kernel_id, discrete_mask, S, ll.data(),
+                       false, nullptr, out);
+  if (loglik_out)
+    for (int64_t s = 0; s < S; ++s) loglik_out[s] = ll[s];
+  if (rc < 0)
+    for (int64_t s = 0; s < S; ++s)
+      if (out[s]) {
+        boss_gp_free(out[s]);
+        out[s] = nullptr;
+      }
+  return rc;
 }
 
 int boss_gp_loglik_grad_batch(const double *X, int d, int n, const double *Y_minus_mean, int64_t ldy,

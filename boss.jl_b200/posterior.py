@@ -3,7 +3,8 @@ from __future__ import annotations
 
 import numpy as np
 
-from .gaussian_process import model_posterior_slice
+from . import _lib
+from .gaussian_process import GaussianProcessPosterior, _as_gp, _kernel_parts, model_posterior_slice
 from .types import BossProblem, get_params
 
 
@@ -39,8 +40,29 @@ def model_posterior(problem_or_model, params=None, data=None):
     model = problem_or_model
     params = get_params(params)
     if isinstance(params, (list, tuple)):
-        return [model_posterior(model, p, data) for p in params]
+        return _model_posterior_batch(model, list(params), data)
     return DefaultModelPosterior([model_posterior_slice(model, params, data, i) for i in range(data.y_dim)])
+
+
+def _model_posterior_batch(model, plist, data):
+    """BI samples (src/posterior.jl:15-16 broadcasts model_posterior over the samples, one Cholesky each): here all
+    samples of one output slice are factored by ONE boss_gp_fit_batch call."""
+    S = len(plist)
+    gms = [_as_gp(model, p) for p in plist]
+    kid, mask = _kernel_parts(gms[0][0].kernel)
+    slices = [[None] * data.y_dim for _ in range(S)]
+    for i in range(data.y_dim):
+        means = [gm.mean_at(i, data.X) for gm, _ in gms]
+        Ymm = np.stack([data.Y[i] - (0.0 if m is None else m) for m in means])
+        L = np.stack([gp.lengthscales[:, i] for _, gp in gms])
+        A = np.array([gp.amplitudes[i] for _, gp in gms])
+        N = np.array([gp.noise_std[i] for _, gp in gms])
+        handles = _lib.gp_fit_batch(data.X, Ymm, L, A, N, kid, mask)
+        for s, h in enumerate(handles):
+            if h is None:
+                raise ValueError("PosDefException: kernel matrix is not positive definite")
+            slices[s][i] = GaussianProcessPosterior(h, gms[s][0], i)
+    return [DefaultModelPosterior(sl) for sl in slices]
 
 
 def average_mean(posteriors, x):

@@ -67,6 +67,15 @@ void *boss_stream(void);              /* the cudaStream_t all library work is or
 int boss_gp_fit(const double *X, int d, int n, const double *y_minus_mean, const double *lengthscales,
                 double amplitude, double noise_std, int kernel_id, const uint8_t *discrete_mask,
                 boss_gp **out, double *loglik_out);
+/* S posterior fits in one call (same X, per-fit hyper-parameters and targets): the batches of
+ * model_posterior over BI samples x output slices (src/posterior.jl:15-19,38-41) -- TuringBI keeps tens to
+ * hundreds of hyper-parameter samples and the reference refactors each one separately.  Arguments as
+ * boss_gp_loglik_batch; out[s] receives a handle or NULL where K_s is not positive definite (return value
+ * BOSS_NOT_POSDEF if any); loglik_out (S) optional. */
+int boss_gp_fit_batch(const double *X, int d, int n, const double *Y_minus_mean, int64_t ldy,
+                      const double *lengthscales, const double *amplitude, const double *noise_std, int kernel_id,
+                      const uint8_t *discrete_mask, int64_t S, boss_gp **out, double *loglik_out);
+
 /* Incremental factor cache: add ONE training point to a fitted GP with unchanged hyper-parameters in O(n^2)
  * (new row of L and of W = L^-1, alpha and the log-likelihood updated in place) instead of the O(n^3)
  * refactorisation the reference performs for every speculative point of SequentialBatchAM

@@ -567,3 +567,40 @@ def test_multistart_discrete_rounding_and_failure(lib):
     chk, _, _ = lib.ei_score([gp], 1, 1, Xd, [1.0], float(np.median(Y[0])), None, lb, ub)
     assert np.array_equal(chk, fd)                                     # re-evaluated after rounding
     gp.free()
+
+
+# ---------------------------------------------------------------------------------------------
+# batched posterior fit (BI samples x slices)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,d,kid,S", [(20, 2, 0, 7), (200, 3, 2, 12), (520, 4, 1, 5)])
+def test_fit_batch_matches_single_fits(lib, n, d, kid, S):
+    X, Y, _, _, _ = make_problem(n, d, seed=2100 + n)
+    L, A, N = make_hyper_samples(S, d, seed=2101 + n)
+    Ymm = Y[0][None, :] - np.linspace(-0.3, 0.3, S)[:, None]
+    gps = lib.gp_fit_batch(X, Ymm, L, A, N, kid)
+    assert len(gps) == S and all(g is not None for g in gps)
+    Xs = np.random.default_rng(5).random((d, 400))
+    for s in (0, S // 2, S - 1):
+        post = O.posterior_fit(X, Ymm[s], L[s], A[s], N[s], kid)
+        mu, var, _ = lib.gp_predict(gps[s], Xs)
+        mr, vr, _ = O.mean_and_var(post, Xs)
+        assert relerr(mu, mr) <= TOL_POST and relerr(var, vr) <= TOL_POST
+        ll = O.gp_loglik(X, Ymm[s], L[s], A[s], N[s], kid)
+        assert abs(gps[s].loglik - ll) <= TOL_LL * abs(ll)
+        assert lib.gp_append(gps[s], Xs[:, 0], 0.1)          # handles from the batch are full handles
+    best = float(np.median(Y[0]))
+    posts = [[O.posterior_fit(X, Ymm[s], L[s], A[s], N[s], kid)] for s in range(S)]
+    gps2 = lib.gp_fit_batch(X, Ymm, L, A, N, kid)
+    acq, _, bi = lib.ei_score(gps2, 1, S, Xs, [1.0], best, None)          # BI average over the S samples
+    ref, _, _ = O.ei_acquisition(posts, Xs, [1.0], best, None)
+    m = ref > 1e-200
+    assert relerr(acq[m], ref[m]) <= TOL_POST and bi == O.julia_argmax_fast(ref)
+    for g in gps + gps2:
+        g.free()
+
+
+def test_fit_batch_reports_non_pd_samples(lib):
+    X = np.zeros((1, 40)); y = np.arange(40.0)
+    gps = lib.gp_fit_batch(X, y, np.array([[1.0], [1.0]]), np.array([1e6, 1.0]), np.array([0.0, 0.5]), 0)
+    assert gps[0] is None and gps[1] is not None
+    gps[1].free()
