@@ -133,3 +133,29 @@ def test_large_training_set_n4096_semiparametric_style(lib):
     assert relerr(val[m], ref[m]) <= 1e-9
     assert np.max(np.abs(grad[:, m] - gref[:, m]) / np.max(np.abs(gref[:, m]), axis=0)) <= 1e-8
     gp.free()
+
+
+def test_concurrent_callers_are_serialised(lib):
+    """The reference may call the acquisition / log-likelihood from several Julia tasks at once when parallel=true
+    (Threads.@threads in src/utils/optim_multistart.jl:62).  Entry points serialise on an internal mutex: results
+    from 4 concurrent host threads equal the serial results bit for bit."""
+    import threading
+    n, d = 300, 3
+    X, Y, ls, amp, ns = make_problem(n, d, seed=9)
+    gp = lib.gp_fit(X, Y[0], ls[0], amp[0], ns[0], 2)
+    rng = np.random.default_rng(10)
+    Xs = [rng.random((d, 3000 + 500 * t)) for t in range(4)]
+    L, A, N = make_hyper_samples(12, d, seed=11)
+    best = float(np.median(Y[0]))
+    serial = [(lib.ei_score([gp], 1, 1, x, [1.0], best, None)[0], lib.loglik_batch(X, Y[0], L, A, N, 2)) for x in Xs]
+    out = [None] * 4
+
+    def work(t):
+        for _ in range(3):
+            out[t] = (lib.ei_score([gp], 1, 1, Xs[t], [1.0], best, None)[0], lib.loglik_batch(X, Y[0], L, A, N, 2))
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    for t in range(4):
+        assert np.array_equal(out[t][0], serial[t][0]) and np.array_equal(out[t][1], serial[t][1])
+    gp.free()
