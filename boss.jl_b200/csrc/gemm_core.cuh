@@ -23,7 +23,7 @@ constexpr int GEMM_STAGE_ELEMS = 2 * TILE_ELEMS;                  // A tile + B 
 constexpr int GEMM_STAGE_BYTES = GEMM_STAGE_ELEMS * 8;            // 32 KB
 constexpr int GEMM_RING_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES;   // 160 KB
 constexpr int GEMM_SCRATCH_BYTES = 4096;                          // epilogue scratch (after the ring)
-constexpr int GEMM_SMEM_BYTES = GEMM_RING_BYTES + GEMM_SCRATCH_BYTES + 64;  // + mbarriers
+constexpr int GEMM_SMEM_BYTES = GEMM_RING_BYTES + GEMM_SCRATCH_BYTES + 128;  // + mbarriers (full[5], empty[5])
 
 // Accumulator fragment coordinates of this lane inside the 128x128 CTA tile:
 //   row(fm)    = 64*wm + 8*fm + (lane>>2)
@@ -42,11 +42,19 @@ __host__ __device__ __forceinline__ int block_offset(int r, int c) {
 }
 
 // It must provide:  bool valid(); const double* A(); const double* B(); bool tile_end(); int tile(); void next();
+//
+// Synchronisation: per stage a `full` mbarrier (TMA transaction bytes) and an `empty` mbarrier (one arrival per
+// consumer warp).  There is no CTA-wide barrier in the mainloop: a warp that finishes a stage releases the slot
+// and moves on, so the eight warps drift apart by up to the ring depth and fill each other's bubbles.  Thread 0
+// doubles as the producer: before consuming stage g it issues every later stage whose slot has already been
+// released (non-blocking probe) and, if stage g itself has not been issued yet, waits for its slot (the other
+// warps can always finish the stages already in flight, so this cannot deadlock).
 template <class It, class Epi>
 __device__ __forceinline__ void gemm_pipeline(It issue_it, It cons_it, Epi &&epi) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   double *ring = reinterpret_cast<double *>(smem_raw);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + GEMM_RING_BYTES + GEMM_SCRATCH_BYTES);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + GEMM_RING_BYTES + GEMM_SCRATCH_BYTES);
+  uint64_t *empty = full + GEMM_STAGES;
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -54,24 +62,35 @@ __device__ __forceinline__ void gemm_pipeline(It issue_it, It cons_it, Epi &&epi
   const int wm = warp >> 2, wn = warp & 3;
 
   if (tid == 0) {
-    for (int s = 0; s < GEMM_STAGES; ++s) mbar_init(smem_u32(&bars[s]), 1);
+    for (int s = 0; s < GEMM_STAGES; ++s) {
+      mbar_init(smem_u32(&full[s]), 1);
+      mbar_init(smem_u32(&empty[s]), GEMM_THREADS / 32);
+    }
     mbar_fence_init();
   }
   __syncthreads();
 
-  auto issue = [&](int slot) {
-    uint32_t bar = smem_u32(&bars[slot]);
-    uint32_t dst = smem_u32(ring + (size_t)slot * GEMM_STAGE_ELEMS);
+  int issued = 0;
+  // issue stage `issued` into its slot; returns false when the slot is still being read and !blocking
+  auto try_issue = [&](bool blocking) -> bool {
+    const int slot = issued % GEMM_STAGES;
+    if (issued >= GEMM_STAGES) {
+      const uint32_t eb = smem_u32(&empty[slot]);
+      const uint32_t par = (uint32_t)((issued / GEMM_STAGES - 1) & 1);
+      if (blocking)
+        mbar_wait(eb, par);
+      else if (!mbar_try_wait(eb, par))
+        return false;
+    }
+    const uint32_t bar = smem_u32(&full[slot]);
+    const uint32_t dst = smem_u32(ring + (size_t)slot * GEMM_STAGE_ELEMS);
     mbar_arrive_expect_tx(bar, GEMM_STAGE_BYTES);
     bulk_g2s(dst, issue_it.A(), TILE_BYTES, bar);
     bulk_g2s(dst + TILE_BYTES, issue_it.B(), TILE_BYTES, bar);
     issue_it.next();
+    ++issued;
+    return true;
   };
-
-  int issued = 0;
-  if (tid == 0) {
-    for (; issued < GEMM_STAGES - 1 && issue_it.valid(); ++issued) issue(issued);
-  }
 
   double acc[8][4][2];
 #pragma unroll
@@ -85,12 +104,12 @@ __device__ __forceinline__ void gemm_pipeline(It issue_it, It cons_it, Epi &&epi
   int g = 0;
   while (cons_it.valid()) {
     const int slot = g % GEMM_STAGES;
-    // refill the slot freed at the end of iteration g-1 (all warps passed that __syncthreads)
-    if (tid == 0 && issue_it.valid()) {
-      issue(issued % GEMM_STAGES);
-      ++issued;
+    if (tid == 0) {
+      while (issue_it.valid() && issued < g + GEMM_STAGES) {
+        if (!try_issue(issued <= g)) break;
+      }
     }
-    mbar_wait(smem_u32(&bars[slot]), (uint32_t)((g / GEMM_STAGES) & 1));
+    mbar_wait(smem_u32(&full[slot]), (uint32_t)((g / GEMM_STAGES) & 1));
 
     const double *As = ring + (size_t)slot * GEMM_STAGE_ELEMS;
     const double *Bs = As + TILE_ELEMS;
@@ -105,12 +124,15 @@ __device__ __forceinline__ void gemm_pipeline(It issue_it, It cons_it, Epi &&epi
       for (int fm = 0; fm < 8; ++fm)
 #pragma unroll
         for (int fn = 0; fn < 4; ++fn) dmma884(acc[fm][fn][0], acc[fm][fn][1], a[fm].x, b[fn].x);
+      if (mc == 1) {   // every LDS.128 of this stage has been consumed by a DMMA above: release the slot
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&empty[slot]));
+      }
 #pragma unroll
       for (int fm = 0; fm < 8; ++fm)
 #pragma unroll
         for (int fn = 0; fn < 4; ++fn) dmma884(acc[fm][fn][0], acc[fm][fn][1], a[fm].y, b[fn].y);
     }
-    __syncthreads();
 
     const bool tile_end = cons_it.tile_end();
     const int tile = cons_it.tile();
@@ -197,33 +219,59 @@ __device__ __forceinline__ void rmw_sub_block(double *dst, double (&acc)[8][4][2
 // ---------------------------------------------------------------------------------------------
 struct TmaRing {
   double *ring;
-  uint64_t *bars;
+  uint64_t *full, *empty;
   int issued;
   __device__ __forceinline__ void init() {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     ring = reinterpret_cast<double *>(smem_raw);
-    bars = reinterpret_cast<uint64_t *>(smem_raw + GEMM_RING_BYTES + GEMM_SCRATCH_BYTES);
+    full = reinterpret_cast<uint64_t *>(smem_raw + GEMM_RING_BYTES + GEMM_SCRATCH_BYTES);
+    empty = full + GEMM_STAGES;
     issued = 0;
     if (threadIdx.x == 0) {
-      for (int s = 0; s < GEMM_STAGES; ++s) mbar_init(smem_u32(&bars[s]), 1);
+      for (int s = 0; s < GEMM_STAGES; ++s) {
+        mbar_init(smem_u32(&full[s]), 1);
+        mbar_init(smem_u32(&empty[s]), GEMM_THREADS / 32);
+      }
       mbar_fence_init();
     }
     __syncthreads();
   }
+  // thread 0 only: issue stage `issued`; false when its slot is still being read and !blocking
   template <class It>
-  __device__ __forceinline__ void issue(It &it) {   // thread 0 only
+  __device__ __forceinline__ bool try_issue(It &it, bool blocking) {
     const int slot = issued % GEMM_STAGES;
-    const uint32_t bar = smem_u32(&bars[slot]);
+    if (issued >= GEMM_STAGES) {
+      const uint32_t eb = smem_u32(&empty[slot]);
+      const uint32_t par = (uint32_t)((issued / GEMM_STAGES - 1) & 1);
+      if (blocking)
+        mbar_wait(eb, par);
+      else if (!mbar_try_wait(eb, par))
+        return false;
+    }
+    const uint32_t bar = smem_u32(&full[slot]);
     const uint32_t dst = smem_u32(ring + (size_t)slot * GEMM_STAGE_ELEMS);
     mbar_arrive_expect_tx(bar, GEMM_STAGE_BYTES);
     bulk_g2s(dst, it.A(), TILE_BYTES, bar);
     bulk_g2s(dst + TILE_BYTES, it.B(), TILE_BYTES, bar);
     it.next();
     ++issued;
+    return true;
+  }
+  // thread 0 only, before consuming stage g: keep up to GEMM_STAGES stages in flight (see gemm_pipeline)
+  template <class It>
+  __device__ __forceinline__ void feed(It &it, int g) {
+    while (it.valid() && issued < g + GEMM_STAGES) {
+      if (!try_issue(it, issued <= g)) break;
+    }
   }
   __device__ __forceinline__ const double *wait(int g) const {
-    mbar_wait(smem_u32(&bars[g % GEMM_STAGES]), (uint32_t)((g / GEMM_STAGES) & 1));
+    mbar_wait(smem_u32(&full[g % GEMM_STAGES]), (uint32_t)((g / GEMM_STAGES) & 1));
     return ring + (size_t)(g % GEMM_STAGES) * GEMM_STAGE_ELEMS;
+  }
+  // all lanes of a warp, after the stage's shared-memory reads have been consumed
+  __device__ __forceinline__ void release(int g) const {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(smem_u32(&empty[g % GEMM_STAGES]));
   }
 };
 
@@ -242,8 +290,6 @@ __device__ __forceinline__ void syrk_diag_pipeline(LinearIt issue_it, LinearIt c
   TmaRing rg;
   rg.init();
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  if (tid == 0)
-    while (rg.issued < GEMM_STAGES - 1 && issue_it.valid()) rg.issue(issue_it);
   double acc[17][2];
 #pragma unroll
   for (int t = 0; t < 17; ++t) acc[t][0] = acc[t][1] = 0.0;
@@ -255,7 +301,7 @@ __device__ __forceinline__ void syrk_diag_pipeline(LinearIt issue_it, LinearIt c
   const int n0 = 16 - w;
   int g = 0;
   while (cons_it.valid()) {
-    if (tid == 0 && issue_it.valid()) rg.issue(issue_it);
+    if (tid == 0) rg.feed(issue_it, g);
     const double *st = rg.wait(g);
 #pragma unroll
     for (int mc = 0; mc < 2; ++mc) {
@@ -265,10 +311,10 @@ __device__ __forceinline__ void syrk_diag_pipeline(LinearIt issue_it, LinearIt c
       for (int t = 0; t < 17; ++t) a[t] = lds128(st + aoff[t] + mc * 64);
 #pragma unroll
       for (int t = 0; t < 17; ++t) dmma884(acc[t][0], acc[t][1], a[t].x, t < n0 ? b0.x : b1.x);
+      if (mc == 1) rg.release(g);   // every load of the stage has been consumed by a DMMA
 #pragma unroll
       for (int t = 0; t < 17; ++t) dmma884(acc[t][0], acc[t][1], a[t].y, t < n0 ? b0.y : b1.y);
     }
-    __syncthreads();
     cons_it.next();
     ++g;
   }
@@ -288,14 +334,12 @@ __device__ __forceinline__ void trsm_tri_pipeline(LinearIt issue_it, LinearIt co
   rg.init();
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int c0 = w, c1 = 15 - w;   // c0 < c1
-  if (tid == 0)
-    while (rg.issued < GEMM_STAGES - 1 && issue_it.valid()) rg.issue(issue_it);
   double acc[16][2][2];
 #pragma unroll
   for (int R = 0; R < 16; ++R) acc[R][0][0] = acc[R][0][1] = acc[R][1][0] = acc[R][1][1] = 0.0;
   int g = 0;
   while (cons_it.valid()) {
-    if (tid == 0 && issue_it.valid()) rg.issue(issue_it);
+    if (tid == 0) rg.feed(issue_it, g);
     const double *As = rg.wait(g) + 2 * lane;
     const double *Bs = As + TILE_ELEMS;
 #pragma unroll
@@ -333,10 +377,12 @@ __device__ __forceinline__ void trsm_tri_pipeline(LinearIt issue_it, LinearIt co
         }
       }
     }
-    __syncthreads();
+    rg.release(g);   // every LDS of the stage fed a DMMA that has already issued (operands were ready)
     cons_it.next();
     ++g;
   }
+  // the epilogue overwrites the A operand's tile in global memory: every warp must have passed its last wait
+  __syncthreads();
   TrsmCoord tc{c0, c1, lane};
   epi(acc, tc);
 }
