@@ -7,7 +7,7 @@ tail -c 3000 gpurun_out/bench.json
 tail -5 gpurun_out/bench.err
 if [ "$1" == "ncu" ]; then
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-configs > gpurun_out/plain.log 2>&1 &&
-  ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
+  ncu --metrics gpu__time_duration.sum --clock-control none -s 500 -c 400 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-configs > gpurun_out/ncu_launch.log 2>&1
   echo "ncu launches exit $?"
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-configs > gpurun_out/plain2.log 2>&1 &&
