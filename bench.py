@@ -62,6 +62,15 @@ def cpu_threads():
         return os.cpu_count() or 1
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 for every rank; the CPU arm is meant to use every host core."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
+
+
 def cpu_score_once(post, Xs, best):
     from oracle import boss_oracle as O
     acq, _, _ = O.ei_acquisition([[post]], Xs, [1.0], best, None)
@@ -73,6 +82,7 @@ def cpu_baseline(budget_s=12.0):
     src/models/gaussian_process.jl:174-178, level-3 BLAS on all host threads) on CPU_SAMPLE_M-candidate tiles,
     plus mode A (the access pattern BOSS.jl ships: one candidate per call, expected_improvement.jl:74-84)."""
     from oracle import boss_oracle as O
+    use_all_host_threads()
     X, y, ls, amp, ns = make_problem()
     post = O.posterior_fit(X, y, ls, amp, ns, KERNEL_ID)
     best = float(np.max(y))
@@ -106,6 +116,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import boss_oracle as O
+    use_all_host_threads()
     X, y, ls, amp, ns = make_problem()
     post = O.posterior_fit(X, y, ls, amp, ns, KERNEL_ID)
     best = float(np.max(y))
