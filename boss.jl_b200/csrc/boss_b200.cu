@@ -303,7 +303,7 @@ int set_kernel_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(chol_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(trtri_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(trtri_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  CUDA_TRY(cudaFuncSetAttribute(dbg_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(kinv_wtw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(chol_update_rl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(trtri_acc_rl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
@@ -1446,8 +1446,8 @@ int boss_gp_cov(const boss_gp *gp, const double *Xs, int64_t M, const double *pr
   sp.ld = Mp;
   sp.VT = g.vt.as<double>();
   score_trmm_kernel<<<dim3(ncb, nsp), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(sp);
-  DbgGemmParams gm{g.vt.as<double>(), g.vt.as<double>(), g.cov_p.as<double>(), h->ktiles, Mp / TK, 1};
-  dbg_gemm_kernel<<<dim3(ncb, ncb), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(gm);
+  GemmNtParams gm{g.vt.as<double>(), g.vt.as<double>(), g.cov_p.as<double>(), h->ktiles, Mp / TK, 1};
+  gemm_nt_kernel<<<dim3(ncb, ncb), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(gm);
   CovFinishParams cf{};
   cf.Xs = g.xs_stage.as<double>();
   cf.M = (int)M;
@@ -1819,8 +1819,8 @@ int boss_dbg_gemm_nt(const double *A, const double *B, int M, int N, int K, doub
   CUDA_TRY(cudaMalloc(&dC, (size_t)Mp * Np * 8));
   CUDA_TRY(cudaMemcpy(dA, pa.data(), pa.size() * 8, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(dB, pb.data(), pb.size() * 8, cudaMemcpyHostToDevice));
-  DbgGemmParams p{dA, dB, dC, Kp / TK, Np / TK, 0};
-  dbg_gemm_kernel<<<dim3(Np / TM, Mp / TM), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(p);
+  GemmNtParams p{dA, dB, dC, Kp / TK, Np / TK, 0};
+  gemm_nt_kernel<<<dim3(Np / TM, Mp / TM), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(p);
   ++g.launches;
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaStreamSynchronize(g.stream));

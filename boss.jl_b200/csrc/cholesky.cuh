@@ -252,15 +252,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) trtri_w_kernel(CholGemmParams
   });
 }
 
-// Generic C = A B^T on P-layout operands (test hook boss_dbg_gemm_nt): grid (N/128, M/128)
-struct DbgGemmParams {
+// Generic C = A B^T on P-layout operands: grid (N/128, M/128).  Used by boss_gp_cov (V^T V, lower tiles only) and by
+// the test hook boss_dbg_gemm_nt.
+struct GemmNtParams {
   const double *A, *B;
   double *C;
   int ktilesAB;  // K/16
   int ktilesC;   // N/16
   int lower_only;  // skip tiles above the block diagonal (symmetric products: boss_gp_cov)
 };
-__global__ void __launch_bounds__(GEMM_THREADS, 1) dbg_gemm_kernel(DbgGemmParams p) {
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_kernel(GemmNtParams p) {
   const int cb = blockIdx.x, rb = blockIdx.y;
   if (p.lower_only && cb > rb) return;
   LinearIt it{p.A + (size_t)rb * p.ktilesAB * TILE_ELEMS, p.B + (size_t)cb * p.ktilesAB * TILE_ELEMS, p.ktilesAB};
