@@ -77,3 +77,14 @@ def test_batch_loglik_matches_single():
     out = O.gp_loglik_batch(X, y, L, A, N, O.KERNEL_SE)
     for s in range(S):
         assert out[s] == O.gp_loglik(X, y, L[s], A[s], N[s], O.KERNEL_SE)
+
+
+def test_longdouble_adjudicator_matches_mpmath():
+    X, y, ls, Xs = _problem(n=24, d=3, seed=5)
+    amp, ns = 1.3, 0.07
+    for kid in (O.KERNEL_SE, O.KERNEL_MATERN32, O.KERNEL_MATERN52):
+        m1, v1, l1 = O.adjudicator_mean_var_loglik(X, y, ls, amp, ns, kid, Xs)
+        m2, v2, l2 = O.adjudicator_longdouble(X, y, ls, amp, ns, kid, Xs)
+        assert np.max(np.abs(m1 - m2) / np.abs(m1)) <= 1e-14
+        assert np.max(np.abs(v1 - v2) / v1) <= 1e-13
+        assert abs(l1 - l2) <= 1e-14 * abs(l1)
