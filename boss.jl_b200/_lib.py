@@ -72,6 +72,7 @@ EXPORTS = {
     "boss_launch_count": (C.c_int64, []),
     "boss_dbg_gemm_nt": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     "boss_dbg_factors": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "boss_dbg_kernel_fn": (C.c_int, [C.c_int, _vp, C.c_int, _vp]),
 }
 for _name, (_res, _args) in EXPORTS.items():
     _f = getattr(lib, _name)          # AttributeError here = header and library disagree
@@ -455,6 +456,13 @@ def dbg_gemm_nt(A, B):
     Cm = np.empty((M, N))
     _check(lib.boss_dbg_gemm_nt(_ptr(A), _ptr(B), M, N, K, _ptr(Cm)), "boss_dbg_gemm_nt")
     return Cm
+
+
+def dbg_kernel_fn(which, t):
+    t = _f64(t)
+    out = np.empty_like(t)
+    _check(lib.boss_dbg_kernel_fn(int(which), _ptr(t), t.size, _ptr(out)), "boss_dbg_kernel_fn")
+    return out
 
 
 def dbg_factors(gp: GP):

@@ -1834,6 +1834,42 @@ int boss_dbg_gemm_nt(const double *A, const double *B, int M, int N, int K, doub
   return 0;
 }
 
+__global__ void dbg_kernel_fn_kernel(int which, const double *t, double *out, int n) {
+  __shared__ double tab[EXPTAB_N];
+  exptab_init(tab);
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double x = t[i];
+    double v;
+    switch (which) {
+      case 0: v = fast_exp_neg(x, tab); break;
+      case 1: v = fast_sqrt(x); break;
+      case 2: v = kappa_fast<0>(x, tab); break;
+      case 3: v = kappa_fast<1>(x, tab); break;
+      case 4: v = kappa_fast<2>(x, tab); break;
+      case 5: v = kappa_dr_over_r_fast<0>(x, tab); break;
+      case 6: v = kappa_dr_over_r_fast<1>(x, tab); break;
+      default: v = kappa_dr_over_r_fast<2>(x, tab); break;
+    }
+    out[i] = v;
+  }
+}
+int boss_dbg_kernel_fn(int which, const double *t, int n, double *out) {
+  std::lock_guard<std::mutex> lk(g.mu);
+  REQUIRE_INIT();
+  if (which < 0 || which > 7 || n < 0) return fail(BOSS_ERR_ARG, "boss_dbg_kernel_fn: bad argument");
+  double *dt, *dout;
+  CUDA_TRY(cudaMalloc(&dt, (size_t)n * 8 + 8));
+  CUDA_TRY(cudaMalloc(&dout, (size_t)n * 8 + 8));
+  CUDA_TRY(cudaMemcpy(dt, t, (size_t)n * 8, cudaMemcpyHostToDevice));
+  dbg_kernel_fn_kernel<<<148, 256, 0, g.stream>>>(which, dt, dout, n);
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaMemcpy(out, dout, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  cudaFree(dt);
+  cudaFree(dout);
+  return 0;
+}
+
 int boss_dbg_factors(const boss_gp *gp, double *L, double *W, double *alpha) {
   std::lock_guard<std::mutex> lk(g.mu);
   REQUIRE_INIT();

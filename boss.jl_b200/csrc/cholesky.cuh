@@ -34,6 +34,8 @@ template <int KID, int DP>
 __global__ void __launch_bounds__(256) build_k_kernel(BuildKParams p) {
   __shared__ double xcol[128 * DP];
   __shared__ double invl[DP];
+  __shared__ double etab[EXPTAB_N];
+  exptab_init(etab);
   const int s = blockIdx.y;
   // decode (rb >= cb) from the linear lower-triangle index
   int t = blockIdx.x, rb = 0;
@@ -79,23 +81,26 @@ __global__ void __launch_bounds__(256) build_k_kernel(BuildKParams p) {
     if (rb == cb && mcol * 8 > r) continue;
     double v[8];
 #pragma unroll
-    for (int kk = 0; kk < 8; ++kk) {
+    for (int kk = 0; kk < 8; ++kk) {   // eight independent, branch-free chains: the scheduler interleaves them
       const int jj = mcol * 8 + kk;
-      const int gj = cb * 128 + jj;
       double d2 = 0.0;
 #pragma unroll
       for (int i = 0; i < DP; ++i) {
         const double df = xr[i] - xcol[jj * DP + i];
         d2 = fma(df, df, d2);
       }
-      double val;
-      if (gi < p.n && gj < p.n) {
-        val = a2 * kappa<KID>(d2);
-        if (gi == gj) val += s2;
-      } else {
-        val = (gi == gj) ? 1.0 : 0.0;  // identity padding: L_pad = I, log-det contribution 0
+      v[kk] = a2 * kappa_fast<KID>(d2, etab);
+    }
+    if (rb == cb || rb == p.nblk - 1) {   // diagonal tile (noise) or last row block (padding): per-element fix-up
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        const int gj = cb * 128 + mcol * 8 + kk;
+        if (gi < p.n && gj < p.n) {
+          if (gi == gj) v[kk] += s2;
+        } else {
+          v[kk] = (gi == gj) ? 1.0 : 0.0;  // identity padding: L_pad = I, log-det contribution 0
+        }
       }
-      v[kk] = val;
     }
     double *dst = blk + (mcol >> 1) * TILE_ELEMS + ((((r >> 3) << 1) + (mcol & 1)) << 6) + ((r & 7) << 3);
 #pragma unroll
@@ -450,6 +455,8 @@ __global__ void __launch_bounds__(256) loglik_grad_tile_kernel(LlGradParams p) {
   __shared__ double acol[128];
   __shared__ double invl[DP];
   __shared__ double red[256];
+  __shared__ double etab[EXPTAB_N];
+  exptab_init(etab);
   const int s = blockIdx.y, tid = threadIdx.x;
   int t = blockIdx.x, rb = 0;
   while (t >= rb + 1) {
@@ -491,24 +498,32 @@ __global__ void __launch_bounds__(256) loglik_grad_tile_kernel(LlGradParams p) {
       kv[q] = v.x;
       kv[q + 4] = v.y;
     }
+    double kap[8], wgt[8];
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {   // independent, branch-free chains
+      const int jj = mcol * 8 + kk;
+      double d2 = 0.0;
+#pragma unroll
+      for (int q = 0; q < DP; ++q) {
+        const double df = xr[q] - xcol[jj * DP + q];
+        d2 = fma(df, df, d2);
+      }
+      kap[kk] = kappa_fast<KID>(d2, etab);
+      wgt[kk] = kappa_dr_over_r_fast<KID>(d2, etab);
+    }
 #pragma unroll
     for (int kk = 0; kk < 8; ++kk) {
       const int jj = mcol * 8 + kk, gj = cb * 128 + jj;
-      if (gi >= p.n || gj > gi) continue;
       const double G = ai * acol[jj] - kv[kk];
-      if (gj == gi) {
-        a2 += G;
-      } else {
-        double df[DP], d2 = 0.0;
+      const double Gd = (gi < p.n && gj == gi) ? G : 0.0;   // selects, not branches: adding 0.0 changes nothing
+      const double Go = (gi < p.n && gj < gi) ? G : 0.0;
+      a2 += Gd;
+      a1 = fma(Go, kap[kk], a1);
+      const double w = Go * wgt[kk];
 #pragma unroll
-        for (int q = 0; q < DP; ++q) {
-          df[q] = xr[q] - xcol[jj * DP + q];
-          d2 = fma(df[q], df[q], d2);
-        }
-        a1 = fma(G, kappa<KID>(d2), a1);
-        const double w = G * kappa_dr_over_r<KID>(d2);
-#pragma unroll
-        for (int q = 0; q < DP; ++q) bq[q] = fma(w * df[q], df[q], bq[q]);
+      for (int q = 0; q < DP; ++q) {
+        const double df = xr[q] - xcol[jj * DP + q];
+        bq[q] = fma(w * df, df, bq[q]);
       }
     }
   }

@@ -67,6 +67,8 @@ template <int KID, int DP>
 __global__ void __launch_bounds__(256) grad_kernel(GradParams p) {
   __shared__ double xt[XCOV_KC * DP];
   __shared__ double al[XCOV_KC];
+  __shared__ double etab[EXPTAB_N];
+  exptab_init(etab);
   const int tid = threadIdx.x, r = tid & 127, kh = tid >> 7;
   const int cb = blockIdx.x;
   const long long m = p.m0 + (long long)cb * 128 + r;
@@ -91,24 +93,31 @@ __global__ void __launch_bounds__(256) grad_kernel(GradParams p) {
         u[q] = v.x;
         u[q + 4] = v.y;
       }
+      double gk[8];
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {   // independent, branch-free chains
+        const int kl = mcol * 8 + kk;
+        double d2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < DP; ++i) {
+          const double df = xc[i] - xt[kl * DP + i];
+          d2 = fma(df, df, d2);
+        }
+        gk[kk] = p.a2 * kappa_dr_over_r_fast<KID>(d2, etab);
+      }
+      if (p.n - k0 < XCOV_KC) {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) gk[kk] = (k0 + mcol * 8 + kk < p.n) ? gk[kk] : 0.0;
+      }
 #pragma unroll
       for (int kk = 0; kk < 8; ++kk) {
         const int kl = mcol * 8 + kk;
-        if (k0 + kl < p.n) {
-          double df[DP];
-          double d2 = 0.0;
+        const double t1 = gk[kk] * al[kl], t2 = gk[kk] * u[kk];
 #pragma unroll
-          for (int i = 0; i < DP; ++i) {
-            df[i] = xc[i] - xt[kl * DP + i];
-            d2 = fma(df[i], df[i], d2);
-          }
-          const double g = p.a2 * kappa_dr_over_r<KID>(d2);
-          const double t1 = g * al[kl], t2 = g * u[kk];
-#pragma unroll
-          for (int i = 0; i < DP; ++i) {
-            gm[i] = fma(t1, df[i], gm[i]);
-            gv[i] = fma(t2, df[i], gv[i]);
-          }
+        for (int i = 0; i < DP; ++i) {
+          const double df = xc[i] - xt[kl * DP + i];
+          gm[i] = fma(t1, df, gm[i]);
+          gv[i] = fma(t2, df, gv[i]);
         }
       }
     }

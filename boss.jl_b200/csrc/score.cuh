@@ -40,6 +40,8 @@ template <int KID, int DP>
 __global__ void __launch_bounds__(256) xcov_kernel(XcovParams p) {
   __shared__ double xt[XCOV_KC * DP];
   __shared__ double al[XCOV_KC];
+  __shared__ double etab[EXPTAB_N];
+  exptab_init(etab);
   const int tid = threadIdx.x, r = tid & 127, kh = tid >> 7;
   const int cb = blockIdx.x;
   const long long m = p.m0 + (long long)cb * 128 + r;
@@ -53,10 +55,12 @@ __global__ void __launch_bounds__(256) xcov_kernel(XcovParams p) {
     for (int e = tid; e < XCOV_KC * DP; e += 256) xt[e] = p.Xt[(size_t)k0 * DP + e];
     if (tid < XCOV_KC) al[tid] = p.alpha[k0 + tid];
     __syncthreads();
+    // the last chunk may run past n: its padded columns must be exactly 0 (W is identity there)
+    const int live = p.n - k0;
     for (int mcol = kh; mcol < XCOV_KC / 8; mcol += 2) {
       double v[8];
 #pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {
+      for (int kk = 0; kk < 8; ++kk) {   // eight independent, branch-free chains: the scheduler interleaves them
         const int kl = mcol * 8 + kk;
         double d2 = 0.0;
 #pragma unroll
@@ -64,10 +68,14 @@ __global__ void __launch_bounds__(256) xcov_kernel(XcovParams p) {
           const double df = xc[i] - xt[kl * DP + i];
           d2 = fma(df, df, d2);
         }
-        const double val = (k0 + kl < p.n) ? p.a2 * kappa<KID>(d2) : 0.0;
-        v[kk] = val;
-        mu_acc = fma(val, al[kl], mu_acc);
+        v[kk] = p.a2 * kappa_fast<KID>(d2, etab);
       }
+      if (live < XCOV_KC) {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) v[kk] = (mcol * 8 + kk < live) ? v[kk] : 0.0;
+      }
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) mu_acc = fma(v[kk], al[mcol * 8 + kk], mu_acc);
       const int kg = k0 + mcol * 8;  // global training index of v[0]
       double *dst = rowbase + (size_t)(kg >> 4) * TILE_ELEMS + (((kg >> 3) & 1) << 6);
 #pragma unroll
@@ -341,6 +349,9 @@ struct CovFinishParams {
 
 template <int KID, int DP>
 __global__ void __launch_bounds__(256) cov_finish_kernel(CovFinishParams p) {
+  __shared__ double etab[EXPTAB_N];
+  exptab_init(etab);
+  __syncthreads();
   const int i = blockIdx.x * 16 + (threadIdx.x & 15), j = blockIdx.y * 16 + (threadIdx.x >> 4);
   if (i >= p.M || j >= p.M) return;
   double xi[DP], xj[DP];
@@ -353,7 +364,7 @@ __global__ void __launch_bounds__(256) cov_finish_kernel(CovFinishParams p) {
     d2 = fma(df, df, d2);
   }
   const int hi = max(i, j), lo = min(i, j);
-  double v = p.a2 * kappa<KID>(d2) - p.C[p_index(hi, lo, p.ktilesC)];
+  double v = p.a2 * kappa_fast<KID>(d2, etab) - p.C[p_index(hi, lo, p.ktilesC)];
   if (i == j) {
     v += VAR_JITTER;
     if (!clip_var(v)) *p.any_fail = 1;

@@ -228,6 +228,9 @@ int64_t boss_launch_count(void);
 
 /* ---- debug / test hooks (used by tests/ only) ------------------------------------------------ */
 int boss_dbg_gemm_nt(const double *A, const double *B, int M, int N, int K, double *C); /* C = A B^T, row-major dense */
+/* device scalar functions of the kernel-matrix stages: which = 0 exp(-t), 1 sqrt(t), 2-4 kappa(d2) SE / Matern32 /
+ * Matern52, 5-7 kappa'(r)/r of the same */
+int boss_dbg_kernel_fn(int which, const double *t, int n, double *out);
 int boss_dbg_factors(const boss_gp *gp, double *L, double *W, double *alpha);          /* dense row-major n x n, n   */
 
 #ifdef __cplusplus

@@ -630,3 +630,41 @@ def test_cuda_as_close_to_extended_precision_truth_as_the_oracle(lib, n, d, kid)
     assert abs(gp.loglik - ll_t) <= max(4 * abs(ll_o - ll_t), 1e-12 * abs(ll_t))
     assert e(mu_g, mu_t) <= 1e-9 and e(var_g, var_t) <= 1e-9 and abs(ll_g - ll_t) <= 1e-8 * abs(ll_t)
     gp.free()
+
+
+def test_fast_kernel_fn(lib):
+    """Device exp(-t) / sqrt / kappa used by the kernel-matrix stages (table + degree-6 polynomial; MUFU seed +
+    Goldschmidt step) against numpy and 40-digit arithmetic."""
+    import mpmath as mp
+    mp.mp.dps = 40
+    rng = np.random.default_rng(0)
+    t = np.concatenate([[0.0, 1e-300, 1e-17, 1e-8, 0.5, 1.0, 699.999, 700.0, 700.5, 1e4],
+                        rng.random(200000) * 60.0, 10.0 ** rng.uniform(-12, 2.8, 200000)])
+    got = lib.dbg_kernel_fn(0, t)
+    ref = np.exp(-t)
+    live = t < 700.0
+    rel = np.abs(got[live] - ref[live]) / ref[live]
+    assert rel.max() <= 1e-15, rel.max()                 # vs numpy (itself ~0.5 ulp)
+    idx = np.argsort(-rel)[:50]                          # worst cases against 40-digit arithmetic
+    worst = max(abs(mp.mpf(float(got[live][i])) - mp.exp(-mp.mpf(float(t[live][i])))) / mp.exp(-mp.mpf(float(t[live][i]))) for i in idx)
+    assert worst <= 6e-16, worst
+    assert np.all(got[~live] == 0.0) and got[0] == 1.0
+
+    x = np.concatenate([[1e-270, 1e-100, 0.25, 1.0, 2.0, 4.0, 1e100, 1e300], 10.0 ** rng.uniform(-30, 30, 200000),
+                        rng.random(200000) * 100.0])
+    s = lib.dbg_kernel_fn(1, x)
+    rel = np.abs(s - np.sqrt(x)) / np.sqrt(x)            # numpy sqrt is correctly rounded
+    assert rel.max() <= 2.3e-16, rel.max()               # <= 1 ulp
+    assert np.allclose(lib.dbg_kernel_fn(1, np.array([0.0, 5e-324, 1e-300])), 1e-145, rtol=1e-15, atol=0)
+
+    d2 = np.concatenate([[0.0, 1e-300, 1e-30, 1e-16], rng.random(100000) * 40.0, 10.0 ** rng.uniform(-20, 4, 100000)])
+    r = np.sqrt(d2)
+    want = {2: np.exp(-0.5 * d2), 3: (1 + np.sqrt(3) * r) * np.exp(-np.sqrt(3) * r),
+            4: (1 + np.sqrt(5) * r + 5 * d2 / 3) * np.exp(-np.sqrt(5) * r),
+            5: -np.exp(-0.5 * d2), 6: -3 * np.exp(-np.sqrt(3) * r),
+            7: -(5 / 3) * (1 + np.sqrt(5) * r) * np.exp(-np.sqrt(5) * r)}
+    for which, w in want.items():
+        g = lib.dbg_kernel_fn(which, d2)
+        ok = np.abs(w) > 1e-290
+        assert np.all(np.abs(g[ok] - w[ok]) <= 2e-15 * np.abs(w[ok])), which
+        assert np.all(np.abs(g[~ok]) <= 1e-280), which
