@@ -301,6 +301,7 @@ int set_kernel_attrs() {
   if (g_attr_done) return 0;
   CUDA_TRY(cudaFuncSetAttribute(chol_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(chol_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(trtri_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(trtri_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
@@ -356,16 +357,21 @@ int run_cholesky(double *L, size_t L_stride, double *Winv, size_t Winv_stride, i
   for (int j = 0; j < nblk; ++j) {
     gp.j = j;
     pp.j = j;
-    if (j > 0 && !right_looking) {
+    // left-looking, column j >= 1: SYRK of the diagonal tile -> potrf -> fused update + panel solve of the rows below
+    const bool fused_panel = j > 0 && !right_looking;
+    if (fused_panel) {
       Timed t(2);
-      chol_update_kernel<<<dim3(nblk - j, S), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(gp);
+      chol_update_kernel<<<dim3(1, S), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(gp);
       ++g.launches;
     }
     potrf_tile_kernel<<<S, 256, PT_SMEM_BYTES, g.stream>>>(pp);
     ++g.launches;
     if (j < nblk - 1) {
       Timed t(2);
-      chol_trsm_kernel<<<dim3(nblk - j - 1, S), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(gp);
+      if (fused_panel)
+        chol_panel_kernel<<<dim3(nblk - j - 1, S), GEMM_THREADS, PANEL_SMEM_BYTES, g.stream>>>(gp);
+      else
+        chol_trsm_kernel<<<dim3(nblk - j - 1, S), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(gp);
       ++g.launches;
       if (right_looking) {
         const int m = nblk - j - 1;

@@ -164,6 +164,122 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) chol_trsm_kernel(CholGemmPara
   });
 }
 
+// Fused panel step of the left-looking factorisation (block column j >= 1, rows i > j):
+//   T    = A_ij - L_i,0:j L_j,0:j^T        phase 1: the common mainloop, accumulators in registers
+//   L_ij = T Winv_jj^T                     phase 2: T goes to shared memory in P-layout (it is the A operand now),
+//                                          Winv_jj's live lower-triangular part is resident in shared memory
+// so the tile makes one trip to HBM instead of three and the K = 128 product needs no pipeline fill of its own.
+// Shared memory: [0, 160 KB) ring, reused after phase 1 as T (128 KB) + Winv k-tiles 0-1 (30 KB); k-tiles 2-7
+// (42 KB live) are prefetched behind the ring while phase 1 runs.
+constexpr int PANEL_WHI_OFF = GEMM_SMEM_BYTES;                        // live parts of Winv k-tiles 2..7, packed
+constexpr int PANEL_WHI_BYTES = (12 + 10 + 8 + 6 + 4 + 2) * 1024;
+constexpr int PANEL_SMEM_BYTES = PANEL_WHI_OFF + PANEL_WHI_BYTES;     // 207 104 B
+// byte offset of the live part of k-tile g (rows >= 16 g, i.e. 16 - 2g KB) inside its home region
+__host__ __device__ constexpr int panel_w_off(int g) {
+  return g == 0 ? 8 * TILE_BYTES : g == 1 ? 9 * TILE_BYTES
+       : PANEL_WHI_OFF + (g == 2 ? 0 : g == 3 ? 12 : g == 4 ? 22 : g == 5 ? 30 : g == 6 ? 36 : 40) * 1024;
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) chol_panel_kernel(CholGemmParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const int i = p.j + 1 + blockIdx.x;
+  double *Lm = p.L + (size_t)blockIdx.y * p.L_stride;
+  LinearIt it{Lm + (size_t)i * p.ktiles * TILE_ELEMS, Lm + (size_t)p.j * p.ktiles * TILE_ELEMS, p.j * KT_PER_BLOCK};
+  double *dst = Lm + ((size_t)i * p.ktiles + (size_t)p.j * KT_PER_BLOCK) * TILE_ELEMS;
+  const unsigned char *wi = reinterpret_cast<const unsigned char *>(p.Winv + (size_t)blockIdx.y * p.Winv_stride +
+                                                                    (size_t)p.j * (TM * TM));
+  uint64_t *wbar = reinterpret_cast<uint64_t *>(smem_raw + GEMM_RING_BYTES + GEMM_SCRATCH_BYTES) + 2 * GEMM_STAGES;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid == 0) {
+    mbar_init(smem_u32(&wbar[0]), 1);
+    mbar_init(smem_u32(&wbar[1]), 1);
+    mbar_fence_init();
+    mbar_arrive_expect_tx(smem_u32(&wbar[0]), PANEL_WHI_BYTES);
+#pragma unroll
+    for (int g = 2; g < 8; ++g)
+      bulk_g2s(smem_u32(smem_raw + panel_w_off(g)), wi + (size_t)g * TILE_BYTES + g * 2048, TILE_BYTES - g * 2048,
+               smem_u32(&wbar[0]));
+  }
+  gemm_pipeline<true>(it, it, [&](int, double(&acc)[8][4][2], const FragCoord &fc) {
+    __syncthreads();   // every warp has consumed its last ring stage
+    if (tid == 0) {
+      mbar_arrive_expect_tx(smem_u32(&wbar[1]), 2 * TILE_BYTES - 2048);
+      bulk_g2s(smem_u32(smem_raw + panel_w_off(0)), wi, TILE_BYTES, smem_u32(&wbar[1]));
+      bulk_g2s(smem_u32(smem_raw + panel_w_off(1)), wi + TILE_BYTES + 2048, TILE_BYTES - 2048, smem_u32(&wbar[1]));
+    }
+    double *Ts = reinterpret_cast<double *>(smem_raw);
+#pragma unroll
+    for (int fm = 0; fm < 8; ++fm)
+#pragma unroll
+      for (int fn = 0; fn < 4; ++fn)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) acc[fm][fn][e] = dst[block_offset(fc.row(fm), fc.col(fn, e))] - acc[fm][fn][e];
+#pragma unroll
+    for (int fm = 0; fm < 8; ++fm)
+#pragma unroll
+      for (int fn = 0; fn < 4; ++fn)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) Ts[block_offset(fc.row(fm), fc.col(fn, e))] = acc[fm][fn][e];
+    __syncthreads();
+    mbar_wait(smem_u32(&wbar[0]), 0);
+    mbar_wait(smem_u32(&wbar[1]), 0);
+
+    // phase 2: warp w owns column slabs c0 = w and c1 = 15 - w (as trsm_tri_pipeline), all 16 row slabs
+    const int c0 = w, c1 = 15 - w;
+    double o[16][2][2];
+#pragma unroll
+    for (int R = 0; R < 16; ++R) o[R][0][0] = o[R][0][1] = o[R][1][0] = o[R][1][1] = 0.0;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const double *As = Ts + g * TILE_ELEMS + 2 * lane;
+      // virtual base of k-tile g: its live part starts at row 16 g = byte 2048 g of the tile
+      const double *Bs = reinterpret_cast<const double *>(smem_raw + panel_w_off(g) - g * 2048) + 2 * lane;
+#pragma unroll
+      for (int mc = 0; mc < 2; ++mc) {
+        const int kk = 2 * g + mc;   // k micro-step 0..15
+        if (kk <= c0) {              // both column slabs live
+          const double2 b0 = lds128(Bs + (c0 * 2 + mc) * 64), b1 = lds128(Bs + (c1 * 2 + mc) * 64);
+#pragma unroll
+          for (int Rg = 0; Rg < 16; Rg += 8) {
+            double2 a[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) a[q] = lds128(As + ((Rg + q) * 2 + mc) * 64);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              dmma884(o[Rg + q][0][0], o[Rg + q][0][1], a[q].x, b0.x);
+              dmma884(o[Rg + q][1][0], o[Rg + q][1][1], a[q].x, b1.x);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              dmma884(o[Rg + q][0][0], o[Rg + q][0][1], a[q].y, b0.y);
+              dmma884(o[Rg + q][1][0], o[Rg + q][1][1], a[q].y, b1.y);
+            }
+          }
+        } else if (kk <= c1) {       // only the far slab
+          const double2 b1 = lds128(Bs + (c1 * 2 + mc) * 64);
+#pragma unroll
+          for (int Rg = 0; Rg < 16; Rg += 8) {
+            double2 a[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) a[q] = lds128(As + ((Rg + q) * 2 + mc) * 64);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) dmma884(o[Rg + q][1][0], o[Rg + q][1][1], a[q].x, b1.x);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) dmma884(o[Rg + q][1][0], o[Rg + q][1][1], a[q].y, b1.y);
+          }
+        }
+      }
+    }
+    const TrsmCoord tc{c0, c1, lane};
+#pragma unroll
+    for (int R = 0; R < 16; ++R)
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) dst[block_offset(tc.row(R), tc.col(h, e))] = o[R][h][e];
+  });
+}
+
 // ---- right-looking variants for small batches (a single posterior fit): every step exposes all tiles of the
 // trailing matrix as independent K = 128 products instead of a few CTAs with a long k-range ----
 // A_ik -= L_ij L_kj^T for j < k <= i  (after block column j has been solved)

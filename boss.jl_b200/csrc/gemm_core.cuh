@@ -49,7 +49,9 @@ __host__ __device__ __forceinline__ int block_offset(int r, int c) {
 // doubles as the producer: before consuming stage g it issues every later stage whose slot has already been
 // released (non-blocking probe) and, if stage g itself has not been issued yet, waits for its slot (the other
 // warps can always finish the stages already in flight, so this cannot deadlock).
-template <class It, class Epi>
+// SINGLE: the iterator yields exactly one output tile; the epilogue then runs after the loop, so none of the
+// pipeline state stays live across it (for epilogues that need the registers, e.g. chol_panel_kernel's phase 2).
+template <bool SINGLE = false, class It, class Epi>
 __device__ __forceinline__ void gemm_pipeline(It issue_it, It cons_it, Epi &&epi) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   double *ring = reinterpret_cast<double *>(smem_raw);
@@ -138,7 +140,7 @@ __device__ __forceinline__ void gemm_pipeline(It issue_it, It cons_it, Epi &&epi
     const int tile = cons_it.tile();
     cons_it.next();
     ++g;
-    if (tile_end) {
+    if (!SINGLE && tile_end) {
       FragCoord fc{wm, wn, lane};
       epi(tile, acc, fc);
 #pragma unroll
@@ -146,6 +148,10 @@ __device__ __forceinline__ void gemm_pipeline(It issue_it, It cons_it, Epi &&epi
 #pragma unroll
         for (int fn = 0; fn < 4; ++fn) acc[fm][fn][0] = acc[fm][fn][1] = 0.0;
     }
+  }
+  if (SINGLE) {
+    FragCoord fc{wm, wn, lane};
+    epi(0, acc, fc);
   }
 }
 
