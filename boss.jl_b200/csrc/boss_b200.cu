@@ -312,7 +312,6 @@ int set_kernel_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(score_trmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(wtv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM_BYTES));
-  CUDA_TRY(cudaFuncSetAttribute(fwd_solve_loglik_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   g_attr_done = true;
   return 0;
 }
@@ -322,9 +321,18 @@ int set_kernel_attrs() {
 // ---------------------------------------------------------------------------------------------
 // On return L holds the factors, Winv the inverted diagonal blocks, logdet_blk / status are filled.
 // W / WT non-null (S must be 1): also form the full triangular inverse.
+// fwd non-null (left-looking only): the forward substitution w = L^-1 delta rides along (r_j in the diagonal-tile
+// SYRK, w_j and |w_j|^2 in potrf_tile_kernel), so the log-likelihood needs no pass over L afterwards.
+struct FwdInline {
+  const double *ymm;   // delta of the first matrix; matrix s reads ymm + s * ldy
+  long long ldy;
+  int n, n_pad;
+  double *r, *w;       // [S][n_pad] scratch / result
+  double *ssq;         // [S][nblk]
+};
 int run_cholesky(double *L, size_t L_stride, double *Winv, size_t Winv_stride, int nblk, int ktiles, int S,
                  double *logdet_blk, int *status, double *W, double *WT, double *TT, size_t W_stride = 0,
-                 size_t TT_stride = 0, bool single_fit = false) {
+                 size_t TT_stride = 0, bool single_fit = false, const FwdInline *fwd = nullptr) {
   CholGemmParams gp{};
   gp.L = L;
   gp.L_stride = L_stride;
@@ -349,6 +357,18 @@ int run_cholesky(double *L, size_t L_stride, double *Winv, size_t Winv_stride, i
   pp.W = W;
   pp.WT = WT;
   pp.W_stride = W_stride;
+  if (fwd) {
+    gp.fwd_w = fwd->w;
+    gp.fwd_r = fwd->r;
+    gp.n_pad = fwd->n_pad;
+    pp.fwd_ymm = fwd->ymm;
+    pp.fwd_ldy = fwd->ldy;
+    pp.fwd_n = fwd->n;
+    pp.n_pad = fwd->n_pad;
+    pp.fwd_r = fwd->r;
+    pp.fwd_w = fwd->w;
+    pp.fwd_ssq = fwd->ssq;
+  }
   // Left-looking keeps accumulators in registers over the whole k-range (best when S x nblk CTAs fill the GPU);
   // a small batch (a single posterior fit) cannot fill 148 SMs that way -> right-looking steps of K = 128 tiles.
   // Only the posterior fit takes this path: batched log-likelihoods always run left-looking, so a sample's value
@@ -1495,7 +1515,6 @@ static int loglik_impl(const double *X, int d, int n, const double *Ymm, int64_t
   if (S == 0) return 0;
   const int n_pad = round_up(n, TM), nblk = n_pad / TM, ktiles = n_pad / TK;
   const size_t mat = (size_t)n_pad * n_pad;
-  if ((size_t)(n_pad + 128) * 8 > 200 * 1024) return fail(BOSS_ERR_ARG, "boss_gp_loglik_batch: n too large");
   const unsigned long long disc = mask_bits(discrete_mask, d);
 
   const bool need_w = grad || fit_out;        // gradient and batched-fit modes also form W = L^-1, W^T and alpha
@@ -1523,7 +1542,7 @@ static int loglik_impl(const double *X, int d, int n, const double *Ymm, int64_t
   const double *dX = X, *dY = Ymm, *dls = ls, *damp = amp, *dnoise = noise;
   double *dll = loglik;
   const size_t ycount = ldy ? (size_t)S * ldy : (size_t)n;
-  // misc: [X | Y | ls | amp | noise | ll] (host variant) then logdet_blk[Sb*nblk] | status[Sb]
+  // misc: [X | Y | ls | amp | noise | ll] (host variant) then logdet_blk[Sb*nblk] | ssq_blk[Sb*nblk] | r, w [Sb*n_pad] | status[Sb]
   size_t off = 0, oX = 0, oY = 0, ols = 0, oamp = 0, onoise = 0, oll = 0;
   if (!dev) {
     oX = off; off += (size_t)n * d;
@@ -1539,6 +1558,12 @@ static int loglik_impl(const double *X, int d, int n, const double *Ymm, int64_t
   }
   const size_t old_ = off;
   off += (size_t)Sb * nblk;
+  const size_t ossq = off;                      // |w_j|^2 per block, then r and w of the in-line forward substitution
+  off += (size_t)Sb * nblk;
+  const size_t orv = off;
+  off += small ? 0 : (size_t)Sb * n_pad;
+  const size_t owv = off;
+  off += small ? 0 : (size_t)Sb * n_pad;
   const size_t ost = off;
   off += (size_t)(Sb + 1) / 2 + 1;
   CUDA_TRY(g.chol_misc.ensure(off * 8));
@@ -1625,23 +1650,11 @@ static int loglik_impl(const double *X, int d, int n, const double *Ymm, int64_t
         cudaMemsetAsync(Wg, 0, (size_t)gs * mat * 8, g.stream);
         cudaMemsetAsync(WTg, 0, (size_t)gs * mat * 8, g.stream);
       }
-      int rc = run_cholesky(Lg, mat, Wig, winv_stride, nblk, ktiles, gs, ldg, stg, Wg, WTg, TTg, mat, tt_stride);
+      FwdInline fw{dY + (ldy ? (size_t)so * ldy : 0), ldy, n, n_pad, misc + orv + (size_t)wo * n_pad,
+                   misc + owv + (size_t)wo * n_pad, misc + ossq + (size_t)wo * nblk};
+      int rc = run_cholesky(Lg, mat, Wig, winv_stride, nblk, ktiles, gs, ldg, stg, Wg, WTg, TTg, mat, tt_stride, false, &fw);
       if (rc) rc_all = rc;
-      FwdParams fp{};
-      fp.L = Lg;
-      fp.L_stride = mat;
-      fp.Winv = Wig;
-      fp.Winv_stride = winv_stride;
-      fp.nblk = nblk;
-      fp.ktiles = ktiles;
-      fp.n = n;
-      fp.ymm = dY + (ldy ? (size_t)so * ldy : 0);
-      fp.ldy = ldy;
-      fp.logdet_blk = ldg;
-      fp.status = stg;
-      fp.loglik = dll + so;
-      fp.w_out = nullptr;
-      fwd_solve_loglik_kernel<<<gs, 256, (size_t)(n_pad + 128) * 8, g.stream>>>(fp);
+      loglik_finish_kernel<<<(gs + 127) / 128, 128, 0, g.stream>>>(ldg, fw.ssq, stg, nblk, n, gs, dll + so);
       ++g.launches;
       double *vec = g.ll_vec.as<double>();
       double *dpad = vec + (size_t)wo * n_pad, *wv = vec + ((size_t)Sb + wo) * n_pad, *al = vec + ((size_t)2 * Sb + wo) * n_pad;

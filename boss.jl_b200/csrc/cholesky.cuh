@@ -120,6 +120,11 @@ struct CholGemmParams {
   int j;                 // block column (UPDATE / TRSM) or block distance delta (TRTRI)
   double *W, *WT, *TT;   // full inverse, its transpose, per-task scratch (TRTRI), one per matrix of the batch
   size_t W_stride, TT_stride;
+  // in-line forward substitution of the batched log-likelihood (null = off): the diagonal-tile SYRK of block
+  // column j also forms r_j = sum_{k<j} L_jk w_k from the row block it streams; potrf_tile_kernel turns it into w_j
+  const double *fwd_w;   // [S][n_pad] w = L^-1 delta, blocks < j valid
+  double *fwd_r;         // [S][n_pad]
+  int n_pad;
 };
 
 // A_ij -= L_i,0:j * L_j,0:j^T   for i = j + blockIdx.x.  The diagonal tile (i == j) is a SYRK: only its lower
@@ -130,7 +135,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) chol_update_kernel(CholGemmPa
   LinearIt it{Lm + (size_t)i * p.ktiles * TILE_ELEMS, Lm + (size_t)p.j * p.ktiles * TILE_ELEMS, p.j * KT_PER_BLOCK};
   double *dst = Lm + ((size_t)i * p.ktiles + (size_t)p.j * KT_PER_BLOCK) * TILE_ELEMS;
   if (blockIdx.x == 0) {
-    syrk_diag_pipeline(it, it, [&](double(&acc)[17][2], const SyrkCoord &sc) {
+    auto epi = [&](double(&acc)[17][2], const SyrkCoord &sc) {
       // single round trip: all loads first, then all stores
 #pragma unroll
       for (int t = 0; t < 17; ++t)
@@ -140,7 +145,39 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) chol_update_kernel(CholGemmPa
       for (int t = 0; t < 17; ++t)
 #pragma unroll
         for (int e = 0; e < 2; ++e) dst[block_offset(sc.row(t), sc.col(t, e))] = acc[t][e];
-    });
+    };
+    if (p.fwd_w) {
+      // warp w owns micro-rows 2w and 2w+1 of the row block; lane T holds (row T/4, k = T%4 and 4 + T%4) of a
+      // micro-tile (the DMMA fragment order), so the partial sums stay per lane until the end
+      const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, c4 = lane & 3;
+      const double *wv = p.fwd_w + (size_t)blockIdx.y * p.n_pad + c4;
+      double r0 = 0.0, r1 = 0.0;
+      syrk_diag_pipeline(it, it, epi, [&](const double *st, int g) {
+        const double *a = st + (4 * w) * 64 + 2 * lane;
+        const double *wk = wv + g * 16;
+        const double w0 = wk[0], w1 = wk[4], w2 = wk[8], w3 = wk[12];
+        const double2 a00 = lds128(a), a01 = lds128(a + 64), a10 = lds128(a + 128), a11 = lds128(a + 192);
+        r0 = fma(a00.x, w0, r0);
+        r0 = fma(a00.y, w1, r0);
+        r0 = fma(a01.x, w2, r0);
+        r0 = fma(a01.y, w3, r0);
+        r1 = fma(a10.x, w0, r1);
+        r1 = fma(a10.y, w1, r1);
+        r1 = fma(a11.x, w2, r1);
+        r1 = fma(a11.y, w3, r1);
+      });
+      r0 += __shfl_xor_sync(0xffffffffu, r0, 1);
+      r0 += __shfl_xor_sync(0xffffffffu, r0, 2);
+      r1 += __shfl_xor_sync(0xffffffffu, r1, 1);
+      r1 += __shfl_xor_sync(0xffffffffu, r1, 2);
+      if (c4 == 0) {
+        double *rv = p.fwd_r + (size_t)blockIdx.y * p.n_pad + p.j * 128 + 16 * w + (lane >> 2);
+        rv[0] = r0;
+        rv[8] = r1;
+      }
+    } else {
+      syrk_diag_pipeline(it, it, epi);
+    }
   } else {
     gemm_pipeline(it, it, [&](int, double(&acc)[8][4][2], const FragCoord &fc) { rmw_sub_block(dst, acc, fc); });
   }
@@ -423,96 +460,23 @@ __global__ void __launch_bounds__(256) matvec_p_kernel(const double *__restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
-// Blocked forward substitution + log-likelihood assembly, one CTA per sample:
-//   w_i = Winv_ii (delta_i - sum_{k<i} L_ik w_k) ;  ll = -(n log 2pi + 2 sum log L_kk + |w|^2)/2
+// Log-likelihood assembly.  The forward substitution  w_i = Winv_ii (delta_i - sum_{k<i} L_ik w_k)  runs inside the
+// factorisation (fwd_* fields of CholGemmParams / PotrfParams), so no kernel re-reads L:
+//   ll = -(n log 2pi + 2 sum log L_kk + |w|^2)/2
 // (AbstractGPs logpdf(::FiniteGP, y), reference call site src/models/gaussian_process.jl:278-279)
 // ---------------------------------------------------------------------------------------------
-struct FwdParams {
-  const double *L;
-  size_t L_stride;
-  const double *Winv;
-  size_t Winv_stride;
-  int nblk, ktiles, n;
-  const double *ymm;   // Y - m(X): shared (ldy = 0) or per sample
-  long long ldy;
-  const double *logdet_blk;
-  const int *status;
-  double *loglik;      // S
-  double *w_out;       // optional S x n_pad (unused for loglik)
-};
-
-__global__ void __launch_bounds__(256) fwd_solve_loglik_kernel(FwdParams p) {
-  extern __shared__ __align__(16) double sm[];
-  double *w = sm;                        // [n_pad]
-  double *t = sm + p.nblk * 128;         // [128]
-  __shared__ double red[8];
-  const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int c4 = lane & 3, r8 = lane >> 2;
-  const double *Lm = p.L + (size_t)s * p.L_stride;
-  const double *Wi = p.Winv + (size_t)s * p.Winv_stride;
-  const double *ymm = p.ymm + (size_t)s * p.ldy;
-
-  for (int i = 0; i < p.nblk; ++i) {
-    for (int mr = warp; mr < 16; mr += 8) {
-      const double *base = Lm + (size_t)i * p.ktiles * TILE_ELEMS + (mr * 2) * 64 + lane * 2;
-      double acc = 0.0;
-      for (int kt = 0; kt < i * KT_PER_BLOCK; ++kt) {
-#pragma unroll
-        for (int mc = 0; mc < 2; ++mc) {
-          const double2 v = *reinterpret_cast<const double2 *>(base + (size_t)kt * TILE_ELEMS + mc * 64);
-          const int k = kt * 16 + mc * 8 + c4;
-          acc = fma(v.x, w[k], acc);
-          acc = fma(v.y, w[k + 4], acc);
-        }
-      }
-      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-      if (c4 == 0) {
-        const int row = i * 128 + mr * 8 + r8;
-        const double dl = (row < p.n) ? ymm[row] : 0.0;
-        t[mr * 8 + r8] = dl - acc;
-      }
-    }
-    __syncthreads();
-    for (int mr = warp; mr < 16; mr += 8) {
-      const double *base = Wi + (size_t)i * (TM * TM) + (mr * 2) * 64 + lane * 2;
-      double acc = 0.0;
-#pragma unroll
-      for (int kt = 0; kt < KT_PER_BLOCK; ++kt) {
-#pragma unroll
-        for (int mc = 0; mc < 2; ++mc) {
-          const double2 v = *reinterpret_cast<const double2 *>(base + kt * TILE_ELEMS + mc * 64);
-          const int k = kt * 16 + mc * 8 + c4;
-          acc = fma(v.x, t[k], acc);
-          acc = fma(v.y, t[k + 4], acc);
-        }
-      }
-      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-      if (c4 == 0) w[i * 128 + mr * 8 + r8] = acc;
-    }
-    __syncthreads();
-  }
-  // |w|^2 : fixed-order reduction (thread-strided partials -> warp shuffle tree -> 8 warp partials in order)
-  double part = 0.0;
-  for (int k = tid; k < p.nblk * 128; k += 256) part = fma(w[k], w[k], part);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-  if (lane == 0) red[warp] = part;
-  if (p.w_out)
-    for (int k = tid; k < p.nblk * 128; k += 256) p.w_out[(size_t)s * p.nblk * 128 + k] = w[k];
-  __syncthreads();
-  if (tid == 0) {
-    double mahal = 0.0;
-    for (int q = 0; q < 8; ++q) mahal += red[q];
-    double ld = 0.0;
-    for (int b = 0; b < p.nblk; ++b) ld += p.logdet_blk[(size_t)s * p.nblk + b];
-    double ll = -((double)p.n * 1.8378770664093453 + 2.0 * ld + mahal) * 0.5;
-    const int st = p.status[s];
-    if (st == 1) ll = -INFINITY;
-    if (st < 0) ll = NAN;
-    p.loglik[s] = ll;
-  }
+__global__ void loglik_finish_kernel(const double *logdet_blk, const double *ssq_blk, const int *status, int nblk, int n,
+                                     int S, double *loglik) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  double ld = 0.0, mahal = 0.0;
+  for (int b = 0; b < nblk; ++b) ld += logdet_blk[(size_t)s * nblk + b];
+  for (int b = 0; b < nblk; ++b) mahal += ssq_blk[(size_t)s * nblk + b];
+  double ll = -((double)n * 1.8378770664093453 + 2.0 * ld + mahal) * 0.5;
+  const int st = status[s];
+  if (st == 1) ll = -INFINITY;
+  if (st < 0) ll = NAN;
+  loglik[s] = ll;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -291,8 +291,13 @@ struct SyrkCoord {
   __device__ __forceinline__ int col(int t, int e) const { return 8 * cslab(t) + 2 * (lane & 3) + e; }
 };
 
-template <class Epi>
-__device__ __forceinline__ void syrk_diag_pipeline(LinearIt issue_it, LinearIt cons_it, Epi &&epi) {
+// `hook(st, g)` runs on every warp for every stage g (st = the stage's A tile) before the slot is released: the
+// batched log-likelihood rides its forward substitution's GEMV on the row block this kernel streams anyway.
+struct NoStageHook {
+  __device__ __forceinline__ void operator()(const double *, int) const {}
+};
+template <class Epi, class Hook = NoStageHook>
+__device__ __forceinline__ void syrk_diag_pipeline(LinearIt issue_it, LinearIt cons_it, Epi &&epi, Hook &&hook = Hook()) {
   TmaRing rg;
   rg.init();
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -317,7 +322,10 @@ __device__ __forceinline__ void syrk_diag_pipeline(LinearIt issue_it, LinearIt c
       for (int t = 0; t < 17; ++t) a[t] = lds128(st + aoff[t] + mc * 64);
 #pragma unroll
       for (int t = 0; t < 17; ++t) dmma884(acc[t][0], acc[t][1], a[t].x, t < n0 ? b0.x : b1.x);
-      if (mc == 1) rg.release(g);   // every load of the stage has been consumed by a DMMA
+      if (mc == 1) {
+        hook(st, g);
+        rg.release(g);   // every load of the stage has been consumed by a DMMA / the hook's FMAs
+      }
 #pragma unroll
       for (int t = 0; t < 17; ++t) dmma884(acc[t][0], acc[t][1], a[t].y, t < n0 ? b0.y : b1.y);
     }

@@ -31,11 +31,19 @@ struct PotrfParams {
   int *status;         // S : BOSS_NOT_POSDEF on a non-positive / NaN pivot
   double *W, *WT;      // optional: also deposit Winv_jj into W(j,j), its transpose into WT(j,j)
   size_t W_stride;     // per matrix of the batch
+  // in-line forward substitution of the batched log-likelihood (fwd_w null = off):
+  //   w_j = Winv_jj (delta_j - r_j),  r_j = sum_{k<j} L_jk w_k from the diagonal-tile SYRK (chol_update_kernel)
+  const double *fwd_ymm;   // delta = y - m(X): shared (fwd_ldy = 0) or one column per matrix
+  long long fwd_ldy;
+  int fwd_n, n_pad;
+  const double *fwd_r;     // [S][n_pad]
+  double *fwd_w;           // [S][n_pad]
+  double *fwd_ssq;         // [S][nblk]  |w_j|^2
 };
 
 constexpr int PT_TILES = 136;                        // 16*17/2 lower micro-tiles
 constexpr int PT_TMP_ELEMS = 64 * 64;                // scratch for the inverse products (one 64x64 block)
-constexpr int PT_SMEM_BYTES = (PT_TILES * 64 + PT_TMP_ELEMS + 128 + 128 + 8) * 8;   // 104 512 B -> 2 CTAs / SM
+constexpr int PT_SMEM_BYTES = (PT_TILES * 64 + PT_TMP_ELEMS + 128 + 128 + 8 + 128 + 8) * 8;   // 105 600 B -> 2 CTAs / SM
 
 // (I, J) of the t-th packed lower micro-tile
 struct PtIJ {
@@ -81,6 +89,7 @@ __global__ void __launch_bounds__(256, 2) potrf_tile_kernel(PotrfParams p) {
   double *lg = dinv + 128;                 // [128] log L_kk
   int *flag = reinterpret_cast<int *>(lg + 128);
   uint64_t *bar = reinterpret_cast<uint64_t *>(lg + 128 + 1);
+  double *fv = lg + 128 + 8;               // [128] delta_j - r_j, then [8] warp partials of |w_j|^2
   const int s_mat = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double *blk = p.L + (size_t)s_mat * p.L_stride + ((size_t)p.j * p.ktiles + (size_t)p.j * KT_PER_BLOCK) * TILE_ELEMS;
 
@@ -296,6 +305,45 @@ __global__ void __launch_bounds__(256, 2) potrf_tile_kernel(PotrfParams p) {
       // element (r, c) of tile (I, J) of W^T is element (c, r) of tile (J, I) of W
       const int r = w >> 3, c = ((w >> 1) & 3) + ((w & 1) << 2);
       wtfull[e] = (I <= J) ? T[pt_tile(J, I) + pt_elem(c, r)] : 0.0;
+    }
+  }
+
+  // ---- forward substitution step of the log-likelihood: w_j = Winv_jj (delta_j - r_j), |w_j|^2 ----
+  if (p.fwd_w) {
+    if (tid < 128) {
+      const int row = p.j * 128 + tid;
+      const double dl = (row < p.fwd_n) ? p.fwd_ymm[(size_t)s_mat * p.fwd_ldy + row] : 0.0;
+      fv[tid] = dl - (p.j > 0 ? p.fwd_r[(size_t)s_mat * p.n_pad + row] : 0.0);
+    }
+    __syncthreads();
+    // warp w: micro-rows 2w, 2w+1; lane T holds (row T/4, columns T%4 and 4 + T%4) of each 8x8 tile
+    const int c4 = lane & 3;
+    double sq = 0.0;
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      const int I = 2 * warp + m;
+      double acc = 0.0;
+      for (int J = 0; J <= I; ++J) {
+        const double2 a = lds128(T + pt_tile(I, J) + 2 * lane);
+        acc = fma(a.x, fv[J * 8 + c4], acc);
+        acc = fma(a.y, fv[J * 8 + c4 + 4], acc);
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      if (c4 == 0) {
+        p.fwd_w[(size_t)s_mat * p.n_pad + p.j * 128 + I * 8 + (lane >> 2)] = acc;
+        sq = fma(acc, acc, sq);
+      }
+    }
+    sq += __shfl_xor_sync(0xffffffffu, sq, 4);    // lanes with c4 == 0 hold the rows; fixed tree
+    sq += __shfl_xor_sync(0xffffffffu, sq, 8);
+    sq += __shfl_xor_sync(0xffffffffu, sq, 16);
+    if (lane == 0) fv[128 + warp] = sq;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int q = 0; q < 8; ++q) t += fv[128 + q];
+      p.fwd_ssq[(size_t)s_mat * p.nblk + p.j] = t;
     }
   }
 }
