@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) chol_trsm_kernel(CholGemmPara
 }
 
 // Fused panel step of the left-looking factorisation (block column j >= 1, rows i > j):
-//   T    = A_ij - L_i,0:j L_j,0:j^T        phase 1: the common mainloop, accumulators in registers
+//   T    = A_ij - L_i,0:j L_j,0:j^T        phase 1: the common mainloop, accumulators in registers (started at -A_ij)
 //   L_ij = T Winv_jj^T                     phase 2: T goes to shared memory in P-layout (it is the A operand now),
 //                                          Winv_jj's live lower-triangular part is resident in shared memory
 // so the tile makes one trip to HBM instead of three and the K = 128 product needs no pipeline fill of its own.
@@ -244,19 +244,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) chol_panel_kernel(CholGemmPar
       bulk_g2s(smem_u32(smem_raw + panel_w_off(0)), wi, TILE_BYTES, smem_u32(&wbar[1]));
       bulk_g2s(smem_u32(smem_raw + panel_w_off(1)), wi + TILE_BYTES + 2048, TILE_BYTES - 2048, smem_u32(&wbar[1]));
     }
-    double *Ts = reinterpret_cast<double *>(smem_raw);
+    double *Ts = reinterpret_cast<double *>(smem_raw);   // acc = L L^T - A_ij = -T
 #pragma unroll
     for (int fm = 0; fm < 8; ++fm)
 #pragma unroll
       for (int fn = 0; fn < 4; ++fn)
 #pragma unroll
-        for (int e = 0; e < 2; ++e) acc[fm][fn][e] = dst[block_offset(fc.row(fm), fc.col(fn, e))] - acc[fm][fn][e];
-#pragma unroll
-    for (int fm = 0; fm < 8; ++fm)
-#pragma unroll
-      for (int fn = 0; fn < 4; ++fn)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) Ts[block_offset(fc.row(fm), fc.col(fn, e))] = acc[fm][fn][e];
+        for (int e = 0; e < 2; ++e) Ts[block_offset(fc.row(fm), fc.col(fn, e))] = -acc[fm][fn][e];
     __syncthreads();
     mbar_wait(smem_u32(&wbar[0]), 0);
     mbar_wait(smem_u32(&wbar[1]), 0);
@@ -314,7 +308,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) chol_panel_kernel(CholGemmPar
       for (int h = 0; h < 2; ++h)
 #pragma unroll
         for (int e = 0; e < 2; ++e) dst[block_offset(tc.row(R), tc.col(h, e))] = o[R][h][e];
-  });
+  }, dst);
 }
 
 // ---- right-looking variants for small batches (a single posterior fit): every step exposes all tiles of the

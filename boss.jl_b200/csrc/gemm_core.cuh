@@ -51,8 +51,10 @@ __host__ __device__ __forceinline__ int block_offset(int r, int c) {
 // warps can always finish the stages already in flight, so this cannot deadlock).
 // SINGLE: the iterator yields exactly one output tile; the epilogue then runs after the loop, so none of the
 // pipeline state stays live across it (for epilogues that need the registers, e.g. chol_panel_kernel's phase 2).
+// neg_init (SINGLE only): the accumulators start at -neg_init[block] instead of 0, i.e. the epilogue receives
+// A B^T - C; the tile's global loads then overlap the pipeline fill instead of sitting in the epilogue.
 template <bool SINGLE = false, class It, class Epi>
-__device__ __forceinline__ void gemm_pipeline(It issue_it, It cons_it, Epi &&epi) {
+__device__ __forceinline__ void gemm_pipeline(It issue_it, It cons_it, Epi &&epi, const double *neg_init = nullptr) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   double *ring = reinterpret_cast<double *>(smem_raw);
   uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + GEMM_RING_BYTES + GEMM_SCRATCH_BYTES);
@@ -95,10 +97,20 @@ __device__ __forceinline__ void gemm_pipeline(It issue_it, It cons_it, Epi &&epi
   };
 
   double acc[8][4][2];
+  if (SINGLE && neg_init) {
+    const FragCoord fc{wm, wn, lane};
 #pragma unroll
-  for (int fm = 0; fm < 8; ++fm)
+    for (int fm = 0; fm < 8; ++fm)
 #pragma unroll
-    for (int fn = 0; fn < 4; ++fn) acc[fm][fn][0] = acc[fm][fn][1] = 0.0;
+      for (int fn = 0; fn < 4; ++fn)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) acc[fm][fn][e] = -neg_init[block_offset(fc.row(fm), fc.col(fn, e))];
+  } else {
+#pragma unroll
+    for (int fm = 0; fm < 8; ++fm)
+#pragma unroll
+      for (int fn = 0; fn < 4; ++fn) acc[fm][fn][0] = acc[fm][fn][1] = 0.0;
+  }
 
   const int a_off = (wm * 8) * 128 + lane * 2;  // micro-row (wm*8+fm) -> +fm*128 ; micro-col mc -> +mc*64
   const int b_off = (wn * 4) * 128 + lane * 2;
