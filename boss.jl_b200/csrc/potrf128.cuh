@@ -7,10 +7,12 @@
 // the DMMA fragment order of the P-layout (common.cuh), 68 KB, so two CTAs share an SM and hide each other's
 // dependency stalls.
 //
-//   factorisation  left-looking over the 16 tile columns s:
-//                    update   C_Is = A_Is - sum_{t<s} L_It L_st^T        DMMA, all warps, accumulators in registers
-//                    potf2    8x8 diagonal tile, one row per lane, pivots broadcast by warp shuffles
-//                    trsm     rows of the panel below by forward substitution, one row per thread
+//   factorisation  over the 16 tile columns s, with one column of look-ahead:
+//                    finish   C_Is -= L_I,s-1 L_s,s-1^T                  DMMA, all warps (one k-step: short)
+//                    potf2    8x8 diagonal tile, redundantly in the registers of every thread of warps 0-3
+//                    trsm     rows of the panel below by forward substitution, one row per thread (warps 0-3)
+//                    ahead    C_I,s+1 -= sum_{t<s} L_It L_s+1,t^T         DMMA, warps 4-7, while warps 0-3 are in
+//                                                                        the latency-bound potf2 / trsm chain
 //   inverse        8x8 diagonal inverses (one column per thread), then recursive doubling
 //                    W21 = -W22 (L21 W11)   for block sizes 8, 16, 32, 64                DMMA
 //
@@ -88,121 +90,139 @@ __global__ void __launch_bounds__(256, 2) potrf_tile_kernel(PotrfParams p) {
   double *dinv = tmp + PT_TMP_ELEMS;       // [128] 1 / L_kk
   double *lg = dinv + 128;                 // [128] log L_kk
   int *flag = reinterpret_cast<int *>(lg + 128);
-  uint64_t *bar = reinterpret_cast<uint64_t *>(lg + 128 + 1);
   double *fv = lg + 128 + 8;               // [128] delta_j - r_j, then [8] warp partials of |w_j|^2
   const int s_mat = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double *blk = p.L + (size_t)s_mat * p.L_stride + ((size_t)p.j * p.ktiles + (size_t)p.j * KT_PER_BLOCK) * TILE_ELEMS;
 
-  // ---- load the lower block triangle: 136 TMA bulk copies of one 512 B micro-tile each, one mbarrier ----
-  if (tid == 0) {
-    *flag = 0;
-    mbar_init(smem_u32(bar), 1);
-    mbar_fence_init();
+  // ---- load the lower block triangle: 136 micro-tiles of 512 B, one per warp pass (coalesced 16 B per lane;
+  //      all 17 loads of a thread are in flight together) ----
+  if (tid == 0) *flag = 0;
+  {
+    double2 buf[PT_TILES / 8];
+#pragma unroll
+    for (int k = 0; k < PT_TILES / 8; ++k) {
+      const int t = warp + 8 * k;
+      buf[k] = *reinterpret_cast<const double2 *>(blk + pt_gtile(PT_IJ.I[t], PT_IJ.J[t]) + 2 * lane);
+    }
+#pragma unroll
+    for (int k = 0; k < PT_TILES / 8; ++k) *reinterpret_cast<double2 *>(T + (warp + 8 * k) * 64 + 2 * lane) = buf[k];
   }
   __syncthreads();
-  if (warp == 0) {
-    if (lane == 0) mbar_arrive_expect_tx(smem_u32(bar), PT_TILES * 512);
-    __syncwarp();
-    for (int t = lane; t < PT_TILES; t += 32)
-      bulk_g2s(smem_u32(T + t * 64), blk + pt_gtile(PT_IJ.I[t], PT_IJ.J[t]), 512, smem_u32(bar));
-  }
-  mbar_wait(smem_u32(bar), 0);
 
   // ---- factorisation ----
-  for (int s = 0; s < 16; ++s) {
-    // (a) update tiles (I, s), I = s + warp, s + warp + 8   (4 independent accumulator pairs)
-    if (s > 0) {
-      for (int I = s + warp; I < 16; I += 8) {
-        double c[4][2];
+  // C(I, col) -= sum_{t in [t0, t1)} L(I, t) L(col, t)^T, four independent accumulator pairs
+  auto apply = [&](int I, int col, int t0, int t1) {
+    double c[4][2];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) c[q][0] = c[q][1] = 0.0;
-        const double *ti = T + pt_tile(I, 0) + 2 * lane, *ts = T + pt_tile(s, 0) + 2 * lane;
-        for (int t = 0; t < s; t += 4) {
-          double2 a[4], b[4];
+    for (int q = 0; q < 4; ++q) c[q][0] = c[q][1] = 0.0;
+    const double *ti = T + pt_tile(I, 0) + 2 * lane, *ts = T + pt_tile(col, 0) + 2 * lane;
+    for (int t = t0; t < t1; t += 4) {
+      double2 a[4], b[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (t + q < s) {
-              a[q] = lds128(ti + (t + q) * 64);
-              b[q] = lds128(ts + (t + q) * 64);
-            }
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (t + q < s) dmma884(c[q][0], c[q][1], a[q].x, b[q].x);
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (t + q < s) dmma884(c[q][0], c[q][1], a[q].y, b[q].y);
+      for (int q = 0; q < 4; ++q) {
+        if (t + q < t1) {
+          a[q] = lds128(ti + (t + q) * 64);
+          b[q] = lds128(ts + (t + q) * 64);
         }
-        double *dst = T + pt_tile(I, s);
-        dst[pt_cpos(lane, 0)] -= (c[0][0] + c[1][0]) + (c[2][0] + c[3][0]);
-        dst[pt_cpos(lane, 1)] -= (c[0][1] + c[1][1]) + (c[2][1] + c[3][1]);
       }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (t + q < t1) dmma884(c[q][0], c[q][1], a[q].x, b[q].x);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (t + q < t1) dmma884(c[q][0], c[q][1], a[q].y, b[q].y);
+    }
+    double *dst = T + pt_tile(I, col);
+    dst[pt_cpos(lane, 0)] -= (c[0][0] + c[1][0]) + (c[2][0] + c[3][0]);
+    dst[pt_cpos(lane, 1)] -= (c[0][1] + c[1][1]) + (c[2][1] + c[3][1]);
+  };
+  for (int s = 0; s < 16; ++s) {
+    // (a) finish column s: the terms t < s-1 were applied ahead of time during step s-1
+    if (s > 0) {
+      for (int I = s + warp; I < 16; I += 8) apply(I, s, s - 1, s);
       __syncthreads();
     }
-    // (b) every participating thread factors the 8x8 diagonal tile redundantly in registers (no shuffles, no
-    //     extra barrier), then solves its own row of the panel below:  x L_ss^T = c.  Thread 0 publishes L_ss.
-    const int nrows = (15 - s) * 8;
-    if (tid < (nrows > 32 ? nrows : 32)) {
-      double *d = T + pt_tile(s, s);
-      double l[8][8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int c = 0; c <= i; ++c) l[i][c] = d[(i << 3) + ((c & 3) << 1) + (c >> 2)];
-      double rsv[8];
-      bool bad = false;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        double piv = l[k][k];
-        if (!(piv > 0.0)) {   // LAPACK dpotrf info > 0 (also catches NaN)
-          bad = true;
-          piv = 1.0;
-        }
-        const double rs = rsqrt(piv);
-        rsv[k] = rs;
-        l[k][k] = piv * rs;
-#pragma unroll
-        for (int i = k + 1; i < 8; ++i) l[i][k] *= rs;
-#pragma unroll
-        for (int jj = k + 1; jj < 8; ++jj)
-#pragma unroll
-          for (int i = jj; i < 8; ++i) l[i][jj] = fma(-l[i][k], l[jj][k], l[i][jj]);
-      }
-      if (tid < nrows) {
-        const int I = s + 1 + (tid >> 3), r = tid & 7;
-        double *row = T + pt_tile(I, s) + (r << 3);
-        double x[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) x[c] = row[((c & 3) << 1) + (c >> 2)];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          double acc = x[k];
-#pragma unroll
-          for (int m = 0; m < k; ++m) acc = fma(-x[m], l[k][m], acc);
-          x[k] = acc * rsv[k];
-        }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) row[((c & 3) << 1) + (c >> 2)] = x[c];
-      }
-      if (tid == 0) {
+    if (warp < 4) {
+      // (b) every participating thread factors the 8x8 diagonal tile redundantly in registers (no shuffles, no
+      //     extra barrier), then solves its own row of the panel below:  x L_ss^T = c.  Thread 0 publishes L_ss.
+      const int nrows = (15 - s) * 8;
+      if (tid < (nrows > 32 ? nrows : 32)) {
+        double *d = T + pt_tile(s, s);
+        double l[8][8];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
-          for (int c = 0; c < 8; ++c) d[(i << 3) + ((c & 3) << 1) + (c >> 2)] = (c <= i) ? l[i][c] : 0.0;
+          for (int c = 0; c <= i; ++c) l[i][c] = d[(i << 3) + ((c & 3) << 1) + (c >> 2)];
+        double rsv[8];
+        bool bad = false;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) dinv[s * 8 + k] = rsv[k];
-        if (bad) *flag = 1;
+        for (int k = 0; k < 8; ++k) {
+          double piv = l[k][k];
+          if (!(piv > 0.0)) {   // LAPACK dpotrf info > 0 (also catches NaN)
+            bad = true;
+            piv = 1.0;
+          }
+          // 1/sqrt(piv) and sqrt(piv): MUFU seed + two coupled Goldschmidt steps (6 dependent FP64 operations; the
+          // pivot chain is this kernel's critical path)
+          double y;
+          asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(piv));
+          double gq = piv * y, hq = 0.5 * y;
+          double rq = fma(-gq, hq, 0.5);
+          gq = fma(gq, rq, gq);
+          hq = fma(hq, rq, hq);
+          rq = fma(-gq, hq, 0.5);
+          gq = fma(gq, rq, gq);
+          hq = fma(hq, rq, hq);
+          const double rs = hq + hq;
+          rsv[k] = rs;
+          l[k][k] = gq;
+#pragma unroll
+          for (int i = k + 1; i < 8; ++i) l[i][k] *= rs;
+#pragma unroll
+          for (int jj = k + 1; jj < 8; ++jj)
+#pragma unroll
+            for (int i = jj; i < 8; ++i) l[i][jj] = fma(-l[i][k], l[jj][k], l[i][jj]);
+        }
+        if (tid < nrows) {
+          const int I = s + 1 + (tid >> 3), r = tid & 7;
+          double *row = T + pt_tile(I, s) + (r << 3);
+          double x[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) x[c] = row[((c & 3) << 1) + (c >> 2)];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            double acc = x[k];
+#pragma unroll
+            for (int m = 0; m < k; ++m) acc = fma(-x[m], l[k][m], acc);
+            x[k] = acc * rsv[k];
+          }
+#pragma unroll
+          for (int c = 0; c < 8; ++c) row[((c & 3) << 1) + (c >> 2)] = x[c];
+        }
+        if (tid == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) d[(i << 3) + ((c & 3) << 1) + (c >> 2)] = (c <= i) ? l[i][c] : 0.0;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) dinv[s * 8 + k] = rsv[k];
+          if (bad) *flag = 1;
+        }
       }
+    } else if (s > 0 && s < 15) {
+      // (c) look-ahead on the otherwise idle warps: columns t < s are final, apply them to column s+1 now
+      //     (tiles (I, s+1) and columns < s are not touched by (b), which works on column s)
+      for (int I = s + 1 + (warp - 4); I < 16; I += 4) apply(I, s + 1, 0, s);
     }
     __syncthreads();
   }
 
   // ---- log L_kk in parallel, L -> global (upper part zero); the fixed-order sum runs on an idle thread below ----
   if (tid < 128) lg[tid] = -log(dinv[tid]);
-  for (int e = tid; e < TM * TM; e += 256) {
+  for (int e = 2 * tid; e < TM * TM; e += 512) {   // 16 B per lane, a micro-tile per warp pass
     const int kt = e >> 11, micro = (e >> 6) & 31, w = e & 63;
     const int I = micro >> 1, J = (kt << 1) + (micro & 1);
-    blk[e] = (J <= I) ? T[pt_tile(I, J) + w] : 0.0;
+    *reinterpret_cast<double2 *>(blk + e) = (J <= I) ? lds128(T + pt_tile(I, J) + w) : make_double2(0.0, 0.0);
   }
   __syncthreads();
   if (tid == 255) {
@@ -237,56 +257,86 @@ __global__ void __launch_bounds__(256, 2) potrf_tile_kernel(PotrfParams p) {
   }
   __syncthreads();
 
-  // ---- inverse, recursive doubling: diagonal blocks of mt tiles are inverted; merge pairs ----
+  // ---- inverse, recursive doubling: diagonal blocks of mt tiles are inverted; merge pairs.  A warp works on two
+  //      output tiles with the same k-range at a time (four independent DMMA chains) ----
   for (int mt = 1; mt < 16; mt <<= 1) {
     const int npair = 16 / (2 * mt), per = mt * mt;
-    // step A: Tm(I, J) = sum_{t = J}^{mt-1} L21(I, t) W11(t, J)        -> tmp tile (pair, I, J)
-    for (int o = warp; o < npair * per; o += 8) {
-      const int pr = o / per, I = (o % per) / mt, J = o % mt;
+    const int hm = mt > 1 ? mt / 2 : 1, two = mt > 1 ? 2 : 1;   // tiles per unit: 2 (mt >= 2) or 1
+    // step A: Tm(I, J) = sum_{t = J}^{mt-1} L21(I, t) W11(t, J)        -> tmp tile (pair, I, J);  unit = (pair, J, I/2)
+    for (int u = warp; u < npair * mt * hm; u += 8) {
+      const int pr = u / (mt * hm), J = (u / hm) % mt, I0 = two * (u % hm);
       const int R0 = 2 * pr * mt + mt, C0 = 2 * pr * mt;
-      double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+      double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0, g0 = 0.0, g1 = 0.0;
+      const int I1 = I0 + two - 1;   // == I0 when mt == 1 (second tile skipped below)
       int t = J;
       for (; t + 1 < mt; t += 2) {
-        const double2 a = lds128(T + pt_tile(R0 + I, C0 + t) + 2 * lane), b = pt_ldT(T + pt_tile(C0 + t, C0 + J), lane);
-        const double2 a2 = lds128(T + pt_tile(R0 + I, C0 + t + 1) + 2 * lane), b2 = pt_ldT(T + pt_tile(C0 + t + 1, C0 + J), lane);
+        const double2 b = pt_ldT(T + pt_tile(C0 + t, C0 + J), lane), b2 = pt_ldT(T + pt_tile(C0 + t + 1, C0 + J), lane);
+        const double2 a = lds128(T + pt_tile(R0 + I0, C0 + t) + 2 * lane), a2 = lds128(T + pt_tile(R0 + I0, C0 + t + 1) + 2 * lane);
+        const double2 p = lds128(T + pt_tile(R0 + I1, C0 + t) + 2 * lane), p2 = lds128(T + pt_tile(R0 + I1, C0 + t + 1) + 2 * lane);
         dmma884(c0, c1, a.x, b.x);
         dmma884(e0, e1, a2.x, b2.x);
+        dmma884(f0, f1, p.x, b.x);
+        dmma884(g0, g1, p2.x, b2.x);
         dmma884(c0, c1, a.y, b.y);
         dmma884(e0, e1, a2.y, b2.y);
+        dmma884(f0, f1, p.y, b.y);
+        dmma884(g0, g1, p2.y, b2.y);
       }
       if (t < mt) {
-        const double2 a = lds128(T + pt_tile(R0 + I, C0 + t) + 2 * lane), b = pt_ldT(T + pt_tile(C0 + t, C0 + J), lane);
+        const double2 b = pt_ldT(T + pt_tile(C0 + t, C0 + J), lane);
+        const double2 a = lds128(T + pt_tile(R0 + I0, C0 + t) + 2 * lane), p = lds128(T + pt_tile(R0 + I1, C0 + t) + 2 * lane);
         dmma884(c0, c1, a.x, b.x);
+        dmma884(f0, f1, p.x, b.x);
         dmma884(c0, c1, a.y, b.y);
+        dmma884(f0, f1, p.y, b.y);
       }
-      double *dst = tmp + (size_t)o * 64;
+      double *dst = tmp + (size_t)(pr * per + I0 * mt + J) * 64;
       dst[pt_cpos(lane, 0)] = c0 + e0;
       dst[pt_cpos(lane, 1)] = c1 + e1;
+      if (two == 2) {
+        dst += (size_t)mt * 64;
+        dst[pt_cpos(lane, 0)] = f0 + g0;
+        dst[pt_cpos(lane, 1)] = f1 + g1;
+      }
     }
     __syncthreads();
-    // step B: W21(I, J) = - sum_{t = 0}^{I} W22(I, t) Tm(t, J)          -> overwrites L21
-    for (int o = warp; o < npair * per; o += 8) {
-      const int pr = o / per, I = (o % per) / mt, J = o % mt;
+    // step B: W21(I, J) = - sum_{t = 0}^{I} W22(I, t) Tm(t, J)          -> overwrites L21;  unit = (pair, I, J/2)
+    for (int u = warp; u < npair * mt * hm; u += 8) {
+      const int pr = u / (mt * hm), I = (u / hm) % mt, J0 = two * (u % hm);
       const int R0 = 2 * pr * mt + mt, C0 = 2 * pr * mt;
       const double *tm = tmp + (size_t)pr * per * 64;
-      double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+      const int J1 = J0 + two - 1;
+      double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0, g0 = 0.0, g1 = 0.0;
       int t = 0;
       for (; t + 1 <= I; t += 2) {
-        const double2 a = lds128(T + pt_tile(R0 + I, R0 + t) + 2 * lane), b = pt_ldT(tm + (t * mt + J) * 64, lane);
-        const double2 a2 = lds128(T + pt_tile(R0 + I, R0 + t + 1) + 2 * lane), b2 = pt_ldT(tm + ((t + 1) * mt + J) * 64, lane);
+        const double2 a = lds128(T + pt_tile(R0 + I, R0 + t) + 2 * lane), a2 = lds128(T + pt_tile(R0 + I, R0 + t + 1) + 2 * lane);
+        const double2 b = pt_ldT(tm + (t * mt + J0) * 64, lane), b2 = pt_ldT(tm + ((t + 1) * mt + J0) * 64, lane);
+        const double2 q = pt_ldT(tm + (t * mt + J1) * 64, lane), q2 = pt_ldT(tm + ((t + 1) * mt + J1) * 64, lane);
         dmma884(c0, c1, a.x, b.x);
         dmma884(e0, e1, a2.x, b2.x);
+        dmma884(f0, f1, a.x, q.x);
+        dmma884(g0, g1, a2.x, q2.x);
         dmma884(c0, c1, a.y, b.y);
         dmma884(e0, e1, a2.y, b2.y);
+        dmma884(f0, f1, a.y, q.y);
+        dmma884(g0, g1, a2.y, q2.y);
       }
       if (t <= I) {
-        const double2 a = lds128(T + pt_tile(R0 + I, R0 + t) + 2 * lane), b = pt_ldT(tm + (t * mt + J) * 64, lane);
+        const double2 a = lds128(T + pt_tile(R0 + I, R0 + t) + 2 * lane);
+        const double2 b = pt_ldT(tm + (t * mt + J0) * 64, lane), q = pt_ldT(tm + (t * mt + J1) * 64, lane);
         dmma884(c0, c1, a.x, b.x);
+        dmma884(f0, f1, a.x, q.x);
         dmma884(c0, c1, a.y, b.y);
+        dmma884(f0, f1, a.y, q.y);
       }
-      double *dst = T + pt_tile(R0 + I, C0 + J);
+      double *dst = T + pt_tile(R0 + I, C0 + J0);
       dst[pt_cpos(lane, 0)] = -(c0 + e0);
       dst[pt_cpos(lane, 1)] = -(c1 + e1);
+      if (two == 2) {
+        dst += 64;   // tile (R0 + I, C0 + J0 + 1)
+        dst[pt_cpos(lane, 0)] = -(f0 + g0);
+        dst[pt_cpos(lane, 1)] = -(f1 + g1);
+      }
     }
     __syncthreads();
   }
@@ -295,16 +345,18 @@ __global__ void __launch_bounds__(256, 2) potrf_tile_kernel(PotrfParams p) {
   double *wi = p.Winv + (size_t)s_mat * p.Winv_stride + (size_t)p.j * (TM * TM);
   double *wfull = p.W ? p.W + (size_t)s_mat * p.W_stride + ((size_t)p.j * p.ktiles + (size_t)p.j * KT_PER_BLOCK) * TILE_ELEMS : nullptr;
   double *wtfull = p.WT ? p.WT + (size_t)s_mat * p.W_stride + ((size_t)p.j * p.ktiles + (size_t)p.j * KT_PER_BLOCK) * TILE_ELEMS : nullptr;
-  for (int e = tid; e < TM * TM; e += 256) {
+  for (int e = 2 * tid; e < TM * TM; e += 512) {   // 16 B per lane, a micro-tile per warp pass
     const int kt = e >> 11, micro = (e >> 6) & 31, w = e & 63;
     const int I = micro >> 1, J = (kt << 1) + (micro & 1);
-    const double v = (J <= I) ? T[pt_tile(I, J) + w] : 0.0;
-    wi[e] = v;
-    if (wfull) wfull[e] = v;
+    const double2 v = (J <= I) ? lds128(T + pt_tile(I, J) + w) : make_double2(0.0, 0.0);
+    *reinterpret_cast<double2 *>(wi + e) = v;
+    if (wfull) *reinterpret_cast<double2 *>(wfull + e) = v;
     if (wtfull) {
-      // element (r, c) of tile (I, J) of W^T is element (c, r) of tile (J, I) of W
-      const int r = w >> 3, c = ((w >> 1) & 3) + ((w & 1) << 2);
-      wtfull[e] = (I <= J) ? T[pt_tile(J, I) + pt_elem(c, r)] : 0.0;
+      // element (r, c) of tile (I, J) of W^T is element (c, r) of tile (J, I) of W; w and w+1 are (r, c) and (r, c+4)
+      const int r = w >> 3, c = (w >> 1) & 3;
+      const double *src = T + pt_tile(J, I);
+      *reinterpret_cast<double2 *>(wtfull + e) =
+          (I <= J) ? make_double2(src[pt_elem(c, r)], src[pt_elem(c + 4, r)]) : make_double2(0.0, 0.0);
     }
   }
 
