@@ -195,7 +195,9 @@ void timing_end() {  // call after the stream has been synchronised
 int pick_dp(int d) {
   if (d <= 2) return 2;
   if (d <= 4) return 4;
+  if (d <= 6) return 6;
   if (d <= 8) return 8;
+  if (d <= 12) return 12;
   if (d <= 16) return 16;
   if (d <= 32) return 32;
   return -1;
@@ -252,17 +254,23 @@ void launch_grad_t(const GradParams &p, dim3 grid) {
     switch ((kid) * 100 + (dp)) {                          \
       case 2: FN<0, 2>(__VA_ARGS__); break;                \
       case 4: FN<0, 4>(__VA_ARGS__); break;                \
+      case 6: FN<0, 6>(__VA_ARGS__); break;                \
       case 8: FN<0, 8>(__VA_ARGS__); break;                \
+      case 12: FN<0, 12>(__VA_ARGS__); break;              \
       case 16: FN<0, 16>(__VA_ARGS__); break;              \
       case 32: FN<0, 32>(__VA_ARGS__); break;              \
       case 102: FN<1, 2>(__VA_ARGS__); break;              \
       case 104: FN<1, 4>(__VA_ARGS__); break;              \
+      case 106: FN<1, 6>(__VA_ARGS__); break;              \
       case 108: FN<1, 8>(__VA_ARGS__); break;              \
+      case 112: FN<1, 12>(__VA_ARGS__); break;             \
       case 116: FN<1, 16>(__VA_ARGS__); break;             \
       case 132: FN<1, 32>(__VA_ARGS__); break;             \
       case 202: FN<2, 2>(__VA_ARGS__); break;              \
       case 204: FN<2, 4>(__VA_ARGS__); break;              \
+      case 206: FN<2, 6>(__VA_ARGS__); break;              \
       case 208: FN<2, 8>(__VA_ARGS__); break;              \
+      case 212: FN<2, 12>(__VA_ARGS__); break;             \
       case 216: FN<2, 16>(__VA_ARGS__); break;             \
       case 232: FN<2, 32>(__VA_ARGS__); break;             \
       default: break;                                      \
