@@ -146,34 +146,32 @@ __global__ void __launch_bounds__(256, 2) potrf_tile_kernel(PotrfParams p) {
       // (b) every participating thread factors the 8x8 diagonal tile redundantly in registers (no shuffles, no
       //     extra barrier), then solves its own row of the panel below:  x L_ss^T = c.  Thread 0 publishes L_ss.
       const int nrows = (15 - s) * 8;
+      double *d = T + pt_tile(s, s);
+      double l[8][8];
+      double rsv[8];
+      bool bad = false;
       if (tid < (nrows > 32 ? nrows : 32)) {
-        double *d = T + pt_tile(s, s);
-        double l[8][8];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
           for (int c = 0; c <= i; ++c) l[i][c] = d[(i << 3) + ((c & 3) << 1) + (c >> 2)];
-        double rsv[8];
-        bool bad = false;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          double piv = l[k][k];
-          if (!(piv > 0.0)) {   // LAPACK dpotrf info > 0 (also catches NaN)
-            bad = true;
-            piv = 1.0;
-          }
-          // 1/sqrt(piv) and sqrt(piv): MUFU seed + two coupled Goldschmidt steps (6 dependent FP64 operations; the
-          // pivot chain is this kernel's critical path)
+          const double piv = l[k][k];
+          bad |= !(piv > 1e-300);   // LAPACK dpotrf info > 0 (also catches NaN and pivots the flush-to-zero seed
+                                    // cannot take); off the dependent chain: a bad pivot only poisons this matrix
+                                    // with NaN / Inf, and its status reports it
+          // 1/sqrt(piv) and sqrt(piv): MUFU seed (2^-22) + two coupled Newton steps on (g, y) -> (sqrt, rsqrt);
+          // five dependent FP64 operations (the pivot chain is this kernel's critical path)
           double y;
           asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(piv));
-          double gq = piv * y, hq = 0.5 * y;
-          double rq = fma(-gq, hq, 0.5);
-          gq = fma(gq, rq, gq);
-          hq = fma(hq, rq, hq);
-          rq = fma(-gq, hq, 0.5);
-          gq = fma(gq, rq, gq);
-          hq = fma(hq, rq, hq);
-          const double rs = hq + hq;
+          double gq = piv * y;
+          double rq = fma(-gq, y, 1.0);
+          gq = fma(0.5 * gq, rq, gq);
+          y = fma(0.5 * y, rq, y);
+          rq = fma(-gq, y, 1.0);
+          gq = fma(0.5 * gq, rq, gq);
+          const double rs = fma(0.5 * y, rq, y);
           rsv[k] = rs;
           l[k][k] = gq;
 #pragma unroll
@@ -199,15 +197,20 @@ __global__ void __launch_bounds__(256, 2) potrf_tile_kernel(PotrfParams p) {
 #pragma unroll
           for (int c = 0; c < 8; ++c) row[((c & 3) << 1) + (c >> 2)] = x[c];
         }
-        if (tid == 0) {
+      }
+      // Thread 0 overwrites the diagonal tile with L_ss.  Every other thread of warps 0-3 reads that tile above, and
+      // the compiler is free to fetch those values late (re-materialised shared-memory loads under register
+      // pressure), so the overwrite needs its own barrier over the four warps: without it a lagging warp factored
+      // a half-published tile once in a few hundred launches (tests: test_loglik_is_repeatable_and_split_invariant).
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (tid == 0) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < 8; ++i)
 #pragma unroll
-            for (int c = 0; c < 8; ++c) d[(i << 3) + ((c & 3) << 1) + (c >> 2)] = (c <= i) ? l[i][c] : 0.0;
+          for (int c = 0; c < 8; ++c) d[(i << 3) + ((c & 3) << 1) + (c >> 2)] = (c <= i) ? l[i][c] : 0.0;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) dinv[s * 8 + k] = rsv[k];
-          if (bad) *flag = 1;
-        }
+        for (int k = 0; k < 8; ++k) dinv[s * 8 + k] = rsv[k];
+        if (bad) *flag = 1;
       }
     } else if (s > 0 && s < 15) {
       // (c) look-ahead on the otherwise idle warps: columns t < s are final, apply them to column s+1 now
