@@ -689,3 +689,32 @@ def test_loglik_is_repeatable_and_split_invariant(lib, n, d, S, reps):
     assert np.array_equal(first, np.concatenate(parts))
     ll_g, _ = lib.loglik_grad_batch(X, Y[0], L, A, N, lib.KERNEL_MATERN52)     # same factorisation, gradient mode
     assert np.array_equal(first, ll_g)
+
+
+@pytest.mark.parametrize("n,d", [(640, 5), (1500, 8)])
+def test_fit_score_gradient_paths_are_repeatable(lib, n, d):
+    """Same idea for the other kernel families (right-looking fit + triangular inverse, scoring, x-gradient, hyper-
+    parameter gradient, batched fit, covariance): repeated calls on identical inputs must agree bit for bit."""
+    X, Y, ls, amp, ns = make_problem(n, d, seed=n + 1)
+    Xs = np.random.default_rng(n).random((d, 5000))
+    best = float(np.quantile(Y[0], 0.8))
+    L, A, N = make_hyper_samples(6, d, seed=n + 2)
+    ref = None
+    for rep in range(8):
+        gp = lib.gp_fit(X, Y[0], ls[0], amp[0], ns[0], lib.KERNEL_MATERN52)
+        Lf, Wf, al = lib.dbg_factors(gp)
+        acq, bv, bi = lib.ei_score([gp], 1, 1, Xs, [1.0], best, None)
+        val, grad = lib.ei_value_grad([gp], 1, 1, Xs[:, :900], [1.0], best, None)
+        mu, cov, _ = lib.gp_cov(gp, Xs[:, :300])
+        ll, llg = lib.loglik_grad_batch(X, Y[0], L, A, N, lib.KERNEL_MATERN52)
+        gps = lib.gp_fit_batch(X, Y[0], L, A, N, lib.KERNEL_MATERN52)
+        mu_b = np.stack([lib.gp_predict(g, Xs[:, :200])[0] for g in gps])
+        for g in gps:
+            g.free()
+        gp.free()
+        out = (Lf, Wf, al, acq, np.array([bv, bi]), val, grad, mu, cov, ll, llg, mu_b)
+        if ref is None:
+            ref = out
+        else:
+            for k, (a, b) in enumerate(zip(ref, out)):
+                assert np.array_equal(a, b), (rep, k)
