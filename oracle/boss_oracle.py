@@ -464,6 +464,61 @@ def ei_acquisition(posts: Sequence[Sequence[GPPosterior]], Xs, coefs, best_yet, 
     return acq, mus, vars_
 
 
+def mc_expected_improvement(fitness, mean, var, eps, best_yet):
+    """`expected_improvement(::NonlinFitness, mean, var, eps::Matrix, best_yet)` expected_improvement.jl:104-107 and
+    the single-column method :108-111 (the BI case hands every posterior one column of eps).
+
+    mean, var: (y_dim, M); eps: (y_dim, K).  `fitness` maps a y_dim vector to a Real.  Returns (M,).
+    Plain loops: this is the arbitrary-closure path, small cases only.
+    """
+    mean = np.asarray(mean, dtype=np.float64)
+    var = np.asarray(var, dtype=np.float64)
+    eps = np.asarray(eps, dtype=np.float64).reshape(mean.shape[0], -1)
+    M, K = mean.shape[1], eps.shape[1]
+    sd = np.sqrt(var)
+    out = np.empty(M)
+    for m in range(M):
+        tot = 0.0
+        for k in range(K):
+            tot += max(0.0, float(fitness(mean[:, m] + sd[:, m] * eps[:, k])) - best_yet)
+        out[m] = tot / K
+    return out
+
+
+def mc_ei_acquisition(posts: Sequence[Sequence[GPPosterior]], Xs, fitness, eps, best_yet, y_max, lb=None, ub=None,
+                      cons_mask=None, prior_mean_s=None):
+    """`ei_acquisition` for a NonlinFitness (expected_improvement.jl:68-90 with the methods at :104-111):
+    one posterior -> all K columns of eps; S > 1 posteriors (BI) -> posterior s gets column s, then the mean."""
+    Xs = np.asarray(Xs, dtype=np.float64)
+    M, S, y_dim = Xs.shape[1], len(posts), len(posts[0])
+    eps = np.asarray(eps, dtype=np.float64)
+    acc = np.zeros(M)
+    failed = np.zeros(M, dtype=bool)
+    for s in range(S):
+        mu = np.empty((y_dim, M))
+        var = np.empty((y_dim, M))
+        for i in range(y_dim):
+            pm = None if prior_mean_s is None else np.asarray(prior_mean_s)[i]
+            mu[i], var[i], st = mean_and_var(posts[s][i], Xs, pm)
+            failed |= st != 0
+        e = eps if S == 1 else eps[:, s:s + 1]
+        if best_yet is None and y_max is None:
+            a = np.zeros(M)
+        elif best_yet is None:
+            a = feas_prob(mu, var, y_max)
+        else:
+            a = mc_expected_improvement(fitness, mu, np.where(var < 0, np.nan, var), e, best_yet)
+            if y_max is not None:
+                a = a * feas_prob(mu, var, y_max)
+        acc = acc + a
+    acq = np.where(failed, -np.inf, acc / S)
+    if lb is not None:
+        acq = np.where(in_bounds(Xs, lb, ub), acq, 0.0)
+    if cons_mask is not None:
+        acq = np.where(np.asarray(cons_mask, dtype=bool), acq, 0.0)
+    return acq
+
+
 def julia_argmax(vals):
     """Julia `argmax(vals)` / `argmax(f, itr)`: first maximal element under `isless`
     (NaN is maximal, -0.0 < +0.0).  Appendix A.11.  Returns a 0-based index."""

@@ -168,3 +168,48 @@ def test_data_loglike_and_grad_matches_finite_differences():
             assert abs(getattr(g, name)[idx] - fd) <= 1e-5 * max(1.0, abs(fd)), (name, idx)
     vals, grads = llg([p, p])
     assert vals[0] == vals[1] == v and np.array_equal(grads[1].lengthscales, g.lengthscales)
+
+
+def test_nonlin_fitness_mc_ei_matches_oracle_map_and_bi():
+    """NonlinFitness (expected_improvement.jl:104-111): posterior mean / variance from the device, Monte-Carlo average
+    over the same eps on the host; single posterior (all eps columns) and BI posteriors (one column each), with
+    y_max constraints, bounds and Domain.cons guards."""
+    f = lambda x: np.array([np.sin(x[0]) + 0.1 * x[1], np.cos(x[0]) - 0.05 * x[1]])
+    fit_scalar = lambda y: float(np.cos(y[0]) + np.sin(y[1]))                 # the reference's docstring example
+    fit_vector = lambda y: np.cos(y[0]) + np.sin(y[1])                        # same, broadcasting over columns
+    Xs = np.random.default_rng(1).random((2, 257)) * 11.0 - 0.5               # some points out of bounds
+    for fit in (fit_scalar, fit_vector):
+        prob = _problem(y_max=[np.inf, 0.5], cons=lambda x: [x[0] + x[1] - 1.0], seed=6, f=f)
+        prob.acquisition = B.ExpectedImprovement(B.NonlinFitness(fit), eps_samples=37)
+        prob.params = B.estimate_parameters(B.SamplingMAP(32, seed=3), prob)
+        eps = np.random.default_rng(5).standard_normal((2, 37))
+        acq = B.construct_acquisition(prob, eps=eps)
+        p = prob.params.params
+        posts = [[O.posterior_fit(prob.data.X, prob.data.Y[i], p.lengthscales[:, i], p.amplitudes[i], p.noise_std[i],
+                                  O.KERNEL_SE) for i in range(2)]]
+        best = B.best_so_far(prob, prob.acquisition.fitness)
+        assert best is not None
+        cm = B.types.cons_mask(Xs, prob.domain)
+        ref = O.mc_ei_acquisition(posts, Xs, fit_scalar, eps, best, prob.y_max, *prob.domain.bounds, cons_mask=cm)
+        got = acq(Xs)
+        assert np.any(ref > 0) and np.any(ref == 0.0)
+        assert np.all(np.abs(got - ref) <= 1e-9 * np.maximum(np.abs(ref), 1e-300))
+        assert acq(Xs[:, 3]) == got[3]
+        k, v = acq.argmax(Xs)
+        assert k == O.julia_argmax_fast(ref) and v == got[k]
+        with pytest.raises(NotImplementedError):
+            acq.value_and_grad(Xs)
+    # BI: three hyper-parameter samples, eps has one column per posterior
+    prob.params = B.estimate_parameters(B.SamplingMAP(32, seed=3), prob)
+    plist = []
+    for s in range(3):
+        q = prob.params.params
+        plist.append(B.GaussianProcessParams(q.lengthscales * (1.0 + 0.2 * s), q.amplitudes * (1.0 + 0.1 * s), q.noise_std))
+    post_bi = B.model_posterior(prob.model, plist, prob.data)
+    eps3 = np.random.default_rng(7).standard_normal((2, 3))
+    acq_bi = B.acquisition.Acquisition(prob, post_bi, prob.acquisition, best, eps3)
+    posts = [[O.posterior_fit(prob.data.X, prob.data.Y[i], q.lengthscales[:, i], q.amplitudes[i], q.noise_std[i], O.KERNEL_SE)
+              for i in range(2)] for q in plist]
+    ref = O.mc_ei_acquisition(posts, Xs, fit_scalar, eps3, best, prob.y_max, *prob.domain.bounds, cons_mask=cm)
+    got = acq_bi(Xs)
+    assert np.all(np.abs(got - ref) <= 1e-9 * np.maximum(np.abs(ref), 1e-300))

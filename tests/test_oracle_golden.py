@@ -165,3 +165,18 @@ def test_loglik_orderings():
 def test_loglik_not_pd_is_minus_inf():
     X = np.zeros((1, 3))                 # three identical points, zero noise -> singular K
     assert O.gp_loglik(X, np.array([1.0, 2.0, 3.0]), [1.0], 1.0, 0.0) == -math.inf
+
+
+def test_mc_expected_improvement_known_answers():
+    """expected_improvement(::NonlinFitness, ...) expected_improvement.jl:104-111: with a linear closure and sigma = 0
+    the Monte-Carlo estimate is exact, and with symmetric eps = +-1 it is the average of the two branches."""
+    fit = lambda y: y[0] + 2.0 * y[1]
+    mean = np.array([[1.0, 0.0], [0.5, -1.0]])            # two candidates
+    zero = np.zeros((2, 2))
+    eps = np.array([[1.0, -1.0], [1.0, -1.0]])
+    assert np.array_equal(O.mc_expected_improvement(fit, mean, zero, eps, 1.0), [1.0, 0.0])     # max(0, f - best)
+    var = np.array([[1.0, 4.0], [0.25, 1.0]])             # sd = [[1, 2], [0.5, 1]]
+    # candidate 0: f = 2 + (1 + 1)*e -> {4, 0} -> improvements {3, 0} -> 1.5 ; candidate 1: f = -2 + 4 e -> {2, -6} -> {1, 0} -> 0.5
+    assert np.allclose(O.mc_expected_improvement(fit, mean, var, eps, 1.0), [1.5, 0.5], rtol=0, atol=1e-15)
+    # a single eps column (the BI method at :108-111)
+    assert np.allclose(O.mc_expected_improvement(fit, mean, var, eps[:, :1], 1.0), [3.0, 1.0], rtol=0, atol=1e-15)
