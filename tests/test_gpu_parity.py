@@ -718,3 +718,31 @@ def test_fit_score_gradient_paths_are_repeatable(lib, n, d):
         else:
             for k, (a, b) in enumerate(zip(ref, out)):
                 assert np.array_equal(a, b), (rep, k)
+
+
+@pytest.mark.parametrize("d", [5, 9, 11, 12, 13, 17, 32])
+def test_every_x_dim_padding_class(lib, d):
+    """x_dim is padded to 2/4/6/8/12/16/32 inside the kernels (template instantiations): one pass over predict, EI
+    value + x-gradient, log-likelihood and its hyper-parameter gradient at dimensions that land in each class."""
+    n, M, S, kid = 150, 300, 5, lib.KERNEL_MATERN52
+    X, Y, ls, amp, ns = make_problem(n, d, seed=40 + d)
+    ls = ls * np.sqrt(d / 3.0)                       # keep the kernel matrix well away from the identity
+    Xs = np.random.default_rng(d).random((d, M))
+    gp = lib.gp_fit(X, Y[0], ls[0], amp[0], ns[0], kid)
+    post = O.posterior_fit(X, Y[0], ls[0], amp[0], ns[0], kid)
+    mu, var, st = lib.gp_predict(gp, Xs)
+    mu_r, var_r, _ = O.mean_and_var(post, Xs)
+    assert relerr(mu, mu_r) <= TOL_POST and relerr(var, var_r) <= TOL_POST and not st.any()
+    best = float(np.quantile(Y[0], 0.7))
+    val, grad = lib.ei_value_grad([gp], 1, 1, Xs, [1.0], best, None)
+    val_r, grad_r = O.ei_value_grad([post], Xs, [1.0], best, None)
+    assert relerr(val, val_r) <= TOL_POST
+    assert np.max(np.abs(grad - grad_r) / np.max(np.abs(grad_r), axis=1, keepdims=True)) <= 1e-8
+    L, A, N = make_hyper_samples(S, d, seed=d)
+    L = L * np.sqrt(d / 3.0)
+    ll, g = lib.loglik_grad_batch(X, Y[0], L, A, N, kid)
+    ll_r, g_r = O.gp_loglik_grad_batch(X, Y[0], L, A, N, kid)
+    assert relerr(ll, ll_r) <= TOL_LL
+    assert np.max(np.abs(g - g_r) / np.linalg.norm(g_r, axis=1, keepdims=True)) <= 1e-8
+    assert np.array_equal(ll, lib.loglik_batch(X, Y[0], L, A, N, kid))
+    gp.free()
