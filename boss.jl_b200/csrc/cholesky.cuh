@@ -253,15 +253,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) chol_panel_kernel(CholGemmPar
         for (int e = 0; e < 2; ++e) Ts[block_offset(fc.row(fm), fc.col(fn, e))] = -acc[fm][fn][e];
     __syncthreads();
     mbar_wait(smem_u32(&wbar[0]), 0);
-    mbar_wait(smem_u32(&wbar[1]), 0);
 
-    // phase 2: warp w owns column slabs c0 = w and c1 = 15 - w (as trsm_tri_pipeline), all 16 row slabs
+    // phase 2: warp w owns column slabs c0 = w and c1 = 15 - w (as trsm_tri_pipeline), all 16 row slabs.  The k-tiles
+    // are consumed from 7 down to 0: tiles 2-7 have been resident since phase 1, so the two tiles requested a moment
+    // ago (0 and 1) arrive while the others are being multiplied.
     const int c0 = w, c1 = 15 - w;
     double o[16][2][2];
 #pragma unroll
     for (int R = 0; R < 16; ++R) o[R][0][0] = o[R][0][1] = o[R][1][0] = o[R][1][1] = 0.0;
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
+    for (int g = 7; g >= 0; --g) {
+      if (g == 1) mbar_wait(smem_u32(&wbar[1]), 0);
       const double *As = Ts + g * TILE_ELEMS + 2 * lane;
       // virtual base of k-tile g: its live part starts at row 16 g = byte 2048 g of the tile
       const double *Bs = reinterpret_cast<const double *>(smem_raw + panel_w_off(g) - g * 2048) + 2 * lane;
