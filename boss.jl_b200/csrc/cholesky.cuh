@@ -249,8 +249,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) chol_panel_kernel(CholGemmPar
     for (int fm = 0; fm < 8; ++fm)
 #pragma unroll
       for (int fn = 0; fn < 4; ++fn)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) Ts[block_offset(fc.row(fm), fc.col(fn, e))] = -acc[fm][fn][e];
+        p_store_cfrag(Ts, 8 * fc.wm + fm, 4 * fc.wn + fn, lane, -acc[fm][fn][0], -acc[fm][fn][1]);
     __syncthreads();
     mbar_wait(smem_u32(&wbar[0]), 0);
 
@@ -303,13 +302,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) chol_panel_kernel(CholGemmPar
         }
       }
     }
-    const TrsmCoord tc{c0, c1, lane};
 #pragma unroll
-    for (int R = 0; R < 16; ++R)
-#pragma unroll
-      for (int h = 0; h < 2; ++h)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) dst[block_offset(tc.row(R), tc.col(h, e))] = o[R][h][e];
+    for (int R = 0; R < 16; ++R) {
+      p_store_cfrag(dst, R, c0, lane, o[R][0][0], o[R][0][1]);
+      p_store_cfrag(dst, R, c1, lane, o[R][1][0], o[R][1][1]);
+    }
   }, dst);
 }
 
