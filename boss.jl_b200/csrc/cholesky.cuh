@@ -231,12 +231,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) chol_panel_kernel(CholGemmPar
     mbar_init(smem_u32(&wbar[0]), 1);
     mbar_init(smem_u32(&wbar[1]), 1);
     mbar_fence_init();
-    mbar_arrive_expect_tx(smem_u32(&wbar[0]), PANEL_WHI_BYTES);
-#pragma unroll
-    for (int g = 2; g < 8; ++g)
-      bulk_g2s(smem_u32(smem_raw + panel_w_off(g)), wi + (size_t)g * TILE_BYTES + g * 2048, TILE_BYTES - g * 2048,
-               smem_u32(&wbar[0]));
   }
+  // requested after the first ring stages: anything queued ahead of stage 0 delays the first DMMA
+  auto prefetch_whi = [&]() {
+    if (tid == 0) {
+      mbar_arrive_expect_tx(smem_u32(&wbar[0]), PANEL_WHI_BYTES);
+#pragma unroll
+      for (int g = 2; g < 8; ++g)
+        bulk_g2s(smem_u32(smem_raw + panel_w_off(g)), wi + (size_t)g * TILE_BYTES + g * 2048, TILE_BYTES - g * 2048,
+                 smem_u32(&wbar[0]));
+    }
+  };
   gemm_pipeline<true>(it, it, [&](int, double(&acc)[8][4][2], const FragCoord &fc) {
     __syncthreads();   // every warp has consumed its last ring stage
     if (tid == 0) {
@@ -307,7 +312,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) chol_panel_kernel(CholGemmPar
       p_store_cfrag(dst, R, c0, lane, o[R][0][0], o[R][0][1]);
       p_store_cfrag(dst, R, c1, lane, o[R][1][0], o[R][1][1]);
     }
-  }, dst);
+  }, dst, prefetch_whi);
 }
 
 // ---- right-looking variants for small batches (a single posterior fit): every step exposes all tiles of the

@@ -41,6 +41,33 @@ __host__ __device__ __forceinline__ int block_offset(int r, int c) {
          ((c & 7) >> 2);
 }
 
+// 16-byte P-layout store of one C fragment.  A lane holds (r, c) and (r, c + 1) of an 8x8 micro-tile, which sit
+// 16 bytes apart in the P-layout; after swapping one value with lane ^ 2 it holds (r, k) and (r, k + 4), which are
+// adjacent.  Halves the store instructions and, in shared memory, is bank-conflict free (the 8-byte scatter is not).
+//   base: first macro-tile of the 128x128 block (shared or global); rslab / cslab: 8-row / 8-column slab of the tile
+__device__ __forceinline__ void p_store_cfrag(double *base, int rslab, int cslab, int lane, double v0, double v1) {
+  const int q = lane & 3;
+  const double recv = __shfl_xor_sync(0xffffffffu, q < 2 ? v1 : v0, 2);
+  const double2 pair = q < 2 ? make_double2(v0, recv) : make_double2(recv, v1);
+  const int k3 = q < 2 ? 2 * q : 2 * q - 3;   // column (mod 4) of the pair's first element
+  double *dst = base + (cslab >> 1) * TILE_ELEMS + (((rslab << 1) + (cslab & 1)) << 6) + ((((lane >> 2) << 2) + k3) << 1);
+  *reinterpret_cast<double2 *>(dst) = pair;
+}
+
+// The inverse: the lane's 16-byte pair of the P-layout (one load), then the lane-pair shuffle back to a C fragment.
+__device__ __forceinline__ double2 p_load_cfrag_raw(const double *base, int rslab, int cslab, int lane) {
+  const int q = lane & 3;
+  const int k3 = q < 2 ? 2 * q : 2 * q - 3;
+  return *reinterpret_cast<const double2 *>(base + (cslab >> 1) * TILE_ELEMS + (((rslab << 1) + (cslab & 1)) << 6) +
+                                            ((((lane >> 2) << 2) + k3) << 1));
+}
+__device__ __forceinline__ void p_unpair_cfrag(double2 pair, int lane, double &v0, double &v1) {
+  const int q = lane & 3;   // q < 2 holds (c, c + 4) with c = 2q: keeps .x, needs c + 1 = partner's .x; q >= 2 vice versa
+  const double recv = __shfl_xor_sync(0xffffffffu, q < 2 ? pair.y : pair.x, 2);
+  v0 = q < 2 ? pair.x : recv;
+  v1 = q < 2 ? recv : pair.y;
+}
+
 // It must provide:  bool valid(); const double* A(); const double* B(); bool tile_end(); int tile(); void next();
 //
 // Synchronisation: per stage a `full` mbarrier (TMA transaction bytes) and an `empty` mbarrier (one arrival per
@@ -53,8 +80,14 @@ __host__ __device__ __forceinline__ int block_offset(int r, int c) {
 // pipeline state stays live across it (for epilogues that need the registers, e.g. chol_panel_kernel's phase 2).
 // neg_init (SINGLE only): the accumulators start at -neg_init[block] instead of 0, i.e. the epilogue receives
 // A B^T - C; the tile's global loads then overlap the pipeline fill instead of sitting in the epilogue.
-template <bool SINGLE = false, class It, class Epi>
-__device__ __forceinline__ void gemm_pipeline(It issue_it, It cons_it, Epi &&epi, const double *neg_init = nullptr) {
+// after_prologue: run by every thread once the first ring stages have been requested (further prefetches belong
+// here: whatever is requested before stage 0 delays the first DMMA).
+struct NoPrologueHook {
+  __device__ __forceinline__ void operator()() const {}
+};
+template <bool SINGLE = false, class It, class Epi, class Pre = NoPrologueHook>
+__device__ __forceinline__ void gemm_pipeline(It issue_it, It cons_it, Epi &&epi, const double *neg_init = nullptr,
+                                              Pre &&after_prologue = Pre()) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   double *ring = reinterpret_cast<double *>(smem_raw);
   uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + GEMM_RING_BYTES + GEMM_SCRATCH_BYTES);
@@ -101,16 +134,23 @@ __device__ __forceinline__ void gemm_pipeline(It issue_it, It cons_it, Epi &&epi
   if (tid == 0) {
     while (issue_it.valid() && issued < GEMM_STAGES) try_issue(false);
   }
+  after_prologue();
 
   double acc[8][4][2];
   if (SINGLE && neg_init) {
-    const FragCoord fc{wm, wn, lane};
+    double2 pr[8][4];   // all 32 16-byte loads in flight together
 #pragma unroll
     for (int fm = 0; fm < 8; ++fm)
 #pragma unroll
-      for (int fn = 0; fn < 4; ++fn)
+      for (int fn = 0; fn < 4; ++fn) pr[fm][fn] = p_load_cfrag_raw(neg_init, 8 * wm + fm, 4 * wn + fn, lane);
 #pragma unroll
-        for (int e = 0; e < 2; ++e) acc[fm][fn][e] = -neg_init[block_offset(fc.row(fm), fc.col(fn, e))];
+    for (int fm = 0; fm < 8; ++fm)
+#pragma unroll
+      for (int fn = 0; fn < 4; ++fn) {
+        p_unpair_cfrag(pr[fm][fn], lane, acc[fm][fn][0], acc[fm][fn][1]);
+        acc[fm][fn][0] = -acc[fm][fn][0];
+        acc[fm][fn][1] = -acc[fm][fn][1];
+      }
   } else {
 #pragma unroll
     for (int fm = 0; fm < 8; ++fm)
@@ -189,19 +229,6 @@ struct LinearIt {
     --left;
   }
 };
-
-// 16-byte P-layout store of one C fragment.  A lane holds (r, c) and (r, c + 1) of an 8x8 micro-tile, which sit
-// 16 bytes apart in the P-layout; after swapping one value with lane ^ 2 it holds (r, k) and (r, k + 4), which are
-// adjacent.  Halves the store instructions and, in shared memory, is bank-conflict free (the 8-byte scatter is not).
-//   base: first macro-tile of the 128x128 block (shared or global); rslab / cslab: 8-row / 8-column slab of the tile
-__device__ __forceinline__ void p_store_cfrag(double *base, int rslab, int cslab, int lane, double v0, double v1) {
-  const int q = lane & 3;
-  const double recv = __shfl_xor_sync(0xffffffffu, q < 2 ? v1 : v0, 2);
-  const double2 pair = q < 2 ? make_double2(v0, recv) : make_double2(recv, v1);
-  const int k3 = q < 2 ? 2 * q : 2 * q - 3;   // column (mod 4) of the pair's first element
-  double *dst = base + (cslab >> 1) * TILE_ELEMS + (((rslab << 1) + (cslab & 1)) << 6) + ((((lane >> 2) << 2) + k3) << 1);
-  *reinterpret_cast<double2 *>(dst) = pair;
-}
 
 // Epilogue helper: write (or read-modify-write) the 128x128 accumulator tile to a block in P-layout.
 //   dst      : pointer to the first macro-tile of the destination block
