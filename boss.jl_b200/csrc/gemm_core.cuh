@@ -54,6 +54,18 @@ __device__ __forceinline__ void p_store_cfrag(double *base, int rslab, int cslab
   *reinterpret_cast<double2 *>(dst) = pair;
 }
 
+// Transposed variant: element (r, c) of the fragment is stored at (c, r).  Rows r and r + 4 of one column are
+// adjacent in the destination, so the exchange partner is lane ^ 16.
+__device__ __forceinline__ void p_store_cfrag_t(double *base, int rslab, int cslab, int lane, double v0, double v1) {
+  const int rr = lane >> 2, q = lane & 3;
+  const bool hi = rr & 4;
+  const double recv = __shfl_xor_sync(0xffffffffu, hi ? v0 : v1, 16);
+  const double2 pair = hi ? make_double2(recv, v1) : make_double2(v0, recv);
+  const int crow = hi ? 2 * q + 1 : 2 * q;   // destination row inside the micro-tile
+  double *dst = base + (rslab >> 1) * TILE_ELEMS + (((cslab << 1) + (rslab & 1)) << 6) + (((crow << 2) + (rr & 3)) << 1);
+  *reinterpret_cast<double2 *>(dst) = pair;
+}
+
 // The inverse: the lane's 16-byte pair of the P-layout (one load), then the lane-pair shuffle back to a C fragment.
 __device__ __forceinline__ double2 p_load_cfrag_raw(const double *base, int rslab, int cslab, int lane) {
   const int q = lane & 3;
@@ -236,6 +248,18 @@ struct LinearIt {
 //   out = (cin ? cin[...] : 0) + scale * acc
 __device__ __forceinline__ void store_block(double *dst, bool transpose, double scale, const double *cin,
                                             const double (&acc)[8][4][2], const FragCoord &fc) {
+  if (!cin) {   // plain store: 16-byte lane-pair stores
+#pragma unroll
+    for (int fm = 0; fm < 8; ++fm)
+#pragma unroll
+      for (int fn = 0; fn < 4; ++fn) {
+        if (transpose)
+          p_store_cfrag_t(dst, 8 * fc.wm + fm, 4 * fc.wn + fn, fc.lane, scale * acc[fm][fn][0], scale * acc[fm][fn][1]);
+        else
+          p_store_cfrag(dst, 8 * fc.wm + fm, 4 * fc.wn + fn, fc.lane, scale * acc[fm][fn][0], scale * acc[fm][fn][1]);
+      }
+    return;
+  }
 #pragma unroll
   for (int fm = 0; fm < 8; ++fm) {
     const int r = fc.row(fm);
@@ -256,18 +280,21 @@ __device__ __forceinline__ void store_block(double *dst, bool transpose, double 
 // In-place trailing update C -= acc.  All 64 loads are issued before the first store (acc is reused as the
 // staging register file), so the tile's read-modify-write costs one memory round trip instead of 64.
 __device__ __forceinline__ void rmw_sub_block(double *dst, double (&acc)[8][4][2], const FragCoord &fc) {
+  // the accumulators are moved into the P-layout's lane-pair arrangement once (one shuffle per fragment); loads,
+  // subtraction and stores then work on 16-byte pairs
+  double2 pr[8][4];
 #pragma unroll
   for (int fm = 0; fm < 8; ++fm)
 #pragma unroll
-    for (int fn = 0; fn < 4; ++fn)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) acc[fm][fn][e] = dst[block_offset(fc.row(fm), fc.col(fn, e))] - acc[fm][fn][e];
+    for (int fn = 0; fn < 4; ++fn) pr[fm][fn] = p_load_cfrag_raw(dst, 8 * fc.wm + fm, 4 * fc.wn + fn, fc.lane);
 #pragma unroll
   for (int fm = 0; fm < 8; ++fm)
 #pragma unroll
-    for (int fn = 0; fn < 4; ++fn)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) dst[block_offset(fc.row(fm), fc.col(fn, e))] = acc[fm][fn][e];
+    for (int fn = 0; fn < 4; ++fn) {
+      double c0, c1;
+      p_unpair_cfrag(pr[fm][fn], fc.lane, c0, c1);
+      p_store_cfrag(dst, 8 * fc.wm + fm, 4 * fc.wn + fn, fc.lane, c0 - acc[fm][fn][0], c1 - acc[fm][fn][1]);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -108,3 +108,21 @@ def test_world_size_2_gloo_argmax_and_loglik_gather():
     for rank, val, idx, got in res:
         assert idx == int(np.argmax(scores)) and val == float(scores.max())
         assert np.array_equal(np.array(got), np.cos(np.arange(S) * 0.11))
+
+
+def test_acquisition_host_helpers():
+    """Host side of the NonlinFitness path: Julia argmax order, the Distributions.jl normal cdf conventions
+    (src/utils/inf.jl:13-15, StatsFuns sigma == 0 case) and the eps sample shape."""
+    from boss_b200.acquisition import _normal_cdf, julia_argmax, sample_eps
+    assert julia_argmax([1.0, 3.0, 3.0, 2.0]) == 1                      # first maximal element
+    assert julia_argmax([1.0, np.nan, 5.0, np.nan]) == 1                # NaN is maximal, first one wins
+    assert julia_argmax([-0.0, 0.0, -0.0, 0.0]) == 1                    # isless(-0.0, 0.0)
+    assert julia_argmax([-np.inf, -np.inf]) == 0
+    # feas_prob values pinned by the reference's tests (test/unit/test/acquisitions/expected_improvement.jl:140-163)
+    mu, sd = np.array([0.0, 0.0, 0.0]), np.array([1.0, 1.0, 1.0])
+    assert np.allclose(_normal_cdf(mu, sd, np.array([np.inf, 0.0, np.inf])), [1.0, 0.5, 1.0], rtol=0, atol=1e-20)
+    assert _normal_cdf(np.array([2.0]), np.array([0.0]), np.array([2.0]))[0] == 1.0      # sigma == 0, x == mu
+    assert _normal_cdf(np.array([2.0]), np.array([0.0]), np.array([1.0]))[0] == 0.0
+    assert abs(_normal_cdf(np.array([0.3]), np.array([2.0]), np.array([1.1]))[0] - 0.6554217416103242) <= 1e-15
+    e = sample_eps(3, 7, np.random.default_rng(0))
+    assert e.shape == (3, 7) and np.array_equal(e, np.random.default_rng(0).standard_normal((3, 7)))
