@@ -746,3 +746,33 @@ def test_every_x_dim_padding_class(lib, d):
     assert np.max(np.abs(g - g_r) / np.linalg.norm(g_r, axis=1, keepdims=True)) <= 1e-8
     assert np.array_equal(ll, lib.loglik_batch(X, Y[0], L, A, N, kid))
     gp.free()
+
+
+def test_small_n_append_and_multistart_paths_are_repeatable(lib):
+    """Warp-register log-likelihood (n <= 32), rank-1 append chain, device-generated candidates and the device
+    multi-start driver: bitwise repeatable."""
+    X, Y, ls, amp, ns = make_problem(30, 2, seed=77)
+    L, A, N = make_hyper_samples(300, 2, seed=78)
+    first = lib.loglik_batch(X, Y[0], L, A, N, lib.KERNEL_MATERN52)
+    for _ in range(30):
+        assert np.array_equal(first, lib.loglik_batch(X, Y[0], L, A, N, lib.KERNEL_MATERN52))
+    n, d = 300, 3
+    X, Y, ls, amp, ns = make_problem(n + 40, d, seed=79)
+    best = float(np.quantile(Y[0][:n], 0.8))
+    lb, ub = np.zeros(d), np.ones(d)
+    starts = np.random.default_rng(80).random((d, 200))
+    ref = None
+    for rep in range(6):
+        gp = lib.gp_fit(X[:, :n], Y[0][:n], ls[0], amp[0], ns[0], lib.KERNEL_MATERN52)
+        for k in range(n, n + 40):
+            assert lib.gp_append(gp, X[:, k], Y[0][k])
+        Lf, Wf, al = lib.dbg_factors(gp)
+        _, bv, bi, bx = lib.ei_score_uniform([gp], 1, 1, 1234, 20000, lb, ub, [1.0], best, None)
+        Xo, fo, bxo, bvo, bio, ev = lib.ei_maximize_multistart([gp], 1, 1, starts, [1.0], best, None, lb, ub, iters=15)
+        gp.free()
+        out = (Lf, Wf, al, np.array([bv, bi]), bx, Xo, fo, bxo, np.array([bvo, bio, ev]))
+        if ref is None:
+            ref = out
+        else:
+            for k, (a, b) in enumerate(zip(ref, out)):
+                assert np.array_equal(a, b), (rep, k)
