@@ -4,11 +4,11 @@
 mkdir -p gpurun_out
 set -x
 python bench.py --only loglik --steps 1 --warmup 3 > gpurun_out/plain_ll.log 2>&1 || exit 1
-# loglik step = 48 launches (build_k, 16x potrf, 15x update, 15x trsm, fwd); skip 3 warm-ups + land mid-factorisation
+# loglik step = 4 stream groups x 48 launches (build_k, 16x potrf, 15x diagonal update, trsm + 14x panel, finish)
 ncu --set full --clock-control none --import-source on -s 165 -c 9 -o gpurun_out/prof_ll_mid \
     python bench.py --only loglik --steps 1 --warmup 3 > gpurun_out/ncu_ll_mid.log 2>&1
 echo "ncu ll mid exit $?"
-ncu --set full --clock-control none --import-source on -k regex:'build_k|fwd_solve' -s 6 -c 2 -o gpurun_out/prof_ll_ends \
+ncu --set full --clock-control none --import-source on -k regex:'build_k|loglik_finish' -s 6 -c 2 -o gpurun_out/prof_ll_ends \
     python bench.py --only loglik --steps 1 --warmup 3 > gpurun_out/ncu_ll_ends.log 2>&1
 echo "ncu ll ends exit $?"
 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-configs > gpurun_out/plain_sc.log 2>&1 || exit 1
