@@ -258,60 +258,68 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) chol_panel_kernel(CholGemmPar
     __syncthreads();
     mbar_wait(smem_u32(&wbar[0]), 0);
 
-    // phase 2: warp w owns column slabs c0 = w and c1 = 15 - w (as trsm_tri_pipeline), all 16 row slabs.  The k-tiles
-    // are consumed from 7 down to 0: tiles 2-7 have been resident since phase 1, so the two tiles requested a moment
-    // ago (0 and 1) arrive while the others are being multiplied.
-    const int c0 = w, c1 = 15 - w;
-    double o[16][2][2];
+    // phase 2: warps tile the output 4 x 2.  Warp w owns row slabs 4 (w & 3) .. + 3 and the eight column slabs of
+    // group cg = w >> 2: {4 cg + i} and {15 - 4 cg - i}, i < 4 (68 live k-steps in either group).  A warp then reads
+    // a quarter of T and half of Winv instead of all of T (shared-memory traffic 1.1 MB -> 0.5 MB per tile).  The
+    // k-tiles are consumed from 7 down to 0: tiles 2-7 have been resident since phase 1, so the two tiles requested
+    // a moment ago (0 and 1) arrive while the others are being multiplied.
+    const int rg = w & 3, cg = w >> 2;
+    double o[4][8][2];
 #pragma unroll
-    for (int R = 0; R < 16; ++R) o[R][0][0] = o[R][0][1] = o[R][1][0] = o[R][1][1] = 0.0;
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int m = 0; m < 8; ++m) o[r][m][0] = o[r][m][1] = 0.0;
 #pragma unroll
     for (int g = 7; g >= 0; --g) {
       if (g == 1) mbar_wait(smem_u32(&wbar[1]), 0);
-      const double *As = Ts + g * TILE_ELEMS + 2 * lane;
+      const double *As = Ts + g * TILE_ELEMS + (8 * rg) * 64 + 2 * lane;
       // virtual base of k-tile g: its live part starts at row 16 g = byte 2048 g of the tile
       const double *Bs = reinterpret_cast<const double *>(smem_raw + panel_w_off(g) - g * 2048) + 2 * lane;
 #pragma unroll
       for (int mc = 0; mc < 2; ++mc) {
-        const int kk = 2 * g + mc;   // k micro-step 0..15
-        if (kk <= c0) {              // both column slabs live
-          const double2 b0 = lds128(Bs + (c0 * 2 + mc) * 64), b1 = lds128(Bs + (c1 * 2 + mc) * 64);
+        const int kk = 2 * g + mc;   // k micro-step 0..15; column slab c is live iff kk <= c
+        double2 a[4];
 #pragma unroll
-          for (int Rg = 0; Rg < 16; Rg += 8) {
-            double2 a[8];
+        for (int r = 0; r < 4; ++r) a[r] = lds128(As + (r * 2 + mc) * 64);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) a[q] = lds128(As + ((Rg + q) * 2 + mc) * 64);
+        for (int half = 0; half < 2; ++half) {   // half 0: slabs 4 cg + i (ascending), half 1: 15 - 4 cg - i (descending)
+          const int cfirst = half ? 15 - 4 * cg : 4 * cg, cstep = half ? -1 : 1;
+          const int cmin = half ? cfirst - 3 : cfirst;
+          if (kk <= cmin) {            // all four slabs live: 16 independent accumulator pairs
+            double2 bq[4];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              dmma884(o[Rg + q][0][0], o[Rg + q][0][1], a[q].x, b0.x);
-              dmma884(o[Rg + q][1][0], o[Rg + q][1][1], a[q].x, b1.x);
+            for (int i = 0; i < 4; ++i) bq[i] = lds128(Bs + ((cfirst + cstep * i) * 2 + mc) * 64);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int r = 0; r < 4; ++r) dmma884(o[r][4 * half + i][0], o[r][4 * half + i][1], a[r].x, bq[i].x);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int r = 0; r < 4; ++r) dmma884(o[r][4 * half + i][0], o[r][4 * half + i][1], a[r].y, bq[i].y);
+          } else if (kk <= cmin + 3) { // the staircase: some of the four
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int c = cfirst + cstep * i;
+              if (kk <= c) {
+                const double2 bb = lds128(Bs + (c * 2 + mc) * 64);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) dmma884(o[r][4 * half + i][0], o[r][4 * half + i][1], a[r].x, bb.x);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) dmma884(o[r][4 * half + i][0], o[r][4 * half + i][1], a[r].y, bb.y);
+              }
             }
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              dmma884(o[Rg + q][0][0], o[Rg + q][0][1], a[q].y, b0.y);
-              dmma884(o[Rg + q][1][0], o[Rg + q][1][1], a[q].y, b1.y);
-            }
-          }
-        } else if (kk <= c1) {       // only the far slab
-          const double2 b1 = lds128(Bs + (c1 * 2 + mc) * 64);
-#pragma unroll
-          for (int Rg = 0; Rg < 16; Rg += 8) {
-            double2 a[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) a[q] = lds128(As + ((Rg + q) * 2 + mc) * 64);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) dmma884(o[Rg + q][1][0], o[Rg + q][1][1], a[q].x, b1.x);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) dmma884(o[Rg + q][1][0], o[Rg + q][1][1], a[q].y, b1.y);
           }
         }
       }
     }
 #pragma unroll
-    for (int R = 0; R < 16; ++R) {
-      p_store_cfrag(dst, R, c0, lane, o[R][0][0], o[R][0][1]);
-      p_store_cfrag(dst, R, c1, lane, o[R][1][0], o[R][1][1]);
-    }
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const int c = m < 4 ? 4 * cg + m : 15 - 4 * cg - (m - 4);
+        p_store_cfrag(dst, 4 * rg + r, c, lane, o[r][m][0], o[r][m][1]);
+      }
   }, dst, prefetch_whi);
 }
 
