@@ -159,3 +159,21 @@ def test_concurrent_callers_are_serialised(lib):
     for t in range(4):
         assert np.array_equal(out[t][0], serial[t][0]) and np.array_equal(out[t][1], serial[t][1])
     gp.free()
+
+
+def test_large_training_set_n_6100(lib):
+    """48 row blocks (n = 6100 is not a multiple of 128): right-looking fit + triangular inverse, scoring chunks and
+    the left-looking batched log-likelihood far beyond the benchmark shapes."""
+    n, d = 6100, 5
+    X, Y, ls, amp, ns = make_problem(n, d, seed=n)
+    gp = lib.gp_fit(X, Y[0], ls[0], amp[0], ns[0], lib.KERNEL_MATERN52)
+    post = O.posterior_fit(X, Y[0], ls[0], amp[0], ns[0], O.KERNEL_MATERN52)
+    Xs = np.random.default_rng(1).random((d, 2000))
+    mu, var, st = lib.gp_predict(gp, Xs)
+    mu_r, var_r, _ = O.mean_and_var(post, Xs)
+    assert relerr(mu, mu_r) <= 1e-9 and relerr(var, var_r) <= 1e-9 and not st.any()
+    ll_r = O.gp_loglik(X, Y[0], ls[0], amp[0], ns[0], O.KERNEL_MATERN52)
+    ll = lib.loglik_batch(X, Y[0], np.vstack([ls[0], 1.3 * ls[0]]), np.r_[amp[0], amp[0]], np.r_[ns[0], ns[0]],
+                          lib.KERNEL_MATERN52)
+    assert abs(gp.loglik - ll_r) <= 1e-8 * abs(ll_r) and abs(ll[0] - ll_r) <= 1e-8 * abs(ll_r)
+    gp.free()
