@@ -202,7 +202,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) chol_trsm_kernel(CholGemmPara
 }
 
 // Fused panel step of the left-looking factorisation (block column j >= 1, rows i > j):
-//   T    = A_ij - L_i,0:j L_j,0:j^T        phase 1: the common mainloop, accumulators in registers (started at -A_ij)
+//   T    = A_ij - L_i,0:j L_j,0:j^T        phase 1: the common mainloop, accumulators in registers; A_ij itself rides
+//                                          through the ring as 8 tail stages (TailIt)
 //   L_ij = T Winv_jj^T                     phase 2: T goes to shared memory in P-layout (it is the A operand now),
 //                                          Winv_jj's live lower-triangular part is resident in shared memory
 // so the tile makes one trip to HBM instead of three and the K = 128 product needs no pipeline fill of its own.
@@ -221,15 +222,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) chol_panel_kernel(CholGemmPar
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int i = p.j + 1 + blockIdx.x;
   double *Lm = p.L + (size_t)blockIdx.y * p.L_stride;
-  LinearIt it{Lm + (size_t)i * p.ktiles * TILE_ELEMS, Lm + (size_t)p.j * p.ktiles * TILE_ELEMS, p.j * KT_PER_BLOCK};
   double *dst = Lm + ((size_t)i * p.ktiles + (size_t)p.j * KT_PER_BLOCK) * TILE_ELEMS;
+  // the last 8 ring stages carry A_ij itself: the accumulators leave the mainloop as T = A_ij - L_i,0:j L_j,0:j^T
+  TailIt it{Lm + (size_t)i * p.ktiles * TILE_ELEMS, Lm + (size_t)p.j * p.ktiles * TILE_ELEMS, dst,
+            (p.j + 1) * KT_PER_BLOCK};
   const unsigned char *wi = reinterpret_cast<const unsigned char *>(p.Winv + (size_t)blockIdx.y * p.Winv_stride +
                                                                     (size_t)p.j * (TM * TM));
   uint64_t *wbar = reinterpret_cast<uint64_t *>(smem_raw + GEMM_RING_BYTES + GEMM_SCRATCH_BYTES) + 2 * GEMM_STAGES;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  if (tid == 0) {
-    mbar_init(smem_u32(&wbar[0]), 1);
-    mbar_init(smem_u32(&wbar[1]), 1);
+  if (tid == 32 || tid == 33) {   // not warp 0: it initialises the ring's barriers at the same time
+    mbar_init(smem_u32(&wbar[tid - 32]), 1);
     mbar_fence_init();
   }
   // requested after the first ring stages: anything queued ahead of stage 0 delays the first DMMA
@@ -249,12 +251,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) chol_panel_kernel(CholGemmPar
       bulk_g2s(smem_u32(smem_raw + panel_w_off(0)), wi, TILE_BYTES, smem_u32(&wbar[1]));
       bulk_g2s(smem_u32(smem_raw + panel_w_off(1)), wi + TILE_BYTES + 2048, TILE_BYTES - 2048, smem_u32(&wbar[1]));
     }
-    double *Ts = reinterpret_cast<double *>(smem_raw);   // acc = L L^T - A_ij = -T
+    double *Ts = reinterpret_cast<double *>(smem_raw);   // acc = T
 #pragma unroll
     for (int fm = 0; fm < 8; ++fm)
 #pragma unroll
       for (int fn = 0; fn < 4; ++fn)
-        p_store_cfrag(Ts, 8 * fc.wm + fm, 4 * fc.wn + fn, lane, -acc[fm][fn][0], -acc[fm][fn][1]);
+        p_store_cfrag(Ts, 8 * fc.wm + fm, 4 * fc.wn + fn, lane, acc[fm][fn][0], acc[fm][fn][1]);
     __syncthreads();
     mbar_wait(smem_u32(&wbar[0]), 0);
 
@@ -320,7 +322,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) chol_panel_kernel(CholGemmPar
         const int c = m < 4 ? 4 * cg + m : 15 - 4 * cg - (m - 4);
         p_store_cfrag(dst, 4 * rg + r, c, lane, o[r][m][0], o[r][m][1]);
       }
-  }, dst, prefetch_whi);
+  }, prefetch_whi);
 }
 
 // ---- right-looking variants for small batches (a single posterior fit): every step exposes all tiles of the

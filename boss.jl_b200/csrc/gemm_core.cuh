@@ -14,6 +14,7 @@
 // posterior-variance kernel (score.cuh).
 #pragma once
 #include "common.cuh"
+#include <type_traits>
 
 namespace boss {
 
@@ -90,16 +91,23 @@ __device__ __forceinline__ void p_unpair_cfrag(double2 pair, int lane, double &v
 // warps can always finish the stages already in flight, so this cannot deadlock).
 // SINGLE: the iterator yields exactly one output tile; the epilogue then runs after the loop, so none of the
 // pipeline state stays live across it (for epilogues that need the registers, e.g. chol_panel_kernel's phase 2).
-// neg_init (SINGLE only): the accumulators start at -neg_init[block] instead of 0, i.e. the epilogue receives
-// A B^T - C; the tile's global loads then overlap the pipeline fill instead of sitting in the epilogue.
+// Optional iterator feature ("tail stages"): when It has is_tail() / tail_index(), the last 8 stages carry the 16 KB
+// macro-tiles m = 0..7 of a tile C0 (A slot only) instead of operands, and the accumulators become C0 - A B^T as
+// those stages are consumed: the tile arrives through the ring that is running anyway, with no exposed latency at
+// either end of the kernel (chol_panel_kernel; clock64 showed 6-9 k cycles of accumulator-initialisation loads
+// ahead of the first DMMA when the tile was read directly).
+template <class T, class = void>
+struct has_tail_stages : std::false_type {};
+template <class T>
+struct has_tail_stages<T, std::void_t<decltype(&T::is_tail)>> : std::true_type {};
+
 // after_prologue: run by every thread once the first ring stages have been requested (further prefetches belong
 // here: whatever is requested before stage 0 delays the first DMMA).
 struct NoPrologueHook {
   __device__ __forceinline__ void operator()() const {}
 };
 template <bool SINGLE = false, class It, class Epi, class Pre = NoPrologueHook>
-__device__ __forceinline__ void gemm_pipeline(It issue_it, It cons_it, Epi &&epi, const double *neg_init = nullptr,
-                                              Pre &&after_prologue = Pre()) {
+__device__ __forceinline__ void gemm_pipeline(It issue_it, It cons_it, Epi &&epi, Pre &&after_prologue = Pre()) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   double *ring = reinterpret_cast<double *>(smem_raw);
   uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + GEMM_RING_BYTES + GEMM_SCRATCH_BYTES);
@@ -110,11 +118,11 @@ __device__ __forceinline__ void gemm_pipeline(It issue_it, It cons_it, Epi &&epi
   const int warp = tid >> 5;
   const int wm = warp >> 2, wn = warp & 3;
 
-  if (tid == 0) {
-    for (int s = 0; s < GEMM_STAGES; ++s) {
-      mbar_init(smem_u32(&full[s]), 1);
-      mbar_init(smem_u32(&empty[s]), GEMM_THREADS / 32);
-    }
+  if (tid < 2 * GEMM_STAGES) {   // one barrier per thread: the CTA waits on this before its first stage
+    if (tid < GEMM_STAGES)
+      mbar_init(smem_u32(&full[tid]), 1);
+    else
+      mbar_init(smem_u32(&empty[tid - GEMM_STAGES]), GEMM_THREADS / 32);
     mbar_fence_init();
   }
   __syncthreads();
@@ -133,42 +141,27 @@ __device__ __forceinline__ void gemm_pipeline(It issue_it, It cons_it, Epi &&epi
     }
     const uint32_t bar = smem_u32(&full[slot]);
     const uint32_t dst = smem_u32(ring + (size_t)slot * GEMM_STAGE_ELEMS);
-    mbar_arrive_expect_tx(bar, GEMM_STAGE_BYTES);
+    bool tail = false;
+    if constexpr (has_tail_stages<It>::value) tail = issue_it.is_tail();
+    mbar_arrive_expect_tx(bar, tail ? TILE_BYTES : GEMM_STAGE_BYTES);
     bulk_g2s(dst, issue_it.A(), TILE_BYTES, bar);
-    bulk_g2s(dst + TILE_BYTES, issue_it.B(), TILE_BYTES, bar);
+    if (!tail) bulk_g2s(dst + TILE_BYTES, issue_it.B(), TILE_BYTES, bar);
     issue_it.next();
     ++issued;
     return true;
   };
 
-  // start the ring before anything else: the (optional) tile loads below and the first TMA stages then share one
-  // memory latency instead of queueing behind each other (clock64: the first stage used to land 4.5 us into the CTA)
+  // start the ring before anything else
   if (tid == 0) {
     while (issue_it.valid() && issued < GEMM_STAGES) try_issue(false);
   }
   after_prologue();
 
   double acc[8][4][2];
-  if (SINGLE && neg_init) {
-    double2 pr[8][4];   // all 32 16-byte loads in flight together
 #pragma unroll
-    for (int fm = 0; fm < 8; ++fm)
+  for (int fm = 0; fm < 8; ++fm)
 #pragma unroll
-      for (int fn = 0; fn < 4; ++fn) pr[fm][fn] = p_load_cfrag_raw(neg_init, 8 * wm + fm, 4 * wn + fn, lane);
-#pragma unroll
-    for (int fm = 0; fm < 8; ++fm)
-#pragma unroll
-      for (int fn = 0; fn < 4; ++fn) {
-        p_unpair_cfrag(pr[fm][fn], lane, acc[fm][fn][0], acc[fm][fn][1]);
-        acc[fm][fn][0] = -acc[fm][fn][0];
-        acc[fm][fn][1] = -acc[fm][fn][1];
-      }
-  } else {
-#pragma unroll
-    for (int fm = 0; fm < 8; ++fm)
-#pragma unroll
-      for (int fn = 0; fn < 4; ++fn) acc[fm][fn][0] = acc[fm][fn][1] = 0.0;
-  }
+    for (int fn = 0; fn < 4; ++fn) acc[fm][fn][0] = acc[fm][fn][1] = 0.0;
 
   const int a_off = (wm * 8) * 128 + lane * 2;  // micro-row (wm*8+fm) -> +fm*128 ; micro-col mc -> +mc*64
   const int b_off = (wn * 4) * 128 + lane * 2;
@@ -185,6 +178,34 @@ __device__ __forceinline__ void gemm_pipeline(It issue_it, It cons_it, Epi &&epi
 
     const double *As = ring + (size_t)slot * GEMM_STAGE_ELEMS;
     const double *Bs = As + TILE_ELEMS;
+    if constexpr (has_tail_stages<It>::value) {
+      if (cons_it.is_tail()) {
+        // macro-tile m of C0 holds column slabs 2m and 2m+1 = (wn, fn) with 4 wn + fn in {2m, 2m+1}
+        const int m = cons_it.tail_index();
+        if (wn == (m >> 1)) {
+#pragma unroll
+          for (int fn = 0; fn < 4; ++fn) {
+            if ((fn >> 1) == (m & 1)) {
+              double2 pr[8];
+#pragma unroll
+              for (int fm = 0; fm < 8; ++fm) pr[fm] = p_load_cfrag_raw(As, 8 * wm + fm, fn & 1, lane);
+#pragma unroll
+              for (int fm = 0; fm < 8; ++fm) {
+                double c0, c1;
+                p_unpair_cfrag(pr[fm], lane, c0, c1);
+                acc[fm][fn][0] = c0 - acc[fm][fn][0];
+                acc[fm][fn][1] = c1 - acc[fm][fn][1];
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&empty[slot]));
+        cons_it.next();
+        ++g;
+        continue;
+      }
+    }
 #pragma unroll
     for (int mc = 0; mc < 2; ++mc) {
       double2 a[8], b[4];
@@ -224,6 +245,28 @@ __device__ __forceinline__ void gemm_pipeline(It issue_it, It cons_it, Epi &&epi
     epi(0, acc, fc);
   }
 }
+
+// One output tile with tail stages: `nk` macro-tiles of A and of B, then the 8 macro-tiles of the tile C0 itself.
+struct TailIt {
+  const double *a, *b, *c0;
+  int left;   // main stages + 8
+  __device__ __forceinline__ bool valid() const { return left > 0; }
+  __device__ __forceinline__ bool is_tail() const { return left <= KT_PER_BLOCK; }
+  __device__ __forceinline__ int tail_index() const { return KT_PER_BLOCK - left; }
+  __device__ __forceinline__ const double *A() const { return left > KT_PER_BLOCK ? a : c0; }
+  __device__ __forceinline__ const double *B() const { return b; }
+  __device__ __forceinline__ bool tile_end() const { return left == 1; }
+  __device__ __forceinline__ int tile() const { return 0; }
+  __device__ __forceinline__ void next() {
+    if (left > KT_PER_BLOCK) {
+      a += TILE_ELEMS;
+      b += TILE_ELEMS;
+    } else {
+      c0 += TILE_ELEMS;
+    }
+    --left;
+  }
+};
 
 // Simple iterator: one output tile, `nk` consecutive macro-tiles of A and of B.
 struct LinearIt {
