@@ -923,7 +923,7 @@ int score_core(ScoreArgs &a) {
       // Small candidate batches (multi-start optimiser iterations, single-point calls) cannot fill 148 SMs
       // with one CTA per 128 candidates: deal the training chunks / W row blocks of a candidate block to
       // several CTAs.  Partial sums are kept per chunk / per row block, so results do not depend on the split.
-      const int want = (2 * 148 + ncb - 1) / ncb;
+      const int want = (16 * 148 + ncb - 1) / ncb;   // >= 16 CTAs per SM in flight over the launch (4 waves of 4)
       const int nks = std::max(1, std::min(h->nblk, want));            // xcov / grad: splits over training chunks
       const int nsp = pick_row_splits(ncb, h->nblk);                   // trmm / wtv: zig-zag row-block splits
       const int cnt = ncb * 128;
