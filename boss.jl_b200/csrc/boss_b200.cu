@@ -310,8 +310,7 @@ int set_kernel_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(chol_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(chol_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM_BYTES));
-  CUDA_TRY(cudaFuncSetAttribute(trtri_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  CUDA_TRY(cudaFuncSetAttribute(trtri_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(trtri_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(kinv_wtw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(chol_update_rl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
@@ -421,9 +420,8 @@ int run_cholesky(double *L, size_t L_stride, double *Winv, size_t Winv_stride, i
     for (int delta = 1; delta < nblk; ++delta) {
       gp.j = delta;
       Timed t(2);
-      trtri_t_kernel<<<dim3(nblk - delta, S), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(gp);
-      trtri_w_kernel<<<dim3(nblk - delta, S), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(gp);
-      g.launches += 2;
+      trtri_fused_kernel<<<dim3(nblk - delta, S), GEMM_THREADS, PANEL_SMEM_BYTES, g.stream>>>(gp);
+      ++g.launches;
     }
   }
   CUDA_TRY(cudaGetLastError());
@@ -601,7 +599,6 @@ int boss_gp_fit(const double *X, int d, int n, const double *y_minus_mean, const
   int *status = reinterpret_cast<int *>(misc + off_st);
 
   FIT_TRY(g.chol_Winv.ensure((size_t)nblk * TM * TM * 8));
-  FIT_TRY(g.tt.ensure((size_t)std::max(1, nblk - 1) * TM * TM * 8));
 
   timing_begin();
   BuildKParams bk{};
@@ -623,7 +620,7 @@ int boss_gp_fit(const double *X, int d, int n, const double *y_minus_mean, const
     ++g.launches;
   }
   int rc = run_cholesky(h->L, mat, g.chol_Winv.as<double>(), (size_t)nblk * TM * TM, nblk, h->ktiles, 1,
-                        misc + off_ld, status, h->W, h->WT, g.tt.as<double>(), 0, 0, true);
+                        misc + off_ld, status, h->W, h->WT, nullptr, 0, 0, true);
   if (rc) return bail(rc);
   // w = W delta ; alpha = W^T w
   matvec_p_kernel<<<h->n_pad / 64, 256, 0, g.stream>>>(h->W, misc + off_y, misc + off_w, h->ktiles);
@@ -1541,7 +1538,6 @@ static int loglik_impl(const double *X, int d, int n, const double *Ymm, int64_t
   if (need_w) {
     CUDA_TRY(g.chol_W.ensure((size_t)Sb * mat * 8));
     CUDA_TRY(g.chol_WT.ensure((size_t)Sb * mat * 8));
-    CUDA_TRY(g.tt.ensure((size_t)Sb * tt_stride * 8));
     CUDA_TRY(g.ll_vec.ensure((size_t)Sb * n_pad * 3 * 8));                 // delta_pad | w | alpha
     if (grad) CUDA_TRY(g.ll_part.ensure((size_t)Sb * ntiles * (dp + 2) * 8));
   }
@@ -1634,7 +1630,7 @@ static int loglik_impl(const double *X, int d, int n, const double *Ymm, int64_t
       int *stg = status + wo;
       double *Wg = need_w ? g.chol_W.as<double>() + (size_t)wo * mat : nullptr;
       double *WTg = need_w ? g.chol_WT.as<double>() + (size_t)wo * mat : nullptr;
-      double *TTg = need_w ? g.tt.as<double>() + (size_t)wo * tt_stride : nullptr;
+      double *TTg = nullptr;   // the fused triangular-inverse step keeps T on chip
       cudaMemsetAsync(stg, 0, (size_t)gs * 4, g.stream);
       BuildKParams bk{};
       bk.X = dX;

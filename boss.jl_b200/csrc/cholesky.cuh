@@ -392,30 +392,115 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) trtri_row_rl_kernel(CholGemmP
   });
 }
 
-// Triangular inverse, block distance delta = i - j (blockIdx.y = matrix of the batch):
-//   T_ij = sum_{k=j}^{i-1} L_ik W_kj   -> stored transposed in TT[task]
-__global__ void __launch_bounds__(GEMM_THREADS, 1) trtri_t_kernel(CholGemmParams p) {
+// Fused step of the (left-looking, batched) triangular inverse, block distance delta = p.j, i = blockIdx.x + delta:
+//   T_ij = sum_{k=j}^{i-1} L_ik W_kj          phase 1: the common mainloop
+//   W_ij = -Winv_ii T_ij                      phase 2: T^T goes to shared memory in P-layout (it is the B operand),
+//                                             Winv_ii's live lower triangle is resident (the A operand)
+// -> W (normal) and WT (transposed).  Same shared-memory plan as chol_panel_kernel with the operand roles swapped:
+// there Winv multiplies from the right (its rows are output columns), here from the left (its rows are output rows).
+__global__ void __launch_bounds__(GEMM_THREADS, 1) trtri_fused_kernel(CholGemmParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int jb = blockIdx.x, i = jb + p.j;
   const double *Lm = p.L + (size_t)blockIdx.y * p.L_stride;
   const double *WTm = p.WT + (size_t)blockIdx.y * p.W_stride;
   LinearIt it{Lm + ((size_t)i * p.ktiles + (size_t)jb * KT_PER_BLOCK) * TILE_ELEMS,
               WTm + ((size_t)jb * p.ktiles + (size_t)jb * KT_PER_BLOCK) * TILE_ELEMS, p.j * KT_PER_BLOCK};
-  double *dst = p.TT + (size_t)blockIdx.y * p.TT_stride + (size_t)blockIdx.x * (TM * TM);
-  gemm_pipeline(it, it, [&](int, const double(&acc)[8][4][2], const FragCoord &fc) {
-    store_block(dst, true, 1.0, nullptr, acc, fc);
-  });
-}
-//   W_ij = -Winv_ii T_ij   -> W (normal) and WT (transposed)
-__global__ void __launch_bounds__(GEMM_THREADS, 1) trtri_w_kernel(CholGemmParams p) {
-  const int jb = blockIdx.x, i = jb + p.j;
-  LinearIt it{p.Winv + (size_t)blockIdx.y * p.Winv_stride + (size_t)i * (TM * TM),
-              p.TT + (size_t)blockIdx.y * p.TT_stride + (size_t)blockIdx.x * (TM * TM), KT_PER_BLOCK};
   double *dW = p.W + (size_t)blockIdx.y * p.W_stride + ((size_t)i * p.ktiles + (size_t)jb * KT_PER_BLOCK) * TILE_ELEMS;
   double *dWT = p.WT + (size_t)blockIdx.y * p.W_stride + ((size_t)jb * p.ktiles + (size_t)i * KT_PER_BLOCK) * TILE_ELEMS;
-  gemm_pipeline(it, it, [&](int, const double(&acc)[8][4][2], const FragCoord &fc) {
-    store_block(dW, false, -1.0, nullptr, acc, fc);
-    store_block(dWT, true, -1.0, nullptr, acc, fc);
-  });
+  const unsigned char *wi = reinterpret_cast<const unsigned char *>(p.Winv + (size_t)blockIdx.y * p.Winv_stride +
+                                                                    (size_t)i * (TM * TM));
+  uint64_t *wbar = reinterpret_cast<uint64_t *>(smem_raw + GEMM_RING_BYTES + GEMM_SCRATCH_BYTES) + 2 * GEMM_STAGES;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid == 32 || tid == 33) {
+    mbar_init(smem_u32(&wbar[tid - 32]), 1);
+    mbar_fence_init();
+  }
+  auto prefetch_whi = [&]() {
+    if (tid == 0) {
+      mbar_arrive_expect_tx(smem_u32(&wbar[0]), PANEL_WHI_BYTES);
+#pragma unroll
+      for (int g = 2; g < 8; ++g)
+        bulk_g2s(smem_u32(smem_raw + panel_w_off(g)), wi + (size_t)g * TILE_BYTES + g * 2048, TILE_BYTES - g * 2048,
+                 smem_u32(&wbar[0]));
+    }
+  };
+  gemm_pipeline<true>(it, it, [&](int, double(&acc)[8][4][2], const FragCoord &fc) {
+    __syncthreads();   // every warp has consumed its last ring stage
+    if (tid == 0) {
+      mbar_arrive_expect_tx(smem_u32(&wbar[1]), 2 * TILE_BYTES - 2048);
+      bulk_g2s(smem_u32(smem_raw + panel_w_off(0)), wi, TILE_BYTES, smem_u32(&wbar[1]));
+      bulk_g2s(smem_u32(smem_raw + panel_w_off(1)), wi + TILE_BYTES + 2048, TILE_BYTES - 2048, smem_u32(&wbar[1]));
+    }
+    double *Ts = reinterpret_cast<double *>(smem_raw);   // T^T: row = column n of T, col = k
+#pragma unroll
+    for (int fm = 0; fm < 8; ++fm)
+#pragma unroll
+      for (int fn = 0; fn < 4; ++fn)
+        p_store_cfrag_t(Ts, 8 * fc.wm + fm, 4 * fc.wn + fn, lane, acc[fm][fn][0], acc[fm][fn][1]);
+    __syncthreads();
+    mbar_wait(smem_u32(&wbar[0]), 0);
+
+    // phase 2: warp w owns column slabs 4 (w & 3) .. + 3 of the output and the eight ROW slabs of group rg = w >> 2:
+    // {4 rg + i} and {15 - 4 rg - i}, i < 4; row slab R of Winv_ii is live for k micro-steps kk <= R.
+    const int cgp = w & 3, rg = w >> 2;
+    double o[8][4][2];
+#pragma unroll
+    for (int m = 0; m < 8; ++m)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) o[m][c][0] = o[m][c][1] = 0.0;
+#pragma unroll
+    for (int g = 7; g >= 0; --g) {
+      if (g == 1) mbar_wait(smem_u32(&wbar[1]), 0);
+      const double *Bs = Ts + g * TILE_ELEMS + (8 * cgp) * 64 + 2 * lane;
+      const double *As = reinterpret_cast<const double *>(smem_raw + panel_w_off(g) - g * 2048) + 2 * lane;
+#pragma unroll
+      for (int mc = 0; mc < 2; ++mc) {
+        const int kk = 2 * g + mc;
+        double2 b[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) b[c] = lds128(Bs + (c * 2 + mc) * 64);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int rfirst = half ? 15 - 4 * rg : 4 * rg, rstep = half ? -1 : 1;
+          const int rmin = half ? rfirst - 3 : rfirst;
+          if (kk <= rmin) {
+            double2 aq[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) aq[q] = lds128(As + ((rfirst + rstep * q) * 2 + mc) * 64);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+              for (int c = 0; c < 4; ++c) dmma884(o[4 * half + q][c][0], o[4 * half + q][c][1], aq[q].x, b[c].x);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+              for (int c = 0; c < 4; ++c) dmma884(o[4 * half + q][c][0], o[4 * half + q][c][1], aq[q].y, b[c].y);
+          } else if (kk <= rmin + 3) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int R = rfirst + rstep * q;
+              if (kk <= R) {
+                const double2 aa = lds128(As + (R * 2 + mc) * 64);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) dmma884(o[4 * half + q][c][0], o[4 * half + q][c][1], aa.x, b[c].x);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) dmma884(o[4 * half + q][c][0], o[4 * half + q][c][1], aa.y, b[c].y);
+              }
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const int R = m < 4 ? 4 * rg + m : 15 - 4 * rg - (m - 4);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        p_store_cfrag(dW, R, 4 * cgp + c, lane, -o[m][c][0], -o[m][c][1]);
+        p_store_cfrag_t(dWT, R, 4 * cgp + c, lane, -o[m][c][0], -o[m][c][1]);
+      }
+    }
+  }, prefetch_whi);
 }
 
 // Generic C = A B^T on P-layout operands: grid (N/128, M/128).  Used by boss_gp_cov (V^T V, lower tiles only) and by
