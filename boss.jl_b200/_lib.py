@@ -28,6 +28,9 @@ _vp = C.c_void_p
 
 EXPORTS = {
     "boss_init": (C.c_int, [C.c_int]),
+    "boss_init_multi": (C.c_int, [C.c_int]),
+    "boss_set_device": (C.c_int, [C.c_int]),
+    "boss_n_devices": (C.c_int, []),
     "boss_shutdown": (None, []),
     "boss_last_error": (C.c_char_p, []),
     "boss_version": (C.c_int, []),
@@ -42,7 +45,7 @@ EXPORTS = {
     "boss_gp_n": (C.c_int, [_vp]),
     "boss_gp_d": (C.c_int, [_vp]),
     "boss_gp_predict": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp, _vp]),
-    "boss_gp_predict_dev": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp, _vp]),
+    "boss_gp_predict_dev": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp]),
     "boss_gp_cov": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp]),
     "boss_ei_score": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                 _dp, _i64p]),
@@ -57,7 +60,9 @@ EXPORTS = {
     "boss_ei_value_grad": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                      _vp]),
     "boss_ei_value_grad_dev": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                         _vp, _vp]),
+                                         _vp, _vp, _vp]),
+    "boss_mcei_score": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int64, _vp, C.c_int, C.c_double, _vp, _vp, _vp, _vp,
+                                  C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _dp, _i64p]),
     "boss_gp_loglik_batch": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, _vp, C.c_int, _vp, C.c_int64,
                                        _vp]),
     "boss_gp_loglik_batch_dev": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, _vp, C.c_int, _vp,
@@ -65,7 +70,7 @@ EXPORTS = {
     "boss_gp_loglik_grad_batch": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, _vp, C.c_int, _vp, C.c_int64,
                                             _vp, _vp]),
     "boss_gp_loglik_grad_batch_dev": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, _vp, C.c_int, _vp,
-                                                C.c_int64, _vp, _vp]),
+                                                C.c_int64, _vp, _vp, _vp]),
     "boss_set_timing": (None, [C.c_int]),
     "boss_last_kernel_ms": (C.c_double, [C.c_int]),
     "boss_last_kernel_count": (C.c_int, [C.c_int]),
@@ -96,6 +101,21 @@ def _check(rc: int, what: str) -> int:
 
 def init(device: int = 0) -> None:
     _check(lib.boss_init(int(device)), "boss_init")
+
+
+def init_multi(n_gpus: int) -> None:
+    """One process drives GPUs 0..n_gpus-1: fits are replicated, host-pointer scoring / log-likelihood / multi-start
+    calls are sharded inside the library (include/boss_b200.h, Devices)."""
+    _check(lib.boss_init_multi(int(n_gpus)), "boss_init_multi")
+
+
+def set_device(device: int) -> None:
+    """Pin the calling thread to one initialised device (-1 = unpin)."""
+    _check(lib.boss_set_device(int(device)), "boss_set_device")
+
+
+def n_devices() -> int:
+    return int(lib.boss_n_devices())
 
 
 def stream_ptr() -> int:
@@ -250,6 +270,34 @@ def ei_score(slices, y_dim, n_samples, Xs, coefs, best, y_max, lb=None, ub=None,
     return acq, bv.value, bi.value
 
 
+FIT_AFFINE, FIT_QUADRATIC, FIT_MAX, FIT_MIN = 1, 2, 3, 4
+
+
+def mcei_score(slices, y_dim, n_samples, Xs, fit_kind, eps, best, y_max, c0=0.0, c=None, q=None, t=None, lb=None, ub=None,
+               cons_mask=None, prior_mean_s=None, want_acq=True):
+    """Monte-Carlo EI of a NonlinFitness expression (include/boss_b200.h, boss_mcei_score) on the device.
+    eps: (y_dim, K).  -> acq (M,) or None, best_val, best_idx."""
+    Xc = _cols(Xs)
+    M, d = Xc.shape
+    arr = _slice_array(slices)
+    ep = np.ascontiguousarray(np.asarray(eps, dtype=np.float64).reshape(y_dim, -1).T)    # (K, y_dim) = column-major y_dim x K
+    K = ep.shape[0]
+    cv, qv, tv = _opt(c), _opt(q), _opt(t)
+    b = None if best is None else np.array([best], dtype=np.float64)
+    ym = None if y_max is None else _f64(y_max, (y_dim,))
+    lbv = None if lb is None else _f64(lb, (d,))
+    ubv = None if ub is None else _f64(ub, (d,))
+    cm = None if cons_mask is None else np.ascontiguousarray(cons_mask, dtype=np.uint8)
+    pm = None if prior_mean_s is None else np.ascontiguousarray(np.asarray(prior_mean_s, dtype=np.float64).T)
+    acq = np.empty(M) if want_acq else None
+    bv = C.c_double()
+    bi = C.c_int64()
+    _check(lib.boss_mcei_score(arr, y_dim, n_samples, _ptr(Xc), M, _ptr(pm), int(fit_kind), float(c0), _ptr(cv), _ptr(qv),
+                               _ptr(tv), _ptr(ep), K, _ptr(b), _ptr(ym), _ptr(lbv), _ptr(ubv), _ptr(cm), _ptr(acq),
+                               C.byref(bv), C.byref(bi)), "boss_mcei_score")
+    return acq, bv.value, bi.value
+
+
 def _opt(a, dtype=np.float64):
     return None if a is None else np.ascontiguousarray(a, dtype=dtype)
 
@@ -353,7 +401,8 @@ def ei_value_grad(slices, y_dim, n_samples, Xs, coefs, best, y_max, lb=None, ub=
 
 
 def ei_value_grad_dev(slices, y_dim, n_samples, Xs_ptr, M, coefs, best, y_max, acq_ptr, grad_ptr, lb=None, ub=None,
-                      prior_mean_ptr=None, prior_mean_grad_ptr=None):
+                      prior_mean_ptr=None, prior_mean_grad_ptr=None, stream=None):
+    """`stream`: raw cudaStream_t the device arrays were produced on (None = legacy default stream)."""
     arr = _slice_array(slices)
     co = _f64(coefs, (y_dim,))
     b = None if best is None else np.array([best], dtype=np.float64)
@@ -364,12 +413,13 @@ def ei_value_grad_dev(slices, y_dim, n_samples, Xs_ptr, M, coefs, best, y_max, a
                                       _vp(prior_mean_ptr) if prior_mean_ptr else None,
                                       _vp(prior_mean_grad_ptr) if prior_mean_grad_ptr else None, _ptr(co), _ptr(b),
                                       _ptr(ym), _ptr(lbv), _ptr(ubv), None, _vp(acq_ptr) if acq_ptr else None,
-                                      _vp(grad_ptr)), "boss_ei_value_grad_dev")
+                                      _vp(grad_ptr), _vp(stream) if stream else None), "boss_ei_value_grad_dev")
 
 
 def ei_score_dev(slices, y_dim, n_samples, Xs_ptr, M, coefs, best, y_max, lb=None, ub=None, acq_ptr=None,
-                 prior_mean_ptr=None, cons_mask_ptr=None):
-    """Device-pointer variant: Xs_ptr etc. are raw CUDA addresses (e.g. torch.Tensor.data_ptr())."""
+                 prior_mean_ptr=None, cons_mask_ptr=None, stream=None):
+    """Device-pointer variant: Xs_ptr etc. are raw CUDA addresses (e.g. torch.Tensor.data_ptr()); `stream` is the raw
+    cudaStream_t they were produced on (None = legacy default stream, torch's default)."""
     arr = _slice_array(slices)
     co = _f64(coefs, (y_dim,))
     b = None if best is None else np.array([best], dtype=np.float64)
@@ -381,7 +431,7 @@ def ei_score_dev(slices, y_dim, n_samples, Xs_ptr, M, coefs, best, y_max, lb=Non
     _check(lib.boss_ei_score_dev(arr, y_dim, n_samples, _vp(Xs_ptr), int(M), _vp(prior_mean_ptr) if prior_mean_ptr else None,
                                  _ptr(co), _ptr(b), _ptr(ym), _ptr(lbv), _ptr(ubv),
                                  _vp(cons_mask_ptr) if cons_mask_ptr else None, _vp(acq_ptr) if acq_ptr else None, None,
-                                 C.byref(bv), C.byref(bi), None), "boss_ei_score_dev")
+                                 C.byref(bv), C.byref(bi), _vp(stream) if stream else None), "boss_ei_score_dev")
     return bv.value, bi.value
 
 
@@ -423,16 +473,19 @@ def loglik_grad_batch(X, Y_minus_mean, lengthscales, amplitude, noise_std, kerne
     return out, grad
 
 
-def loglik_grad_batch_dev(X_ptr, d, n, Y_ptr, ldy, ls_ptr, amp_ptr, noise_ptr, kernel_id, S, out_ptr, grad_ptr):
+def loglik_grad_batch_dev(X_ptr, d, n, Y_ptr, ldy, ls_ptr, amp_ptr, noise_ptr, kernel_id, S, out_ptr, grad_ptr,
+                          stream=None):
     _check(lib.boss_gp_loglik_grad_batch_dev(_vp(X_ptr), d, n, _vp(Y_ptr), ldy, _vp(ls_ptr), _vp(amp_ptr), _vp(noise_ptr),
-                                             int(kernel_id), None, int(S), _vp(out_ptr), _vp(grad_ptr)),
+                                             int(kernel_id), None, int(S), _vp(out_ptr), _vp(grad_ptr),
+                                             _vp(stream) if stream else None),
            "boss_gp_loglik_grad_batch_dev")
 
 
-def loglik_batch_dev(X_ptr, d, n, Y_ptr, ldy, ls_ptr, amp_ptr, noise_ptr, kernel_id, S, out_ptr, discrete_mask=None):
+def loglik_batch_dev(X_ptr, d, n, Y_ptr, ldy, ls_ptr, amp_ptr, noise_ptr, kernel_id, S, out_ptr, discrete_mask=None,
+                     stream=None):
     dm = None if discrete_mask is None else np.ascontiguousarray(discrete_mask, dtype=np.uint8)
     _check(lib.boss_gp_loglik_batch_dev(_vp(X_ptr), d, n, _vp(Y_ptr), ldy, _vp(ls_ptr), _vp(amp_ptr), _vp(noise_ptr),
-                                        int(kernel_id), _ptr(dm), int(S), _vp(out_ptr), None),
+                                        int(kernel_id), _ptr(dm), int(S), _vp(out_ptr), _vp(stream) if stream else None),
            "boss_gp_loglik_batch_dev")
 
 

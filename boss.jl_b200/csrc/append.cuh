@@ -15,30 +15,6 @@
 
 namespace boss {
 
-// k[i] = a^2 kappa(|x~_i - x~+|), i < n (zero beyond); also appends the scaled point as row n of Xt.
-template <int KID, int DP>
-__global__ void append_kvec_kernel(const double *xnew, int d, int n, int n_pad, const double *invl,
-                                   unsigned long long disc_bits, double a2, double *Xt, double *kvec) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_pad) return;
-  double xn[DP];
-  load_scaled_point<DP>(xn, xnew, d, invl, disc_bits, true);
-  double val = 0.0;
-  if (i < n) {
-    double d2 = 0.0;
-#pragma unroll
-    for (int q = 0; q < DP; ++q) {
-      const double df = Xt[(size_t)i * DP + q] - xn[q];
-      d2 = fma(df, df, d2);
-    }
-    val = a2 * kappa<KID>(d2);
-  }
-  kvec[i] = val;
-  if (i == n) {
-#pragma unroll
-    for (int q = 0; q < DP; ++q) Xt[(size_t)n * DP + q] = xn[q];
-  }
-}
 
 // One CTA: lambda, w+ and status from l = W k (fixed-order reductions).
 //   out[0] = lambda, out[1] = w+, out[2] = l.l ; status = 1 when a^2 + s^2 - l.l <= 0 (not positive definite)

@@ -15,6 +15,9 @@
 #include <limits>
 #include <map>
 #include <mutex>
+#include <set>
+#include <thread>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -22,11 +25,12 @@
 #include "cholesky.cuh"
 #include "score.cuh"
 #include "grad.cuh"
-#include "small.cuh"
 #include "append.cuh"
 #include "multistart.cuh"
 
 using namespace boss;
+
+struct boss_gp;
 
 // ---------------------------------------------------------------------------------------------
 // context
@@ -64,14 +68,19 @@ struct DevBuf {
 constexpr int N_TIMERS = 4;
 constexpr int LL_GROUPS = 16;  // max concurrent sub-batches of a log-likelihood window (separate streams)
 constexpr int EV_POOL = 512;
+constexpr int MAX_DEV = 16;
 
+// One context per device.  A process may drive one GPU (boss_init: the torchrun-style one-process-per-GPU layout)
+// or several (boss_init_multi: the single-process layout a Julia caller has).  Every entry point
+// works inside exactly one context at a time: it locks the context, makes its device current and publishes it as
+// the calling thread's current context (tl_ctx), which is what C() returns to the launch helpers below.
 struct Ctx {
   int device = -1;
   cudaStream_t stream = nullptr;
-  std::mutex mu;
-  std::string err;
+  std::recursive_mutex mu;
   int64_t launches = 0;
   bool timing = false;
+  bool attrs_done = false;
   // workspaces
   DevBuf ks, muv, sumsq, xs_stage, pm_stage, cm_stage, acq_stage, mu_stage, var_stage, st_stage, grad_stage;
   DevBuf blk_val, blk_idx, small, chol_L, chol_Winv, chol_misc, tt, vt, ut, dmu, dvar, pmg_stage;
@@ -84,6 +93,7 @@ struct Ctx {
   double last_ms[N_TIMERS] = {0, 0, 0, 0};
   int last_cnt[N_TIMERS] = {0, 0, 0, 0};
   cudaEvent_t call_a = nullptr, call_b = nullptr;
+  cudaEvent_t caller_ev = nullptr;   // orders the library stream after the caller's stream (_dev entry points)
   // handle-buffer pool: a BO loop refits GPs of the same size every iteration; cudaMalloc / cudaFree of the three
   // n_pad^2 factors cost more than the factorisation itself.  Freed buffers are kept (up to POOL_CAP bytes) by size.
   std::multimap<size_t, void *> pool;
@@ -91,58 +101,89 @@ struct Ctx {
   size_t pool_bytes = 0;
   cudaStream_t ll_stream[LL_GROUPS] = {};
   cudaEvent_t ll_fork = nullptr, ll_join[LL_GROUPS] = {};
+  std::set<boss_gp *> live;          // handles whose buffers live on this device (boss_shutdown invalidates them)
+  void *pinned = nullptr;            // pinned bounce buffer for pageable host candidates (see stage_h2d)
+  size_t pinned_cap = 0;
+  cudaEvent_t pin_ev[2] = {nullptr, nullptr};
 };
 
-Ctx g;
+Ctx *g_ctx[MAX_DEV] = {};            // created by boss_init / boss_init_multi, emptied by boss_shutdown
+std::mutex g_reg_mu;                 // guards g_ctx / g_primary / g_ndev
+int g_primary = -1;                  // device of boss_init, or the first device of boss_init_multi
+int g_ndev = 0;                      // number of devices multi-device calls fan out to (0 or 1: single device)
+thread_local Ctx *tl_ctx = nullptr;  // context the calling thread is working in
+thread_local int tl_dev = -1;        // boss_set_device(): device of this thread's _dev calls and new handles
+thread_local std::string tl_err;     // boss_last_error() of the calling thread
+
+inline Ctx &C() { return *tl_ctx; }
+
+Ctx *ctx_of(int dev) { return (dev >= 0 && dev < MAX_DEV && g_ctx[dev] && g_ctx[dev]->device == dev) ? g_ctx[dev] : nullptr; }
+Ctx *ctx_current() { return ctx_of(tl_dev >= 0 ? tl_dev : g_primary); }
+
+// RAII: lock a context, make it (and its device) current for this thread
+struct Enter {
+  Ctx *prev;
+  std::unique_lock<std::recursive_mutex> lk;
+  explicit Enter(Ctx *c) : prev(tl_ctx) {
+    if (c) {
+      lk = std::unique_lock<std::recursive_mutex>(c->mu);
+      tl_ctx = c;
+      cudaSetDevice(c->device);
+    }
+  }
+  ~Enter() { tl_ctx = prev; }
+  Enter(const Enter &) = delete;
+  Enter &operator=(const Enter &) = delete;
+};
 
 constexpr size_t POOL_CAP = (size_t)16 << 30;
 
 cudaError_t pool_alloc(double **out, size_t bytes) {
-  auto it = g.pool.find(bytes);
-  if (it != g.pool.end()) {
+  auto it = C().pool.find(bytes);
+  if (it != C().pool.end()) {
     *out = reinterpret_cast<double *>(it->second);
-    g.pool_bytes -= bytes;
-    g.pool.erase(it);
+    C().pool_bytes -= bytes;
+    C().pool.erase(it);
     return cudaSuccess;
   }
   void *p = nullptr;
   cudaError_t e = cudaMalloc(&p, bytes);
-  if (e != cudaSuccess && !g.pool.empty()) {   // out of memory: drop the pooled buffers and retry
-    for (auto &kv : g.pool) {
+  if (e != cudaSuccess && !C().pool.empty()) {   // out of memory: drop the pooled buffers and retry
+    for (auto &kv : C().pool) {
       cudaFree(kv.second);
-      g.pool_sizes.erase(kv.second);
+      C().pool_sizes.erase(kv.second);
     }
-    g.pool.clear();
-    g.pool_bytes = 0;
+    C().pool.clear();
+    C().pool_bytes = 0;
     cudaGetLastError();
     e = cudaMalloc(&p, bytes);
   }
   if (e == cudaSuccess) {
-    g.pool_sizes[p] = bytes;
+    C().pool_sizes[p] = bytes;
     *out = reinterpret_cast<double *>(p);
   }
   return e;
 }
 void pool_free(void *p) {
   if (!p) return;
-  auto it = g.pool_sizes.find(p);
-  if (it == g.pool_sizes.end() || g.pool_bytes + it->second > POOL_CAP || g.device < 0) {
-    if (it != g.pool_sizes.end()) g.pool_sizes.erase(it);
+  auto it = C().pool_sizes.find(p);
+  if (it == C().pool_sizes.end() || C().pool_bytes + it->second > POOL_CAP || C().device < 0) {
+    if (it != C().pool_sizes.end()) C().pool_sizes.erase(it);
     cudaFree(p);
     return;
   }
-  g.pool.emplace(it->second, p);
-  g.pool_bytes += it->second;
+  C().pool.emplace(it->second, p);
+  C().pool_bytes += it->second;
 }
 void pool_release_all() {
-  for (auto &kv : g.pool) cudaFree(kv.second);
-  g.pool.clear();
-  g.pool_sizes.clear();
-  g.pool_bytes = 0;
+  for (auto &kv : C().pool) cudaFree(kv.second);
+  C().pool.clear();
+  C().pool_sizes.clear();
+  C().pool_bytes = 0;
 }
 
 int fail(int code, const std::string &msg) {
-  g.err = msg;
+  tl_err = msg;
   return code;
 }
 
@@ -158,37 +199,37 @@ int fail(int code, const std::string &msg) {
 struct Timed {
   int slot = -1;
   Timed(int cls) {
-    if (g.timing && g.ev_used < EV_POOL) {
-      slot = g.ev_used++;
-      g.ev_class[slot] = cls;
-      cudaEventRecord(g.ev_a[slot], g.stream);
+    if (C().timing && C().ev_used < EV_POOL) {
+      slot = C().ev_used++;
+      C().ev_class[slot] = cls;
+      cudaEventRecord(C().ev_a[slot], C().stream);
     }
   }
   ~Timed() {
-    if (slot >= 0) cudaEventRecord(g.ev_b[slot], g.stream);
+    if (slot >= 0) cudaEventRecord(C().ev_b[slot], C().stream);
   }
 };
 
 void timing_begin() {
-  g.ev_used = 0;
-  if (g.timing) cudaEventRecord(g.call_a, g.stream);
+  C().ev_used = 0;
+  if (C().timing) cudaEventRecord(C().call_a, C().stream);
 }
 void timing_end() {  // call after the stream has been synchronised
   for (int c = 0; c < N_TIMERS; ++c) {
-    g.last_ms[c] = 0;
-    g.last_cnt[c] = 0;
+    C().last_ms[c] = 0;
+    C().last_cnt[c] = 0;
   }
-  if (!g.timing) return;
-  cudaEventRecord(g.call_b, g.stream);
-  cudaEventSynchronize(g.call_b);
+  if (!C().timing) return;
+  cudaEventRecord(C().call_b, C().stream);
+  cudaEventSynchronize(C().call_b);
   float ms = 0;
-  cudaEventElapsedTime(&ms, g.call_a, g.call_b);
-  g.last_ms[3] = ms;
-  g.last_cnt[3] = 1;
-  for (int i = 0; i < g.ev_used; ++i) {
-    cudaEventElapsedTime(&ms, g.ev_a[i], g.ev_b[i]);
-    g.last_ms[g.ev_class[i]] += ms;
-    g.last_cnt[g.ev_class[i]] += 1;
+  cudaEventElapsedTime(&ms, C().call_a, C().call_b);
+  C().last_ms[3] = ms;
+  C().last_cnt[3] = 1;
+  for (int i = 0; i < C().ev_used; ++i) {
+    cudaEventElapsedTime(&ms, C().ev_a[i], C().ev_b[i]);
+    C().last_ms[C().ev_class[i]] += ms;
+    C().last_cnt[C().ev_class[i]] += 1;
   }
 }
 
@@ -210,72 +251,6 @@ unsigned long long mask_bits(const uint8_t *mask, int d) {
       if (mask[i]) b |= (1ull << i);
   return b;
 }
-
-struct boss_gp_view {   // the fields append_kvec needs (boss_gp is defined after the anonymous namespace)
-  int d, n, n_pad;
-  const double *invl;
-  unsigned long long disc;
-  double a2;
-  double *Xt;
-};
-
-// ---- kernel dispatch on (kernel_id, DP) ----
-template <int KID, int DP>
-void launch_build_k_t(const BuildKParams &p, dim3 grid) {
-  build_k_kernel<KID, DP><<<grid, 256, 0, g.stream>>>(p);
-}
-template <int KID, int DP>
-void launch_loglik_small_t(const SmallLoglikParams &p, int nblocks) {
-  loglik_small_kernel<KID, DP><<<nblocks, SMALL_WARPS * 32, 0, g.stream>>>(p);
-}
-template <int KID, int DP>
-void launch_append_kvec_t(const double *xnew, const boss_gp_view &v, double *kvec) {
-  append_kvec_kernel<KID, DP><<<(v.n_pad + 255) / 256, 256, 0, g.stream>>>(xnew, v.d, v.n, v.n_pad, v.invl, v.disc, v.a2,
-                                                                        v.Xt, kvec);
-}
-template <int KID, int DP>
-void launch_llgrad_tile_t(const LlGradParams &p, dim3 grid) {
-  loglik_grad_tile_kernel<KID, DP><<<grid, 256, 0, g.stream>>>(p);
-}
-template <int KID, int DP>
-void launch_xcov_t(const XcovParams &p, dim3 grid) {
-  xcov_kernel<KID, DP><<<grid, 256, 0, g.stream>>>(p);
-}
-template <int KID, int DP>
-void launch_cov_finish_t(const CovFinishParams &p, dim3 grid) {
-  cov_finish_kernel<KID, DP><<<grid, 256, 0, g.stream>>>(p);
-}
-template <int KID, int DP>
-void launch_grad_t(const GradParams &p, dim3 grid) {
-  grad_kernel<KID, DP><<<grid, 256, 0, g.stream>>>(p);
-}
-#define DISPATCH_KID_DP(FN, kid, dp, ...)                  \
-  do {                                                     \
-    switch ((kid) * 100 + (dp)) {                          \
-      case 2: FN<0, 2>(__VA_ARGS__); break;                \
-      case 4: FN<0, 4>(__VA_ARGS__); break;                \
-      case 6: FN<0, 6>(__VA_ARGS__); break;                \
-      case 8: FN<0, 8>(__VA_ARGS__); break;                \
-      case 12: FN<0, 12>(__VA_ARGS__); break;              \
-      case 16: FN<0, 16>(__VA_ARGS__); break;              \
-      case 32: FN<0, 32>(__VA_ARGS__); break;              \
-      case 102: FN<1, 2>(__VA_ARGS__); break;              \
-      case 104: FN<1, 4>(__VA_ARGS__); break;              \
-      case 106: FN<1, 6>(__VA_ARGS__); break;              \
-      case 108: FN<1, 8>(__VA_ARGS__); break;              \
-      case 112: FN<1, 12>(__VA_ARGS__); break;             \
-      case 116: FN<1, 16>(__VA_ARGS__); break;             \
-      case 132: FN<1, 32>(__VA_ARGS__); break;             \
-      case 202: FN<2, 2>(__VA_ARGS__); break;              \
-      case 204: FN<2, 4>(__VA_ARGS__); break;              \
-      case 206: FN<2, 6>(__VA_ARGS__); break;              \
-      case 208: FN<2, 8>(__VA_ARGS__); break;              \
-      case 212: FN<2, 12>(__VA_ARGS__); break;             \
-      case 216: FN<2, 16>(__VA_ARGS__); break;             \
-      case 232: FN<2, 32>(__VA_ARGS__); break;             \
-      default: break;                                      \
-    }                                                      \
-  } while (0)
 
 // Number of zig-zag row-block splits per candidate block for the triangular products (score_trmm / wtv):
 // minimise waves x (largest per-CTA share of the nblk(nblk+1)/2 block-steps + ~1 block-step of pipeline fill).
@@ -304,9 +279,9 @@ int pick_row_splits(int ncb, int nblk) {
   return best;
 }
 
-bool g_attr_done = false;
+// dynamic shared-memory opt-in is per device: once per context
 int set_kernel_attrs() {
-  if (g_attr_done) return 0;
+  if (C().attrs_done) return 0;
   CUDA_TRY(cudaFuncSetAttribute(chol_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(chol_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM_BYTES));
@@ -319,7 +294,7 @@ int set_kernel_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(score_trmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(wtv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM_BYTES));
-  g_attr_done = true;
+  C().attrs_done = true;
   return 0;
 }
 
@@ -388,22 +363,22 @@ int run_cholesky(double *L, size_t L_stride, double *Winv, size_t Winv_stride, i
     const bool fused_panel = j > 0 && !right_looking;
     if (fused_panel) {
       Timed t(2);
-      chol_update_kernel<<<dim3(1, S), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(gp);
-      ++g.launches;
+      chol_update_kernel<<<dim3(1, S), GEMM_THREADS, GEMM_SMEM_BYTES, C().stream>>>(gp);
+      ++C().launches;
     }
-    potrf_tile_kernel<<<S, 256, PT_SMEM_BYTES, g.stream>>>(pp);
-    ++g.launches;
+    potrf_tile_kernel<<<S, 256, PT_SMEM_BYTES, C().stream>>>(pp);
+    ++C().launches;
     if (j < nblk - 1) {
       Timed t(2);
       if (fused_panel)
-        chol_panel_kernel<<<dim3(nblk - j - 1, S), GEMM_THREADS, PANEL_SMEM_BYTES, g.stream>>>(gp);
+        chol_panel_kernel<<<dim3(nblk - j - 1, S), GEMM_THREADS, PANEL_SMEM_BYTES, C().stream>>>(gp);
       else
-        chol_trsm_kernel<<<dim3(nblk - j - 1, S), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(gp);
-      ++g.launches;
+        chol_trsm_kernel<<<dim3(nblk - j - 1, S), GEMM_THREADS, GEMM_SMEM_BYTES, C().stream>>>(gp);
+      ++C().launches;
       if (right_looking) {
         const int m = nblk - j - 1;
-        chol_update_rl_kernel<<<dim3(m * (m + 1) / 2, S), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(gp);
-        ++g.launches;
+        chol_update_rl_kernel<<<dim3(m * (m + 1) / 2, S), GEMM_THREADS, GEMM_SMEM_BYTES, C().stream>>>(gp);
+        ++C().launches;
       }
     }
   }
@@ -411,17 +386,17 @@ int run_cholesky(double *L, size_t L_stride, double *Winv, size_t Winv_stride, i
     for (int k = 0; k + 1 < nblk; ++k) {
       Timed t(2);
       gp.j = k;
-      trtri_acc_rl_kernel<<<dim3((nblk - k - 1) * (k + 1), S), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(gp);
+      trtri_acc_rl_kernel<<<dim3((nblk - k - 1) * (k + 1), S), GEMM_THREADS, GEMM_SMEM_BYTES, C().stream>>>(gp);
       gp.j = k + 1;
-      trtri_row_rl_kernel<<<dim3(k + 1, S), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(gp);
-      g.launches += 2;
+      trtri_row_rl_kernel<<<dim3(k + 1, S), GEMM_THREADS, GEMM_SMEM_BYTES, C().stream>>>(gp);
+      C().launches += 2;
     }
   } else if (W) {
     for (int delta = 1; delta < nblk; ++delta) {
       gp.j = delta;
       Timed t(2);
-      trtri_fused_kernel<<<dim3(nblk - delta, S), GEMM_THREADS, PANEL_SMEM_BYTES, g.stream>>>(gp);
-      ++g.launches;
+      trtri_fused_kernel<<<dim3(nblk - delta, S), GEMM_THREADS, PANEL_SMEM_BYTES, C().stream>>>(gp);
+      ++C().launches;
     }
   }
   CUDA_TRY(cudaGetLastError());
@@ -440,7 +415,11 @@ struct boss_gp {
   double loglik = 0;
   double *W = nullptr, *WT = nullptr, *L = nullptr, *alpha = nullptr, *Xt = nullptr, *invl = nullptr;
   double *wvec = nullptr, *ymm = nullptr;   // w = L^-1 delta and delta = y - m(X), kept for boss_gp_append
-  void free_dev() {
+  int dev = -1;                             // device the buffers live on (-1: invalidated by boss_shutdown)
+  // multi-device mode (boss_init_multi): the handle the caller holds is the replica on the primary device; rep[k]
+  // is the bit-identical replica on device k (rep[dev] == this).  Replicas are owned by the primary handle.
+  boss_gp *rep[MAX_DEV] = {};
+  void free_dev() {   // call inside the handle's context
     for (double **q : {&W, &WT, &L, &alpha, &Xt, &invl, &wvec, &ymm}) {
       if (*q) pool_free(*q);
       *q = nullptr;
@@ -448,88 +427,219 @@ struct boss_gp {
   }
 };
 
-extern "C" {
+namespace {
 
-int boss_version(void) { return 100; }
-int boss_device(void) { return g.device; }
-void *boss_stream(void) { return (void *)g.stream; }
-const char *boss_last_error(void) { return g.err.c_str(); }
-int64_t boss_launch_count(void) { return g.launches; }
-double boss_last_kernel_ms(int which) { return (which >= 0 && which < N_TIMERS) ? g.last_ms[which] : 0.0; }
-int boss_last_kernel_count(int which) { return (which >= 0 && which < N_TIMERS) ? g.last_cnt[which] : 0; }
-void boss_set_timing(int on) { g.timing = on != 0; }
+// the replica of `h` that lives on device `dev` (nullptr if there is none)
+const boss_gp *replica_on(const boss_gp *h, int dev) {
+  if (!h) return nullptr;
+  if (h->dev == dev) return h;
+  return (dev >= 0 && dev < MAX_DEV) ? h->rep[dev] : nullptr;
+}
 
-int boss_init(int device) {
-  std::lock_guard<std::mutex> lk(g.mu);
-  if (g.device == device && g.stream) return 0;
-  if (g.device >= 0 && g.device != device) return fail(BOSS_ERR_STATE, "boss_init: already initialised on another device");
+int init_device(int device) {   // g_reg_mu held
   int count = 0;
   CUDA_TRY(cudaGetDeviceCount(&count));
-  if (device < 0 || device >= count) return fail(BOSS_ERR_ARG, "boss_init: no such CUDA device");
+  if (device < 0 || device >= count || device >= MAX_DEV) return fail(BOSS_ERR_ARG, "boss_init: no such CUDA device");
+  if (g_ctx[device] && g_ctx[device]->device == device) return 0;
+  if (!g_ctx[device]) g_ctx[device] = new Ctx();
+  Ctx *cx = g_ctx[device];
+  Enter en(cx);
   CUDA_TRY(cudaSetDevice(device));
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) return fail(BOSS_ERR_STATE, std::string("boss_init: built for sm_100a, device is ") + prop.name);
-  CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&cx->stream, cudaStreamNonBlocking));
   for (int i = 0; i < EV_POOL; ++i) {
-    CUDA_TRY(cudaEventCreate(&g.ev_a[i]));
-    CUDA_TRY(cudaEventCreate(&g.ev_b[i]));
+    CUDA_TRY(cudaEventCreate(&cx->ev_a[i]));
+    CUDA_TRY(cudaEventCreate(&cx->ev_b[i]));
   }
-  CUDA_TRY(cudaEventCreate(&g.call_a));
-  CUDA_TRY(cudaEventCreate(&g.call_b));
-  CUDA_TRY(cudaEventCreateWithFlags(&g.ll_fork, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreate(&cx->call_a));
+  CUDA_TRY(cudaEventCreate(&cx->call_b));
+  CUDA_TRY(cudaEventCreateWithFlags(&cx->caller_ev, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&cx->ll_fork, cudaEventDisableTiming));
+  for (int i = 0; i < 2; ++i) CUDA_TRY(cudaEventCreateWithFlags(&cx->pin_ev[i], cudaEventDisableTiming));
   for (int i = 0; i < LL_GROUPS; ++i) {
-    CUDA_TRY(cudaStreamCreateWithFlags(&g.ll_stream[i], cudaStreamNonBlocking));
-    CUDA_TRY(cudaEventCreateWithFlags(&g.ll_join[i], cudaEventDisableTiming));
+    CUDA_TRY(cudaStreamCreateWithFlags(&cx->ll_stream[i], cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&cx->ll_join[i], cudaEventDisableTiming));
   }
-  g.ev_ready = true;
-  g.device = device;
+  cx->ev_ready = true;
+  cx->device = device;
   return set_kernel_attrs();
 }
 
-void boss_shutdown(void) {
-  std::lock_guard<std::mutex> lk(g.mu);
-  if (g.device < 0) return;
-  cudaSetDevice(g.device);
-  cudaStreamSynchronize(g.stream);
-  for (DevBuf *b : {&g.ks, &g.muv, &g.sumsq, &g.xs_stage, &g.pm_stage, &g.cm_stage, &g.acq_stage, &g.mu_stage,
-                    &g.var_stage, &g.st_stage, &g.grad_stage, &g.blk_val, &g.blk_idx, &g.small, &g.chol_L,
-                    &g.chol_Winv, &g.chol_misc, &g.tt, &g.vt, &g.ut, &g.dmu, &g.dvar, &g.pmg_stage, &g.part_mu,
-                    &g.part_ss, &g.part_gm, &g.part_gv, &g.cov_p, &g.cov_stage, &g.chol_W, &g.chol_WT, &g.ll_vec,
-                    &g.ll_part, &g.ms_buf})
+void shutdown_device(Ctx *cx) {   // g_reg_mu held
+  Enter en(cx);
+  if (cx->device < 0) return;
+  cudaStreamSynchronize(cx->stream);
+  // handles that are still alive lose their device buffers; later calls on them fail with BOSS_ERR_STATE and
+  // boss_gp_free only releases the host structure
+  for (boss_gp *h : cx->live) {
+    h->free_dev();
+    h->dev = -1;
+  }
+  cx->live.clear();
+  for (DevBuf *b : {&cx->ks, &cx->muv, &cx->sumsq, &cx->xs_stage, &cx->pm_stage, &cx->cm_stage, &cx->acq_stage,
+                    &cx->mu_stage, &cx->var_stage, &cx->st_stage, &cx->grad_stage, &cx->blk_val, &cx->blk_idx, &cx->small,
+                    &cx->chol_L, &cx->chol_Winv, &cx->chol_misc, &cx->tt, &cx->vt, &cx->ut, &cx->dmu, &cx->dvar,
+                    &cx->pmg_stage, &cx->part_mu, &cx->part_ss, &cx->part_gm, &cx->part_gv, &cx->cov_p, &cx->cov_stage,
+                    &cx->chol_W, &cx->chol_WT, &cx->ll_vec, &cx->ll_part, &cx->ms_buf})
     b->release();
   pool_release_all();
-  if (g.ev_ready) {
+  if (cx->pinned) cudaFreeHost(cx->pinned);
+  cx->pinned = nullptr;
+  cx->pinned_cap = 0;
+  if (cx->ev_ready) {
     for (int i = 0; i < EV_POOL; ++i) {
-      cudaEventDestroy(g.ev_a[i]);
-      cudaEventDestroy(g.ev_b[i]);
+      cudaEventDestroy(cx->ev_a[i]);
+      cudaEventDestroy(cx->ev_b[i]);
     }
-    cudaEventDestroy(g.call_a);
-    cudaEventDestroy(g.call_b);
-    cudaEventDestroy(g.ll_fork);
+    cudaEventDestroy(cx->call_a);
+    cudaEventDestroy(cx->call_b);
+    cudaEventDestroy(cx->caller_ev);
+    cudaEventDestroy(cx->ll_fork);
+    for (int i = 0; i < 2; ++i) cudaEventDestroy(cx->pin_ev[i]);
     for (int i = 0; i < LL_GROUPS; ++i) {
-      cudaStreamDestroy(g.ll_stream[i]);
-      cudaEventDestroy(g.ll_join[i]);
+      cudaStreamDestroy(cx->ll_stream[i]);
+      cudaEventDestroy(cx->ll_join[i]);
     }
-    g.ev_ready = false;
+    cx->ev_ready = false;
   }
-  cudaStreamDestroy(g.stream);
-  g.stream = nullptr;
-  g.device = -1;
+  cudaStreamDestroy(cx->stream);
+  cx->stream = nullptr;
+  cx->attrs_done = false;
+  cx->device = -1;
 }
 
-#define REQUIRE_INIT()                                                                  \
-  if (g.device < 0) return fail(BOSS_ERR_STATE, "boss_init() has not been called");    \
-  CUDA_TRY(cudaSetDevice(g.device))
+// Run fn(k, context of device k) for the ndev devices of a multi-device call on one host thread each and return the
+// first non-zero status in device order.  Each worker enters its own context, so the calls below it are exactly the
+// single-device code paths.
+int for_each_device(int ndev, const std::function<int(int, Ctx *)> &fn) {
+  std::vector<int> rc(ndev, 0);
+  std::vector<std::string> err(ndev);
+  std::vector<std::thread> th;
+  for (int k = 0; k < ndev; ++k)
+    th.emplace_back([&, k]() {
+      Ctx *cx = ctx_of(k);
+      if (!cx) {
+        rc[k] = BOSS_ERR_STATE;
+        err[k] = "multi-device call: device not initialised";
+        return;
+      }
+      Enter en(cx);
+      rc[k] = fn(k, cx);
+      if (rc[k]) err[k] = tl_err;
+    });
+  for (auto &t : th) t.join();
+  for (int k = 0; k < ndev; ++k)
+    if (rc[k] < 0) return fail(rc[k], err[k]);
+  for (int k = 0; k < ndev; ++k)
+    if (rc[k]) {
+      tl_err = err[k];
+      return rc[k];
+    }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int boss_version(void) { return 200; }
+int boss_device(void) {
+  Ctx *cx = ctx_current();
+  return cx ? cx->device : -1;
+}
+int boss_n_devices(void) { return g_ndev; }
+void *boss_stream(void) {
+  Ctx *cx = ctx_current();
+  return cx ? (void *)cx->stream : nullptr;
+}
+const char *boss_last_error(void) { return tl_err.c_str(); }
+int64_t boss_launch_count(void) {
+  int64_t t = 0;
+  for (int k = 0; k < MAX_DEV; ++k)
+    if (g_ctx[k]) t += g_ctx[k]->launches;
+  return t;
+}
+double boss_last_kernel_ms(int which) {
+  Ctx *cx = ctx_current();
+  return (cx && which >= 0 && which < N_TIMERS) ? cx->last_ms[which] : 0.0;
+}
+int boss_last_kernel_count(int which) {
+  Ctx *cx = ctx_current();
+  return (cx && which >= 0 && which < N_TIMERS) ? cx->last_cnt[which] : 0;
+}
+void boss_set_timing(int on) {
+  for (int k = 0; k < MAX_DEV; ++k)
+    if (g_ctx[k]) g_ctx[k]->timing = on != 0;
+}
+
+int boss_init(int device) {
+  std::lock_guard<std::mutex> lk(g_reg_mu);
+  if (g_primary >= 0 && g_primary != device && g_ndev <= 1)
+    return fail(BOSS_ERR_STATE, "boss_init: already initialised on another device (use boss_init_multi to drive several)");
+  int rc = init_device(device);
+  if (rc) return rc;
+  if (g_primary < 0) {
+    g_primary = device;
+    g_ndev = 1;
+  }
+  return 0;
+}
+
+int boss_init_multi(int n_gpus) {
+  std::lock_guard<std::mutex> lk(g_reg_mu);
+  int count = 0;
+  CUDA_TRY(cudaGetDeviceCount(&count));
+  if (n_gpus < 1 || n_gpus > count || n_gpus > MAX_DEV) return fail(BOSS_ERR_ARG, "boss_init_multi: bad device count");
+  if (g_primary > 0) return fail(BOSS_ERR_STATE, "boss_init_multi: already initialised on a device other than 0");
+  for (int k = 0; k < n_gpus; ++k) {
+    int rc = init_device(k);
+    if (rc) return rc;
+  }
+  g_primary = 0;
+  g_ndev = std::max(g_ndev, n_gpus);
+  return 0;
+}
+
+int boss_set_device(int device) {
+  if (device < 0) {
+    tl_dev = -1;
+    return 0;
+  }
+  if (!ctx_of(device)) return fail(BOSS_ERR_STATE, "boss_set_device: device not initialised");
+  tl_dev = device;
+  return 0;
+}
+
+void boss_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g_reg_mu);
+  for (int k = 0; k < MAX_DEV; ++k)
+    if (g_ctx[k]) shutdown_device(g_ctx[k]);
+  g_primary = -1;
+  g_ndev = 0;
+  tl_dev = -1;
+}
+
+// pick the calling thread's context, lock it and make it current; `cx` is visible to the rest of the function
+#define REQUIRE_INIT()                                                                    \
+  Ctx *cx = ctx_current();                                                                \
+  if (!cx) return fail(BOSS_ERR_STATE, "boss_init() has not been called");                \
+  Enter _enter(cx)
+// the same for calls that work on a fitted handle: the context is the one the handle lives in
+#define REQUIRE_HANDLE_CTX(h)                                                                              \
+  Ctx *cx = (h) ? ctx_of((h)->dev) : ctx_current();                                                        \
+  if (!cx) return fail(BOSS_ERR_STATE, (h) ? "handle is not valid any more (boss_shutdown was called)"     \
+                                           : "boss_init() has not been called");                           \
+  Enter _enter(cx)
 
 // ---------------------------------------------------------------------------------------------
 // fit
 // ---------------------------------------------------------------------------------------------
-int boss_gp_fit(const double *X, int d, int n, const double *y_minus_mean, const double *lengthscales,
-                double amplitude, double noise_std, int kernel_id, const uint8_t *discrete_mask, boss_gp **out,
-                double *loglik_out) {
-  std::lock_guard<std::mutex> lk(g.mu);
-  REQUIRE_INIT();
+// one posterior fit inside the current context
+static int fit_single(const double *X, int d, int n, const double *y_minus_mean, const double *lengthscales,
+                      double amplitude, double noise_std, int kernel_id, const uint8_t *discrete_mask, boss_gp **out,
+                      double *loglik_out) {
   if (!out) return fail(BOSS_ERR_ARG, "boss_gp_fit: out is NULL");
   *out = nullptr;
   if (!X || !y_minus_mean || !lengthscales || d < 1 || n < 1) return fail(BOSS_ERR_ARG, "boss_gp_fit: bad arguments");
@@ -577,28 +687,28 @@ int boss_gp_fit(const double *X, int d, int n, const double *y_minus_mean, const
   FIT_TRY(pool_alloc(&h->invl, dp * 8));
   FIT_TRY(pool_alloc(&h->wvec, npad * 8));
   FIT_TRY(pool_alloc(&h->ymm, npad * 8));
-  FIT_TRY(cudaMemsetAsync(h->L, 0, mat * 8, g.stream));
-  FIT_TRY(cudaMemsetAsync(h->W, 0, mat * 8, g.stream));
-  FIT_TRY(cudaMemsetAsync(h->WT, 0, mat * 8, g.stream));
+  FIT_TRY(cudaMemsetAsync(h->L, 0, mat * 8, C().stream));
+  FIT_TRY(cudaMemsetAsync(h->W, 0, mat * 8, C().stream));
+  FIT_TRY(cudaMemsetAsync(h->WT, 0, mat * 8, C().stream));
 
   // misc device scratch: X | ymm_pad | ls | amp | noise | invl(host computed) | logdet_blk | w | status
   const size_t off_X = 0, off_y = off_X + (size_t)n * d, off_ls = off_y + npad, off_amp = off_ls + d,
                off_noise = off_amp + 1, off_ld = off_noise + 1, off_w = off_ld + nblk, off_st = off_w + npad,
                total = off_st + 2;
-  FIT_TRY(g.chol_misc.ensure(total * 8));
-  double *misc = g.chol_misc.as<double>();
-  FIT_TRY(cudaMemsetAsync(misc, 0, total * 8, g.stream));
-  FIT_TRY(cudaMemcpyAsync(misc + off_X, X, (size_t)n * d * 8, cudaMemcpyHostToDevice, g.stream));
-  FIT_TRY(cudaMemcpyAsync(misc + off_y, y_minus_mean, (size_t)n * 8, cudaMemcpyHostToDevice, g.stream));
-  FIT_TRY(cudaMemcpyAsync(misc + off_ls, lengthscales, (size_t)d * 8, cudaMemcpyHostToDevice, g.stream));
-  FIT_TRY(cudaMemcpyAsync(misc + off_amp, &amplitude, 8, cudaMemcpyHostToDevice, g.stream));
-  FIT_TRY(cudaMemcpyAsync(misc + off_noise, &noise_std, 8, cudaMemcpyHostToDevice, g.stream));
+  FIT_TRY(C().chol_misc.ensure(total * 8));
+  double *misc = C().chol_misc.as<double>();
+  FIT_TRY(cudaMemsetAsync(misc, 0, total * 8, C().stream));
+  FIT_TRY(cudaMemcpyAsync(misc + off_X, X, (size_t)n * d * 8, cudaMemcpyHostToDevice, C().stream));
+  FIT_TRY(cudaMemcpyAsync(misc + off_y, y_minus_mean, (size_t)n * 8, cudaMemcpyHostToDevice, C().stream));
+  FIT_TRY(cudaMemcpyAsync(misc + off_ls, lengthscales, (size_t)d * 8, cudaMemcpyHostToDevice, C().stream));
+  FIT_TRY(cudaMemcpyAsync(misc + off_amp, &amplitude, 8, cudaMemcpyHostToDevice, C().stream));
+  FIT_TRY(cudaMemcpyAsync(misc + off_noise, &noise_std, 8, cudaMemcpyHostToDevice, C().stream));
   std::vector<double> invl(dp, 0.0);
   for (int i = 0; i < d; ++i) invl[i] = 1.0 / (lengthscales[i] + MIN_PARAM_VALUE);
-  FIT_TRY(cudaMemcpyAsync(h->invl, invl.data(), dp * 8, cudaMemcpyHostToDevice, g.stream));
+  FIT_TRY(cudaMemcpyAsync(h->invl, invl.data(), dp * 8, cudaMemcpyHostToDevice, C().stream));
   int *status = reinterpret_cast<int *>(misc + off_st);
 
-  FIT_TRY(g.chol_Winv.ensure((size_t)nblk * TM * TM * 8));
+  FIT_TRY(C().chol_Winv.ensure((size_t)nblk * TM * TM * 8));
 
   timing_begin();
   BuildKParams bk{};
@@ -616,33 +726,33 @@ int boss_gp_fit(const double *X, int d, int n, const double *y_minus_mean, const
   bk.status = status;
   {
     Timed t(1);
-    DISPATCH_KID_DP(launch_build_k_t, kernel_id, dp, bk, dim3(nblk * (nblk + 1) / 2, 1));
-    ++g.launches;
+    launch_build_k(kernel_id, dp, bk, dim3(nblk * (nblk + 1) / 2, 1), C().stream);
+    ++C().launches;
   }
-  int rc = run_cholesky(h->L, mat, g.chol_Winv.as<double>(), (size_t)nblk * TM * TM, nblk, h->ktiles, 1,
+  int rc = run_cholesky(h->L, mat, C().chol_Winv.as<double>(), (size_t)nblk * TM * TM, nblk, h->ktiles, 1,
                         misc + off_ld, status, h->W, h->WT, nullptr, 0, 0, true);
   if (rc) return bail(rc);
   // w = W delta ; alpha = W^T w
-  matvec_p_kernel<<<h->n_pad / 64, 256, 0, g.stream>>>(h->W, misc + off_y, misc + off_w, h->ktiles);
-  matvec_p_kernel<<<h->n_pad / 64, 256, 0, g.stream>>>(h->WT, misc + off_w, h->alpha, h->ktiles);
+  matvec_p_kernel<<<h->n_pad / 64, 256, 0, C().stream>>>(h->W, misc + off_y, misc + off_w, h->ktiles);
+  matvec_p_kernel<<<h->n_pad / 64, 256, 0, C().stream>>>(h->WT, misc + off_w, h->alpha, h->ktiles);
   {
     const int tot = h->n_pad * dp;
-    scale_train_kernel<<<(tot + 255) / 256, 256, 0, g.stream>>>(misc + off_X, d, n, h->n_pad, dp, h->invl, h->disc, h->Xt);
+    scale_train_kernel<<<(tot + 255) / 256, 256, 0, C().stream>>>(misc + off_X, d, n, h->n_pad, dp, h->invl, h->disc, h->Xt);
   }
-  g.launches += 3;
+  C().launches += 3;
   FIT_TRY(cudaGetLastError());
-  FIT_TRY(cudaMemcpyAsync(h->wvec, misc + off_w, npad * 8, cudaMemcpyDeviceToDevice, g.stream));
-  FIT_TRY(cudaMemcpyAsync(h->ymm, misc + off_y, npad * 8, cudaMemcpyDeviceToDevice, g.stream));
+  FIT_TRY(cudaMemcpyAsync(h->wvec, misc + off_w, npad * 8, cudaMemcpyDeviceToDevice, C().stream));
+  FIT_TRY(cudaMemcpyAsync(h->ymm, misc + off_y, npad * 8, cudaMemcpyDeviceToDevice, C().stream));
   std::vector<double> host(nblk + npad + 2);
-  FIT_TRY(cudaMemcpyAsync(host.data(), misc + off_ld, (nblk + npad + 2) * 8, cudaMemcpyDeviceToHost, g.stream));
-  FIT_TRY(cudaStreamSynchronize(g.stream));
+  FIT_TRY(cudaMemcpyAsync(host.data(), misc + off_ld, (nblk + npad + 2) * 8, cudaMemcpyDeviceToHost, C().stream));
+  FIT_TRY(cudaStreamSynchronize(C().stream));
   timing_end();
   int st;
   std::memcpy(&st, &host[nblk + npad], sizeof(int));
   if (st != 0) {
     bail(0);
     if (loglik_out) *loglik_out = -std::numeric_limits<double>::infinity();
-    g.err = "boss_gp_fit: kernel matrix is not positive definite";
+    tl_err = "boss_gp_fit: kernel matrix is not positive definite";
     return BOSS_NOT_POSDEF;
   }
   double ld = 0.0, mahal = 0.0;
@@ -650,17 +760,67 @@ int boss_gp_fit(const double *X, int d, int n, const double *y_minus_mean, const
   for (size_t k = 0; k < npad; ++k) mahal = std::fma(host[nblk + k], host[nblk + k], mahal);
   h->loglik = -((double)n * 1.8378770664093453 + 2.0 * ld + mahal) * 0.5;
   if (loglik_out) *loglik_out = h->loglik;
+  h->dev = C().device;
+  h->rep[h->dev] = h;
+  C().live.insert(h);
   *out = h;
   return 0;
 #undef FIT_TRY
 }
 
+// release one replica (its own context is entered here)
+static void free_replica(boss_gp *r) {
+  if (!r) return;
+  Ctx *cx = ctx_of(r->dev);
+  if (cx) {
+    Enter en(cx);
+    cx->live.erase(r);
+    r->free_dev();
+  }
+  delete r;
+}
+
+// Tie the per-device fits of one posterior together: reps[k] is the fit on device k (all non-null, bit-identical
+// because every device runs the same deterministic kernels on the same inputs).
+static boss_gp *link_replicas(const std::vector<boss_gp *> &reps) {
+  boss_gp *prim = reps[0];
+  for (size_t k = 0; k < reps.size(); ++k) prim->rep[reps[k]->dev] = reps[k];
+  return prim;
+}
+
+int boss_gp_fit(const double *X, int d, int n, const double *y_minus_mean, const double *lengthscales,
+                double amplitude, double noise_std, int kernel_id, const uint8_t *discrete_mask, boss_gp **out,
+                double *loglik_out) {
+  if (!out) return fail(BOSS_ERR_ARG, "boss_gp_fit: out is NULL");
+  *out = nullptr;
+  if (g_ndev > 1 && tl_dev < 0) {
+    // multi-device mode: the same deterministic fit on every device (2.9 GF at n = 2048 - cheaper than shipping
+    // 3 x 32 MB of factors over NVLink, and it needs no peer access)
+    const int nd = g_ndev;
+    std::vector<boss_gp *> reps(nd, nullptr);
+    std::vector<double> ll(nd, 0.0);
+    int rc = for_each_device(nd, [&](int k, Ctx *) {
+      return fit_single(X, d, n, y_minus_mean, lengthscales, amplitude, noise_std, kernel_id, discrete_mask, &reps[k], &ll[k]);
+    });
+    if (loglik_out) *loglik_out = ll[0];
+    if (rc) {
+      const std::string keep = tl_err;
+      for (boss_gp *r : reps) free_replica(r);
+      tl_err = keep;
+      return rc;
+    }
+    *out = link_replicas(reps);
+    return 0;
+  }
+  REQUIRE_INIT();
+  return fit_single(X, d, n, y_minus_mean, lengthscales, amplitude, noise_std, kernel_id, discrete_mask, out, loglik_out);
+}
+
 void boss_gp_free(boss_gp *gp) {
   if (!gp) return;
-  std::lock_guard<std::mutex> lk(g.mu);
-  if (g.device >= 0) cudaSetDevice(g.device);
-  gp->free_dev();
-  delete gp;
+  for (int k = 0; k < MAX_DEV; ++k)
+    if (gp->rep[k] && gp->rep[k] != gp) free_replica(gp->rep[k]);
+  free_replica(gp);
 }
 // Grow a handle's capacity by one 128-block (P-layout stride changes -> repack on the device).
 static int grow_handle(boss_gp *h) {
@@ -687,10 +847,10 @@ static int grow_handle(boss_gp *h) {
   GROW_TRY(pool_alloc(&nw, (size_t)npad_new * 8));
   GROW_TRY(pool_alloc(&ny, (size_t)npad_new * 8));
   const unsigned nb = (unsigned)((mat_new + 255) / 256);
-  repack_grow_kernel<<<nb, 256, 0, g.stream>>>(h->L, h->ktiles, h->n_pad, nL, kt_new, npad_new);
-  repack_grow_kernel<<<nb, 256, 0, g.stream>>>(h->W, h->ktiles, h->n_pad, nW, kt_new, npad_new);
-  repack_grow_kernel<<<nb, 256, 0, g.stream>>>(h->WT, h->ktiles, h->n_pad, nWT, kt_new, npad_new);
-  g.launches += 3;
+  repack_grow_kernel<<<nb, 256, 0, C().stream>>>(h->L, h->ktiles, h->n_pad, nL, kt_new, npad_new);
+  repack_grow_kernel<<<nb, 256, 0, C().stream>>>(h->W, h->ktiles, h->n_pad, nW, kt_new, npad_new);
+  repack_grow_kernel<<<nb, 256, 0, C().stream>>>(h->WT, h->ktiles, h->n_pad, nWT, kt_new, npad_new);
+  C().launches += 3;
   struct {
     double *dst, *src;
     size_t n_new, n_old;
@@ -699,11 +859,11 @@ static int grow_handle(boss_gp *h) {
                {nw, h->wvec, (size_t)npad_new, (size_t)h->n_pad},
                {ny, h->ymm, (size_t)npad_new, (size_t)h->n_pad}};
   for (auto &v : vecs) {
-    GROW_TRY(cudaMemsetAsync(v.dst, 0, v.n_new * 8, g.stream));
-    GROW_TRY(cudaMemcpyAsync(v.dst, v.src, v.n_old * 8, cudaMemcpyDeviceToDevice, g.stream));
+    GROW_TRY(cudaMemsetAsync(v.dst, 0, v.n_new * 8, C().stream));
+    GROW_TRY(cudaMemcpyAsync(v.dst, v.src, v.n_old * 8, cudaMemcpyDeviceToDevice, C().stream));
   }
   GROW_TRY(cudaGetLastError());
-  GROW_TRY(cudaStreamSynchronize(g.stream));
+  GROW_TRY(cudaStreamSynchronize(C().stream));
 #undef GROW_TRY
   for (double *q : {h->L, h->W, h->WT, h->alpha, h->Xt, h->wvec, h->ymm}) pool_free(q);
   h->L = nL; h->W = nW; h->WT = nWT; h->alpha = nal; h->Xt = nXt; h->wvec = nw; h->ymm = ny;
@@ -713,9 +873,7 @@ static int grow_handle(boss_gp *h) {
   return 0;
 }
 
-int boss_gp_append(boss_gp *h, const double *x_new, double y_minus_mean_new, double *loglik_out) {
-  std::lock_guard<std::mutex> lk(g.mu);
-  REQUIRE_INIT();
+static int append_single(boss_gp *h, const double *x_new, double y_minus_mean_new, double *loglik_out) {
   if (!h || !x_new) return fail(BOSS_ERR_ARG, "boss_gp_append: bad arguments");
   if (h->n == h->n_pad) {
     int rc = grow_handle(h);
@@ -724,39 +882,75 @@ int boss_gp_append(boss_gp *h, const double *x_new, double y_minus_mean_new, dou
   const int n = h->n, npad = h->n_pad, d = h->d;
   // workspace: xnew[32] | kvec[npad] | l[npad] | u[npad] | sc[4] | status
   const size_t o_k = 32, o_l = o_k + npad, o_u = o_l + npad, o_sc = o_u + npad, o_st = o_sc + 4, total = o_st + 1;
-  CUDA_TRY(g.chol_misc.ensure(total * 8));
-  double *ws = g.chol_misc.as<double>();
+  CUDA_TRY(C().chol_misc.ensure(total * 8));
+  double *ws = C().chol_misc.as<double>();
   int *status = reinterpret_cast<int *>(ws + o_st);
-  CUDA_TRY(cudaMemsetAsync(status, 0, 8, g.stream));
-  CUDA_TRY(cudaMemcpyAsync(ws, x_new, (size_t)d * 8, cudaMemcpyHostToDevice, g.stream));
-  boss_gp_view v{d, n, npad, h->invl, h->disc, h->a2, h->Xt};
-  DISPATCH_KID_DP(launch_append_kvec_t, h->kernel_id, h->dp, ws, v, ws + o_k);
-  matvec_p_kernel<<<npad / 64, 256, 0, g.stream>>>(h->W, ws + o_k, ws + o_l, h->ktiles);
-  append_scalars_kernel<<<1, 256, 0, g.stream>>>(ws + o_l, h->wvec, n, h->a2 + h->noise * h->noise, y_minus_mean_new,
+  CUDA_TRY(cudaMemsetAsync(status, 0, 8, C().stream));
+  CUDA_TRY(cudaMemcpyAsync(ws, x_new, (size_t)d * 8, cudaMemcpyHostToDevice, C().stream));
+  launch_append_kvec(h->kernel_id, h->dp, ws, d, n, npad, h->invl, h->disc, h->a2, h->Xt, ws + o_k, C().stream);
+  matvec_p_kernel<<<npad / 64, 256, 0, C().stream>>>(h->W, ws + o_k, ws + o_l, h->ktiles);
+  append_scalars_kernel<<<1, 256, 0, C().stream>>>(ws + o_l, h->wvec, n, h->a2 + h->noise * h->noise, y_minus_mean_new,
                                                  ws + o_sc, status);
-  matvec_p_kernel<<<npad / 64, 256, 0, g.stream>>>(h->WT, ws + o_l, ws + o_u, h->ktiles);
-  append_scatter_kernel<<<(n + 256) / 256, 256, 0, g.stream>>>(h->L, h->W, h->WT, n, h->ktiles, ws + o_l, ws + o_u,
+  matvec_p_kernel<<<npad / 64, 256, 0, C().stream>>>(h->WT, ws + o_l, ws + o_u, h->ktiles);
+  append_scatter_kernel<<<(n + 256) / 256, 256, 0, C().stream>>>(h->L, h->W, h->WT, n, h->ktiles, ws + o_l, ws + o_u,
                                                               ws + o_sc, status, h->wvec, h->ymm, y_minus_mean_new);
-  g.launches += 5;
+  C().launches += 5;
   CUDA_TRY(cudaGetLastError());
   double hs[5];
-  CUDA_TRY(cudaMemcpyAsync(hs, ws + o_sc, 40, cudaMemcpyDeviceToHost, g.stream));
-  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaMemcpyAsync(hs, ws + o_sc, 40, cudaMemcpyDeviceToHost, C().stream));
+  CUDA_TRY(cudaStreamSynchronize(C().stream));
   int st;
   std::memcpy(&st, &hs[4], sizeof(int));
   if (st != 0) {
     if (loglik_out) *loglik_out = -std::numeric_limits<double>::infinity();
-    g.err = "boss_gp_append: the extended kernel matrix is not positive definite (handle left unchanged)";
+    tl_err = "boss_gp_append: the extended kernel matrix is not positive definite (handle left unchanged)";
     return BOSS_NOT_POSDEF;
   }
   h->n = n + 1;
-  matvec_p_kernel<<<npad / 64, 256, 0, g.stream>>>(h->WT, h->wvec, h->alpha, h->ktiles);   // alpha = W^T w
-  ++g.launches;
+  matvec_p_kernel<<<npad / 64, 256, 0, C().stream>>>(h->WT, h->wvec, h->alpha, h->ktiles);   // alpha = W^T w
+  ++C().launches;
   CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaStreamSynchronize(C().stream));
   h->loglik += -0.5 * 1.8378770664093453 - std::log(hs[0]) - 0.5 * hs[1] * hs[1];
   if (loglik_out) *loglik_out = h->loglik;
   return 0;
+}
+
+int boss_gp_append(boss_gp *h, const double *x_new, double y_minus_mean_new, double *loglik_out) {
+  if (!h || !x_new) return fail(BOSS_ERR_ARG, "boss_gp_append: bad arguments");
+  int nrep = 0;
+  for (int k = 0; k < MAX_DEV; ++k) nrep += h->rep[k] != nullptr;
+  if (nrep > 1) {
+    // every replica takes the same O(n^2) update; a non-positive-definite extension is detected identically on all
+    // of them (same arithmetic), so the replicas stay in step
+    std::vector<boss_gp *> reps;
+    for (int k = 0; k < MAX_DEV; ++k)
+      if (h->rep[k]) reps.push_back(h->rep[k]);
+    std::vector<int> rc(reps.size(), 0);
+    std::vector<std::string> err(reps.size());
+    std::vector<double> ll(reps.size(), 0.0);
+    std::vector<std::thread> th;
+    for (size_t q = 0; q < reps.size(); ++q)
+      th.emplace_back([&, q]() {
+        Ctx *cx = ctx_of(reps[q]->dev);
+        if (!cx) {
+          rc[q] = BOSS_ERR_STATE;
+          err[q] = "boss_gp_append: handle is not valid any more";
+          return;
+        }
+        Enter en(cx);
+        rc[q] = append_single(reps[q], x_new, y_minus_mean_new, &ll[q]);
+        if (rc[q]) err[q] = tl_err;
+      });
+    for (auto &t : th) t.join();
+    for (size_t q = 0; q < reps.size(); ++q)
+      if (reps[q] == h && loglik_out) *loglik_out = ll[q];
+    for (size_t q = 0; q < reps.size(); ++q)
+      if (rc[q]) return fail(rc[q], err[q]);
+    return 0;
+  }
+  REQUIRE_HANDLE_CTX(h);
+  return append_single(h, x_new, y_minus_mean_new, loglik_out);
 }
 
 int boss_gp_n(const boss_gp *gp) { return gp ? gp->n : -1; }
@@ -785,23 +979,95 @@ struct ScoreArgs {
   bool want_argmax;
   int any_fail;      // out
   const CandGen *gen = nullptr;   // candidates generated on the device (Xs == NULL); other arrays are host pointers
+  void *caller_stream = nullptr;  // dev == true: the stream the caller produced its device arrays on (NULL = legacy default stream)
+  bool internal = false;          // dev == true from inside the library (arrays were produced on the library stream)
+  const MixParams *mix = nullptr; // MC-EI for NonlinFitness expression sets (score.cuh); null = LinFitness closed form
+};
+
+// Julia's isless order on (value, index): NaN maximal, -0.0 < +0.0, ties -> lowest index (host twin of acq_better)
+bool acq_better_host(double va, long long ia, double vb, long long ib) {
+  const bool na = va != va, nb = vb != vb;
+  if (na || nb) {
+    if (na && nb) return ia < ib;
+    return na;
+  }
+  if (va > vb) return true;
+  if (va < vb) return false;
+  long long ba, bb;
+  std::memcpy(&ba, &va, 8);
+  std::memcpy(&bb, &vb, 8);
+  if (ba != bb) return ba >= 0 && bb < 0;
+  return ia < ib;
+}
+
+// order the library stream after whatever the caller enqueued on `caller_stream` (its device inputs)
+int wait_for_caller(void *caller_stream) {
+  cudaStream_t cs = caller_stream ? (cudaStream_t)caller_stream : cudaStreamLegacy;
+  CUDA_TRY(cudaEventRecord(C().caller_ev, cs));
+  CUDA_TRY(cudaStreamWaitEvent(C().stream, C().caller_ev, 0));
+  return 0;
+}
+
+bool is_pinned_host(const void *p) {
+  if (!p) return false;
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
+}
+
+// Host <-> device staging of a chunked call with HOST arrays.  The caller's arrays are ordinary pageable memory in
+// the drop-in case (a Julia Matrix{Float64}); a cudaMemcpyAsync from pageable memory first drains the stream and then
+// copies synchronously, so the GPU would idle during every chunk's transfer.  Instead each chunk's inputs go through
+// one of two pinned slots (host memcpy -> DMA on a copy stream) into one of two device slots while the previous chunk
+// computes, and the outputs of chunk c are copied out of their pinned slot while chunk c+1 runs.
+struct Stager {
+  size_t in_bytes = 0, out_bytes = 0;   // per slot
+  unsigned char *pin_in[2] = {}, *pin_out[2] = {};
+  int ensure(size_t in_b, size_t out_b) {
+    in_bytes = (in_b + 255) / 256 * 256;
+    out_bytes = (out_b + 255) / 256 * 256;
+    const size_t need = 2 * (in_bytes + out_bytes) + 256;
+    if (need > C().pinned_cap) {
+      if (C().pinned) cudaFreeHost(C().pinned);
+      C().pinned = nullptr;
+      C().pinned_cap = 0;
+      CUDA_TRY(cudaHostAlloc(&C().pinned, need + need / 4, cudaHostAllocDefault));
+      C().pinned_cap = need + need / 4;
+    }
+    unsigned char *b = reinterpret_cast<unsigned char *>(C().pinned);
+    pin_in[0] = b;
+    pin_in[1] = b + in_bytes;
+    pin_out[0] = b + 2 * in_bytes;
+    pin_out[1] = b + 2 * in_bytes + out_bytes;
+    return 0;
+  }
 };
 
 int score_core(ScoreArgs &a) {
   const int nsl = a.y_dim * a.n_samples;
   if (nsl < 1 || a.y_dim > MAX_YDIM) return fail(BOSS_ERR_ARG, "score: y_dim must be in 1..16");
-  const boss_gp *g0 = a.slices[0];
+  // the replicas of the slices on this context's device
+  std::vector<const boss_gp *> sl(nsl);
   for (int q = 0; q < nsl; ++q) {
     if (!a.slices[q]) return fail(BOSS_ERR_ARG, "score: NULL slice handle");
-    if (a.slices[q]->d != g0->d) return fail(BOSS_ERR_ARG, "score: slices disagree on x_dim");
+    sl[q] = replica_on(a.slices[q], C().device);
+    if (!sl[q]) return fail(BOSS_ERR_STATE, "score: a slice handle has no replica on this device (or was invalidated by boss_shutdown)");
+    if (sl[q]->d != sl[0]->d) return fail(BOSS_ERR_ARG, "score: slices disagree on x_dim");
   }
-  const int d = g0->d;
+  const int d = sl[0]->d;
   int max_npad = 0;
-  for (int q = 0; q < nsl; ++q) max_npad = std::max(max_npad, a.slices[q]->n_pad);
+  for (int q = 0; q < nsl; ++q) max_npad = std::max(max_npad, sl[q]->n_pad);
   a.any_fail = 0;
   if (a.M <= 0) {
     if (a.best_idx) *a.best_idx = -1;
     return 0;
+  }
+  if (a.dev && !a.internal) {
+    int rc = wait_for_caller(a.caller_stream);
+    if (rc) return rc;
   }
   // chunk size: K*^T scratch budget 4 GiB, at most 4 waves of 148 CTAs
   long long ncb_max = (4ll << 30) / (1024ll * max_npad);
@@ -813,30 +1079,30 @@ int score_core(ScoreArgs &a) {
   const int ncb_cap = (int)std::min<long long>(ncb_max, need_cb);
   const int CH = ncb_cap * 128;
 
-  CUDA_TRY(g.ks.ensure((size_t)CH * max_npad * 8));
-  CUDA_TRY(g.muv.ensure((size_t)nsl * CH * 8));
-  CUDA_TRY(g.sumsq.ensure((size_t)nsl * CH * 8));
+  CUDA_TRY(C().ks.ensure((size_t)CH * max_npad * 8));
+  CUDA_TRY(C().muv.ensure((size_t)nsl * CH * 8));
+  CUDA_TRY(C().sumsq.ensure((size_t)nsl * CH * 8));
   const int max_nblk = max_npad / TM;
-  CUDA_TRY(g.part_mu.ensure((size_t)2 * max_nblk * CH * 8));
-  CUDA_TRY(g.part_ss.ensure((size_t)2 * max_nblk * CH * 8));
+  CUDA_TRY(C().part_mu.ensure((size_t)2 * max_nblk * CH * 8));
+  CUDA_TRY(C().part_ss.ensure((size_t)2 * max_nblk * CH * 8));
   if (a.grad) {
     if (d > 32) return fail(BOSS_ERR_ARG, "score: gradients need x_dim <= 32");
-    CUDA_TRY(g.vt.ensure((size_t)CH * max_npad * 8));
-    CUDA_TRY(g.ut.ensure((size_t)CH * max_npad * 8));
-    CUDA_TRY(g.dmu.ensure((size_t)nsl * d * CH * 8));
-    CUDA_TRY(g.dvar.ensure((size_t)nsl * d * CH * 8));
-    CUDA_TRY(g.part_gm.ensure((size_t)2 * max_nblk * d * CH * 8));
-    CUDA_TRY(g.part_gv.ensure((size_t)2 * max_nblk * d * CH * 8));
+    CUDA_TRY(C().vt.ensure((size_t)CH * max_npad * 8));
+    CUDA_TRY(C().ut.ensure((size_t)CH * max_npad * 8));
+    CUDA_TRY(C().dmu.ensure((size_t)nsl * d * CH * 8));
+    CUDA_TRY(C().dvar.ensure((size_t)nsl * d * CH * 8));
+    CUDA_TRY(C().part_gm.ensure((size_t)2 * max_nblk * d * CH * 8));
+    CUDA_TRY(C().part_gv.ensure((size_t)2 * max_nblk * d * CH * 8));
   }
   const int nblk_acq_max = (CH + 255) / 256;
-  CUDA_TRY(g.blk_val.ensure((size_t)nblk_acq_max * 8));
-  CUDA_TRY(g.blk_idx.ensure((size_t)nblk_acq_max * 8));
+  CUDA_TRY(C().blk_val.ensure((size_t)nblk_acq_max * 8));
+  CUDA_TRY(C().blk_idx.ensure((size_t)nblk_acq_max * 8));
   // small: a2[nsl] | lb[d] | ub[d] | best(1) | bidx(1 as int64) | any_fail(int)
   const size_t sm_n = (size_t)nsl + 2 * d + 4;
-  CUDA_TRY(g.small.ensure(sm_n * 8));
-  double *small = g.small.as<double>();
+  CUDA_TRY(C().small.ensure(sm_n * 8));
+  double *small = C().small.as<double>();
   std::vector<double> hs(sm_n, 0.0);
-  for (int q = 0; q < nsl; ++q) hs[q] = a.slices[q]->a2;
+  for (int q = 0; q < nsl; ++q) hs[q] = sl[q]->a2;
   if (a.lb && a.ub) {
     for (int i = 0; i < d; ++i) {
       hs[nsl + i] = a.lb[i];
@@ -845,27 +1111,112 @@ int score_core(ScoreArgs &a) {
   }
   long long neg1 = -1;
   std::memcpy(&hs[nsl + 2 * d + 1], &neg1, 8);
-  CUDA_TRY(cudaMemcpyAsync(small, hs.data(), sm_n * 8, cudaMemcpyHostToDevice, g.stream));
+  CUDA_TRY(cudaMemcpyAsync(small, hs.data(), sm_n * 8, cudaMemcpyHostToDevice, C().stream));
+  CUDA_TRY(cudaStreamSynchronize(C().stream));   // hs is a stack temporary (pageable)
   double *d_best = small + nsl + 2 * d;
   long long *d_bidx = reinterpret_cast<long long *>(small + nsl + 2 * d + 1);
   int *d_anyfail = reinterpret_cast<int *>(small + nsl + 2 * d + 2);
-
-  if (!a.dev) {
-    CUDA_TRY(g.xs_stage.ensure((size_t)CH * d * 8));
-    if (a.prior_mean) CUDA_TRY(g.pm_stage.ensure((size_t)CH * a.y_dim * 8));
-    if (a.cons_mask) CUDA_TRY(g.cm_stage.ensure((size_t)CH));
-    if (a.acq) CUDA_TRY(g.acq_stage.ensure((size_t)CH * 8));
-    if (a.mu_out) CUDA_TRY(g.mu_stage.ensure((size_t)CH * 8));
-    if (a.var_out) CUDA_TRY(g.var_stage.ensure((size_t)CH * 8));
-    if (a.status_out) CUDA_TRY(g.st_stage.ensure((size_t)CH * 4));
-    if (a.grad) CUDA_TRY(g.grad_stage.ensure((size_t)CH * d * 8));
-    if (a.grad && a.prior_mean_grad) CUDA_TRY(g.pmg_stage.ensure((size_t)CH * d * a.y_dim * 8));
+  MixParams mixp{};
+  if (a.mix) {   // MC-EI: the eps matrix (y_dim x n_eps) goes to the device once per call
+    mixp = *a.mix;
+    const size_t eb = (size_t)a.y_dim * mixp.n_eps * 8;
+    CUDA_TRY(C().tt.ensure(eb));
+    CUDA_TRY(cudaMemcpyAsync(C().tt.p, mixp.eps_host, eb, cudaMemcpyHostToDevice, C().stream));
+    CUDA_TRY(cudaStreamSynchronize(C().stream));
+    mixp.eps = C().tt.as<double>();
   }
 
+  // ---- host staging plan (two slots): byte offsets of every array inside a slot ----
+  const bool host = !a.dev;
+  const bool has_pmg = a.grad && a.prior_mean_grad;
+  size_t in_off_xs = 0, in_off_pm = 0, in_off_cm = 0, in_off_pmg = 0, in_total = 0;
+  size_t out_off_acq = 0, out_off_mu = 0, out_off_var = 0, out_off_st = 0, out_off_gr = 0, out_total = 0;
+  Stager stg;
+  bool xs_direct = false;   // the caller's candidate matrix is pinned already: DMA straight from it
+  if (host) {
+    auto take = [](size_t &tot, size_t bytes) {
+      const size_t o = tot;
+      tot += (bytes + 255) / 256 * 256;
+      return o;
+    };
+    xs_direct = !a.gen && is_pinned_host(a.Xs);
+    in_off_xs = take(in_total, (size_t)CH * d * 8);   // device slot always holds the candidates
+    if (a.prior_mean) in_off_pm = take(in_total, (size_t)CH * a.y_dim * 8);
+    if (a.cons_mask) in_off_cm = take(in_total, (size_t)CH);
+    if (has_pmg) in_off_pmg = take(in_total, (size_t)CH * d * a.y_dim * 8);
+    if (a.acq) out_off_acq = take(out_total, (size_t)CH * 8);
+    if (a.mu_out) out_off_mu = take(out_total, (size_t)CH * 8);
+    if (a.var_out) out_off_var = take(out_total, (size_t)CH * 8);
+    if (a.status_out) out_off_st = take(out_total, (size_t)CH * 4);
+    if (a.grad) out_off_gr = take(out_total, (size_t)CH * d * 8);
+    CUDA_TRY(C().xs_stage.ensure(2 * in_total));     // both device input slots
+    CUDA_TRY(C().acq_stage.ensure(2 * std::max<size_t>(out_total, 256)));   // both device output slots
+    int rc = stg.ensure(in_total, out_total);
+    if (rc) return rc;
+  }
+  unsigned char *dev_in[2] = {C().xs_stage.as<unsigned char>(), C().xs_stage.as<unsigned char>() + in_total};
+  unsigned char *dev_out[2] = {C().acq_stage.as<unsigned char>(), C().acq_stage.as<unsigned char>() + std::max<size_t>(out_total, 256)};
+  cudaStream_t cp = C().ll_stream[LL_GROUPS - 1];   // copy stream (the last log-likelihood group stream is idle here)
+  cudaEvent_t ev_in[2] = {C().ll_join[LL_GROUPS - 1], C().ll_join[LL_GROUPS - 2]};     // H2D of the slot done
+  cudaEvent_t ev_free[2] = {C().ll_join[LL_GROUPS - 3], C().ll_join[LL_GROUPS - 4]};   // compute done with the device slot
+  cudaEvent_t ev_out[2] = {C().pin_ev[0], C().pin_ev[1]};                              // outputs of the slot are in pinned memory
+  bool in_used[2] = {false, false}, free_rec[2] = {false, false};
+
+  // inputs of chunk [m0, m0 + ch) -> device slot; returns after the copies have been ENQUEUED on the copy stream
+  auto stage_in = [&](long long m0, int ch, int slot) -> int {
+    if (in_used[slot]) CUDA_TRY(cudaEventSynchronize(ev_in[slot]));   // the pinned slot's previous DMA has completed
+    if (free_rec[slot]) CUDA_TRY(cudaStreamWaitEvent(cp, ev_free[slot], 0));   // kernels of chunk c-2 are done with the device slot
+    unsigned char *pin = stg.pin_in[slot], *dv = dev_in[slot];
+    if (!a.gen) {
+      const double *src = a.Xs + (size_t)m0 * d;
+      if (xs_direct) {
+        CUDA_TRY(cudaMemcpyAsync(dv + in_off_xs, src, (size_t)ch * d * 8, cudaMemcpyHostToDevice, cp));
+      } else {
+        std::memcpy(pin + in_off_xs, src, (size_t)ch * d * 8);
+        CUDA_TRY(cudaMemcpyAsync(dv + in_off_xs, pin + in_off_xs, (size_t)ch * d * 8, cudaMemcpyHostToDevice, cp));
+      }
+    }
+    if (a.prior_mean) {
+      std::memcpy(pin + in_off_pm, a.prior_mean + (size_t)m0 * a.y_dim, (size_t)ch * a.y_dim * 8);
+      CUDA_TRY(cudaMemcpyAsync(dv + in_off_pm, pin + in_off_pm, (size_t)ch * a.y_dim * 8, cudaMemcpyHostToDevice, cp));
+    }
+    if (a.cons_mask) {
+      std::memcpy(pin + in_off_cm, a.cons_mask + m0, (size_t)ch);
+      CUDA_TRY(cudaMemcpyAsync(dv + in_off_cm, pin + in_off_cm, (size_t)ch, cudaMemcpyHostToDevice, cp));
+    }
+    if (has_pmg) {
+      std::memcpy(pin + in_off_pmg, a.prior_mean_grad + (size_t)m0 * d * a.y_dim, (size_t)ch * d * a.y_dim * 8);
+      CUDA_TRY(cudaMemcpyAsync(dv + in_off_pmg, pin + in_off_pmg, (size_t)ch * d * a.y_dim * 8, cudaMemcpyHostToDevice, cp));
+    }
+    CUDA_TRY(cudaEventRecord(ev_in[slot], cp));
+    in_used[slot] = true;
+    return 0;
+  };
+  // outputs of chunk [m0, m0 + ch): pinned slot -> the caller's arrays (after the chunk's D2H has completed)
+  auto drain_out = [&](long long m0, int ch, int slot) -> int {
+    if (out_total == 0) return 0;
+    CUDA_TRY(cudaEventSynchronize(ev_out[slot]));
+    const unsigned char *pin = stg.pin_out[slot];
+    if (a.acq) std::memcpy(a.acq + m0, pin + out_off_acq, (size_t)ch * 8);
+    if (a.mu_out) std::memcpy(a.mu_out + m0, pin + out_off_mu, (size_t)ch * 8);
+    if (a.var_out) std::memcpy(a.var_out + m0, pin + out_off_var, (size_t)ch * 8);
+    if (a.status_out) std::memcpy(a.status_out + m0, pin + out_off_st, (size_t)ch * 4);
+    if (a.grad) std::memcpy(a.grad + (size_t)m0 * d, pin + out_off_gr, (size_t)ch * d * 8);
+    return 0;
+  };
+
   timing_begin();
-  for (long long m0 = 0; m0 < a.M; m0 += CH) {
+  if (host) {
+    CUDA_TRY(cudaEventRecord(ev_free[0], C().stream));   // nothing enqueued before this point reads the slots
+    int rc = stage_in(0, (int)std::min<long long>(CH, a.M), 0);
+    if (rc) return rc;
+  }
+  long long prev_m0 = -1;
+  int prev_ch = 0, cidx = 0;
+  for (long long m0 = 0; m0 < a.M; m0 += CH, ++cidx) {
     const int ch = (int)std::min<long long>(CH, a.M - m0);
     const int ncb = (ch + 127) / 128;
+    const int slot = cidx & 1;
     const double *xs_dev;
     const double *pm_dev = nullptr;
     const unsigned char *cm_dev = nullptr;
@@ -886,37 +1237,26 @@ int score_core(ScoreArgs &a) {
       grad_dev = a.grad;
       pmg_dev = a.prior_mean_grad;
     } else {
+      // this chunk's inputs were staged while the previous chunk was being launched; the next chunk's go now
+      CUDA_TRY(cudaStreamWaitEvent(C().stream, ev_in[slot], 0));
+      xs_dev = reinterpret_cast<const double *>(dev_in[slot] + in_off_xs);
       if (a.gen) {
-        gen_candidates_kernel<<<(ch * d + 255) / 256, 256, 0, g.stream>>>(*a.gen, m0, ch, g.xs_stage.as<double>());
-        ++g.launches;
-      } else {
-        CUDA_TRY(cudaMemcpyAsync(g.xs_stage.p, a.Xs + (size_t)m0 * d, (size_t)ch * d * 8, cudaMemcpyHostToDevice, g.stream));
+        gen_candidates_kernel<<<(ch * d + 255) / 256, 256, 0, C().stream>>>(*a.gen, m0, ch, const_cast<double *>(xs_dev));
+        ++C().launches;
       }
-      xs_dev = g.xs_stage.as<double>();
-      if (a.prior_mean) {
-        CUDA_TRY(cudaMemcpyAsync(g.pm_stage.p, a.prior_mean + (size_t)m0 * a.y_dim, (size_t)ch * a.y_dim * 8,
-                                 cudaMemcpyHostToDevice, g.stream));
-        pm_dev = g.pm_stage.as<double>();
-      }
-      if (a.cons_mask) {
-        CUDA_TRY(cudaMemcpyAsync(g.cm_stage.p, a.cons_mask + m0, (size_t)ch, cudaMemcpyHostToDevice, g.stream));
-        cm_dev = g.cm_stage.as<unsigned char>();
-      }
+      if (a.prior_mean) pm_dev = reinterpret_cast<const double *>(dev_in[slot] + in_off_pm);
+      if (a.cons_mask) cm_dev = dev_in[slot] + in_off_cm;
+      if (has_pmg) pmg_dev = reinterpret_cast<const double *>(dev_in[slot] + in_off_pmg);
       in_off = m0;
       out_off = m0;
-      if (a.acq) acq_dev = g.acq_stage.as<double>();
-      if (a.mu_out) mu_dev = g.mu_stage.as<double>();
-      if (a.var_out) var_dev = g.var_stage.as<double>();
-      if (a.status_out) st_dev = g.st_stage.as<int>();
-      if (a.grad) grad_dev = g.grad_stage.as<double>();
-      if (a.grad && a.prior_mean_grad) {
-        CUDA_TRY(cudaMemcpyAsync(g.pmg_stage.p, a.prior_mean_grad + (size_t)m0 * d * a.y_dim,
-                                 (size_t)ch * d * a.y_dim * 8, cudaMemcpyHostToDevice, g.stream));
-        pmg_dev = g.pmg_stage.as<double>();
-      }
+      if (a.acq) acq_dev = reinterpret_cast<double *>(dev_out[slot] + out_off_acq);
+      if (a.mu_out) mu_dev = reinterpret_cast<double *>(dev_out[slot] + out_off_mu);
+      if (a.var_out) var_dev = reinterpret_cast<double *>(dev_out[slot] + out_off_var);
+      if (a.status_out) st_dev = reinterpret_cast<int *>(dev_out[slot] + out_off_st);
+      if (a.grad) grad_dev = reinterpret_cast<double *>(dev_out[slot] + out_off_gr);
     }
     for (int q = 0; q < nsl; ++q) {
-      const boss_gp *h = a.slices[q];
+      const boss_gp *h = sl[q];
       // Small candidate batches (multi-start optimiser iterations, single-point calls) cannot fill 148 SMs
       // with one CTA per 128 candidates: deal the training chunks / W row blocks of a candidate block to
       // several CTAs.  Partial sums are kept per chunk / per row block, so results do not depend on the split.
@@ -938,35 +1278,35 @@ int score_core(ScoreArgs &a) {
       xp.disc_bits = h->disc;
       xp.alpha = h->alpha;
       xp.a2 = h->a2;
-      xp.Ks = g.ks.as<double>();
-      xp.mu_part = g.part_mu.as<double>();
+      xp.Ks = C().ks.as<double>();
+      xp.mu_part = C().part_mu.as<double>();
       xp.ld = CH;
       {
         Timed t(1);
-        DISPATCH_KID_DP(launch_xcov_t, h->kernel_id, h->dp, xp, dim3(ncb, nks));
+        launch_xcov(h->kernel_id, h->dp, xp, dim3(ncb, nks), C().stream);
       }
-      reduce_rows_kernel<<<(cnt + 255) / 256, 256, 0, g.stream>>>(g.part_mu.as<double>(), 2 * h->nblk, (size_t)CH,
-                                                                 g.muv.as<double>() + (size_t)q * CH, cnt);
+      reduce_rows_kernel<<<(cnt + 255) / 256, 256, 0, C().stream>>>(C().part_mu.as<double>(), 2 * h->nblk, (size_t)CH,
+                                                                 C().muv.as<double>() + (size_t)q * CH, cnt);
       ScoreParams sp{};
       sp.W = h->W;
-      sp.Ks = g.ks.as<double>();
+      sp.Ks = C().ks.as<double>();
       sp.nblk = h->nblk;
       sp.ktiles = h->ktiles;
-      sp.ss_part = g.part_ss.as<double>();
+      sp.ss_part = C().part_ss.as<double>();
       sp.ld = CH;
-      sp.VT = a.grad ? g.vt.as<double>() : nullptr;
+      sp.VT = a.grad ? C().vt.as<double>() : nullptr;
       {
         Timed t(0);
-        score_trmm_kernel<<<dim3(ncb, nsp), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(sp);
+        score_trmm_kernel<<<dim3(ncb, nsp), GEMM_THREADS, GEMM_SMEM_BYTES, C().stream>>>(sp);
       }
-      reduce_rows_kernel<<<(cnt + 255) / 256, 256, 0, g.stream>>>(g.part_ss.as<double>(), 2 * h->nblk, (size_t)CH,
-                                                                 g.sumsq.as<double>() + (size_t)q * CH, cnt);
-      g.launches += 4;
+      reduce_rows_kernel<<<(cnt + 255) / 256, 256, 0, C().stream>>>(C().part_ss.as<double>(), 2 * h->nblk, (size_t)CH,
+                                                                 C().sumsq.as<double>() + (size_t)q * CH, cnt);
+      C().launches += 4;
       if (a.grad) {
-        WtvParams wp{h->WT, g.vt.as<double>(), g.ut.as<double>(), h->nblk, h->ktiles};
+        WtvParams wp{h->WT, C().vt.as<double>(), C().ut.as<double>(), h->nblk, h->ktiles};
         {
           Timed t(0);
-          wtv_kernel<<<dim3(ncb, nsp), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(wp);
+          wtv_kernel<<<dim3(ncb, nsp), GEMM_THREADS, GEMM_SMEM_BYTES, C().stream>>>(wp);
         }
         GradParams gq{};
         gq.Xs = xs_dev;
@@ -983,17 +1323,17 @@ int score_core(ScoreArgs &a) {
         gq.alpha = h->alpha;
         gq.disc_bits = h->disc;
         gq.a2 = h->a2;
-        gq.UT = g.ut.as<double>();
-        gq.gm_part = g.part_gm.as<double>();
-        gq.gv_part = g.part_gv.as<double>();
+        gq.UT = C().ut.as<double>();
+        gq.gm_part = C().part_gm.as<double>();
+        gq.gv_part = C().part_gv.as<double>();
         {
           Timed t(1);
-          DISPATCH_KID_DP(launch_grad_t, h->kernel_id, h->dp, gq, dim3(ncb, nks));
+          launch_grad(h->kernel_id, h->dp, gq, dim3(ncb, nks), C().stream);
         }
-        GradReduceParams gr{g.part_gm.as<double>(), g.part_gv.as<double>(), 2 * h->nblk, d, CH, cnt, h->invl, h->disc,
-                            g.dmu.as<double>() + (size_t)q * d * CH, g.dvar.as<double>() + (size_t)q * d * CH};
-        grad_reduce_kernel<<<dim3((cnt + 255) / 256, d), 256, 0, g.stream>>>(gr);
-        g.launches += 3;
+        GradReduceParams gr{C().part_gm.as<double>(), C().part_gv.as<double>(), 2 * h->nblk, d, CH, cnt, h->invl, h->disc,
+                            C().dmu.as<double>() + (size_t)q * d * CH, C().dvar.as<double>() + (size_t)q * d * CH};
+        grad_reduce_kernel<<<dim3((cnt + 255) / 256, d), 256, 0, C().stream>>>(gr);
+        C().launches += 3;
       }
     }
     AcqParams ap{};
@@ -1002,12 +1342,12 @@ int score_core(ScoreArgs &a) {
     ap.d = d;
     ap.M = a.M;
     ap.m0 = m0;
-    ap.in_off = in_off;
-    ap.out_off = out_off;
+    ap.in_off = host ? m0 : in_off;     // host mode: the slot arrays start at the chunk's first candidate
+    ap.out_off = host ? m0 : out_off;
     ap.chunk = ch;
     ap.chunk_ld = CH;
-    ap.mu = g.muv.as<double>();
-    ap.sumsq = g.sumsq.as<double>();
+    ap.mu = C().muv.as<double>();
+    ap.sumsq = C().sumsq.as<double>();
     ap.a2 = small;
     ap.prior_mean = pm_dev;
     for (int i = 0; i < a.y_dim; ++i) {
@@ -1026,34 +1366,50 @@ int score_core(ScoreArgs &a) {
     ap.var_out = var_dev;
     ap.status_out = st_dev;
     ap.any_fail = d_anyfail;
-    ap.blk_val = a.want_argmax ? g.blk_val.as<double>() : nullptr;
-    ap.blk_idx = a.want_argmax ? g.blk_idx.as<long long>() : nullptr;
+    ap.blk_val = a.want_argmax ? C().blk_val.as<double>() : nullptr;
+    ap.blk_idx = a.want_argmax ? C().blk_idx.as<long long>() : nullptr;
+    ap.mix = mixp;
     const int nb = (ch + 255) / 256;
-    acq_kernel<<<nb, 256, 0, g.stream>>>(ap);
-    ++g.launches;
+    acq_kernel<<<nb, 256, 0, C().stream>>>(ap);
+    ++C().launches;
     if (a.want_argmax) {
-      argmax_final_kernel<<<1, 256, 0, g.stream>>>(g.blk_val.as<double>(), g.blk_idx.as<long long>(), nb, d_best, d_bidx);
-      ++g.launches;
+      argmax_final_kernel<<<1, 256, 0, C().stream>>>(C().blk_val.as<double>(), C().blk_idx.as<long long>(), nb, d_best, d_bidx);
+      ++C().launches;
     }
     if (a.grad) {
-      AcqGradParams gp2{ap, g.dmu.as<double>(), g.dvar.as<double>(), pmg_dev, grad_dev};
-      acq_grad_kernel<<<(ch + 127) / 128, 128, 0, g.stream>>>(gp2);
-      ++g.launches;
-      if (!a.dev)
-        CUDA_TRY(cudaMemcpyAsync(a.grad + (size_t)m0 * d, grad_dev, (size_t)ch * d * 8, cudaMemcpyDeviceToHost, g.stream));
+      AcqGradParams gp2{ap, C().dmu.as<double>(), C().dvar.as<double>(), pmg_dev, grad_dev};
+      acq_grad_kernel<<<(ch + 127) / 128, 128, 0, C().stream>>>(gp2);
+      ++C().launches;
     }
-    if (!a.dev) {
-      if (a.acq) CUDA_TRY(cudaMemcpyAsync(a.acq + m0, acq_dev, (size_t)ch * 8, cudaMemcpyDeviceToHost, g.stream));
-      if (a.mu_out) CUDA_TRY(cudaMemcpyAsync(a.mu_out + m0, mu_dev, (size_t)ch * 8, cudaMemcpyDeviceToHost, g.stream));
-      if (a.var_out) CUDA_TRY(cudaMemcpyAsync(a.var_out + m0, var_dev, (size_t)ch * 8, cudaMemcpyDeviceToHost, g.stream));
-      if (a.status_out)
-        CUDA_TRY(cudaMemcpyAsync(a.status_out + m0, st_dev, (size_t)ch * 4, cudaMemcpyDeviceToHost, g.stream));
+    if (host) {
+      CUDA_TRY(cudaEventRecord(ev_free[slot], C().stream));   // the kernels above were the last readers of the input slot
+      free_rec[slot] = true;
+      if (out_total) {
+        CUDA_TRY(cudaMemcpyAsync(stg.pin_out[slot], dev_out[slot], out_total, cudaMemcpyDeviceToHost, C().stream));
+        CUDA_TRY(cudaEventRecord(ev_out[slot], C().stream));
+      }
+      // while this chunk runs: stage the next chunk's inputs, then hand the previous chunk's outputs to the caller
+      if (m0 + CH < a.M) {
+        int rc = stage_in(m0 + CH, (int)std::min<long long>(CH, a.M - m0 - CH), slot ^ 1);
+        if (rc) return rc;
+      }
+      if (prev_m0 >= 0) {
+        int rc = drain_out(prev_m0, prev_ch, slot ^ 1);
+        if (rc) return rc;
+      }
+      prev_m0 = m0;
+      prev_ch = ch;
     }
   }
   CUDA_TRY(cudaGetLastError());
-  double hres[3];
-  CUDA_TRY(cudaMemcpyAsync(hres, d_best, 24, cudaMemcpyDeviceToHost, g.stream));
-  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  if (host && prev_m0 >= 0) {
+    int rc = drain_out(prev_m0, prev_ch, (cidx - 1) & 1);
+    if (rc) return rc;
+  }
+  double *hres = reinterpret_cast<double *>(hs.data());   // reuse: 3 doubles
+  CUDA_TRY(cudaMemcpyAsync(hres, d_best, 24, cudaMemcpyDeviceToHost, C().stream));
+  CUDA_TRY(cudaStreamSynchronize(C().stream));
+  if (host) CUDA_TRY(cudaStreamSynchronize(cp));
   timing_end();
   long long bidx;
   std::memcpy(&bidx, &hres[1], 8);
@@ -1067,12 +1423,93 @@ int score_core(ScoreArgs &a) {
   return 0;
 }
 
+// Scoring entry: one device, or -- in multi-device mode, for host arrays and large enough batches -- contiguous
+// 128-aligned candidate ranges dealt to the devices (each scores its range against its own replica of the factors;
+// a candidate's score does not depend on the batch it arrives in, so the result is bit-identical to the
+// single-device call) and the (best value, index) pairs reduced on the host in Julia's argmax order.
+int score_dispatch(ScoreArgs &a) {
+  const boss_gp *h0 = (a.slices && a.y_dim >= 1 && a.n_samples >= 1) ? a.slices[0] : nullptr;
+  const int nsl = a.y_dim * a.n_samples;
+  int nd = (g_ndev > 1 && tl_dev < 0 && !a.dev && h0) ? g_ndev : 1;
+  if (nd > 1) {
+    for (int q = 0; q < nsl && nd > 1; ++q)
+      for (int k = 0; k < nd; ++k)
+        if (!replica_on(a.slices[q], k)) {
+          nd = 1;
+          break;
+        }
+    const long long blocks = (a.M + 127) / 128;
+    if (blocks < 2LL * nd) nd = 1;
+  }
+  if (nd <= 1) {
+    Ctx *cx = nullptr;
+    if (a.dev || tl_dev >= 0 || !h0)
+      cx = ctx_current();
+    else
+      cx = ctx_of(h0->dev);
+    if (!cx) return fail(BOSS_ERR_STATE, h0 && h0->dev < 0 ? "handle is not valid any more (boss_shutdown was called)"
+                                                           : "boss_init() has not been called");
+    Enter en(cx);
+    return score_core(a);
+  }
+  const long long blocks = (a.M + 127) / 128, per = (blocks + nd - 1) / nd * 128;
+  const int d = h0->d;
+  std::vector<ScoreArgs> sub(nd, a);
+  std::vector<CandGen> gens(nd);
+  std::vector<double> bv(nd, 0.0);
+  std::vector<int64_t> bi(nd, -1);
+  std::vector<long long> first(nd, 0);
+  int rc = for_each_device(nd, [&](int k, Ctx *) {
+    ScoreArgs &s = sub[k];
+    const long long off = std::min<long long>(a.M, (long long)k * per), cnt = std::min<long long>(per, a.M - off);
+    first[k] = off;
+    s.M = cnt;
+    if (cnt <= 0) return 0;
+    if (a.gen) {
+      gens[k] = *a.gen;
+      gens[k].first = a.gen->first + off;
+      s.gen = &gens[k];
+    } else {
+      s.Xs = a.Xs + (size_t)off * d;
+    }
+    if (a.prior_mean) s.prior_mean = a.prior_mean + (size_t)off * a.y_dim;
+    if (a.prior_mean_grad) s.prior_mean_grad = a.prior_mean_grad + (size_t)off * d * a.y_dim;
+    if (a.cons_mask) s.cons_mask = a.cons_mask + off;
+    if (a.acq) s.acq = a.acq + off;
+    if (a.grad) s.grad = a.grad + (size_t)off * d;
+    if (a.mu_out) s.mu_out = a.mu_out + off;
+    if (a.var_out) s.var_out = a.var_out + off;
+    if (a.status_out) s.status_out = a.status_out + off;
+    s.best_val = &bv[k];
+    s.best_idx = &bi[k];
+    return score_core(s);
+  });
+  if (rc) return rc;
+  a.any_fail = 0;
+  double best_v = 0.0;
+  long long best_i = -1;
+  for (int k = 0; k < nd; ++k) {
+    if (sub[k].M <= 0) continue;
+    a.any_fail |= sub[k].any_fail;
+    if (a.want_argmax && bi[k] >= 0) {
+      const long long gi = first[k] + bi[k];
+      if (best_i < 0 || acq_better_host(bv[k], gi, best_v, best_i)) {
+        best_v = bv[k];
+        best_i = gi;
+      }
+    }
+  }
+  if (a.want_argmax) {
+    if (a.best_val) *a.best_val = best_v;
+    if (a.best_idx) *a.best_idx = best_i;
+  }
+  return 0;
+}
+
 }  // namespace
 
 int boss_gp_predict(const boss_gp *gp, const double *Xs, int64_t M, const double *prior_mean_s, double *mu,
                     double *var, int32_t *status) {
-  std::lock_guard<std::mutex> lk(g.mu);
-  REQUIRE_INIT();
   if (!gp || (!Xs && M > 0)) return fail(BOSS_ERR_ARG, "boss_gp_predict: bad arguments");
   const boss_gp *sl[1] = {gp};
   ScoreArgs a{};
@@ -1087,15 +1524,13 @@ int boss_gp_predict(const boss_gp *gp, const double *Xs, int64_t M, const double
   a.status_out = status;
   a.dev = false;
   a.want_argmax = false;
-  int rc = score_core(a);
+  int rc = score_dispatch(a);
   if (rc) return rc;
   return a.any_fail ? BOSS_NEG_VARIANCE : 0;
 }
 
 int boss_gp_predict_dev(const boss_gp *gp, const double *Xs_dev, int64_t M, const double *prior_mean_s_dev,
-                        double *mu_dev, double *var_dev, int32_t *status_dev) {
-  std::lock_guard<std::mutex> lk(g.mu);
-  REQUIRE_INIT();
+                        double *mu_dev, double *var_dev, int32_t *status_dev, void *stream) {
   if (!gp || (!Xs_dev && M > 0)) return fail(BOSS_ERR_ARG, "boss_gp_predict_dev: bad arguments");
   const boss_gp *sl[1] = {gp};
   ScoreArgs a{};
@@ -1109,8 +1544,9 @@ int boss_gp_predict_dev(const boss_gp *gp, const double *Xs_dev, int64_t M, cons
   a.var_out = var_dev;
   a.status_out = status_dev;
   a.dev = true;
+  a.caller_stream = stream;
   a.want_argmax = false;
-  int rc = score_core(a);
+  int rc = score_dispatch(a);
   if (rc) return rc;
   return a.any_fail ? BOSS_NEG_VARIANCE : 0;
 }
@@ -1119,10 +1555,8 @@ static int ei_score_impl(const boss_gp *const *slices, int y_dim, int n_samples,
                          const double *prior_mean_s, const double *fit_coefs, const double *best,
                          const double *y_max, const double *lb, const double *ub, const uint8_t *cons_mask,
                          double *acq, double *grad, double *best_val, int64_t *best_idx, bool dev,
-                         const double *prior_mean_grad = nullptr) {
-  std::lock_guard<std::mutex> lk(g.mu);
-  REQUIRE_INIT();
-  if (!slices || y_dim < 1 || n_samples < 1 || (!Xs && M > 0) || !fit_coefs)
+                         const double *prior_mean_grad = nullptr, void *stream = nullptr, const MixParams *mix = nullptr) {
+  if (!slices || y_dim < 1 || n_samples < 1 || (!Xs && M > 0) || (!fit_coefs && !mix))
     return fail(BOSS_ERR_ARG, "boss_ei_score: bad arguments");
   if ((lb == nullptr) != (ub == nullptr)) return fail(BOSS_ERR_ARG, "boss_ei_score: lb and ub must be given together");
   ScoreArgs a{};
@@ -1144,8 +1578,10 @@ static int ei_score_impl(const boss_gp *const *slices, int y_dim, int n_samples,
   a.best_val = best_val;
   a.best_idx = best_idx;
   a.dev = dev;
+  a.caller_stream = stream;
+  a.mix = mix;
   a.want_argmax = (best_val != nullptr) || (best_idx != nullptr);
-  return score_core(a);
+  return score_dispatch(a);
 }
 
 int boss_ei_score(const boss_gp *const *slices, int y_dim, int n_samples, const double *Xs, int64_t M,
@@ -1160,17 +1596,42 @@ int boss_ei_score_dev(const boss_gp *const *slices, int y_dim, int n_samples, co
                       const double *prior_mean_s_dev, const double *fit_coefs, const double *best,
                       const double *y_max, const double *lb, const double *ub, const uint8_t *cons_mask_dev,
                       double *acq_dev, double *grad_dev, double *best_val, int64_t *best_idx, void *stream) {
-  (void)stream;  // work is ordered on the library stream and synchronised before return
   return ei_score_impl(slices, y_dim, n_samples, Xs_dev, M, prior_mean_s_dev, fit_coefs, best, y_max, lb, ub,
-                       cons_mask_dev, acq_dev, grad_dev, best_val, best_idx, true);
+                       cons_mask_dev, acq_dev, grad_dev, best_val, best_idx, true, nullptr, stream);
+}
+
+// Monte-Carlo EI of a NonlinFitness from the small expression set of MixParams (score.cuh), on the device:
+// replaces expected_improvement(::NonlinFitness, ...) (src/acquisitions/expected_improvement.jl:104-111) inside the
+// same construct_ei cases (:68-90).  eps is y_dim x n_eps (column-major, the reference's sample_eps matrix, :119);
+// with n_samples > 1 posteriors (BI) posterior s gets column s (n_eps must equal n_samples, :87-90).
+int boss_mcei_score(const boss_gp *const *slices, int y_dim, int n_samples, const double *Xs, int64_t M,
+                    const double *prior_mean_s, int fit_kind, double fit_c0, const double *fit_c, const double *fit_q,
+                    const double *fit_t, const double *eps, int n_eps, const double *best, const double *y_max,
+                    const double *lb, const double *ub, const uint8_t *cons_mask, double *acq, double *best_val,
+                    int64_t *best_idx) {
+  if (fit_kind < 1 || fit_kind > 4) return fail(BOSS_ERR_ARG, "boss_mcei_score: fit_kind must be 1 (affine), 2 (quadratic), 3 (max) or 4 (min)");
+  if (!eps || n_eps < 1 || y_dim < 1 || y_dim > MAX_YDIM) return fail(BOSS_ERR_ARG, "boss_mcei_score: bad eps / y_dim");
+  if (n_eps > MIX_MAX_EPS) return fail(BOSS_ERR_ARG, "boss_mcei_score: more than 4096 eps samples");
+  if (n_samples > 1 && n_eps != n_samples)
+    return fail(BOSS_ERR_ARG, "boss_mcei_score: with BI posteriors eps must hold one column per posterior");
+  MixParams mix{};
+  mix.kind = fit_kind;
+  mix.n_eps = n_eps;
+  mix.c0 = fit_c0;
+  for (int i = 0; i < y_dim; ++i) {
+    mix.c[i] = fit_c ? fit_c[i] : 0.0;
+    mix.q[i] = fit_q ? fit_q[i] : 0.0;
+    mix.t[i] = fit_t ? fit_t[i] : 0.0;
+  }
+  mix.eps_host = eps;
+  return ei_score_impl(slices, y_dim, n_samples, Xs, M, prior_mean_s, nullptr, best, y_max, lb, ub, cons_mask, acq, nullptr,
+                       best_val, best_idx, false, nullptr, nullptr, &mix);
 }
 
 static int ei_score_generated(const CandGen &gen, int64_t M, const boss_gp *const *slices, int y_dim, int n_samples,
                               const double *prior_mean_s, const double *fit_coefs, const double *best, const double *y_max,
                               const double *lb, const double *ub, const uint8_t *cons_mask, double *acq, double *best_val,
                               int64_t *best_idx, double *best_x) {
-  std::lock_guard<std::mutex> lk(g.mu);
-  REQUIRE_INIT();
   if (!slices || y_dim < 1 || n_samples < 1 || !fit_coefs || !slices[0]) return fail(BOSS_ERR_ARG, "boss_ei_score_*: bad arguments");
   if ((lb == nullptr) != (ub == nullptr)) return fail(BOSS_ERR_ARG, "boss_ei_score_*: lb and ub must be given together");
   if (gen.d != slices[0]->d) return fail(BOSS_ERR_ARG, "boss_ei_score_*: x_dim mismatch");
@@ -1195,7 +1656,7 @@ static int ei_score_generated(const CandGen &gen, int64_t M, const boss_gp *cons
   a.dev = false;
   a.want_argmax = true;
   a.gen = &gen;
-  int rc = score_core(a);
+  int rc = score_dispatch(a);
   if (rc) return rc;
   if (best_val) *best_val = bv;
   if (best_idx) *best_idx = bi < 0 ? bi : gen.first + bi;                  // global index
@@ -1250,15 +1711,12 @@ int boss_ei_score_uniform(const boss_gp *const *slices, int y_dim, int n_samples
 }
 
 // Device-resident lock-step multi-start maximisation of the acquisition (multistart.cuh).
-int boss_ei_maximize_multistart(const boss_gp *const *slices, int y_dim, int n_samples, const double *starts, int64_t M,
-                                int iters, int history, const double *prior_mean_affine, const double *fit_coefs,
-                                const double *best, const double *y_max, const double *lb, const double *ub,
-                                const uint8_t *discrete_mask, double *x_out, double *f_out, double *best_x,
-                                double *best_val, int64_t *best_idx, int *evals_out) {
-  std::lock_guard<std::mutex> lk(g.mu);
-  REQUIRE_INIT();
-  if (!slices || !slices[0] || y_dim < 1 || n_samples < 1 || !starts || M < 1 || !fit_coefs || !lb || !ub)
-    return fail(BOSS_ERR_ARG, "boss_ei_maximize_multistart: bad arguments (the box lb/ub is required)");
+// the whole multi-start solve inside the current context (all starts on this device)
+static int multistart_single(const boss_gp *const *slices, int y_dim, int n_samples, const double *starts, int64_t M,
+                             int iters, int history, const double *prior_mean_affine, const double *fit_coefs,
+                             const double *best, const double *y_max, const double *lb, const double *ub,
+                             const uint8_t *discrete_mask, double *x_out, double *f_out, double *best_x,
+                             double *best_val, int64_t *best_idx, int *evals_out) {
   const int d = slices[0]->d;
   if (d > MS_MAXD) return fail(BOSS_ERR_ARG, "boss_ei_maximize_multistart: x_dim > 32");
   const int H = std::max(1, std::min(history, MS_MAXH - 1));
@@ -1269,8 +1727,8 @@ int boss_ei_maximize_multistart(const boss_gp *const *slices, int y_dim, int n_s
   const size_t FANCAP = 4;   // compact trial buffers hold up to 4 M points (fan of MS_FAN steps for <= 0.4 M stragglers)
   const size_t n_aff = prior_mean_affine ? (size_t)y_dim * (d + 1) + FANCAP * ((size_t)M * y_dim + Md * y_dim) : 0;
   const size_t n_dbl = 3 * Md + 3 * Md + Md + 2 * (size_t)RC * Md + 4 * (size_t)M + n_aff + FANCAP * (2 * Md + M);
-  CUDA_TRY(g.ms_buf.ensure(n_dbl * 8 + (size_t)M * 12 + 64));
-  double *base = g.ms_buf.as<double>();
+  CUDA_TRY(C().ms_buf.ensure(n_dbl * 8 + (size_t)M * 12 + 64));
+  double *base = C().ms_buf.as<double>();
   MsState st{};
   st.d = d;
   st.H = RC;
@@ -1290,7 +1748,7 @@ int boss_ei_maximize_multistart(const boss_gp *const *slices, int y_dim, int n_s
   st.t = st.fn + M;
   double *aff = st.t + M, *pm = aff + (size_t)y_dim * (d + 1), *pmg = pm + FANCAP * (size_t)M * y_dim;
   if (prior_mean_affine)
-    CUDA_TRY(cudaMemcpyAsync(aff, prior_mean_affine, (size_t)y_dim * (d + 1) * 8, cudaMemcpyHostToDevice, g.stream));
+    CUDA_TRY(cudaMemcpyAsync(aff, prior_mean_affine, (size_t)y_dim * (d + 1) * 8, cudaMemcpyHostToDevice, C().stream));
   st.Xc = st.t + M + n_aff;
   st.gc = st.Xc + FANCAP * Md;
   st.fc = st.gc + FANCAP * Md;
@@ -1299,7 +1757,7 @@ int boss_ei_maximize_multistart(const boss_gp *const *slices, int y_dim, int n_s
   st.done = st.counters + 4;
   st.frozen = st.done + M;
   st.idx = st.frozen + M;
-  CUDA_TRY(cudaMemsetAsync(st.frozen, 0, (size_t)M * 4, g.stream));
+  CUDA_TRY(cudaMemsetAsync(st.frozen, 0, (size_t)M * 4, C().stream));
   double span = 0.0;
   for (int j = 0; j < d; ++j) {
     st.lb[j] = lb[j];
@@ -1319,8 +1777,8 @@ int boss_ei_maximize_multistart(const boss_gp *const *slices, int y_dim, int n_s
     a.M = Mp;
     evaluated += Mp;
     if (prior_mean_affine) {
-      ms_affine_mean_kernel<<<(unsigned)((Mp + 127) / 128), 128, 0, g.stream>>>(Xp, Mp, d, y_dim, aff, pm, pmg);
-      ++g.launches;
+      ms_affine_mean_kernel<<<(unsigned)((Mp + 127) / 128), 128, 0, C().stream>>>(Xp, Mp, d, y_dim, aff, pm, pmg);
+      ++C().launches;
       a.prior_mean = pm;
       a.prior_mean_grad = gp ? pmg : nullptr;
     }
@@ -1334,51 +1792,52 @@ int boss_ei_maximize_multistart(const boss_gp *const *slices, int y_dim, int n_s
     a.best_val = bv;
     a.best_idx = bi;
     a.dev = true;
+    a.internal = true;
     a.want_argmax = want_best;
     return score_core(a);
   };
 
-  CUDA_TRY(cudaMemcpyAsync(st.Xt, starts, Md * 8, cudaMemcpyHostToDevice, g.stream));
-  ms_init_kernel<<<nbm, 128, 0, g.stream>>>(st, st.Xt);
+  CUDA_TRY(cudaMemcpyAsync(st.Xt, starts, Md * 8, cudaMemcpyHostToDevice, C().stream));
+  ms_init_kernel<<<nbm, 128, 0, C().stream>>>(st, st.Xt);
   int rc = eval(st.X, M, st.f, st.g, false, nullptr, nullptr);
   if (rc) return rc;
-  ms_sanitize_kernel<<<nbm, 128, 0, g.stream>>>(st.f, M);
+  ms_sanitize_kernel<<<nbm, 128, 0, C().stream>>>(st.f, M);
   int hist_len = 0, hist_start = 0;
   for (int it = 0; it < iters; ++it) {
-    ms_direction_kernel<<<nbm, 128, 0, g.stream>>>(st, hist_len, hist_start);
+    ms_direction_kernel<<<nbm, 128, 0, C().stream>>>(st, hist_len, hist_start);
     for (int trial = 0; trial < 12; ++trial) {
       // only the starts that have not yet accepted a step are evaluated again (compacted batch)
-      CUDA_TRY(cudaMemsetAsync(st.counters, 0, 16, g.stream));
-      ms_compact_kernel<<<nbm, 128, 0, g.stream>>>(st);
+      CUDA_TRY(cudaMemsetAsync(st.counters, 0, 16, C().stream));
+      ms_compact_kernel<<<nbm, 128, 0, C().stream>>>(st);
       int count = 0;
-      CUDA_TRY(cudaMemcpyAsync(&count, st.counters, 4, cudaMemcpyDeviceToHost, g.stream));
-      CUDA_TRY(cudaStreamSynchronize(g.stream));
-      ++g.launches;
+      CUDA_TRY(cudaMemcpyAsync(&count, st.counters, 4, cudaMemcpyDeviceToHost, C().stream));
+      CUDA_TRY(cudaStreamSynchronize(C().stream));
+      ++C().launches;
       if (count == 0) break;
       if (trial >= 2 && (size_t)count * MS_FAN <= FANCAP * (size_t)M) {
         // few stragglers left: all remaining step sizes in one batch instead of up to 10 tiny sequential ones
-        ms_fan_kernel<<<(count * MS_FAN + 127) / 128, 128, 0, g.stream>>>(st, count);
+        ms_fan_kernel<<<(count * MS_FAN + 127) / 128, 128, 0, C().stream>>>(st, count);
         rc = eval(st.Xc, (long long)count * MS_FAN, st.fc, st.gc, false, nullptr, nullptr);
         if (rc) return rc;
-        ms_accept_fan_kernel<<<(count + 127) / 128, 128, 0, g.stream>>>(st, count);
-        g.launches += 2;
+        ms_accept_fan_kernel<<<(count + 127) / 128, 128, 0, C().stream>>>(st, count);
+        C().launches += 2;
         break;
       }
       rc = eval(st.Xc, count, st.fc, st.gc, false, nullptr, nullptr);
       if (rc) return rc;
-      ms_accept_kernel<<<(count + 127) / 128, 128, 0, g.stream>>>(st, count);
-      ++g.launches;
+      ms_accept_kernel<<<(count + 127) / 128, 128, 0, C().stream>>>(st, count);
+      ++C().launches;
     }
-    ms_freeze_kernel<<<nbm, 128, 0, g.stream>>>(st);
-    CUDA_TRY(cudaMemsetAsync(st.moved_bits, 0, 8 + 16, g.stream));
-    ms_update_kernel<<<nbm, 128, 0, g.stream>>>(st, (hist_start + hist_len) % RC);   // always a free slot
-    g.launches += 3;
+    ms_freeze_kernel<<<nbm, 128, 0, C().stream>>>(st);
+    CUDA_TRY(cudaMemsetAsync(st.moved_bits, 0, 8 + 16, C().stream));
+    ms_update_kernel<<<nbm, 128, 0, C().stream>>>(st, (hist_start + hist_len) % RC);   // always a free slot
+    C().launches += 3;
     struct {
       unsigned long long moved;
       int cnt[4];
     } hs;
-    CUDA_TRY(cudaMemcpyAsync(&hs, st.moved_bits, 24, cudaMemcpyDeviceToHost, g.stream));
-    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    CUDA_TRY(cudaMemcpyAsync(&hs, st.moved_bits, 24, cudaMemcpyDeviceToHost, C().stream));
+    CUDA_TRY(cudaStreamSynchronize(C().stream));
     if (hs.cnt[1]) {   // at least one start produced a valid pair: commit the slot
       if (hist_len == H)
         hist_start = (hist_start + 1) % RC;   // drop the oldest pair
@@ -1391,18 +1850,83 @@ int boss_ei_maximize_multistart(const boss_gp *const *slices, int y_dim, int n_s
   }
   // final rounding of discrete dimensions and re-evaluation (optimization.jl:116-117), argmax over the starts
   const unsigned long long disc = mask_bits(discrete_mask, d);
-  if (disc) ms_round_kernel<<<(unsigned)((Md + 255) / 256), 256, 0, g.stream>>>(st.X, M, d, disc);
+  if (disc) ms_round_kernel<<<(unsigned)((Md + 255) / 256), 256, 0, C().stream>>>(st.X, M, d, disc);
   double bv = 0.0;
   int64_t bi = -1;
   rc = eval(st.X, M, st.f, nullptr, true, &bv, &bi);
   if (rc) return rc;
-  if (x_out) CUDA_TRY(cudaMemcpyAsync(x_out, st.X, Md * 8, cudaMemcpyDeviceToHost, g.stream));
-  if (f_out) CUDA_TRY(cudaMemcpyAsync(f_out, st.f, (size_t)M * 8, cudaMemcpyDeviceToHost, g.stream));
-  if (best_x && bi >= 0) CUDA_TRY(cudaMemcpyAsync(best_x, st.X + (size_t)bi * d, (size_t)d * 8, cudaMemcpyDeviceToHost, g.stream));
-  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  if (x_out) CUDA_TRY(cudaMemcpyAsync(x_out, st.X, Md * 8, cudaMemcpyDeviceToHost, C().stream));
+  if (f_out) CUDA_TRY(cudaMemcpyAsync(f_out, st.f, (size_t)M * 8, cudaMemcpyDeviceToHost, C().stream));
+  if (best_x && bi >= 0) CUDA_TRY(cudaMemcpyAsync(best_x, st.X + (size_t)bi * d, (size_t)d * 8, cudaMemcpyDeviceToHost, C().stream));
+  CUDA_TRY(cudaStreamSynchronize(C().stream));
   if (best_val) *best_val = bv;
   if (best_idx) *best_idx = bi;
   if (evals_out) *evals_out = (int)((evaluated + M - 1) / M);   // work in units of full-batch evaluations
+  return 0;
+}
+
+int boss_ei_maximize_multistart(const boss_gp *const *slices, int y_dim, int n_samples, const double *starts, int64_t M,
+                                int iters, int history, const double *prior_mean_affine, const double *fit_coefs,
+                                const double *best, const double *y_max, const double *lb, const double *ub,
+                                const uint8_t *discrete_mask, double *x_out, double *f_out, double *best_x,
+                                double *best_val, int64_t *best_idx, int *evals_out) {
+  if (!slices || !slices[0] || y_dim < 1 || n_samples < 1 || !starts || M < 1 || !fit_coefs || !lb || !ub)
+    return fail(BOSS_ERR_ARG, "boss_ei_maximize_multistart: bad arguments (the box lb/ub is required)");
+  const int nsl = y_dim * n_samples;
+  for (int q = 0; q < nsl; ++q)
+    if (!slices[q]) return fail(BOSS_ERR_ARG, "boss_ei_maximize_multistart: NULL slice handle");
+  const int d = slices[0]->d;
+  int nd = (g_ndev > 1 && tl_dev < 0) ? g_ndev : 1;
+  for (int q = 0; q < nsl && nd > 1; ++q)
+    for (int k = 0; k < nd; ++k)
+      if (!replica_on(slices[q], k)) {
+        nd = 1;
+        break;
+      }
+  if (M < 256LL * nd) nd = 1;
+  if (nd <= 1) {
+    Ctx *cx = tl_dev >= 0 ? ctx_current() : ctx_of(slices[0]->dev);
+    if (!cx) return fail(BOSS_ERR_STATE, "boss_ei_maximize_multistart: no usable device context for the handle");
+    Enter en(cx);
+    return multistart_single(slices, y_dim, n_samples, starts, M, iters, history, prior_mean_affine, fit_coefs, best, y_max,
+                             lb, ub, discrete_mask, x_out, f_out, best_x, best_val, best_idx, evals_out);
+  }
+  // multi-device: the starts are independent local solves (optimize_multistart, src/utils/optim_multistart.jl:10-90):
+  // contiguous ranges of starts per device, the winners compared on the host in Julia's argmax order
+  const int64_t per = ((M + nd - 1) / nd + 127) / 128 * 128;
+  std::vector<double> bv(nd, 0.0), bx((size_t)nd * d, 0.0);
+  std::vector<int64_t> bi(nd, -1), first(nd, 0), cnt(nd, 0);
+  std::vector<int> ev(nd, 0);
+  int rc = for_each_device(nd, [&](int k, Ctx *) {
+    first[k] = std::min<int64_t>(M, (int64_t)k * per);
+    cnt[k] = std::min<int64_t>(per, M - first[k]);
+    if (cnt[k] <= 0) return 0;
+    return multistart_single(slices, y_dim, n_samples, starts + (size_t)first[k] * d, cnt[k], iters, history,
+                             prior_mean_affine, fit_coefs, best, y_max, lb, ub, discrete_mask,
+                             x_out ? x_out + (size_t)first[k] * d : nullptr, f_out ? f_out + first[k] : nullptr,
+                             bx.data() + (size_t)k * d, &bv[k], &bi[k], &ev[k]);
+  });
+  if (rc) return rc;
+  double v = -std::numeric_limits<double>::infinity();
+  int64_t ix = -1;
+  int kbest = -1;
+  for (int k = 0; k < nd; ++k) {
+    if (cnt[k] <= 0 || bi[k] < 0) continue;
+    const int64_t gi = first[k] + bi[k];
+    if (ix < 0 || acq_better_host(bv[k], gi, v, ix)) {
+      v = bv[k];
+      ix = gi;
+      kbest = k;
+    }
+  }
+  if (best_val) *best_val = v;
+  if (best_idx) *best_idx = ix;
+  if (best_x && kbest >= 0)
+    for (int j = 0; j < d; ++j) best_x[j] = bx[(size_t)kbest * d + j];
+  if (evals_out) {
+    *evals_out = 0;
+    for (int k = 0; k < nd; ++k) *evals_out = std::max(*evals_out, ev[k]);
+  }
   return 0;
 }
 
@@ -1418,40 +1942,40 @@ int boss_ei_value_grad(const boss_gp *const *slices, int y_dim, int n_samples, c
 int boss_ei_value_grad_dev(const boss_gp *const *slices, int y_dim, int n_samples, const double *Xs_dev, int64_t M,
                            const double *prior_mean_s_dev, const double *prior_mean_grad_s_dev,
                            const double *fit_coefs, const double *best, const double *y_max, const double *lb,
-                           const double *ub, const uint8_t *cons_mask_dev, double *acq_dev, double *grad_dev) {
+                           const double *ub, const uint8_t *cons_mask_dev, double *acq_dev, double *grad_dev,
+                           void *stream) {
   if (!grad_dev) return fail(BOSS_ERR_ARG, "boss_ei_value_grad_dev: grad is NULL");
   return ei_score_impl(slices, y_dim, n_samples, Xs_dev, M, prior_mean_s_dev, fit_coefs, best, y_max, lb, ub,
-                       cons_mask_dev, acq_dev, grad_dev, nullptr, nullptr, true, prior_mean_grad_s_dev);
+                       cons_mask_dev, acq_dev, grad_dev, nullptr, nullptr, true, prior_mean_grad_s_dev, stream);
 }
 
 int boss_gp_cov(const boss_gp *gp, const double *Xs, int64_t M, const double *prior_mean_s, double *mu, double *cov) {
-  std::lock_guard<std::mutex> lk(g.mu);
-  REQUIRE_INIT();
   if (!gp || !Xs || !cov || M < 1) return fail(BOSS_ERR_ARG, "boss_gp_cov: bad arguments");
+  REQUIRE_HANDLE_CTX(gp);
   if (M > 8192) return fail(BOSS_ERR_ARG, "boss_gp_cov: M > 8192 (the full covariance is meant for small batches)");
   const boss_gp *h = gp;
   const int d = h->d, ncb = (int)((M + 127) / 128), Mp = ncb * 128, cnt = Mp;
   const size_t blk_elems = (size_t)Mp * h->n_pad;
-  CUDA_TRY(g.ks.ensure(blk_elems * 8));
-  CUDA_TRY(g.vt.ensure(blk_elems * 8));
-  CUDA_TRY(g.part_mu.ensure((size_t)2 * h->nblk * Mp * 8));
-  CUDA_TRY(g.part_ss.ensure((size_t)2 * h->nblk * Mp * 8));
-  CUDA_TRY(g.muv.ensure((size_t)Mp * 8));
-  CUDA_TRY(g.cov_p.ensure((size_t)Mp * Mp * 8));
-  CUDA_TRY(g.cov_stage.ensure((size_t)M * M * 8));
-  CUDA_TRY(g.xs_stage.ensure((size_t)Mp * d * 8));
-  CUDA_TRY(g.mu_stage.ensure((size_t)Mp * 8));
-  CUDA_TRY(g.small.ensure(64));
-  if (prior_mean_s) CUDA_TRY(g.pm_stage.ensure((size_t)M * 8));
-  int *d_fail = g.small.as<int>();
-  CUDA_TRY(cudaMemsetAsync(d_fail, 0, 4, g.stream));
-  CUDA_TRY(cudaMemcpyAsync(g.xs_stage.p, Xs, (size_t)M * d * 8, cudaMemcpyHostToDevice, g.stream));
-  if (prior_mean_s) CUDA_TRY(cudaMemcpyAsync(g.pm_stage.p, prior_mean_s, (size_t)M * 8, cudaMemcpyHostToDevice, g.stream));
+  CUDA_TRY(C().ks.ensure(blk_elems * 8));
+  CUDA_TRY(C().vt.ensure(blk_elems * 8));
+  CUDA_TRY(C().part_mu.ensure((size_t)2 * h->nblk * Mp * 8));
+  CUDA_TRY(C().part_ss.ensure((size_t)2 * h->nblk * Mp * 8));
+  CUDA_TRY(C().muv.ensure((size_t)Mp * 8));
+  CUDA_TRY(C().cov_p.ensure((size_t)Mp * Mp * 8));
+  CUDA_TRY(C().cov_stage.ensure((size_t)M * M * 8));
+  CUDA_TRY(C().xs_stage.ensure((size_t)Mp * d * 8));
+  CUDA_TRY(C().mu_stage.ensure((size_t)Mp * 8));
+  CUDA_TRY(C().small.ensure(64));
+  if (prior_mean_s) CUDA_TRY(C().pm_stage.ensure((size_t)M * 8));
+  int *d_fail = C().small.as<int>();
+  CUDA_TRY(cudaMemsetAsync(d_fail, 0, 4, C().stream));
+  CUDA_TRY(cudaMemcpyAsync(C().xs_stage.p, Xs, (size_t)M * d * 8, cudaMemcpyHostToDevice, C().stream));
+  if (prior_mean_s) CUDA_TRY(cudaMemcpyAsync(C().pm_stage.p, prior_mean_s, (size_t)M * 8, cudaMemcpyHostToDevice, C().stream));
   const int want = (2 * 148 + ncb - 1) / ncb;
   const int nks = std::max(1, std::min(h->nblk, want));
   const int nsp = pick_row_splits(ncb, h->nblk);
   XcovParams xp{};
-  xp.Xs = g.xs_stage.as<double>();
+  xp.Xs = C().xs_stage.as<double>();
   xp.M = M;
   xp.d = d;
   xp.n = h->n;
@@ -1462,62 +1986,69 @@ int boss_gp_cov(const boss_gp *gp, const double *Xs, int64_t M, const double *pr
   xp.disc_bits = h->disc;
   xp.alpha = h->alpha;
   xp.a2 = h->a2;
-  xp.Ks = g.ks.as<double>();
-  xp.mu_part = g.part_mu.as<double>();
+  xp.Ks = C().ks.as<double>();
+  xp.mu_part = C().part_mu.as<double>();
   xp.ld = Mp;
-  DISPATCH_KID_DP(launch_xcov_t, h->kernel_id, h->dp, xp, dim3(ncb, nks));
-  reduce_rows_kernel<<<(cnt + 255) / 256, 256, 0, g.stream>>>(g.part_mu.as<double>(), 2 * h->nblk, (size_t)Mp,
-                                                             g.muv.as<double>(), cnt);
+  launch_xcov(h->kernel_id, h->dp, xp, dim3(ncb, nks), C().stream);
+  reduce_rows_kernel<<<(cnt + 255) / 256, 256, 0, C().stream>>>(C().part_mu.as<double>(), 2 * h->nblk, (size_t)Mp,
+                                                             C().muv.as<double>(), cnt);
   ScoreParams sp{};
   sp.W = h->W;
-  sp.Ks = g.ks.as<double>();
+  sp.Ks = C().ks.as<double>();
   sp.nblk = h->nblk;
   sp.ktiles = h->ktiles;
-  sp.ss_part = g.part_ss.as<double>();
+  sp.ss_part = C().part_ss.as<double>();
   sp.ld = Mp;
-  sp.VT = g.vt.as<double>();
-  score_trmm_kernel<<<dim3(ncb, nsp), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(sp);
-  GemmNtParams gm{g.vt.as<double>(), g.vt.as<double>(), g.cov_p.as<double>(), h->ktiles, Mp / TK, 1};
-  gemm_nt_kernel<<<dim3(ncb, ncb), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(gm);
+  sp.VT = C().vt.as<double>();
+  score_trmm_kernel<<<dim3(ncb, nsp), GEMM_THREADS, GEMM_SMEM_BYTES, C().stream>>>(sp);
+  GemmNtParams gm{C().vt.as<double>(), C().vt.as<double>(), C().cov_p.as<double>(), h->ktiles, Mp / TK, 1};
+  gemm_nt_kernel<<<dim3(ncb, ncb), GEMM_THREADS, GEMM_SMEM_BYTES, C().stream>>>(gm);
   CovFinishParams cf{};
-  cf.Xs = g.xs_stage.as<double>();
+  cf.Xs = C().xs_stage.as<double>();
   cf.M = (int)M;
   cf.d = d;
   cf.ktilesC = Mp / TK;
   cf.invl = h->invl;
   cf.disc_bits = h->disc;
   cf.a2 = h->a2;
-  cf.C = g.cov_p.as<double>();
-  cf.mu = g.muv.as<double>();
-  cf.prior_mean = prior_mean_s ? g.pm_stage.as<double>() : nullptr;
-  cf.mu_out = mu ? g.mu_stage.as<double>() : nullptr;
-  cf.cov = g.cov_stage.as<double>();
+  cf.C = C().cov_p.as<double>();
+  cf.mu = C().muv.as<double>();
+  cf.prior_mean = prior_mean_s ? C().pm_stage.as<double>() : nullptr;
+  cf.mu_out = mu ? C().mu_stage.as<double>() : nullptr;
+  cf.cov = C().cov_stage.as<double>();
   cf.any_fail = d_fail;
-  DISPATCH_KID_DP(launch_cov_finish_t, h->kernel_id, h->dp, cf, dim3((unsigned)((M + 15) / 16), (unsigned)((M + 15) / 16)));
-  g.launches += 5;
+  launch_cov_finish(h->kernel_id, h->dp, cf, dim3((unsigned)((M + 15) / 16), (unsigned)((M + 15) / 16)), C().stream);
+  C().launches += 5;
   CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaMemcpyAsync(cov, g.cov_stage.p, (size_t)M * M * 8, cudaMemcpyDeviceToHost, g.stream));
-  if (mu) CUDA_TRY(cudaMemcpyAsync(mu, g.mu_stage.p, (size_t)M * 8, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaMemcpyAsync(cov, C().cov_stage.p, (size_t)M * M * 8, cudaMemcpyDeviceToHost, C().stream));
+  if (mu) CUDA_TRY(cudaMemcpyAsync(mu, C().mu_stage.p, (size_t)M * 8, cudaMemcpyDeviceToHost, C().stream));
   int hfail = 0;
-  CUDA_TRY(cudaMemcpyAsync(&hfail, d_fail, 4, cudaMemcpyDeviceToHost, g.stream));
-  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaMemcpyAsync(&hfail, d_fail, 4, cudaMemcpyDeviceToHost, C().stream));
+  CUDA_TRY(cudaStreamSynchronize(C().stream));
   return hfail ? BOSS_NEG_VARIANCE : 0;
 }
 
 // ---------------------------------------------------------------------------------------------
 // batched log marginal likelihood
 // ---------------------------------------------------------------------------------------------
-static int loglik_impl(const double *X, int d, int n, const double *Ymm, int64_t ldy, const double *ls,
+// restores the context's main stream when a log-likelihood window leaves early (its groups run on their own streams)
+struct StreamGuard {
+  cudaStream_t keep;
+  StreamGuard() : keep(C().stream) {}
+  ~StreamGuard() { C().stream = keep; }
+};
+
+// one batch inside the current context
+static int loglik_core(const double *X, int d, int n, const double *Ymm, int64_t ldy, const double *ls,
                        const double *amp, const double *noise, int kernel_id, const uint8_t *discrete_mask, int64_t S,
-                       double *loglik, bool dev, double *grad = nullptr, boss_gp **fit_out = nullptr) {
-  std::lock_guard<std::mutex> lk(g.mu);
-  REQUIRE_INIT();
-  if (!X || !Ymm || !ls || !amp || !noise || !loglik || d < 1 || n < 1 || S < 0)
-    return fail(BOSS_ERR_ARG, "boss_gp_loglik_batch: bad arguments");
-  if (kernel_id < 0 || kernel_id > 2) return fail(BOSS_ERR_ARG, "boss_gp_loglik_batch: unknown kernel_id");
+                       double *loglik, bool dev, double *grad, boss_gp **fit_out, void *caller_stream) {
   const int dp = pick_dp(d);
-  if (dp < 0) return fail(BOSS_ERR_ARG, "boss_gp_loglik_batch: x_dim > 32 is not supported");
   if (S == 0) return 0;
+  if (dev) {
+    int rc = wait_for_caller(caller_stream);
+    if (rc) return rc;
+  }
+  StreamGuard stream_guard;
   const int n_pad = round_up(n, TM), nblk = n_pad / TM, ktiles = n_pad / TK;
   const size_t mat = (size_t)n_pad * n_pad;
   const unsigned long long disc = mask_bits(discrete_mask, d);
@@ -1530,16 +2061,16 @@ static int loglik_impl(const double *X, int d, int n, const double *Ymm, int64_t
   Sb = std::min<long long>(Sb, 32768);
   if (small) Sb = 1;
   if (!small) {
-    CUDA_TRY(g.chol_L.ensure((size_t)Sb * mat * 8));
-    CUDA_TRY(g.chol_Winv.ensure((size_t)Sb * nblk * TM * TM * 8));
+    CUDA_TRY(C().chol_L.ensure((size_t)Sb * mat * 8));
+    CUDA_TRY(C().chol_Winv.ensure((size_t)Sb * nblk * TM * TM * 8));
   }
   const int ntiles = nblk * (nblk + 1) / 2;
   const size_t tt_stride = (size_t)std::max(1, nblk - 1) * TM * TM;
   if (need_w) {
-    CUDA_TRY(g.chol_W.ensure((size_t)Sb * mat * 8));
-    CUDA_TRY(g.chol_WT.ensure((size_t)Sb * mat * 8));
-    CUDA_TRY(g.ll_vec.ensure((size_t)Sb * n_pad * 3 * 8));                 // delta_pad | w | alpha
-    if (grad) CUDA_TRY(g.ll_part.ensure((size_t)Sb * ntiles * (dp + 2) * 8));
+    CUDA_TRY(C().chol_W.ensure((size_t)Sb * mat * 8));
+    CUDA_TRY(C().chol_WT.ensure((size_t)Sb * mat * 8));
+    CUDA_TRY(C().ll_vec.ensure((size_t)Sb * n_pad * 3 * 8));                 // delta_pad | w | alpha
+    if (grad) CUDA_TRY(C().ll_part.ensure((size_t)Sb * ntiles * (dp + 2) * 8));
   }
 
   // device copies of the inputs when called with host pointers
@@ -1570,14 +2101,14 @@ static int loglik_impl(const double *X, int d, int n, const double *Ymm, int64_t
   off += small ? 0 : (size_t)Sb * n_pad;
   const size_t ost = off;
   off += (size_t)(Sb + 1) / 2 + 1;
-  CUDA_TRY(g.chol_misc.ensure(off * 8));
-  double *misc = g.chol_misc.as<double>();
+  CUDA_TRY(C().chol_misc.ensure(off * 8));
+  double *misc = C().chol_misc.as<double>();
   if (!dev) {
-    CUDA_TRY(cudaMemcpyAsync(misc + oX, X, (size_t)n * d * 8, cudaMemcpyHostToDevice, g.stream));
-    CUDA_TRY(cudaMemcpyAsync(misc + oY, Ymm, ycount * 8, cudaMemcpyHostToDevice, g.stream));
-    CUDA_TRY(cudaMemcpyAsync(misc + ols, ls, (size_t)S * d * 8, cudaMemcpyHostToDevice, g.stream));
-    CUDA_TRY(cudaMemcpyAsync(misc + oamp, amp, (size_t)S * 8, cudaMemcpyHostToDevice, g.stream));
-    CUDA_TRY(cudaMemcpyAsync(misc + onoise, noise, (size_t)S * 8, cudaMemcpyHostToDevice, g.stream));
+    CUDA_TRY(cudaMemcpyAsync(misc + oX, X, (size_t)n * d * 8, cudaMemcpyHostToDevice, C().stream));
+    CUDA_TRY(cudaMemcpyAsync(misc + oY, Ymm, ycount * 8, cudaMemcpyHostToDevice, C().stream));
+    CUDA_TRY(cudaMemcpyAsync(misc + ols, ls, (size_t)S * d * 8, cudaMemcpyHostToDevice, C().stream));
+    CUDA_TRY(cudaMemcpyAsync(misc + oamp, amp, (size_t)S * 8, cudaMemcpyHostToDevice, C().stream));
+    CUDA_TRY(cudaMemcpyAsync(misc + onoise, noise, (size_t)S * 8, cudaMemcpyHostToDevice, C().stream));
     dX = misc + oX; dY = misc + oY; dls = misc + ols; damp = misc + oamp; dnoise = misc + onoise; dll = misc + oll;
   }
   double *dgrad = (grad && !dev) ? misc + ogr : grad;
@@ -1599,21 +2130,21 @@ static int loglik_impl(const double *X, int d, int n, const double *Ymm, int64_t
     sp.S = S;
     sp.loglik = dll;
     Timed t(2);
-    DISPATCH_KID_DP(launch_loglik_small_t, kernel_id, dp, sp, (int)((S + SMALL_WARPS - 1) / SMALL_WARPS));
-    ++g.launches;
+    launch_loglik_small(kernel_id, dp, sp, (int)((S + SMALL_WARPS - 1) / SMALL_WARPS), C().stream);
+    ++C().launches;
   }
   // A window of up to Sb matrices is live at a time.  Inside a window the matrices are processed as up to
   // LL_GROUPS independent groups on separate streams: one group's latency-bound steps (diagonal-block
   // factorisation, forward solve) and partially filled last waves overlap with another group's GEMM launches.
-  cudaStream_t main_stream = g.stream;
+  cudaStream_t main_stream = C().stream;
   const size_t winv_stride = (size_t)nblk * TM * TM;
   for (long long s0 = 0; s0 < S && !small; s0 += Sb) {
     const int sb = (int)std::min<long long>(Sb, S - s0);
     int want_groups = 4;
     if (const char *e = getenv("BOSS_LL_GROUPS")) want_groups = std::max(1, std::min(LL_GROUPS, atoi(e)));
-    const int ngroups = (g.timing || sb < 2 * want_groups) ? 1 : want_groups;   // per-kernel-class timing needs one stream
+    const int ngroups = (C().timing || sb < 2 * want_groups) ? 1 : want_groups;   // per-kernel-class timing needs one stream
     const int gsz = (sb + ngroups - 1) / ngroups;
-    if (ngroups > 1) CUDA_TRY(cudaEventRecord(g.ll_fork, main_stream));
+    if (ngroups > 1) CUDA_TRY(cudaEventRecord(C().ll_fork, main_stream));
     int rc_all = 0;
     for (int gi = 0; gi < ngroups; ++gi) {
       const int wo = gi * gsz;                           // offset of the group inside the window
@@ -1621,17 +2152,17 @@ static int loglik_impl(const double *X, int d, int n, const double *Ymm, int64_t
       if (gs <= 0) break;
       const long long so = s0 + wo;                      // offset of the group inside the batch
       if (ngroups > 1) {
-        g.stream = g.ll_stream[gi];
-        CUDA_TRY(cudaStreamWaitEvent(g.stream, g.ll_fork, 0));
+        C().stream = C().ll_stream[gi];
+        CUDA_TRY(cudaStreamWaitEvent(C().stream, C().ll_fork, 0));
       }
-      double *Lg = g.chol_L.as<double>() + (size_t)wo * mat;
-      double *Wig = g.chol_Winv.as<double>() + (size_t)wo * winv_stride;
+      double *Lg = C().chol_L.as<double>() + (size_t)wo * mat;
+      double *Wig = C().chol_Winv.as<double>() + (size_t)wo * winv_stride;
       double *ldg = logdet_blk + (size_t)wo * nblk;
       int *stg = status + wo;
-      double *Wg = need_w ? g.chol_W.as<double>() + (size_t)wo * mat : nullptr;
-      double *WTg = need_w ? g.chol_WT.as<double>() + (size_t)wo * mat : nullptr;
+      double *Wg = need_w ? C().chol_W.as<double>() + (size_t)wo * mat : nullptr;
+      double *WTg = need_w ? C().chol_WT.as<double>() + (size_t)wo * mat : nullptr;
       double *TTg = nullptr;   // the fused triangular-inverse step keeps T on chip
-      cudaMemsetAsync(stg, 0, (size_t)gs * 4, g.stream);
+      CUDA_TRY(cudaMemsetAsync(stg, 0, (size_t)gs * 4, C().stream));
       BuildKParams bk{};
       bk.X = dX;
       bk.d = d;
@@ -1647,34 +2178,34 @@ static int loglik_impl(const double *X, int d, int n, const double *Ymm, int64_t
       bk.status = stg;
       {
         Timed t(1);
-        DISPATCH_KID_DP(launch_build_k_t, kernel_id, dp, bk, dim3(nblk * (nblk + 1) / 2, gs));
-        ++g.launches;
+        launch_build_k(kernel_id, dp, bk, dim3(nblk * (nblk + 1) / 2, gs), C().stream);
+        ++C().launches;
       }
       if (need_w) {   // zero initial state of W and W^T (strictly-upper resp. strictly-lower blocks are never written)
-        cudaMemsetAsync(Wg, 0, (size_t)gs * mat * 8, g.stream);
-        cudaMemsetAsync(WTg, 0, (size_t)gs * mat * 8, g.stream);
+        CUDA_TRY(cudaMemsetAsync(Wg, 0, (size_t)gs * mat * 8, C().stream));
+        CUDA_TRY(cudaMemsetAsync(WTg, 0, (size_t)gs * mat * 8, C().stream));
       }
       FwdInline fw{dY + (ldy ? (size_t)so * ldy : 0), ldy, n, n_pad, misc + orv + (size_t)wo * n_pad,
                    misc + owv + (size_t)wo * n_pad, misc + ossq + (size_t)wo * nblk};
       int rc = run_cholesky(Lg, mat, Wig, winv_stride, nblk, ktiles, gs, ldg, stg, Wg, WTg, TTg, mat, tt_stride, false, &fw);
       if (rc) rc_all = rc;
-      loglik_finish_kernel<<<(gs + 127) / 128, 128, 0, g.stream>>>(ldg, fw.ssq, stg, nblk, n, gs, dll + so);
-      ++g.launches;
-      double *vec = g.ll_vec.as<double>();
+      loglik_finish_kernel<<<(gs + 127) / 128, 128, 0, C().stream>>>(ldg, fw.ssq, stg, nblk, n, gs, dll + so);
+      ++C().launches;
+      double *vec = C().ll_vec.as<double>();
       double *dpad = vec + (size_t)wo * n_pad, *wv = vec + ((size_t)Sb + wo) * n_pad, *al = vec + ((size_t)2 * Sb + wo) * n_pad;
       if (need_w) {   // alpha = W^T (W delta)
-        pad_delta_kernel<<<dim3((n_pad + 255) / 256, gs), 256, 0, g.stream>>>(dY + (ldy ? (size_t)so * ldy : 0), ldy, n, n_pad, dpad);
-        matvec_p_kernel<<<dim3(n_pad / 64, gs), 256, 0, g.stream>>>(Wg, dpad, wv, ktiles, mat, n_pad, n_pad);
-        matvec_p_kernel<<<dim3(n_pad / 64, gs), 256, 0, g.stream>>>(WTg, wv, al, ktiles, mat, n_pad, n_pad);
-        g.launches += 3;
+        pad_delta_kernel<<<dim3((n_pad + 255) / 256, gs), 256, 0, C().stream>>>(dY + (ldy ? (size_t)so * ldy : 0), ldy, n, n_pad, dpad);
+        matvec_p_kernel<<<dim3(n_pad / 64, gs), 256, 0, C().stream>>>(Wg, dpad, wv, ktiles, mat, n_pad, n_pad);
+        matvec_p_kernel<<<dim3(n_pad / 64, gs), 256, 0, C().stream>>>(WTg, wv, al, ktiles, mat, n_pad, n_pad);
+        C().launches += 3;
       }
       if (grad) {
         // K^-1 = W^T W over the factor's storage;  tile partial sums;  final scaling
-        double *partg = g.ll_part.as<double>() + (size_t)wo * ntiles * (dp + 2);
+        double *partg = C().ll_part.as<double>() + (size_t)wo * ntiles * (dp + 2);
         KinvParams kp{WTg, mat, Lg, mat, nblk, ktiles};
         {
           Timed t(2);
-          kinv_wtw_kernel<<<dim3(ntiles, gs), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(kp);
+          kinv_wtw_kernel<<<dim3(ntiles, gs), GEMM_THREADS, GEMM_SMEM_BYTES, C().stream>>>(kp);
         }
         LlGradParams lg{};
         lg.X = dX;
@@ -1692,28 +2223,28 @@ static int loglik_impl(const double *X, int d, int n, const double *Ymm, int64_t
         lg.part = partg;
         {
           Timed t(1);
-          DISPATCH_KID_DP(launch_llgrad_tile_t, kernel_id, dp, lg, dim3(ntiles, gs));
+          launch_loglik_grad_tile(kernel_id, dp, lg, dim3(ntiles, gs), C().stream);
         }
-        loglik_grad_final_kernel<<<(gs + 127) / 128, 128, 0, g.stream>>>(partg, ntiles, dp, d, lg.ls, lg.amp, lg.noise, stg,
+        loglik_grad_final_kernel<<<(gs + 127) / 128, 128, 0, C().stream>>>(partg, ntiles, dp, d, lg.ls, lg.amp, lg.noise, stg,
                                                                         dgrad + (size_t)so * (d + 2), gs);
-        g.launches += 3;
+        C().launches += 3;
       }
       if (ngroups > 1) {
-        cudaEventRecord(g.ll_join[gi], g.stream);
-        g.stream = main_stream;
-        cudaStreamWaitEvent(main_stream, g.ll_join[gi], 0);
+        CUDA_TRY(cudaEventRecord(C().ll_join[gi], C().stream));
+        C().stream = main_stream;
+        CUDA_TRY(cudaStreamWaitEvent(main_stream, C().ll_join[gi], 0));
       }
     }
-    g.stream = main_stream;
+    C().stream = main_stream;
     if (rc_all) return rc_all;
     if (fit_out) {
       // batched posterior fit: detach every factorisation of the window into its own handle
       std::vector<int> hst(sb);
       std::vector<double> hll(sb);
-      CUDA_TRY(cudaMemcpyAsync(hst.data(), status, (size_t)sb * 4, cudaMemcpyDeviceToHost, g.stream));
-      CUDA_TRY(cudaMemcpyAsync(hll.data(), dll + s0, (size_t)sb * 8, cudaMemcpyDeviceToHost, g.stream));
-      CUDA_TRY(cudaStreamSynchronize(g.stream));
-      double *vec = g.ll_vec.as<double>();
+      CUDA_TRY(cudaMemcpyAsync(hst.data(), status, (size_t)sb * 4, cudaMemcpyDeviceToHost, C().stream));
+      CUDA_TRY(cudaMemcpyAsync(hll.data(), dll + s0, (size_t)sb * 8, cudaMemcpyDeviceToHost, C().stream));
+      CUDA_TRY(cudaStreamSynchronize(C().stream));
+      double *vec = C().ll_vec.as<double>();
       for (int q = 0; q < sb; ++q) {
         const long long sidx = s0 + q;
         fit_out[sidx] = nullptr;
@@ -1738,36 +2269,73 @@ static int loglik_impl(const double *X, int d, int n, const double *Ymm, int64_t
         }
         std::vector<double> invl(dp, 0.0);
         for (int i = 0; i < d; ++i) invl[i] = 1.0 / (ls[(size_t)sidx * d + i] + MIN_PARAM_VALUE);
-        cudaMemcpyAsync(h->invl, invl.data(), (size_t)dp * 8, cudaMemcpyHostToDevice, g.stream);
-        cudaStreamSynchronize(g.stream);   // invl is a stack temporary
-        cudaMemcpyAsync(h->L, g.chol_L.as<double>() + (size_t)q * mat, mat * 8, cudaMemcpyDeviceToDevice, g.stream);
-        cudaMemcpyAsync(h->W, g.chol_W.as<double>() + (size_t)q * mat, mat * 8, cudaMemcpyDeviceToDevice, g.stream);
-        cudaMemcpyAsync(h->WT, g.chol_WT.as<double>() + (size_t)q * mat, mat * 8, cudaMemcpyDeviceToDevice, g.stream);
-        cudaMemcpyAsync(h->ymm, vec + (size_t)q * n_pad, (size_t)n_pad * 8, cudaMemcpyDeviceToDevice, g.stream);
-        cudaMemcpyAsync(h->wvec, vec + ((size_t)Sb + q) * n_pad, (size_t)n_pad * 8, cudaMemcpyDeviceToDevice, g.stream);
-        cudaMemcpyAsync(h->alpha, vec + ((size_t)2 * Sb + q) * n_pad, (size_t)n_pad * 8, cudaMemcpyDeviceToDevice, g.stream);
-        scale_train_kernel<<<(n_pad * dp + 255) / 256, 256, 0, g.stream>>>(dX, d, n, n_pad, dp, h->invl, disc, h->Xt);
-        ++g.launches;
+        cudaMemcpyAsync(h->invl, invl.data(), (size_t)dp * 8, cudaMemcpyHostToDevice, C().stream);
+        cudaStreamSynchronize(C().stream);   // invl is a stack temporary
+        cudaMemcpyAsync(h->L, C().chol_L.as<double>() + (size_t)q * mat, mat * 8, cudaMemcpyDeviceToDevice, C().stream);
+        cudaMemcpyAsync(h->W, C().chol_W.as<double>() + (size_t)q * mat, mat * 8, cudaMemcpyDeviceToDevice, C().stream);
+        cudaMemcpyAsync(h->WT, C().chol_WT.as<double>() + (size_t)q * mat, mat * 8, cudaMemcpyDeviceToDevice, C().stream);
+        cudaMemcpyAsync(h->ymm, vec + (size_t)q * n_pad, (size_t)n_pad * 8, cudaMemcpyDeviceToDevice, C().stream);
+        cudaMemcpyAsync(h->wvec, vec + ((size_t)Sb + q) * n_pad, (size_t)n_pad * 8, cudaMemcpyDeviceToDevice, C().stream);
+        cudaMemcpyAsync(h->alpha, vec + ((size_t)2 * Sb + q) * n_pad, (size_t)n_pad * 8, cudaMemcpyDeviceToDevice, C().stream);
+        scale_train_kernel<<<(n_pad * dp + 255) / 256, 256, 0, C().stream>>>(dX, d, n, n_pad, dp, h->invl, disc, h->Xt);
+        ++C().launches;
+        h->dev = C().device;
+        h->rep[h->dev] = h;
+        C().live.insert(h);
         fit_out[sidx] = h;
       }
       CUDA_TRY(cudaGetLastError());
-      CUDA_TRY(cudaStreamSynchronize(g.stream));
+      CUDA_TRY(cudaStreamSynchronize(C().stream));
     }
   }
   CUDA_TRY(cudaGetLastError());
-  if (!dev) CUDA_TRY(cudaMemcpyAsync(loglik, dll, (size_t)S * 8, cudaMemcpyDeviceToHost, g.stream));
-  if (!dev && grad) CUDA_TRY(cudaMemcpyAsync(grad, dgrad, (size_t)S * (d + 2) * 8, cudaMemcpyDeviceToHost, g.stream));
-  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  if (!dev) CUDA_TRY(cudaMemcpyAsync(loglik, dll, (size_t)S * 8, cudaMemcpyDeviceToHost, C().stream));
+  if (!dev && grad) CUDA_TRY(cudaMemcpyAsync(grad, dgrad, (size_t)S * (d + 2) * 8, cudaMemcpyDeviceToHost, C().stream));
+  CUDA_TRY(cudaStreamSynchronize(C().stream));
   timing_end();
   if (!dev) {
     int any = 0;
-    for (int64_t s = 0; s < S; ++s) {
-      if (std::isnan(loglik[s])) return fail(BOSS_ERR_ARG, "boss_gp_loglik_batch: negative hyper-parameter");
-      if (std::isinf(loglik[s])) any = 1;
-    }
+    for (int64_t s = 0; s < S; ++s)
+      if (std::isinf(loglik[s]) && loglik[s] < 0) any = 1;
     return any ? BOSS_NOT_POSDEF : 0;
   }
   return 0;
+}
+
+// Argument checks (the reference's asserts, src/models/gaussian_process.jl:227-229, are made on the host where the
+// hyper-parameters are host arrays), then one device or -- multi-device mode, host arrays -- contiguous sample ranges
+// dealt to the devices.  A sample's value does not depend on the batch it is evaluated in (left-looking
+// factorisation, fixed-order sums), so the sharded result is bit-identical to the single-device one.
+static int loglik_impl(const double *X, int d, int n, const double *Ymm, int64_t ldy, const double *ls,
+                       const double *amp, const double *noise, int kernel_id, const uint8_t *discrete_mask, int64_t S,
+                       double *loglik, bool dev, double *grad = nullptr, boss_gp **fit_out = nullptr,
+                       void *caller_stream = nullptr) {
+  if (!X || !Ymm || !ls || !amp || !noise || !loglik || d < 1 || n < 1 || S < 0)
+    return fail(BOSS_ERR_ARG, "boss_gp_loglik_batch: bad arguments");
+  if (kernel_id < 0 || kernel_id > 2) return fail(BOSS_ERR_ARG, "boss_gp_loglik_batch: unknown kernel_id");
+  if (pick_dp(d) < 0) return fail(BOSS_ERR_ARG, "boss_gp_loglik_batch: x_dim > 32 is not supported");
+  if (!dev) {
+    for (int64_t s = 0; s < S; ++s) {
+      for (int i = 0; i < d; ++i)
+        if (!(ls[(size_t)s * d + i] >= 0)) return fail(BOSS_ERR_ARG, "boss_gp_loglik_batch: negative (or NaN) lengthscale");
+      if (!(amp[s] >= 0) || !(noise[s] >= 0))
+        return fail(BOSS_ERR_ARG, "boss_gp_loglik_batch: negative (or NaN) amplitude / noise_std");
+    }
+  }
+  const int nd = (g_ndev > 1 && tl_dev < 0 && !dev && !fit_out && S >= 2LL * g_ndev) ? g_ndev : 1;
+  if (nd <= 1) {
+    REQUIRE_INIT();
+    return loglik_core(X, d, n, Ymm, ldy, ls, amp, noise, kernel_id, discrete_mask, S, loglik, dev, grad, fit_out, caller_stream);
+  }
+  const int64_t per = (S + nd - 1) / nd;
+  int rc = for_each_device(nd, [&](int k, Ctx *) {
+    const int64_t s0 = std::min<int64_t>(S, (int64_t)k * per), cnt = std::min<int64_t>(per, S - s0);
+    if (cnt <= 0) return 0;
+    return loglik_core(X, d, n, ldy ? Ymm + (size_t)s0 * ldy : Ymm, ldy, ls + (size_t)s0 * d, amp + s0, noise + s0, kernel_id,
+                       discrete_mask, cnt, loglik + s0, false, grad ? grad + (size_t)s0 * (d + 2) : nullptr,
+                       fit_out ? fit_out + s0 : nullptr, nullptr);
+  });
+  return rc;
 }
 
 int boss_gp_loglik_batch(const double *X, int d, int n, const double *Y_minus_mean, int64_t ldy,
@@ -1779,9 +2347,8 @@ int boss_gp_loglik_batch(const double *X, int d, int n, const double *Y_minus_me
 int boss_gp_loglik_batch_dev(const double *X_dev, int d, int n, const double *Y_minus_mean_dev, int64_t ldy,
                              const double *lengthscales_dev, const double *amplitude_dev, const double *noise_std_dev,
                              int kernel_id, const uint8_t *discrete_mask, int64_t S, double *loglik_dev, void *stream) {
-  (void)stream;
   return loglik_impl(X_dev, d, n, Y_minus_mean_dev, ldy, lengthscales_dev, amplitude_dev, noise_std_dev, kernel_id,
-                     discrete_mask, S, loglik_dev, true);
+                     discrete_mask, S, loglik_dev, true, nullptr, nullptr, stream);
 }
 
 int boss_gp_fit_batch(const double *X, int d, int n, const double *Y_minus_mean, int64_t ldy, const double *lengthscales,
@@ -1790,16 +2357,50 @@ int boss_gp_fit_batch(const double *X, int d, int n, const double *Y_minus_mean,
   if (!out) return fail(BOSS_ERR_ARG, "boss_gp_fit_batch: out is NULL");
   for (int64_t s = 0; s < S; ++s) out[s] = nullptr;
   std::vector<double> ll((size_t)std::max<int64_t>(S, 1));
-  int rc = loglik_impl(X, d, n, Y_minus_mean, ldy, lengthscales, amplitude, noise_std, kernel_id, discrete_mask, S, ll.data(),
-                       false, nullptr, out);
+  int rc;
+  if (g_ndev > 1 && tl_dev < 0 && S > 0) {
+    // multi-device mode: every device fits all S posteriors (replicas), exactly like boss_gp_fit
+    const int nd = g_ndev;
+    std::vector<std::vector<boss_gp *>> reps(nd, std::vector<boss_gp *>((size_t)S, nullptr));
+    std::vector<std::vector<double>> lls(nd, std::vector<double>((size_t)S, 0.0));
+    if (!X || !Y_minus_mean || !lengthscales || !amplitude || !noise_std || d < 1 || n < 1 || kernel_id < 0 ||
+        kernel_id > 2 || pick_dp(d) < 0)
+      return fail(BOSS_ERR_ARG, "boss_gp_fit_batch: bad arguments");
+    rc = for_each_device(nd, [&](int k, Ctx *) {
+      return loglik_core(X, d, n, Y_minus_mean, ldy, lengthscales, amplitude, noise_std, kernel_id, discrete_mask, S,
+                         lls[k].data(), false, nullptr, reps[k].data(), nullptr);
+    });
+    ll = lls[0];
+    if (rc >= 0) {
+      for (int64_t s = 0; s < S; ++s) {
+        bool all = true;
+        for (int k = 0; k < nd; ++k) all = all && reps[k][s];
+        if (!all) {   // not positive definite (on every device alike)
+          for (int k = 0; k < nd; ++k) free_replica(reps[k][s]);
+          continue;
+        }
+        std::vector<boss_gp *> r(nd);
+        for (int k = 0; k < nd; ++k) r[k] = reps[k][s];
+        out[s] = link_replicas(r);
+      }
+    } else {
+      const std::string keep = tl_err;
+      for (int k = 0; k < nd; ++k)
+        for (boss_gp *r : reps[k]) free_replica(r);
+      tl_err = keep;
+    }
+  } else {
+    rc = loglik_impl(X, d, n, Y_minus_mean, ldy, lengthscales, amplitude, noise_std, kernel_id, discrete_mask, S, ll.data(),
+                     false, nullptr, out);
+    if (rc < 0)
+      for (int64_t s = 0; s < S; ++s)
+        if (out[s]) {
+          boss_gp_free(out[s]);
+          out[s] = nullptr;
+        }
+  }
   if (loglik_out)
     for (int64_t s = 0; s < S; ++s) loglik_out[s] = ll[s];
-  if (rc < 0)
-    for (int64_t s = 0; s < S; ++s)
-      if (out[s]) {
-        boss_gp_free(out[s]);
-        out[s] = nullptr;
-      }
   return rc;
 }
 
@@ -1813,10 +2414,10 @@ int boss_gp_loglik_grad_batch(const double *X, int d, int n, const double *Y_min
 int boss_gp_loglik_grad_batch_dev(const double *X_dev, int d, int n, const double *Y_minus_mean_dev, int64_t ldy,
                                   const double *lengthscales_dev, const double *amplitude_dev, const double *noise_std_dev,
                                   int kernel_id, const uint8_t *discrete_mask, int64_t S, double *loglik_dev,
-                                  double *grad_dev) {
+                                  double *grad_dev, void *stream) {
   if (!grad_dev) return fail(BOSS_ERR_ARG, "boss_gp_loglik_grad_batch_dev: grad is NULL");
   return loglik_impl(X_dev, d, n, Y_minus_mean_dev, ldy, lengthscales_dev, amplitude_dev, noise_std_dev, kernel_id,
-                     discrete_mask, S, loglik_dev, true, grad_dev);
+                     discrete_mask, S, loglik_dev, true, grad_dev, nullptr, stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1829,8 +2430,7 @@ static void pack_host(const double *dense, int R, int C, int Rp, int Cp, std::ve
     for (int c = 0; c < C; ++c) out[p_index(r, c, kt)] = dense[(size_t)r * C + c];
 }
 
-int boss_dbg_gemm_nt(const double *A, const double *B, int M, int N, int K, double *C) {
-  std::lock_guard<std::mutex> lk(g.mu);
+int boss_dbg_gemm_nt(const double *A, const double *B, int M, int N, int K, double *Cout) {
   REQUIRE_INIT();
   const int Mp = round_up(M, TM), Np = round_up(N, TM), Kp = round_up(K, TK);
   std::vector<double> pa, pb;
@@ -1843,14 +2443,14 @@ int boss_dbg_gemm_nt(const double *A, const double *B, int M, int N, int K, doub
   CUDA_TRY(cudaMemcpy(dA, pa.data(), pa.size() * 8, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(dB, pb.data(), pb.size() * 8, cudaMemcpyHostToDevice));
   GemmNtParams p{dA, dB, dC, Kp / TK, Np / TK, 0};
-  gemm_nt_kernel<<<dim3(Np / TM, Mp / TM), GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(p);
-  ++g.launches;
+  gemm_nt_kernel<<<dim3(Np / TM, Mp / TM), GEMM_THREADS, GEMM_SMEM_BYTES, C().stream>>>(p);
+  ++C().launches;
   CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  CUDA_TRY(cudaStreamSynchronize(C().stream));
   std::vector<double> pc((size_t)Mp * Np);
   CUDA_TRY(cudaMemcpy(pc.data(), dC, pc.size() * 8, cudaMemcpyDeviceToHost));
   for (int r = 0; r < M; ++r)
-    for (int c = 0; c < N; ++c) C[(size_t)r * N + c] = pc[p_index(r, c, Np / TK)];
+    for (int c = 0; c < N; ++c) Cout[(size_t)r * N + c] = pc[p_index(r, c, Np / TK)];
   cudaFree(dA);
   cudaFree(dB);
   cudaFree(dC);
@@ -1878,15 +2478,14 @@ __global__ void dbg_kernel_fn_kernel(int which, const double *t, double *out, in
   }
 }
 int boss_dbg_kernel_fn(int which, const double *t, int n, double *out) {
-  std::lock_guard<std::mutex> lk(g.mu);
   REQUIRE_INIT();
   if (which < 0 || which > 7 || n < 0) return fail(BOSS_ERR_ARG, "boss_dbg_kernel_fn: bad argument");
   double *dt, *dout;
   CUDA_TRY(cudaMalloc(&dt, (size_t)n * 8 + 8));
   CUDA_TRY(cudaMalloc(&dout, (size_t)n * 8 + 8));
   CUDA_TRY(cudaMemcpy(dt, t, (size_t)n * 8, cudaMemcpyHostToDevice));
-  dbg_kernel_fn_kernel<<<148, 256, 0, g.stream>>>(which, dt, dout, n);
-  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  dbg_kernel_fn_kernel<<<148, 256, 0, C().stream>>>(which, dt, dout, n);
+  CUDA_TRY(cudaStreamSynchronize(C().stream));
   CUDA_TRY(cudaMemcpy(out, dout, (size_t)n * 8, cudaMemcpyDeviceToHost));
   cudaFree(dt);
   cudaFree(dout);
@@ -1894,9 +2493,9 @@ int boss_dbg_kernel_fn(int which, const double *t, int n, double *out) {
 }
 
 int boss_dbg_factors(const boss_gp *gp, double *L, double *W, double *alpha) {
-  std::lock_guard<std::mutex> lk(g.mu);
-  REQUIRE_INIT();
   if (!gp) return fail(BOSS_ERR_ARG, "boss_dbg_factors: NULL handle");
+  if (tl_dev >= 0 && replica_on(gp, tl_dev)) gp = replica_on(gp, tl_dev);   // inspect a specific replica
+  REQUIRE_HANDLE_CTX(gp);
   const size_t mat = (size_t)gp->n_pad * gp->n_pad;
   std::vector<double> buf(mat);
   const int n = gp->n;

@@ -52,85 +52,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) wtv_kernel(WtvParams p) {
 }
 
 // d mu / dx and d var / dx for one slice and one chunk.
-struct GradParams {
-  const double *Xs;
-  long long M, m0, in_off;
-  int d, n, n_pad, ktiles, chunk_ld;
-  const double *Xt, *invl, *alpha;
-  unsigned long long disc_bits;
-  double a2;
-  const double *UT;    // chunk scratch (P-layout), u = K^-1 k*
-  double *gm_part, *gv_part;  // [2*nblk][d][chunk_ld] per-(training chunk, k-half) partial sums (unscaled)
-};
 
-template <int KID, int DP>
-__global__ void __launch_bounds__(256) grad_kernel(GradParams p) {
-  __shared__ double xt[XCOV_KC * DP];
-  __shared__ double al[XCOV_KC];
-  __shared__ double etab[EXPTAB_N];
-  exptab_init(etab);
-  const int tid = threadIdx.x, r = tid & 127, kh = tid >> 7;
-  const int cb = blockIdx.x;
-  const long long m = p.m0 + (long long)cb * 128 + r;
-  double xc[DP];
-  load_scaled_point<DP>(xc, p.Xs + (size_t)(m - p.in_off) * p.d, p.d, p.invl, p.disc_bits, m < p.M);
-  const double *rowbase = p.UT + (size_t)cb * p.ktiles * TILE_ELEMS + (((r >> 3) << 1) << 6) + ((r & 7) << 3);
-  for (int k0 = blockIdx.y * XCOV_KC; k0 < p.n_pad; k0 += gridDim.y * XCOV_KC) {
-    double gm[DP], gv[DP];
-#pragma unroll
-    for (int i = 0; i < DP; ++i) gm[i] = gv[i] = 0.0;
-    __syncthreads();
-    for (int e = tid; e < XCOV_KC * DP; e += 256) xt[e] = p.Xt[(size_t)k0 * DP + e];
-    if (tid < XCOV_KC) al[tid] = p.alpha[k0 + tid];
-    __syncthreads();
-    for (int mcol = kh; mcol < XCOV_KC / 8; mcol += 2) {
-      const int kg = k0 + mcol * 8;
-      const double *src = rowbase + (size_t)(kg >> 4) * TILE_ELEMS + (((kg >> 3) & 1) << 6);
-      double u[8];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const double2 v = *reinterpret_cast<const double2 *>(src + 2 * q);
-        u[q] = v.x;
-        u[q + 4] = v.y;
-      }
-      double gk[8];
-#pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {   // independent, branch-free chains
-        const int kl = mcol * 8 + kk;
-        double d2 = 0.0;
-#pragma unroll
-        for (int i = 0; i < DP; ++i) {
-          const double df = xc[i] - xt[kl * DP + i];
-          d2 = fma(df, df, d2);
-        }
-        gk[kk] = p.a2 * kappa_dr_over_r_fast<KID>(d2, etab);
-      }
-      if (p.n - k0 < XCOV_KC) {
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) gk[kk] = (k0 + mcol * 8 + kk < p.n) ? gk[kk] : 0.0;
-      }
-#pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {
-        const int kl = mcol * 8 + kk;
-        const double t1 = gk[kk] * al[kl], t2 = gk[kk] * u[kk];
-#pragma unroll
-        for (int i = 0; i < DP; ++i) {
-          const double df = xc[i] - xt[kl * DP + i];
-          gm[i] = fma(t1, df, gm[i]);
-          gv[i] = fma(t2, df, gv[i]);
-        }
-      }
-    }
-    const size_t prow = (size_t)(2 * (k0 / XCOV_KC) + kh) * p.d;
-#pragma unroll
-    for (int i = 0; i < DP; ++i) {
-      if (i < p.d) {
-        p.gm_part[(prow + i) * p.chunk_ld + cb * 128 + r] = gm[i];
-        p.gv_part[(prow + i) * p.chunk_ld + cb * 128 + r] = gv[i];
-      }
-    }
-  }
-}
 
 // Fixed-order sum of the per-chunk partials, then 1/l_j, the -2 of d var and the discrete mask:
 //   dmu[j][c] = invl_j * sum_p gm_part[p][j][c] ;  dvar[j][c] = -2 invl_j * sum_p gv_part[p][j][c]

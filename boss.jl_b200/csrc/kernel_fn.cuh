@@ -118,6 +118,16 @@ __device__ __forceinline__ double kappa_dr_over_r(double d2) {
   }
 }
 
+// _clip_var, src/models/gaussian_process.jl:186-194.  returns false where the reference throws.
+__device__ __forceinline__ bool clip_var(double &v) {
+  if (v >= 0.0) return true;
+  if (v >= -MAX_NEG_VAR) {
+    v = 0.0;
+    return true;
+  }
+  return false;
+}
+
 // Load point `p` (d raw coordinates), round flagged dims (ties-to-even like Julia's round), scale by 1/l.
 template <int DP>
 __device__ __forceinline__ void load_scaled_point(double (&x)[DP], const double *p, int d, const double *invl,

@@ -12,78 +12,17 @@
 #pragma once
 #include "gemm_core.cuh"
 #include "kernel_fn.cuh"
+#include "tk_params.cuh"
 
 namespace boss {
 
 // ---------------------------------------------------------------------------------------------
 // cross-covariance of a candidate chunk with the training set, + posterior mean
 // ---------------------------------------------------------------------------------------------
-struct XcovParams {
-  const double *Xs;        // d x . raw candidates (device), candidate m at column (m - in_off)
-  long long M, m0, in_off; // global count, first candidate of this chunk
-  int d, n, n_pad, ktiles;
-  const double *Xt;        // [n_pad][DP] scaled (and rounded) training inputs
-  const double *invl;      // [DP]
-  unsigned long long disc_bits;
-  const double *alpha;     // [n_pad] K^-1 (y - m), zero padded
-  double a2;
-  double *Ks;              // chunk scratch, P-layout: rows = candidates of the chunk, cols = training index
-  double *mu_part;         // [2*nblk][ld] per-(128-chunk of training points, k-half) partials of K*^T alpha
-  int ld;                  // leading dimension of mu_part (= chunk capacity)
-};
 
-constexpr int XCOV_KC = 128;  // training points staged per shared-memory pass
 
 // grid = (candidate blocks, splits over the 128-point training chunks).  Every chunk's contribution to
 // mu is written as its own partial (fixed summation order downstream), so results do not depend on the split.
-template <int KID, int DP>
-__global__ void __launch_bounds__(256) xcov_kernel(XcovParams p) {
-  __shared__ double xt[XCOV_KC * DP];
-  __shared__ double al[XCOV_KC];
-  __shared__ double etab[EXPTAB_N];
-  exptab_init(etab);
-  const int tid = threadIdx.x, r = tid & 127, kh = tid >> 7;
-  const int cb = blockIdx.x;
-  const long long m = p.m0 + (long long)cb * 128 + r;
-  double xc[DP];
-  load_scaled_point<DP>(xc, p.Xs + (size_t)(m - p.in_off) * p.d, p.d, p.invl, p.disc_bits, m < p.M);
-
-  double *rowbase = p.Ks + (size_t)cb * p.ktiles * TILE_ELEMS + (((r >> 3) << 1) << 6) + ((r & 7) << 3);
-  for (int k0 = blockIdx.y * XCOV_KC; k0 < p.n_pad; k0 += gridDim.y * XCOV_KC) {
-    double mu_acc = 0.0;
-    __syncthreads();
-    for (int e = tid; e < XCOV_KC * DP; e += 256) xt[e] = p.Xt[(size_t)k0 * DP + e];
-    if (tid < XCOV_KC) al[tid] = p.alpha[k0 + tid];
-    __syncthreads();
-    // the last chunk may run past n: its padded columns must be exactly 0 (W is identity there)
-    const int live = p.n - k0;
-    for (int mcol = kh; mcol < XCOV_KC / 8; mcol += 2) {
-      double v[8];
-#pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {   // eight independent, branch-free chains: the scheduler interleaves them
-        const int kl = mcol * 8 + kk;
-        double d2 = 0.0;
-#pragma unroll
-        for (int i = 0; i < DP; ++i) {
-          const double df = xc[i] - xt[kl * DP + i];
-          d2 = fma(df, df, d2);
-        }
-        v[kk] = p.a2 * kappa_fast<KID>(d2, etab);
-      }
-      if (live < XCOV_KC) {
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) v[kk] = (mcol * 8 + kk < live) ? v[kk] : 0.0;
-      }
-#pragma unroll
-      for (int kk = 0; kk < 8; ++kk) mu_acc = fma(v[kk], al[mcol * 8 + kk], mu_acc);
-      const int kg = k0 + mcol * 8;  // global training index of v[0]
-      double *dst = rowbase + (size_t)(kg >> 4) * TILE_ELEMS + (((kg >> 3) & 1) << 6);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) *reinterpret_cast<double2 *>(dst + 2 * q) = make_double2(v[q], v[q + 4]);
-    }
-    p.mu_part[(size_t)(2 * (k0 / XCOV_KC) + kh) * p.ld + (size_t)cb * 128 + r] = mu_acc;
-  }
-}
 
 // out[c] = sum_{p = 0}^{P-1} in[p*ld + c]  (ascending p: the fixed order that makes results split-invariant)
 __global__ void __launch_bounds__(256) reduce_rows_kernel(const double *__restrict__ in, int P, size_t ld,
@@ -162,6 +101,52 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) score_trmm_kernel(ScoreParams
 // ---------------------------------------------------------------------------------------------
 constexpr int MAX_YDIM = 16;
 
+// Monte-Carlo expected improvement for a NonlinFitness drawn from a small expression set
+// (expected_improvement(::NonlinFitness, ...), src/acquisitions/expected_improvement.jl:104-111):
+//   EI = 1/K sum_k max(0, f(mu + sqrt(var) .* eps_k) - best),   f one of
+//   kind 1  affine     f(y) = c0 + sum_i c_i y_i
+//   kind 2  quadratic  f(y) = c0 + sum_i c_i y_i + sum_i q_i (y_i - t_i)^2
+//   kind 3  max        f(y) = c0 + max_i (c_i y_i + t_i)   over the outputs with c_i != 0
+//   kind 4  min        f(y) = c0 + min_i (c_i y_i + t_i)   over the outputs with c_i != 0
+// kind 0 = off (LinFitness closed form).  An arbitrary Julia closure stays a host job.
+constexpr int MIX_MAX_EPS = 4096;
+struct MixParams {
+  int kind = 0, n_eps = 0;
+  double c0 = 0.0;
+  double c[MAX_YDIM] = {}, q[MAX_YDIM] = {}, t[MAX_YDIM] = {};
+  const double *eps = nullptr;        // device, y_dim x n_eps column-major
+  const double *eps_host = nullptr;   // host copy handed in by the caller (uploaded by score_core)
+};
+__host__ __device__ __forceinline__ double mix_fitness(const MixParams &mx, const double *y, int y_dim) {
+  double f = mx.c0;
+  if (mx.kind == 1) {
+    for (int i = 0; i < y_dim; ++i) f = fma(mx.c[i], y[i], f);
+  } else if (mx.kind == 2) {
+    for (int i = 0; i < y_dim; ++i) {
+      const double dv = y[i] - mx.t[i];
+      f = fma(mx.c[i], y[i], f);
+      f = fma(mx.q[i] * dv, dv, f);
+    }
+  } else {
+    bool any = false;
+    double ext = 0.0;
+    for (int i = 0; i < y_dim; ++i) {
+      if (mx.c[i] == 0.0) continue;
+      const double v = fma(mx.c[i], y[i], mx.t[i]);
+      if (!any) {
+        ext = v;
+        any = true;
+      } else if (v != v || ext != ext) {
+        ext = NAN;
+      } else {
+        ext = mx.kind == 3 ? (v > ext ? v : ext) : (v < ext ? v : ext);
+      }
+    }
+    f += ext;
+  }
+  return f;
+}
+
 struct AcqParams {
   int y_dim, n_samples, d;
   long long M, m0;       // global candidate count / chunk start
@@ -186,20 +171,12 @@ struct AcqParams {
   int *any_fail;         // device flag
   double *blk_val;       // per-block winners
   long long *blk_idx;
+  MixParams mix;         // kind != 0: Monte-Carlo EI of a NonlinFitness expression instead of the closed form
 };
 
 __device__ __forceinline__ double norm_cdf(double z) { return 0.5 * erfc(-z * 0.7071067811865476); }
 __device__ __forceinline__ double norm_pdf(double z) { return exp(-0.5 * z * z) * 0.3989422804014327; }
 
-// _clip_var, src/models/gaussian_process.jl:186-194.  returns false where the reference throws.
-__device__ __forceinline__ bool clip_var(double &v) {
-  if (v >= 0.0) return true;
-  if (v >= -MAX_NEG_VAR) {
-    v = 0.0;
-    return true;
-  }
-  return false;
-}
 
 __global__ void __launch_bounds__(256) acq_kernel(AcqParams p) {
   __shared__ double sv[256];
@@ -214,6 +191,7 @@ __global__ void __launch_bounds__(256) acq_kernel(AcqParams p) {
     bool failed = false;
     for (int s = 0; s < p.n_samples; ++s) {
       double mu_f = 0.0, s2 = 0.0, pof = 1.0;
+      double mu_i[MAX_YDIM], sd_i[MAX_YDIM];
       for (int i = 0; i < p.y_dim; ++i) {
         const size_t row = (size_t)(s * p.y_dim + i) * p.chunk_ld + c;
         double mu = p.mu[row];
@@ -226,6 +204,8 @@ __global__ void __launch_bounds__(256) acq_kernel(AcqParams p) {
         if (p.status_out) p.status_out[m - p.out_off] = ok ? 0 : 2;
         mu_f = fma(p.coefs[i], mu, mu_f);
         s2 = fma(p.coefs[i] * p.coefs[i], var, s2);
+        mu_i[i] = mu;
+        sd_i[i] = sqrt(var);
         if (p.has_ymax) {
           const double ym = p.y_max[i];
           if (!(ym == INFINITY)) {                 // cdf(., Infinity()) == 1 exactly (src/utils/inf.jl:13-15)
@@ -237,7 +217,19 @@ __global__ void __launch_bounds__(256) acq_kernel(AcqParams p) {
         }
       }
       double a;
-      if (p.has_best) {
+      if (p.has_best && p.mix.kind != 0) {
+        // one posterior: all eps columns; BI posteriors: posterior s takes column s (expected_improvement.jl:87-90,108-111)
+        const int k0 = p.n_samples > 1 ? s : 0, k1 = p.n_samples > 1 ? s + 1 : p.mix.n_eps;
+        double tot = 0.0;
+        for (int k = k0; k < k1; ++k) {
+          double ys[MAX_YDIM];
+          for (int i = 0; i < p.y_dim; ++i) ys[i] = mu_i[i] + sd_i[i] * p.mix.eps[(size_t)k * p.y_dim + i];
+          const double imp = mix_fitness(p.mix, ys, p.y_dim) - p.best;
+          tot += (imp != imp) ? imp : (imp > 0.0 ? imp : 0.0);   // max(0, NaN) = NaN in Julia
+        }
+        const double ei = tot / (double)(k1 - k0);
+        a = p.has_ymax ? ei * pof : ei;
+      } else if (p.has_best) {
         const double sf = sqrt(s2);
         const double diff = mu_f - p.best;
         double ei;
@@ -333,45 +325,7 @@ __global__ void argmax_final_kernel(const double *blk_val, const long long *blk_
 //   cov[i][j] = k(x*_i, x*_j) - (V^T V)[i][j] + 1e-18 [i == j],   diagonal through _clip_var
 // C = V^T V arrives tile-packed (lower block triangle computed; mirrored here so the result is exactly symmetric).
 // ---------------------------------------------------------------------------------------------
-struct CovFinishParams {
-  const double *Xs;     // d x M raw candidates
-  int M, d, ktilesC;    // ktilesC = M_pad / 16
-  const double *invl;
-  unsigned long long disc_bits;
-  double a2;
-  const double *C;      // P-layout M_pad x M_pad
-  const double *mu;     // [M] K*^T alpha
-  const double *prior_mean;  // [M] or null
-  double *mu_out;       // [M] or null
-  double *cov;          // M x M column-major
-  int *any_fail;
-};
 
-template <int KID, int DP>
-__global__ void __launch_bounds__(256) cov_finish_kernel(CovFinishParams p) {
-  __shared__ double etab[EXPTAB_N];
-  exptab_init(etab);
-  __syncthreads();
-  const int i = blockIdx.x * 16 + (threadIdx.x & 15), j = blockIdx.y * 16 + (threadIdx.x >> 4);
-  if (i >= p.M || j >= p.M) return;
-  double xi[DP], xj[DP];
-  load_scaled_point<DP>(xi, p.Xs + (size_t)i * p.d, p.d, p.invl, p.disc_bits, true);
-  load_scaled_point<DP>(xj, p.Xs + (size_t)j * p.d, p.d, p.invl, p.disc_bits, true);
-  double d2 = 0.0;
-#pragma unroll
-  for (int q = 0; q < DP; ++q) {
-    const double df = xi[q] - xj[q];
-    d2 = fma(df, df, d2);
-  }
-  const int hi = max(i, j), lo = min(i, j);
-  double v = p.a2 * kappa_fast<KID>(d2, etab) - p.C[p_index(hi, lo, p.ktilesC)];
-  if (i == j) {
-    v += VAR_JITTER;
-    if (!clip_var(v)) *p.any_fail = 1;
-    if (p.mu_out) p.mu_out[i] = p.prior_mean ? p.prior_mean[i] + p.mu[i] : p.mu[i];
-  }
-  p.cov[(size_t)j * p.M + i] = v;
-}
 
 // ---------------------------------------------------------------------------------------------
 // device-side candidate generation: the batch never exists in host memory

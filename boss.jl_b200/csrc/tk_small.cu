@@ -1,4 +1,5 @@
-// small.cuh -- warp-register batched log marginal likelihood for small training sets (n <= 32).
+// tk_small.cu -- warp-register batched log marginal likelihood for small training sets (n <= 32) and the
+// covariance vector of boss_gp_append; instantiated for every (covariance function, padded input dimension).
 //
 // One warp per hyper-parameter sample; lane i owns row i of K in registers.  Kernel-matrix construction,
 // right-looking Cholesky (pivot and column broadcast by warp shuffles), log-determinant and the forward
@@ -8,25 +9,10 @@
 // (SamplingMAP src/model_fitters/sampling.jl:59-78, OptimizationMAP multistart optimization.jl:116-119,
 // TuringBI ext/TuringExt.jl:78-86) and a 128-padded blocked factorisation would be almost all padding.
 // Reference arithmetic: gp_data_loglike_slice (src/models/gaussian_process.jl:269-280) -> logpdf(::FiniteGP).
-#pragma once
-#include "kernel_fn.cuh"
+#include "common.cuh"
+#include "tk_params.cuh"
 
 namespace boss {
-
-constexpr int SMALL_N = 32;
-constexpr int SMALL_WARPS = 8;
-
-struct SmallLoglikParams {
-  const double *X;      // d x n raw training inputs (shared)
-  int d, n;
-  const double *ymm;    // n (ldy = 0) or per sample at ymm + s*ldy
-  long long ldy;
-  const double *ls;     // d x S raw length-scales
-  const double *amp, *noise;  // S each, raw
-  unsigned long long disc_bits;
-  long long S;
-  double *loglik;       // S: value, -Inf (not positive definite) or NaN (negative hyper-parameter)
-};
 
 template <int KID, int DP>
 __global__ void __launch_bounds__(SMALL_WARPS * 32) loglik_small_kernel(SmallLoglikParams p) {
@@ -118,6 +104,43 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) loglik_small_kernel(SmallLog
     if (neg) ll = NAN;
     p.loglik[s] = ll;
   }
+}
+
+// k[i] = a^2 kappa(|x~_i - x~+|), i < n (zero beyond); also appends the scaled point as row n of Xt.
+template <int KID, int DP>
+__global__ void append_kvec_kernel(const double *xnew, int d, int n, int n_pad, const double *invl,
+                                   unsigned long long disc_bits, double a2, double *Xt, double *kvec) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pad) return;
+  double xn[DP];
+  load_scaled_point<DP>(xn, xnew, d, invl, disc_bits, true);
+  double val = 0.0;
+  if (i < n) {
+    double d2 = 0.0;
+#pragma unroll
+    for (int q = 0; q < DP; ++q) {
+      const double df = Xt[(size_t)i * DP + q] - xn[q];
+      d2 = fma(df, df, d2);
+    }
+    val = a2 * kappa<KID>(d2);
+  }
+  kvec[i] = val;
+  if (i == n) {
+#pragma unroll
+    for (int q = 0; q < DP; ++q) Xt[(size_t)n * DP + q] = xn[q];
+  }
+}
+
+bool launch_loglik_small(int kid, int dp, const SmallLoglikParams &p, int nblocks, cudaStream_t st) {
+#define CALL(K, D) loglik_small_kernel<K, D><<<nblocks, SMALL_WARPS * 32, 0, st>>>(p)
+  BOSS_DISPATCH_KID_DP(CALL, kid, dp)
+#undef CALL
+}
+bool launch_append_kvec(int kid, int dp, const double *xnew, int d, int n, int n_pad, const double *invl,
+                        unsigned long long disc_bits, double a2, double *Xt, double *kvec, cudaStream_t st) {
+#define CALL(K, D) append_kvec_kernel<K, D><<<(n_pad + 255) / 256, 256, 0, st>>>(xnew, d, n, n_pad, invl, disc_bits, a2, Xt, kvec)
+  BOSS_DISPATCH_KID_DP(CALL, kid, dp)
+#undef CALL
 }
 
 }  // namespace boss

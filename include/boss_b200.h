@@ -8,19 +8,34 @@
  * Conventions
  *   - All matrices are Float64, column-major with points as columns, exactly BOSS.jl's layout
  *     (src/types/data.jl:19-22): X is d x n  => point k is the d contiguous doubles at X + k*d.
- *   - Pointers are caller-owned HOST memory valid for the duration of the call, except in the
- *     `_dev` variants where every array argument is a DEVICE pointer on the library's device and the
- *     work is enqueued on the caller-supplied CUDA stream (0 = the library's own stream).
+ *   - Pointers are caller-owned HOST memory (pageable or pinned) valid for the duration of the call, except in
+ *     the `_dev` variants where every array argument is a DEVICE pointer on the calling thread's device.  All
+ *     library work runs on the library's own stream (boss_stream()).  The last argument `stream` of a `_dev`
+ *     entry point is the CUDA stream on which the caller PRODUCED those device arrays (NULL = the legacy default
+ *     stream, which is what torch and CUDA.jl use unless told otherwise): the library orders its stream after
+ *     that stream before it reads them, and every entry point synchronises its own stream before it returns, so
+ *     results are visible to any stream afterwards.
  *   - Raw hyper-parameters are passed exactly as the reference passes them to `finite_gp`
  *     (src/models/gaussian_process.jl:216-245): the library asserts >= 0 and adds MIN_PARAM_VALUE
  *     = 1e-8 itself.
  *   - Return value: 0 ok; > 0 a numerical condition that the reference reports by throwing and that
  *     its SafeFunction wrappers map to -Inf (BOSS_NOT_POSDEF, BOSS_NEG_VARIANCE); < 0 argument /
  *     CUDA errors with text in boss_last_error().  Nothing aborts, nothing throws across the ABI.
- *   - One process drives one GPU (boss_init(device)); multi-GPU = one process per GPU, sharding
- *     candidates / samples in the caller (see boss.jl_b200/parallel.py and DESIGN.md).
- *   - Thread-safe: entry points serialise on an internal mutex (the reference may call from
- *     Threads.@threads tasks when parallel=true, src/utils/optim_multistart.jl:62).
+ *   - Devices.  boss_init(device): one process drives one GPU (the one-process-per-GPU layout of torchrun;
+ *     candidates / samples are then sharded by the caller, boss.jl_b200/parallel.py).  boss_init_multi(n): ONE
+ *     process drives GPUs 0..n-1 -- the layout a Julia caller has.  Fits are then replicated on every device
+ *     (bit-identical: same deterministic kernels, same inputs), and the host-pointer scoring / log-likelihood /
+ *     multi-start calls deal contiguous candidate blocks / sample ranges / starts to the devices (one host thread
+ *     and one stream set per device) and reduce the (best value, index) pairs on the host in Julia's argmax
+ *     order.  Results are bit-identical to the single-device call.  These are the reference's thread-parallel
+ *     axes: src/acquisition_maximizers/grid.jl:58-62, sampling.jl:50-52, src/model_fitters/sampling.jl:40-49,
+ *     src/utils/optim_multistart.jl:62.  boss_set_device(k) pins the calling thread to device k (for `_dev`
+ *     calls and single-device use of a multi-device process); boss_set_device(-1) undoes it.
+ *   - Thread-safe: entry points serialise on a per-device mutex (the reference may call from
+ *     Threads.@threads tasks when parallel=true, src/utils/optim_multistart.jl:62).  boss_last_error() is
+ *     per calling thread.  boss_shutdown() invalidates the handles that are still alive: later calls on them
+ *     return BOSS_ERR_STATE, boss_gp_free() on them stays valid.
+ *   - Limits that the reference does not have: x_dim <= 32, y_dim <= 16 (argument errors otherwise).
  */
 #ifndef BOSS_B200_H
 #define BOSS_B200_H
@@ -47,11 +62,14 @@ typedef struct boss_gp boss_gp; /* opaque: one fitted GP = one output slice x on
 
 /* ---- runtime ---------------------------------------------------------------------------- */
 int boss_init(int device);            /* select device, create streams + workspace; idempotent      */
+int boss_init_multi(int n_gpus);      /* drive devices 0..n_gpus-1 from this process (see Devices above) */
+int boss_set_device(int device);      /* pin the calling thread to one initialised device; -1 = unpin */
+int boss_n_devices(void);             /* devices multi-device calls fan out to (1 after boss_init)  */
 void boss_shutdown(void);
-const char *boss_last_error(void);
+const char *boss_last_error(void);    /* of the calling thread; valid until its next library call   */
 int boss_version(void);
-int boss_device(void);                /* device ordinal in use, -1 before boss_init                 */
-void *boss_stream(void);              /* the cudaStream_t all library work is ordered on (for event timing) */
+int boss_device(void);                /* device of the calling thread's context, -1 before boss_init */
+void *boss_stream(void);              /* the cudaStream_t library work on that device is ordered on (for event timing) */
 
 /* ---- a1 + a2 : fit -----------------------------------------------------------------------
  * Replaces posterior_gp (src/models/gaussian_process.jl:199-211) -> finite_gp (:216-248) ->
@@ -99,7 +117,7 @@ int boss_gp_predict(const boss_gp *gp, const double *Xs, int64_t M, const double
 
 /* Same with device pointers (Xs, prior mean and outputs already resident in HBM). */
 int boss_gp_predict_dev(const boss_gp *gp, const double *Xs_dev, int64_t M, const double *prior_mean_s_dev,
-                        double *mu_dev, double *var_dev, int32_t *status_dev);
+                        double *mu_dev, double *var_dev, int32_t *status_dev, void *stream);
 
 /* Replaces cov / mean_and_cov(::GaussianProcessPosterior, X) (gaussian_process.jl:163-167,180-184):
  * full M x M posterior covariance (column-major), diagonal clipped.  Intended for small M. */
@@ -126,8 +144,8 @@ int boss_ei_score(const boss_gp *const *slices, int y_dim, int n_samples, const 
                   const double *y_max, const double *lb, const double *ub, const uint8_t *cons_mask,
                   double *acq, double *grad, double *best_val, int64_t *best_idx);
 
-/* Same, every array argument a device pointer (candidates already resident in HBM); enqueued on
- * `stream` and synchronised before return.  best_val / best_idx are HOST pointers. */
+/* Same, every array argument a device pointer (candidates already resident in HBM); ordered after `stream`
+ * (see Conventions) and synchronised before return.  best_val / best_idx are HOST pointers. */
 int boss_ei_score_dev(const boss_gp *const *slices, int y_dim, int n_samples, const double *Xs_dev,
                       int64_t M, const double *prior_mean_s_dev, const double *fit_coefs, const double *best,
                       const double *y_max, const double *lb, const double *ub, const uint8_t *cons_mask_dev,
@@ -152,6 +170,24 @@ int boss_ei_score_uniform(const boss_gp *const *slices, int y_dim, int n_samples
                           const double *fit_coefs, const double *best, const double *y_max, const uint8_t *cons_mask,
                           double *acq, double *best_val, int64_t *best_idx, double *best_x);
 
+/* Monte-Carlo expected improvement of a NonlinFitness on the device, for fitness functions from a small expression
+ * set; replaces expected_improvement(::NonlinFitness, mean, var, eps, best) (src/acquisitions/expected_improvement.jl:104-111)
+ * inside the same four construct_ei cases, guards and argmax as boss_ei_score:
+ *   EI(x) = 1/K sum_k max(0, f(mu(x) + sqrt(var(x)) .* eps[:,k]) - best)
+ *   fit_kind 1  f(y) = c0 + sum_i c_i y_i                          (affine)
+ *            2  f(y) = c0 + sum_i c_i y_i + sum_i q_i (y_i - t_i)^2 (diagonal quadratic)
+ *            3  f(y) = c0 + max_i (c_i y_i + t_i) over outputs with c_i != 0
+ *            4  f(y) = c0 + min_i (c_i y_i + t_i) over outputs with c_i != 0
+ *   fit_c / fit_q / fit_t  y_dim each (NULL = zeros);  eps  y_dim x n_eps column-major = the reference's
+ *   sample_eps matrix (:119), n_eps <= 4096; with n_samples > 1 (BI) posterior s uses column s and n_eps == n_samples.
+ * A fitness that is an arbitrary Julia closure cannot run on the device: boss_gp_predict returns mu, var and the
+ * host finishes. */
+int boss_mcei_score(const boss_gp *const *slices, int y_dim, int n_samples, const double *Xs, int64_t M,
+                    const double *prior_mean_s, int fit_kind, double fit_c0, const double *fit_c, const double *fit_q,
+                    const double *fit_t, const double *eps, int n_eps, const double *best, const double *y_max,
+                    const double *lb, const double *ub, const uint8_t *cons_mask, double *acq, double *best_val,
+                    int64_t *best_idx);
+
 /* Value + analytic x-gradient of the same acquisition for a batch of points: what OptimizationAM's
  * multi-start solver needs per iteration over all starts (src/acquisition_maximizers/optimization.jl:89-118;
  * the reference obtains the gradient by pushing ForwardDiff.Dual numbers through the posterior).
@@ -164,7 +200,8 @@ int boss_ei_value_grad(const boss_gp *const *slices, int y_dim, int n_samples, c
 int boss_ei_value_grad_dev(const boss_gp *const *slices, int y_dim, int n_samples, const double *Xs_dev, int64_t M,
                            const double *prior_mean_s_dev, const double *prior_mean_grad_s_dev,
                            const double *fit_coefs, const double *best, const double *y_max, const double *lb,
-                           const double *ub, const uint8_t *cons_mask_dev, double *acq_dev, double *grad_dev);
+                           const double *ub, const uint8_t *cons_mask_dev, double *acq_dev, double *grad_dev,
+                           void *stream);
 
 /* Device-resident multi-start maximisation: OptimizationAM (src/acquisition_maximizers/optimization.jl:55-118)
  * with all `multistart` local solves advancing in lock-step as projected L-BFGS with Armijo backtracking; every
@@ -194,7 +231,9 @@ int boss_ei_maximize_multistart(const boss_gp *const *slices, int y_dim, int n_s
  *                 (Semiparametric: the mean depends on theta_s)
  *   lengthscales  d x S (sample s = d contiguous doubles), amplitude S, noise_std S (raw values)
  *   loglik        S results; -Inf where K is not positive definite (safe_data_loglike)
- * Returns 0 or BOSS_NOT_POSDEF if any sample failed. */
+ * Returns 0 or BOSS_NOT_POSDEF if any sample failed; BOSS_ERR_ARG for a negative or NaN hyper-parameter (the
+ * reference's asserts).  The `_dev` variants cannot inspect device-resident hyper-parameters on the host: a
+ * negative one yields NaN for that sample.  NaN in X or Y yields -Inf (LAPACK's potrf rejects a NaN pivot). */
 int boss_gp_loglik_batch(const double *X, int d, int n, const double *Y_minus_mean, int64_t ldy,
                          const double *lengthscales, const double *amplitude, const double *noise_std,
                          int kernel_id, const uint8_t *discrete_mask, int64_t S, double *loglik);
@@ -216,7 +255,7 @@ int boss_gp_loglik_grad_batch(const double *X, int d, int n, const double *Y_min
 int boss_gp_loglik_grad_batch_dev(const double *X_dev, int d, int n, const double *Y_minus_mean_dev, int64_t ldy,
                                   const double *lengthscales_dev, const double *amplitude_dev,
                                   const double *noise_std_dev, int kernel_id, const uint8_t *discrete_mask,
-                                  int64_t S, double *loglik_dev, double *grad_dev);
+                                  int64_t S, double *loglik_dev, double *grad_dev, void *stream);
 
 /* ---- instrumentation ---------------------------------------------------------------------
  * CUDA-event time (ms) of the dominant kernel class inside the last scoring / loglik call, and the
