@@ -29,9 +29,12 @@ constexpr int GEMM_SMEM_BYTES = GEMM_RING_BYTES + GEMM_SCRATCH_BYTES + 128;  // 
 // Accumulator fragment coordinates of this lane inside the 128x128 CTA tile:
 //   row(fm)    = 64*wm + 8*fm + (lane>>2)
 //   col(fn, e) = 32*wn + 8*fn + 2*(lane&3) + e
+//   (il: interleaved row slabs, rslab(fm) = 2*fm + wm -- the triangular-operand kernels, see has_tri_stages)
 struct FragCoord {
   int wm, wn, lane;
-  __device__ __forceinline__ int row(int fm) const { return 64 * wm + 8 * fm + (lane >> 2); }
+  bool il = false;
+  __device__ __forceinline__ int rslab(int fm) const { return il ? 2 * fm + wm : 8 * wm + fm; }
+  __device__ __forceinline__ int row(int fm) const { return 8 * rslab(fm) + (lane >> 2); }
   __device__ __forceinline__ int col(int fn, int e) const { return 32 * wn + 8 * fn + 2 * (lane & 3) + e; }
 };
 
@@ -101,6 +104,18 @@ struct has_tail_stages : std::false_type {};
 template <class T>
 struct has_tail_stages<T, std::void_t<decltype(&T::is_tail)>> : std::true_type {};
 
+// Optional iterator feature ("triangular stages"): when It has tri_mode() / tri_g(), the stages of a tile whose A
+// operand is a DIAGONAL block of a triangular matrix skip the structurally zero fragments.  tri_mode() = 1: A block
+// lower triangular (row slab R is non-zero for k micro-steps kk <= R), 2: upper triangular (kk >= R), 0: dense;
+// tri_g() = k-tile 0..7 inside the diagonal block.  Such iterators also switch the warp's row-slab ownership from
+// blocked (8 wm + fm) to interleaved (2 fm + wm), which deals the live fragments of a triangular block evenly to
+// the two warp rows: 72 + 64 of 256 (fm, kk) pairs instead of 100 + 36, so the skipped work (47 % of the block)
+// actually comes off the critical path.  5.2 % fewer DMMAs in score_trmm_kernel at n = 2048.
+template <class T, class = void>
+struct has_tri_stages : std::false_type {};
+template <class T>
+struct has_tri_stages<T, std::void_t<decltype(&T::tri_mode)>> : std::true_type {};
+
 // after_prologue: run by every thread once the first ring stages have been requested (further prefetches belong
 // here: whatever is requested before stage 0 delays the first DMMA).
 struct NoPrologueHook {
@@ -163,7 +178,9 @@ __device__ __forceinline__ void gemm_pipeline(It issue_it, It cons_it, Epi &&epi
 #pragma unroll
     for (int fn = 0; fn < 4; ++fn) acc[fm][fn][0] = acc[fm][fn][1] = 0.0;
 
-  const int a_off = (wm * 8) * 128 + lane * 2;  // micro-row (wm*8+fm) -> +fm*128 ; micro-col mc -> +mc*64
+  constexpr bool IL = has_tri_stages<It>::value;            // interleaved row slabs: 2 fm + wm instead of 8 wm + fm
+  constexpr int A_FM_STRIDE = IL ? 256 : 128;
+  const int a_off = (IL ? wm : wm * 8) * 128 + lane * 2;   // row slab R -> +R*128 ; micro-col mc -> +mc*64
   const int b_off = (wn * 4) * 128 + lane * 2;
 
   int g = 0;
@@ -206,11 +223,57 @@ __device__ __forceinline__ void gemm_pipeline(It issue_it, It cons_it, Epi &&epi
         continue;
       }
     }
+    if constexpr (has_tri_stages<It>::value) {
+      const int tmode = cons_it.tri_mode();
+      if (tmode != 0) {
+        const int tg = cons_it.tri_g();
+#pragma unroll
+        for (int mc = 0; mc < 2; ++mc) {
+          const int kk = 2 * tg + mc;
+          // live row slabs R = 2 fm + wm:  lower (mode 1) R >= kk  <=>  fm >= lo;   upper (mode 2) R <= kk  <=>  fm <= hi
+          const int lo = tmode == 1 ? ((kk - wm + 1) >> 1) : 0;
+          const int hi = tmode == 1 ? 7 : ((kk - wm) >> 1);     // arithmetic shift: -1 when kk < wm (nothing live)
+          double2 a[8], b[4];
+#pragma unroll
+          for (int fn = 0; fn < 4; ++fn) b[fn] = lds128(Bs + b_off + fn * 128 + mc * 64);
+#pragma unroll
+          for (int fm = 0; fm < 8; ++fm)
+            if (fm >= lo && fm <= hi) a[fm] = lds128(As + a_off + fm * A_FM_STRIDE + mc * 64);
+#pragma unroll
+          for (int fm = 0; fm < 8; ++fm)
+            if (fm >= lo && fm <= hi) {
+#pragma unroll
+              for (int fn = 0; fn < 4; ++fn) dmma884(acc[fm][fn][0], acc[fm][fn][1], a[fm].x, b[fn].x);
+            }
+#pragma unroll
+          for (int fm = 0; fm < 8; ++fm)
+            if (fm >= lo && fm <= hi) {
+#pragma unroll
+              for (int fn = 0; fn < 4; ++fn) dmma884(acc[fm][fn][0], acc[fm][fn][1], a[fm].y, b[fn].y);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&empty[slot]));
+        const bool t_end = cons_it.tile_end();
+        const int t_id = cons_it.tile();
+        cons_it.next();
+        ++g;
+        if (!SINGLE && t_end) {
+          FragCoord fc{wm, wn, lane, IL};
+          epi(t_id, acc, fc);
+#pragma unroll
+          for (int fm = 0; fm < 8; ++fm)
+#pragma unroll
+            for (int fn = 0; fn < 4; ++fn) acc[fm][fn][0] = acc[fm][fn][1] = 0.0;
+        }
+        continue;
+      }
+    }
 #pragma unroll
     for (int mc = 0; mc < 2; ++mc) {
       double2 a[8], b[4];
 #pragma unroll
-      for (int fm = 0; fm < 8; ++fm) a[fm] = lds128(As + a_off + fm * 128 + mc * 64);
+      for (int fm = 0; fm < 8; ++fm) a[fm] = lds128(As + a_off + fm * A_FM_STRIDE + mc * 64);
 #pragma unroll
       for (int fn = 0; fn < 4; ++fn) b[fn] = lds128(Bs + b_off + fn * 128 + mc * 64);
 #pragma unroll
@@ -232,7 +295,7 @@ __device__ __forceinline__ void gemm_pipeline(It issue_it, It cons_it, Epi &&epi
     cons_it.next();
     ++g;
     if (!SINGLE && tile_end) {
-      FragCoord fc{wm, wn, lane};
+      FragCoord fc{wm, wn, lane, IL};
       epi(tile, acc, fc);
 #pragma unroll
       for (int fm = 0; fm < 8; ++fm)
@@ -241,7 +304,7 @@ __device__ __forceinline__ void gemm_pipeline(It issue_it, It cons_it, Epi &&epi
     }
   }
   if (SINGLE) {
-    FragCoord fc{wm, wn, lane};
+    FragCoord fc{wm, wn, lane, IL};
     epi(0, acc, fc);
   }
 }
@@ -297,9 +360,9 @@ __device__ __forceinline__ void store_block(double *dst, bool transpose, double 
 #pragma unroll
       for (int fn = 0; fn < 4; ++fn) {
         if (transpose)
-          p_store_cfrag_t(dst, 8 * fc.wm + fm, 4 * fc.wn + fn, fc.lane, scale * acc[fm][fn][0], scale * acc[fm][fn][1]);
+          p_store_cfrag_t(dst, fc.rslab(fm), 4 * fc.wn + fn, fc.lane, scale * acc[fm][fn][0], scale * acc[fm][fn][1]);
         else
-          p_store_cfrag(dst, 8 * fc.wm + fm, 4 * fc.wn + fn, fc.lane, scale * acc[fm][fn][0], scale * acc[fm][fn][1]);
+          p_store_cfrag(dst, fc.rslab(fm), 4 * fc.wn + fn, fc.lane, scale * acc[fm][fn][0], scale * acc[fm][fn][1]);
       }
     return;
   }
@@ -329,14 +392,14 @@ __device__ __forceinline__ void rmw_sub_block(double *dst, double (&acc)[8][4][2
 #pragma unroll
   for (int fm = 0; fm < 8; ++fm)
 #pragma unroll
-    for (int fn = 0; fn < 4; ++fn) pr[fm][fn] = p_load_cfrag_raw(dst, 8 * fc.wm + fm, 4 * fc.wn + fn, fc.lane);
+    for (int fn = 0; fn < 4; ++fn) pr[fm][fn] = p_load_cfrag_raw(dst, fc.rslab(fm), 4 * fc.wn + fn, fc.lane);
 #pragma unroll
   for (int fm = 0; fm < 8; ++fm)
 #pragma unroll
     for (int fn = 0; fn < 4; ++fn) {
       double c0, c1;
       p_unpair_cfrag(pr[fm][fn], fc.lane, c0, c1);
-      p_store_cfrag(dst, 8 * fc.wm + fm, 4 * fc.wn + fn, fc.lane, c0 - acc[fm][fn][0], c1 - acc[fm][fn][1]);
+      p_store_cfrag(dst, fc.rslab(fm), 4 * fc.wn + fn, fc.lane, c0 - acc[fm][fn][0], c1 - acc[fm][fn][1]);
     }
 }
 

@@ -30,6 +30,9 @@ struct WtvIt {
   __device__ __forceinline__ const double *B() const { return vt + (size_t)kt * TILE_ELEMS; }
   __device__ __forceinline__ bool tile_end() const { return kt == ktiles - 1; }
   __device__ __forceinline__ int tile() const { return i; }
+  // the first 8 k-tiles of row block i are the diagonal block W_ii^T: upper triangular (gemm_core.cuh, has_tri_stages)
+  __device__ __forceinline__ int tri_mode() const { return kt < (i + 1) * KT_PER_BLOCK ? 2 : 0; }
+  __device__ __forceinline__ int tri_g() const { return kt - i * KT_PER_BLOCK; }
   __device__ __forceinline__ void next() {
     if (kt == ktiles - 1) {
       ++j;

@@ -56,6 +56,35 @@ INVSQRT2 = 1.0 / math.sqrt(2.0)
 INVSQRT2PI = 1.0 / math.sqrt(2.0 * math.pi)
 
 
+# Appendix A items marked "(verify)": details of the un-vendored packages that could not be checked against a Julia
+# install.  The defaults are what SURVEY.md Appendix A states; tests/test_appendixA_sensitivity.py flips each one to
+# measure how far a wrong guess could move a result (the honest size of "parity unpinned").
+VARIANTS = {
+    "distances": "gemm",        # A.3: "gemm" = Distances.jl pairwise GEMM trick | "direct" = sum of squared differences
+    "jitter": DEFAULT_JITTER,   # A.7: observation jitter of post_gp(X*) added to var / diag(cov)
+    "cdf_sigma0_equal": 1.0,    # A.9: cdf(Normal(mu, 0), mu) -- StatsFuns returns 1 ("x >= mu"); 0.5 is the other reading
+}
+
+
+class variant:
+    """Context manager: temporarily switch Appendix A (verify) items, e.g. `with O.variant(distances="direct"): ...`"""
+
+    def __init__(self, **kw):
+        for k in kw:
+            if k not in VARIANTS:
+                raise KeyError(k)
+        self.kw = kw
+
+    def __enter__(self):
+        self.old = {k: VARIANTS[k] for k in self.kw}
+        VARIANTS.update(self.kw)
+        return self
+
+    def __exit__(self, *exc):
+        VARIANTS.update(self.old)
+        return False
+
+
 class DomainError(ValueError):
     """Mirror of Julia's DomainError thrown by `_clip_var` (gaussian_process.jl:191)."""
 
@@ -139,7 +168,7 @@ def kernel_matrix(X1, X2, ls, amp, kernel_id, discrete_mask=None):
     else:
         A = X1 * inv[:, None]
         B = A if sym else X2 * inv[:, None]
-        D = _pairwise_sqdist_gemm(A, B, symmetric=sym)
+        D = _pairwise_sqdist_gemm(A, B, symmetric=sym) if VARIANTS["distances"] == "gemm" else _pairwise_sqdist_direct(A, B)
     return (amp * amp) * _kappa(D, kernel_id)
 
 
@@ -222,7 +251,7 @@ def mean_and_var_raw(post: GPPosterior, Xs, prior_mean_s=None):
     if prior_mean_s is not None:
         mu = np.asarray(prior_mean_s, dtype=np.float64) + mu
     V = sl.solve_triangular(post.U, Ks, trans='T', lower=False, check_finite=False)
-    var = (post.amp * post.amp) - np.sum(V * V, axis=0) + DEFAULT_JITTER
+    var = (post.amp * post.amp) - np.sum(V * V, axis=0) + VARIANTS["jitter"]
     return mu, var
 
 
@@ -363,6 +392,8 @@ def normal_cdf(mu, sigma, x):
         z = (x - mu) / sigma
     z = np.where((sigma == 0.0) & (x == mu), np.inf, z)    # StatsFuns: x == mu, sigma == 0 -> 1
     c = normcdf(z)
+    if VARIANTS["cdf_sigma0_equal"] != 1.0:
+        c = np.where((sigma == 0.0) & (x == mu), VARIANTS["cdf_sigma0_equal"], c)
     return np.where(np.isposinf(x), 1.0, c)
 
 

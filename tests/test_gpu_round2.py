@@ -1,0 +1,321 @@
+"""GPU tests added in round 2: the exact BASELINE config shapes C3 / C5 at parity, device MC-EI for NonlinFitness
+expression sets, pageable-vs-pinned host arrays, caller-stream ordering of the `_dev` entry points, error text per
+thread, handle invalidation by boss_shutdown, and the single-process multi-GPU path (needs >= 2 devices)."""
+import ctypes
+import threading
+
+import numpy as np
+import pytest
+
+from oracle import boss_oracle as O
+from tests.util_problems import make_hyper_samples, make_problem, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE config shapes, exactly (VERDICT r01 weak #1c)
+# ---------------------------------------------------------------------------------------------
+def test_config_c5_exact_shape_parity(lib):
+    """C5: 4 independent GP outputs with y_max constraints, EI x PoF, n = 1024, d = 10."""
+    n, d, y_dim, M = 1024, 10, 4, 8192
+    X, Y, ls, amp, ns = make_problem(n, d, seed=1005, y_dim=y_dim)
+    gps = [lib.gp_fit(X, Y[i], ls[i], amp[i], ns[i], lib.KERNEL_MATERN52) for i in range(y_dim)]
+    posts = [O.posterior_fit(X, Y[i], ls[i], amp[i], ns[i], O.KERNEL_MATERN52) for i in range(y_dim)]
+    y_max = np.array([np.inf] + [float(np.quantile(Y[i], 0.7)) for i in range(1, y_dim)])
+    coefs = np.array([1.0, 0, 0, 0])
+    best = O.best_so_far(coefs, Y, y_max)
+    assert best is not None
+    Xs = np.random.default_rng(5005).random((d, M))
+    acq, bv, bi = lib.ei_score(gps, y_dim, 1, Xs, coefs, best, y_max, lb=np.zeros(d), ub=np.ones(d))
+    ref, mus, vars_ = O.ei_acquisition([posts], Xs, coefs, best, y_max, lb=np.zeros(d), ub=np.ones(d))
+    m = ref > 1e-30 * np.max(ref)          # deeper in the tail EI's relative error is amplified by z^2
+    assert m.sum() > M // 4
+    assert relerr(acq[m], ref[m]) <= 1e-9
+    assert bi == O.julia_argmax_fast(ref)
+    for i in range(y_dim):
+        mu, var, st = lib.gp_predict(gps[i], Xs[:, :2048])
+        assert relerr(var, vars_[0, i, :2048]) <= 1e-9
+        assert np.max(np.abs(mu - mus[0, i, :2048])) <= 1e-9 * np.max(np.abs(mus[0, i]))
+    for g in gps:
+        g.free()
+
+
+@pytest.mark.parametrize("kid", [0, 2])
+def test_config_c3_exact_shape_parity(lib, kid):
+    """C3: batched hyper-parameter posterior, S = 512 samples (one GPU's share of 4096) x loglik(n = 512, d = 6)."""
+    n, d, S = 512, 6, 512
+    X, Y, _, _, _ = make_problem(n, d, seed=1003)
+    L, A, N = make_hyper_samples(S, d, seed=3003)
+    ll = lib.loglik_batch(X, Y[0], L, A, N, kid)
+    ref = O.gp_loglik_batch(X, Y[0], L, A, N, kid)
+    assert np.all(np.isfinite(ref))
+    assert relerr(ll, ref) <= 1e-8
+    assert int(np.argmax(ll)) == int(np.argmax(ref))        # SamplingMAP's pick (sampling.jl:59-78)
+    # bitwise repeatability and independence of the batch composition (the small-matrix path runs several matrices per SM)
+    ll2 = lib.loglik_batch(X, Y[0], L, A, N, kid)
+    assert np.array_equal(ll, ll2)
+    perm = np.random.default_rng(1).permutation(S)[:100]
+    ll3 = lib.loglik_batch(X, Y[0], L[perm], A[perm], N[perm], kid)
+    assert np.array_equal(ll3, ll[perm])
+
+
+@pytest.mark.parametrize("n,d,S,kid", [(100, 3, 300, 2), (129, 2, 64, 0), (256, 6, 200, 1), (300, 4, 77, 2), (384, 8, 130, 0),
+                                       (500, 5, 50, 1)])
+def test_small_matrix_loglik_paths(lib, n, d, S, kid):
+    """n <= 512 (1..4 diagonal blocks): the fused diagonal-block kernel path, every block count and ragged sizes;
+    per-sample targets (Semiparametric) included."""
+    X, Y, _, _, _ = make_problem(n, d, seed=n + S)
+    L, A, N = make_hyper_samples(S, d, seed=S)
+    rng = np.random.default_rng(n)
+    Ys = Y[0][None, :] + 0.1 * rng.standard_normal((S, n))
+    ll = lib.loglik_batch(X, Ys, L, A, N, kid)
+    ref = O.gp_loglik_batch(X, Ys, L, A, N, kid)
+    assert relerr(ll, ref) <= 1e-8
+    llg, grad = lib.loglik_grad_batch(X, Ys, L, A, N, kid)
+    assert relerr(llg, ref) <= 1e-8
+    _, gref = O.gp_loglik_grad_batch(X, Ys[:8], L[:8], A[:8], N[:8], kid)
+    gn = np.linalg.norm(gref, axis=1, keepdims=True)
+    assert np.max(np.abs(grad[:8] - gref) / gn) <= 1e-8
+
+
+# ---------------------------------------------------------------------------------------------
+# device MC-EI for NonlinFitness expression sets
+# ---------------------------------------------------------------------------------------------
+def _fitness(kind, c0, c, q, t):
+    c, q, t = np.asarray(c), np.asarray(q), np.asarray(t)
+    if kind == 1:
+        return lambda y: c0 + float(c @ y)
+    if kind == 2:
+        return lambda y: c0 + float(c @ y) + float(q @ ((y - t) ** 2))
+    live = c != 0
+    if kind == 3:
+        return lambda y: c0 + float(np.max((c * y + t)[live]))
+    return lambda y: c0 + float(np.min((c * y + t)[live]))
+
+
+@pytest.mark.parametrize("kind", [1, 2, 3, 4])
+@pytest.mark.parametrize("with_ymax", [False, True])
+def test_mcei_device_matches_oracle(lib, kind, with_ymax):
+    n, d, y_dim, M, K = 150, 3, 3, 700, 200
+    X, Y, ls, amp, ns = make_problem(n, d, seed=60 + kind, y_dim=y_dim)
+    gps = [lib.gp_fit(X, Y[i], ls[i], amp[i], ns[i], 2) for i in range(y_dim)]
+    posts = [O.posterior_fit(X, Y[i], ls[i], amp[i], ns[i], 2) for i in range(y_dim)]
+    rng = np.random.default_rng(kind)
+    eps = rng.standard_normal((y_dim, K))
+    c0, c, q, t = 0.3, np.array([1.0, -0.5, 0.0]), np.array([0.0, -0.7, 0.2]), np.array([0.1, 0.5, -0.2])
+    f = _fitness(kind, c0, c, q, t)
+    y_max = np.array([np.inf, float(np.quantile(Y[1], 0.8)), np.inf]) if with_ymax else None
+    fit_obs = np.array([f(Y[:, i]) for i in range(n)])
+    feas = np.all(Y <= (y_max if y_max is not None else np.full(y_dim, np.inf))[:, None], axis=0)
+    best = float(np.max(fit_obs[feas]))
+    Xs = rng.random((d, M)) * 1.2 - 0.1
+    lb, ub = np.zeros(d), np.ones(d)
+    acq, bv, bi = lib.mcei_score(gps, y_dim, 1, Xs, kind, eps, best, y_max, c0=c0, c=c, q=q, t=t, lb=lb, ub=ub)
+    ref = O.mc_ei_acquisition([posts], Xs, f, eps, best, y_max, lb=lb, ub=ub)
+    scale = np.max(np.abs(ref))
+    assert np.max(np.abs(acq - ref)) <= 1e-9 * scale
+    assert bi == O.julia_argmax_fast(acq)
+    for g in gps:
+        g.free()
+
+
+def test_mcei_bi_posteriors_take_one_eps_column_each(lib):
+    n, d, y_dim, M, S = 80, 2, 2, 300, 5
+    X, Y, _, _, _ = make_problem(n, d, seed=71, y_dim=y_dim)
+    rng = np.random.default_rng(3)
+    Ls = np.exp(rng.normal(0, 0.3, (S, y_dim, d))); As = np.exp(rng.normal(0, 0.2, (S, y_dim))); Ns = np.full((S, y_dim), 0.1)
+    gps, posts = [], []
+    for s in range(S):
+        gps += [lib.gp_fit(X, Y[i], Ls[s, i], As[s, i], Ns[s, i], 1) for i in range(y_dim)]
+        posts.append([O.posterior_fit(X, Y[i], Ls[s, i], As[s, i], Ns[s, i], 1) for i in range(y_dim)])
+    eps = rng.standard_normal((y_dim, S))
+    c = np.array([1.0, 0.4])
+    f = _fitness(1, 0.0, c, np.zeros(2), np.zeros(2))
+    best = float(np.max(c @ Y))
+    Xs = rng.random((d, M))
+    acq, _, _ = lib.mcei_score(gps, y_dim, S, Xs, 1, eps, best, None, c=c)
+    ref = O.mc_ei_acquisition(posts, Xs, f, eps, best, None)
+    assert np.max(np.abs(acq - ref)) <= 1e-9 * np.max(np.abs(ref))
+    for g in gps:
+        g.free()
+
+
+# ---------------------------------------------------------------------------------------------
+# host staging: pageable == pinned, bit for bit; multi-chunk batches with every optional array
+# ---------------------------------------------------------------------------------------------
+def test_pageable_and_pinned_host_arrays_give_identical_results(lib):
+    torch = pytest.importorskip("torch")
+    n, d, M = 256, 5, 200_000                     # > 2 chunks of 75 776 candidates
+    X, Y, ls, amp, ns = make_problem(n, d, seed=81)
+    gp = lib.gp_fit(X, Y[0], ls[0], amp[0], ns[0], 2)
+    rng = np.random.default_rng(82)
+    Xs = rng.random((d, M)) * 1.1 - 0.05
+    pm = 0.1 * rng.standard_normal((1, M))
+    cm = (rng.random(M) > 0.1).astype(np.uint8)
+    best = float(np.max(Y[0]))
+    lb, ub = np.zeros(d), np.ones(d)
+    a1, bv1, bi1 = lib.ei_score([gp], 1, 1, Xs, [1.0], best, None, lb=lb, ub=ub, cons_mask=cm, prior_mean_s=pm)
+    # the same candidates from pinned memory (d x M view of a pinned M x d tensor)
+    tp = torch.empty((M, d), dtype=torch.float64, pin_memory=True)
+    tp.copy_(torch.from_numpy(np.ascontiguousarray(Xs.T)))
+    a2, bv2, bi2 = lib.ei_score([gp], 1, 1, tp.numpy().T, [1.0], best, None, lb=lb, ub=ub, cons_mask=cm, prior_mean_s=pm)
+    assert np.array_equal(a1, a2) and bv1 == bv2 and bi1 == bi2
+    post = O.posterior_fit(X, Y[0], ls[0], amp[0], ns[0], 2)
+    k = 4096
+    sel = np.r_[0:k, M - k:M]
+    ref, _, _ = O.ei_acquisition([[post]], Xs[:, sel], [1.0], best, None, lb=lb, ub=ub, cons_mask=cm[sel], prior_mean_s=pm[:, sel])
+    m = ref > 1e-30 * np.max(ref)
+    assert relerr(a1[sel][m], ref[m]) <= 1e-9
+    assert bi1 == O.julia_argmax_fast(a1)
+    mu, var, st = lib.gp_predict(gp, Xs, prior_mean_s=pm[0])
+    mu_o, var_o, st_o = O.mean_and_var(post, Xs[:, sel], pm[0, sel])
+    assert relerr(var[sel], var_o) <= 1e-9 and np.max(np.abs(mu[sel] - mu_o)) <= 1e-9 * np.max(np.abs(mu_o))
+    acq_g, grad_g = lib.ei_value_grad([gp], 1, 1, Xs[:, :40_000], [1.0], best, None, lb=lb, ub=ub)
+    assert np.array_equal(acq_g, lib.ei_score([gp], 1, 1, Xs[:, :40_000], [1.0], best, None, lb=lb, ub=ub)[0])
+    gp.free()
+
+
+def test_dev_entry_points_wait_for_the_callers_stream(lib):
+    """The candidates are produced by a long kernel chain on a side stream; the library must not read them early."""
+    torch = pytest.importorskip("torch")
+    n, d, M = 200, 4, 1 << 16
+    X, Y, ls, amp, ns = make_problem(n, d, seed=91)
+    gp = lib.gp_fit(X, Y[0], ls[0], amp[0], ns[0], 2)
+    best = float(np.max(Y[0]))
+    base = torch.rand((M, d), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    ref_bv, ref_bi = lib.ei_score_dev([gp], 1, 1, base.data_ptr(), M, [1.0], best, None)
+    side = torch.cuda.Stream()
+    for trial in range(3):
+        buf = torch.zeros_like(base)
+        big = torch.rand((4096, 4096), device="cuda")
+        torch.cuda.synchronize()
+        with torch.cuda.stream(side):
+            for _ in range(20):                       # keep the side stream busy for a few ms
+                big = big @ big * 1e-3
+            buf.copy_(base)                           # the inputs appear only at the end of that chain
+        bv, bi = lib.ei_score_dev([gp], 1, 1, buf.data_ptr(), M, [1.0], best, None, stream=side.cuda_stream)
+        assert (bv, bi) == (ref_bv, ref_bi)
+    # default (legacy) stream producer, stream=None
+    buf = torch.zeros_like(base)
+    big = torch.rand((4096, 4096), device="cuda")
+    for _ in range(20):
+        big = big @ big * 1e-3
+    buf.copy_(base)
+    bv, bi = lib.ei_score_dev([gp], 1, 1, buf.data_ptr(), M, [1.0], best, None)
+    assert (bv, bi) == (ref_bv, ref_bi)
+    gp.free()
+
+
+def test_last_error_is_per_thread(lib):
+    X, Y, ls, amp, ns = make_problem(10, 2, seed=5)
+    msgs = {}
+
+    def bad_fit(tag, amp_value):
+        out = ctypes.c_void_p()
+        Xc = np.ascontiguousarray(X.T)
+        rc = lib.lib.boss_gp_fit(Xc.ctypes.data_as(ctypes.c_void_p), 2, 10, Y[0].ctypes.data_as(ctypes.c_void_p),
+                                 ls[0].ctypes.data_as(ctypes.c_void_p), amp_value, 0.1, 7 if tag == "b" else 2, None,
+                                 ctypes.byref(out), None)
+        msgs[tag] = (rc, lib.last_error())
+    ta = threading.Thread(target=bad_fit, args=("a", -1.0)); tb = threading.Thread(target=bad_fit, args=("b", 1.0))
+    ta.start(); ta.join(); tb.start(); tb.join()
+    assert msgs["a"][0] < 0 and "negative" in msgs["a"][1]
+    assert msgs["b"][0] < 0 and "kernel_id" in msgs["b"][1]
+
+
+def test_loglik_negative_hyperparameter_is_an_argument_error_and_nan_data_is_minus_inf(lib):
+    X, Y, _, _, _ = make_problem(200, 3, seed=9)
+    L, A, N = make_hyper_samples(6, 3, seed=9)
+    Lbad = L.copy(); Lbad[2, 1] = -0.5
+    with pytest.raises(lib.BossError, match="negative"):
+        lib.loglik_batch(X, Y[0], Lbad, A, N, 2)
+    Ynan = Y[0].copy(); Ynan[17] = np.nan
+    ll = lib.loglik_batch(X, Ynan, L, A, N, 2)
+    assert np.all(np.isnan(ll) | np.isneginf(ll))          # NaN targets: Mahalanobis term NaN (reference: NaN, not an error)
+    Xnan = X.copy(); Xnan[0, 5] = np.nan
+    ll = lib.loglik_batch(Xnan, Y[0], L, A, N, 2)
+    assert np.all(np.isneginf(ll))                          # NaN pivot -> potrf info > 0 -> PosDefException -> -Inf
+
+
+# ---------------------------------------------------------------------------------------------
+# single-process multi-GPU (boss_init_multi): bit-identical to one device
+# ---------------------------------------------------------------------------------------------
+def _n_gpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs >= 2 GPUs")
+def test_multi_gpu_in_library_matches_single_gpu_bit_for_bit(lib):
+    nd = min(_n_gpus(), 8)
+    n, d, M, S = 300, 4, 150_000, 64
+    X, Y, ls, amp, ns = make_problem(n, d, seed=101, y_dim=2)
+    rng = np.random.default_rng(102)
+    Xs = rng.random((d, M))
+    y_max = np.array([np.inf, float(np.quantile(Y[1], 0.7))])
+    coefs = np.array([1.0, 0.0])
+    best = O.best_so_far(coefs, Y, y_max)
+    L, A, N = make_hyper_samples(S, d, seed=103)
+    starts = rng.random((d, 512 * nd))
+    # single device
+    gps = [lib.gp_fit(X, Y[i], ls[i], amp[i], ns[i], 2) for i in range(2)]
+    a1, bv1, bi1 = lib.ei_score(gps, 2, 1, Xs, coefs, best, y_max)
+    _, gbv1, gbi1, gbx1 = lib.ei_score_uniform(gps, 2, 1, 77, M, np.zeros(d), np.ones(d), coefs, best, y_max)
+    mu1, var1, _ = lib.gp_predict(gps[0], Xs)
+    ll1 = lib.loglik_batch(X, Y[0], L, A, N, 2)
+    llg1, gr1 = lib.loglik_grad_batch(X, Y[0], L, A, N, 2)
+    xo1, fo1, bx1, mbv1, mbi1, _ = lib.ei_maximize_multistart(gps, 2, 1, starts, coefs, best, y_max, np.zeros(d), np.ones(d), iters=15)
+    for g in gps:
+        g.free()
+    # the same process now drives nd devices
+    lib.init_multi(nd)
+    assert lib.n_devices() == nd
+    gps = [lib.gp_fit(X, Y[i], ls[i], amp[i], ns[i], 2) for i in range(2)]
+    a2, bv2, bi2 = lib.ei_score(gps, 2, 1, Xs, coefs, best, y_max)
+    _, gbv2, gbi2, gbx2 = lib.ei_score_uniform(gps, 2, 1, 77, M, np.zeros(d), np.ones(d), coefs, best, y_max)
+    mu2, var2, _ = lib.gp_predict(gps[0], Xs)
+    ll2 = lib.loglik_batch(X, Y[0], L, A, N, 2)
+    llg2, gr2 = lib.loglik_grad_batch(X, Y[0], L, A, N, 2)
+    xo2, fo2, bx2, mbv2, mbi2, _ = lib.ei_maximize_multistart(gps, 2, 1, starts, coefs, best, y_max, np.zeros(d), np.ones(d), iters=15)
+    assert np.array_equal(a1, a2) and bv1 == bv2 and bi1 == bi2
+    assert (gbv1, gbi1) == (gbv2, gbi2) and np.array_equal(gbx1, gbx2)
+    assert np.array_equal(mu1, mu2) and np.array_equal(var1, var2)
+    assert np.array_equal(ll1, ll2) and np.array_equal(llg1, llg2) and np.array_equal(gr1, gr2)
+    # the starts are independent local solves: the sharded run reproduces every start's end point
+    assert np.array_equal(fo1, fo2) and np.array_equal(xo1, xo2) and (mbv1, mbi1) == (mbv2, mbi2)
+    # replicas are bit-identical, and an append keeps them in step
+    for k in range(nd):
+        lib.set_device(k)
+        Lk, Wk, ak = lib.dbg_factors(gps[0])
+        if k == 0:
+            L0, W0, a0 = Lk, Wk, ak
+        assert np.array_equal(Lk, L0) and np.array_equal(Wk, W0) and np.array_equal(ak, a0)
+    lib.set_device(-1)
+    assert lib.gp_append(gps[0], rng.random(d), 0.3)
+    a3, _, _ = lib.ei_score(gps, 2, 1, Xs, coefs, best, y_max)
+    lib.set_device(0)
+    a4, _, _ = lib.ei_score(gps, 2, 1, Xs, coefs, best, y_max)        # pinned to device 0: single-device path
+    lib.set_device(-1)
+    assert np.array_equal(a3, a4)
+    for g in gps:
+        g.free()
+
+
+def test_zzz_shutdown_invalidates_live_handles(lib):
+    """Last test of the session: boss_shutdown with a live handle; the handle then fails cleanly and can be freed."""
+    X, Y, ls, amp, ns = make_problem(50, 2, seed=3)
+    gp = lib.gp_fit(X, Y[0], ls[0], amp[0], ns[0], 2)
+    lib.shutdown()
+    with pytest.raises(lib.BossError):
+        lib.gp_predict(gp, X)
+    gp.free()
+    lib.init(0)
+    gp = lib.gp_fit(X, Y[0], ls[0], amp[0], ns[0], 2)
+    mu, _, _ = lib.gp_predict(gp, X)
+    assert np.all(np.isfinite(mu))
+    gp.free()
