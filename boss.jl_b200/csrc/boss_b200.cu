@@ -294,6 +294,7 @@ int set_kernel_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(score_trmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(wtv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(potrf_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM_BYTES));
   C().attrs_done = true;
   return 0;
 }
@@ -312,9 +313,16 @@ struct FwdInline {
   double *r, *w;       // [S][n_pad] scratch / result
   double *ssq;         // [S][nblk]
 };
+// gen non-null (left-looking only): the diagonal-block kernel forms its own input tile (potrf_fused_kernel: K_jj from
+// the hyper-parameters minus the SYRK of row block j) -- build_k must then have been launched with skip_diag.
+bool unfused_diag() {
+  static const bool v = getenv("BOSS_UNFUSED_DIAG") != nullptr;   // A/B knob: the round-1 three-kernel diagonal step
+  return v;
+}
 int run_cholesky(double *L, size_t L_stride, double *Winv, size_t Winv_stride, int nblk, int ktiles, int S,
                  double *logdet_blk, int *status, double *W, double *WT, double *TT, size_t W_stride = 0,
-                 size_t TT_stride = 0, bool single_fit = false, const FwdInline *fwd = nullptr) {
+                 size_t TT_stride = 0, bool single_fit = false, const FwdInline *fwd = nullptr,
+                 const BuildKParams *gen = nullptr, int gen_kid = 0, int gen_dp = 0, bool store_L = true) {
   CholGemmParams gp{};
   gp.L = L;
   gp.L_stride = L_stride;
@@ -356,18 +364,37 @@ int run_cholesky(double *L, size_t L_stride, double *Winv, size_t Winv_stride, i
   // Only the posterior fit takes this path: batched log-likelihoods always run left-looking, so a sample's value
   // never depends on how the batch was split (over sub-batches, streams or GPUs).
   const bool right_looking = single_fit && (long long)S * nblk <= 148;
+  const bool fused_diag = gen != nullptr && !right_looking;
+  if (fused_diag) {
+    pp.gen_X = gen->X;
+    pp.gen_d = gen->d;
+    pp.gen_dp = gen_dp;
+    pp.gen_n = gen->n;
+    pp.gen_kid = gen_kid;
+    pp.gen_ls = gen->ls;
+    pp.gen_amp = gen->amp;
+    pp.gen_noise = gen->noise;
+    pp.gen_disc = gen->disc_bits;
+    pp.store_L = store_L ? 1 : 0;
+  }
   for (int j = 0; j < nblk; ++j) {
     gp.j = j;
     pp.j = j;
-    // left-looking, column j >= 1: SYRK of the diagonal tile -> potrf -> fused update + panel solve of the rows below
+    // left-looking, column j >= 1: SYRK of the diagonal tile + potrf (one kernel) -> fused update + panel solve of the rows below
     const bool fused_panel = j > 0 && !right_looking;
-    if (fused_panel) {
+    if (fused_diag) {
       Timed t(2);
-      chol_update_kernel<<<dim3(1, S), GEMM_THREADS, GEMM_SMEM_BYTES, C().stream>>>(gp);
+      potrf_fused_kernel<<<S, 256, PF_SMEM_BYTES, C().stream>>>(pp);
+      ++C().launches;
+    } else {
+      if (fused_panel) {
+        Timed t(2);
+        chol_update_kernel<<<dim3(1, S), GEMM_THREADS, GEMM_SMEM_BYTES, C().stream>>>(gp);
+        ++C().launches;
+      }
+      potrf_tile_kernel<<<S, 256, PT_SMEM_BYTES, C().stream>>>(pp);
       ++C().launches;
     }
-    potrf_tile_kernel<<<S, 256, PT_SMEM_BYTES, C().stream>>>(pp);
-    ++C().launches;
     if (j < nblk - 1) {
       Timed t(2);
       if (fused_panel)
@@ -2176,7 +2203,9 @@ static int loglik_core(const double *X, int d, int n, const double *Ymm, int64_t
       bk.K = Lg;
       bk.K_stride = mat;
       bk.status = stg;
-      {
+      const bool fuse_diag = !unfused_diag();
+      bk.skip_diag = fuse_diag ? 1 : 0;     // the diagonal tiles are generated inside potrf_fused_kernel
+      if (!(fuse_diag && nblk == 1)) {
         Timed t(1);
         launch_build_k(kernel_id, dp, bk, dim3(nblk * (nblk + 1) / 2, gs), C().stream);
         ++C().launches;
@@ -2187,7 +2216,8 @@ static int loglik_core(const double *X, int d, int n, const double *Ymm, int64_t
       }
       FwdInline fw{dY + (ldy ? (size_t)so * ldy : 0), ldy, n, n_pad, misc + orv + (size_t)wo * n_pad,
                    misc + owv + (size_t)wo * n_pad, misc + ossq + (size_t)wo * nblk};
-      int rc = run_cholesky(Lg, mat, Wig, winv_stride, nblk, ktiles, gs, ldg, stg, Wg, WTg, TTg, mat, tt_stride, false, &fw);
+      int rc = run_cholesky(Lg, mat, Wig, winv_stride, nblk, ktiles, gs, ldg, stg, Wg, WTg, TTg, mat, tt_stride, false, &fw,
+                            fuse_diag ? &bk : nullptr, kernel_id, dp, fit_out != nullptr);
       if (rc) rc_all = rc;
       loglik_finish_kernel<<<(gs + 127) / 128, 128, 0, C().stream>>>(ldg, fw.ssq, stg, nblk, n, gs, dll + so);
       ++C().launches;

@@ -20,6 +20,7 @@
 // (src/models/gaussian_process.jl:199-211, :269-280).
 #pragma once
 #include "common.cuh"
+#include "kernel_fn.cuh"
 
 namespace boss {
 
@@ -41,11 +42,24 @@ struct PotrfParams {
   const double *fwd_r;     // [S][n_pad]
   double *fwd_w;           // [S][n_pad]
   double *fwd_ssq;         // [S][nblk]  |w_j|^2
+  // fused diagonal step (potrf_fused_kernel, the left-looking batch paths): the CTA forms its own input tile
+  //   A_jj = K_jj - sum_{k<j} L_jk L_jk^T
+  // K_jj from the hyper-parameters (what build_k_kernel would have written), the SYRK from row block j of L, and
+  // r_j = sum_{k<j} L_jk w_k of the forward substitution from the same stream of tiles; nothing of it touches HBM.
+  const double *gen_X;     // d x n raw training inputs
+  int gen_d, gen_dp, gen_n, gen_kid;
+  const double *gen_ls, *gen_amp, *gen_noise;   // per-matrix raw hyper-parameters
+  unsigned long long gen_disc;
+  int store_L;             // also write L_jj back to global (batched posterior fit: L is part of the handle)
 };
 
 constexpr int PT_TILES = 136;                        // 16*17/2 lower micro-tiles
 constexpr int PT_TMP_ELEMS = 64 * 64;                // scratch for the inverse products (one 64x64 block)
 constexpr int PT_SMEM_BYTES = (PT_TILES * 64 + PT_TMP_ELEMS + 128 + 128 + 8 + 128 + 8) * 8;   // 105 600 B -> 2 CTAs / SM
+// the fused kernel adds: 12 mbarriers (16 doubles), the exp table (32), 1/l (32), per-row forward-substitution sums (128)
+constexpr int PF_RING_STAGES = 6;                    // 6 x 16 KB single-tile stages live in the (not yet used) T | tmp area
+constexpr int PF_EXTRA_ELEMS = 16 + EXPTAB_N + 32 + 128;
+constexpr int PF_SMEM_BYTES = PT_SMEM_BYTES + PF_EXTRA_ELEMS * 8;   // 107 264 B -> still 2 CTAs / SM
 
 // (I, J) of the t-th packed lower micro-tile
 struct PtIJ {
@@ -83,7 +97,60 @@ __device__ __forceinline__ int pt_cpos(int lane, int e) {
   return (r << 3) + ((q & 1) << 2) + (e << 1) + (q >> 1);
 }
 
-__global__ void __launch_bounds__(256, 2) potrf_tile_kernel(PotrfParams p) {
+// K values of the thread's 17 live micro-tiles of the diagonal block (accumulator fragment positions), minus the SYRK
+// accumulators, into the packed tile store.  Same arithmetic as build_k_kernel followed by chol_update_kernel's
+// `A - acc`, so the fused path reproduces the unfused one bit for bit.
+// On entry the tile store holds the SYRK accumulators at the same positions (the loop over the tiles is not unrolled,
+// and a dynamically indexed accumulator array would be demoted to local memory for the whole kernel).
+template <int KID>
+__device__ __forceinline__ void pf_generate_tile(double *T, const double *xs, int dp, int warp, int lane, int row0, int n,
+                                                 double a2, double s2, const double *etab) {
+#pragma unroll 1
+  for (int t = 0; t < 17; ++t) {
+    const int R = t < 16 - warp ? warp + t : t - 1, Cs = t < 16 - warp ? warp : 15 - warp;
+    const int r = 8 * R + (lane >> 2), c0 = 8 * Cs + 2 * (lane & 3);
+    const double *xr = xs + r * dp, *xc = xs + c0 * dp;
+    double d20 = 0.0, d21 = 0.0;
+    for (int i = 0; i < dp; ++i) {
+      const double x = xr[i], df0 = x - xc[i], df1 = x - xc[dp + i];
+      d20 = fma(df0, df0, d20);
+      d21 = fma(df1, df1, d21);
+    }
+    double v0 = a2 * kappa_fast<KID>(d20, etab), v1 = a2 * kappa_fast<KID>(d21, etab);
+    const int gi = row0 + r, gj = row0 + c0;
+    if (gi < n && gj < n) {
+      if (gi == gj) v0 += s2;
+    } else {
+      v0 = (gi == gj) ? 1.0 : 0.0;   // identity padding: L_pad = I, log-det contribution 0
+    }
+    if (gi < n && gj + 1 < n) {
+      if (gi == gj + 1) v1 += s2;
+    } else {
+      v1 = (gi == gj + 1) ? 1.0 : 0.0;
+    }
+    double *dst = T + ((R * (R + 1)) / 2 + Cs) * 64;
+    dst[pt_cpos(lane, 0)] = v0 - dst[pt_cpos(lane, 0)];
+    dst[pt_cpos(lane, 1)] = v1 - dst[pt_cpos(lane, 1)];
+  }
+}
+
+// live micro-tiles T0 .. T1-1 of the warp, one k micro-step (8 wide): fragments, then both halves of the DMMAs
+template <int T0, int T1>
+__device__ __forceinline__ void pf_syrk_batch(double (&acc)[17][2], const double *st, int warp, int n0, double2 b0, double2 b1) {
+  double2 a[T1 - T0];
+#pragma unroll
+  for (int t = T0; t < T1; ++t) a[t - T0] = lds128(st + (t < n0 ? warp + t : t - 1) * 128);
+#pragma unroll
+  for (int t = T0; t < T1; ++t) dmma884(acc[t][0], acc[t][1], a[t - T0].x, t < n0 ? b0.x : b1.x);
+#pragma unroll
+  for (int t = T0; t < T1; ++t) dmma884(acc[t][0], acc[t][1], a[t - T0].y, t < n0 ? b0.y : b1.y);
+}
+
+// FUSED = false: the diagonal tile is read from global memory (posterior fit, right-looking steps).
+// FUSED = true : the CTA generates K_jj, subtracts the SYRK of row block j of L (streamed through a 6-stage TMA ring
+//                that lives in the tile store before it is needed) and carries the forward substitution's r_j.
+template <bool FUSED>
+__device__ __forceinline__ void potrf_tile_body(const PotrfParams &p) {
   extern __shared__ __align__(16) double sm[];
   double *T = sm;                          // [136][64] packed lower tiles: A -> L -> W
   double *tmp = sm + PT_TILES * 64;        // [64][64] as 8x8 tiles (row-major tile grid, 8 tiles per row)
@@ -94,10 +161,10 @@ __global__ void __launch_bounds__(256, 2) potrf_tile_kernel(PotrfParams p) {
   const int s_mat = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double *blk = p.L + (size_t)s_mat * p.L_stride + ((size_t)p.j * p.ktiles + (size_t)p.j * KT_PER_BLOCK) * TILE_ELEMS;
 
-  // ---- load the lower block triangle: 136 micro-tiles of 512 B, one per warp pass (coalesced 16 B per lane;
-  //      all 17 loads of a thread are in flight together) ----
   if (tid == 0) *flag = 0;
-  {
+  if constexpr (!FUSED) {
+    // ---- load the lower block triangle: 136 micro-tiles of 512 B, one per warp pass (coalesced 16 B per lane;
+    //      all 17 loads of a thread are in flight together) ----
     double2 buf[PT_TILES / 8];
 #pragma unroll
     for (int k = 0; k < PT_TILES / 8; ++k) {
@@ -106,6 +173,139 @@ __global__ void __launch_bounds__(256, 2) potrf_tile_kernel(PotrfParams p) {
     }
 #pragma unroll
     for (int k = 0; k < PT_TILES / 8; ++k) *reinterpret_cast<double2 *>(T + (warp + 8 * k) * 64 + 2 * lane) = buf[k];
+  } else {
+    uint64_t *bars = reinterpret_cast<uint64_t *>(fv + 136);          // full[6], empty[6]
+    double *etab = fv + 136 + 16;
+    double *invl = etab + EXPTAB_N;
+    double *rsum = invl + 32;                                         // [128] r_j = sum_{k<j} L_jk w_k
+    exptab_init(etab);
+    if (tid >= 32 && tid < 64) {
+      const int i = tid - 32;
+      double l = (i < p.gen_d) ? p.gen_ls[(size_t)s_mat * p.gen_d + i] : 1.0;
+      if (i < p.gen_d && !(l >= 0.0)) p.status[s_mat] = -1;
+      invl[i] = (i < p.gen_d) ? 1.0 / (l + MIN_PARAM_VALUE) : 0.0;
+    }
+    const double a_raw = p.gen_amp[s_mat], s_raw = p.gen_noise[s_mat];
+    if (tid == 64 && (!(a_raw >= 0.0) || !(s_raw >= 0.0))) p.status[s_mat] = -1;
+    const double amp = a_raw + MIN_PARAM_VALUE, sn = s_raw + MIN_PARAM_VALUE;
+    double acc[17][2];
+#pragma unroll
+    for (int t = 0; t < 17; ++t) acc[t][0] = acc[t][1] = 0.0;
+    if (p.j > 0) {
+      // ---- SYRK of the diagonal tile: both operands are row block j of L, so a stage is ONE 16 KB macro-tile ----
+      uint64_t *full = bars, *empty = bars + PF_RING_STAGES;
+      if (tid < 2 * PF_RING_STAGES) {
+        if (tid < PF_RING_STAGES)
+          mbar_init(smem_u32(&full[tid]), 1);
+        else
+          mbar_init(smem_u32(&empty[tid - PF_RING_STAGES]), 8);
+        mbar_fence_init();
+      }
+      __syncthreads();
+      const double *src = p.L + (size_t)s_mat * p.L_stride + (size_t)p.j * p.ktiles * TILE_ELEMS;
+      const int nk = p.j * KT_PER_BLOCK;
+      int issued = 0;
+      auto try_issue = [&](bool blocking) -> bool {
+        const int slot = issued % PF_RING_STAGES;
+        if (issued >= PF_RING_STAGES) {
+          const uint32_t eb = smem_u32(&empty[slot]);
+          const uint32_t par = (uint32_t)((issued / PF_RING_STAGES - 1) & 1);
+          if (blocking)
+            mbar_wait(eb, par);
+          else if (!mbar_try_wait(eb, par))
+            return false;
+        }
+        const uint32_t bar = smem_u32(&full[slot]);
+        mbar_arrive_expect_tx(bar, TILE_BYTES);
+        bulk_g2s(smem_u32(sm + (size_t)slot * TILE_ELEMS), src + (size_t)issued * TILE_ELEMS, TILE_BYTES, bar);
+        ++issued;
+        return true;
+      };
+      if (tid == 0)
+        while (issued < nk && issued < PF_RING_STAGES) try_issue(false);
+      const int n0 = 16 - warp, c4 = lane & 3;
+      const int b0off = warp * 128 + 2 * lane, b1off = (15 - warp) * 128 + 2 * lane;
+      const bool fwd = p.fwd_w != nullptr;
+      const double *wv = fwd ? p.fwd_w + (size_t)s_mat * p.n_pad + c4 : nullptr;
+      double r0 = 0.0, r1 = 0.0;
+      for (int g = 0; g < nk; ++g) {
+        const int slot = g % PF_RING_STAGES;
+        if (tid == 0) {
+          while (issued < nk && issued < g + PF_RING_STAGES) {
+            if (!try_issue(issued <= g)) break;
+          }
+        }
+        mbar_wait(smem_u32(&full[slot]), (uint32_t)((g / PF_RING_STAGES) & 1));
+        const double *st = sm + (size_t)slot * TILE_ELEMS;
+#pragma unroll
+        for (int mc = 0; mc < 2; ++mc) {
+          const double2 b0 = lds128(st + b0off + mc * 64), b1 = lds128(st + b1off + mc * 64);
+          // two batches of fragments (9 + 8 tiles) keep the kernel inside its 128-register budget (2 CTAs / SM)
+          pf_syrk_batch<0, 9>(acc, st + 2 * lane + mc * 64, warp, n0, b0, b1);
+          pf_syrk_batch<9, 17>(acc, st + 2 * lane + mc * 64, warp, n0, b0, b1);
+          if (mc == 1) {
+            if (fwd) {
+              // warp w owns micro-rows 2w and 2w+1 of the row block; lane T holds (row T/4, k = T%4 and 4 + T%4)
+              const double *ar = st + (4 * warp) * 64 + 2 * lane;
+              const double *wk = wv + g * 16;
+              const double w0 = wk[0], w1 = wk[4], w2 = wk[8], w3 = wk[12];
+              const double2 a00 = lds128(ar), a01 = lds128(ar + 64), a10 = lds128(ar + 128), a11 = lds128(ar + 192);
+              r0 = fma(a00.x, w0, r0);
+              r0 = fma(a00.y, w1, r0);
+              r0 = fma(a01.x, w2, r0);
+              r0 = fma(a01.y, w3, r0);
+              r1 = fma(a10.x, w0, r1);
+              r1 = fma(a10.y, w1, r1);
+              r1 = fma(a11.x, w2, r1);
+              r1 = fma(a11.y, w3, r1);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&empty[slot]));
+          }
+        }
+      }
+      if (fwd) {
+        r0 += __shfl_xor_sync(0xffffffffu, r0, 1);
+        r0 += __shfl_xor_sync(0xffffffffu, r0, 2);
+        r1 += __shfl_xor_sync(0xffffffffu, r1, 1);
+        r1 += __shfl_xor_sync(0xffffffffu, r1, 2);
+        if (c4 == 0) {
+          rsum[16 * warp + (lane >> 2)] = r0;
+          rsum[16 * warp + 8 + (lane >> 2)] = r1;
+        }
+      }
+    } else if (tid < 128) {
+      rsum[tid] = 0.0;
+    }
+    __syncthreads();   // every warp is through the ring: the tile store and tmp are free
+    // ---- scaled (and rounded) training inputs of this block into tmp, then K_jj - acc into the tile store ----
+    const int dp = p.gen_dp, row0 = p.j * 128;
+    for (int e = tid; e < 128 * dp; e += 256) {
+      const int rr = e / dp, i = e - rr * dp, gi = row0 + rr;
+      double v = 0.0;
+      if (gi < p.gen_n && i < p.gen_d) {
+        v = p.gen_X[(size_t)gi * p.gen_d + i];
+        if ((p.gen_disc >> i) & 1ull) v = rint(v);
+        v *= invl[i];
+      }
+      tmp[e] = v;
+    }
+    __syncthreads();
+    // accumulators -> tile store (static indices), each thread re-reads only its own elements below
+#pragma unroll
+    for (int t = 0; t < 17; ++t) {
+      const int R = t < 16 - warp ? warp + t : t - 1, Cs = t < 16 - warp ? warp : 15 - warp;
+      double *dst = T + ((R * (R + 1)) / 2 + Cs) * 64;
+      dst[pt_cpos(lane, 0)] = acc[t][0];
+      dst[pt_cpos(lane, 1)] = acc[t][1];
+    }
+    const double a2 = amp * amp, s2 = sn * sn;
+    if (p.gen_kid == 0)
+      pf_generate_tile<0>(T, tmp, dp, warp, lane, row0, p.gen_n, a2, s2, etab);
+    else if (p.gen_kid == 1)
+      pf_generate_tile<1>(T, tmp, dp, warp, lane, row0, p.gen_n, a2, s2, etab);
+    else
+      pf_generate_tile<2>(T, tmp, dp, warp, lane, row0, p.gen_n, a2, s2, etab);
   }
   __syncthreads();
 
@@ -222,10 +422,12 @@ __global__ void __launch_bounds__(256, 2) potrf_tile_kernel(PotrfParams p) {
 
   // ---- log L_kk in parallel, L -> global (upper part zero); the fixed-order sum runs on an idle thread below ----
   if (tid < 128) lg[tid] = -log(dinv[tid]);
-  for (int e = 2 * tid; e < TM * TM; e += 512) {   // 16 B per lane, a micro-tile per warp pass
-    const int kt = e >> 11, micro = (e >> 6) & 31, w = e & 63;
-    const int I = micro >> 1, J = (kt << 1) + (micro & 1);
-    *reinterpret_cast<double2 *>(blk + e) = (J <= I) ? lds128(T + pt_tile(I, J) + w) : make_double2(0.0, 0.0);
+  if (!FUSED || p.store_L) {   // the left-looking batch paths never read L_jj again (only Winv_jj)
+    for (int e = 2 * tid; e < TM * TM; e += 512) {   // 16 B per lane, a micro-tile per warp pass
+      const int kt = e >> 11, micro = (e >> 6) & 31, w = e & 63;
+      const int I = micro >> 1, J = (kt << 1) + (micro & 1);
+      *reinterpret_cast<double2 *>(blk + e) = (J <= I) ? lds128(T + pt_tile(I, J) + w) : make_double2(0.0, 0.0);
+    }
   }
   __syncthreads();
   if (tid == 255) {
@@ -368,7 +570,12 @@ __global__ void __launch_bounds__(256, 2) potrf_tile_kernel(PotrfParams p) {
     if (tid < 128) {
       const int row = p.j * 128 + tid;
       const double dl = (row < p.fwd_n) ? p.fwd_ymm[(size_t)s_mat * p.fwd_ldy + row] : 0.0;
-      fv[tid] = dl - (p.j > 0 ? p.fwd_r[(size_t)s_mat * p.n_pad + row] : 0.0);
+      double rj;
+      if constexpr (FUSED)
+        rj = (fv + 136 + 16 + EXPTAB_N + 32)[tid];
+      else
+        rj = p.j > 0 ? p.fwd_r[(size_t)s_mat * p.n_pad + row] : 0.0;
+      fv[tid] = dl - rj;
     }
     __syncthreads();
     // warp w: micro-rows 2w, 2w+1; lane T holds (row T/4, columns T%4 and 4 + T%4) of each 8x8 tile
@@ -402,5 +609,8 @@ __global__ void __launch_bounds__(256, 2) potrf_tile_kernel(PotrfParams p) {
     }
   }
 }
+
+__global__ void __launch_bounds__(256, 2) potrf_tile_kernel(PotrfParams p) { potrf_tile_body<false>(p); }
+__global__ void __launch_bounds__(256, 2) potrf_fused_kernel(PotrfParams p) { potrf_tile_body<true>(p); }
 
 }  // namespace boss

@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(256) build_k_kernel(BuildKParams p) {
     ++rb;
   }
   const int cb = t;
+  if (p.skip_diag && rb == cb) return;
   const int tid = threadIdx.x;
   if (tid < DP) {
     double l = (tid < p.d) ? p.ls[(size_t)s * p.d + tid] : 1.0;

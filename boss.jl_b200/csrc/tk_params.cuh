@@ -17,6 +17,7 @@ struct BuildKParams {
   double *K;                // S matrices, P-layout, stride K_stride
   size_t K_stride;
   int *status;              // S; set to -1 on negative hyper-parameters (reference asserts)
+  int skip_diag;            // diagonal tiles are produced elsewhere (potrf_fused_kernel generates K_jj on chip)
 };
 
 struct LlGradParams {
