@@ -6,7 +6,8 @@ M = 2 Mi candidates per GPU, n = 2048 training points, d = 8, Matern52 ARD  (16 
 weak scaling, candidates sharded by contiguous block, (best value, index) pairs all-gathered over NCCL).
 A "step" = one scoring pass over the rank's candidates.  `value` = candidates/s with candidates resident
 in HBM; `e2e` = the same through the host-pointer C-ABI call (pinned host candidates, H2D inside the
-timed region, D2H of the argmax pair).  The second headline metric, batched GP log-likelihood evals/s at
+timed region, D2H of the argmax pair; `e2e.pageable` = the same from ordinary pageable host memory).  The FP64 roofline
+denominator (cuBLAS DGEMM 8192^3) is measured inside this run.  The second headline metric, batched GP log-likelihood evals/s at
 n = 2048, d = 8 (S = 256 hyper-parameter vectors per GPU per step), is reported under "loglik".
 
 `--impl reference` times the CPU restatement of the reference path (oracle/, numpy + OpenBLAS with all host
@@ -35,14 +36,43 @@ F_LLG = N_TRAIN ** 3 + N_TRAIN * (N_TRAIN + 1) // 2 * (6 * X_DIM + 14) + 3 * N_T
 CPU_SAMPLE_M = 8192
 
 
-def fp64_peak():
-    """Measured cuBLAS DGEMM TFLOP/s on this pool's B200 (profiles/fp64_peaks_r01.json); MEASURED_PEAKS.json
-    only carries HBM and bf16 figures."""
+def fp64_peak_static():
+    """cuBLAS DGEMM TFLOP/s measured on this pool's B200 in round 1 (profiles/fp64_peaks_r01.json); MEASURED_PEAKS.json
+    only carries HBM and bf16 figures.  Used only if the in-run measurement below fails."""
     try:
         with open(os.path.join(ROOT, "profiles", "fp64_peaks_r01.json")) as f:
-            return float(json.load(f)["fp64_tflops_peak_used"]), "measured cuBLAS DGEMM 8192^3 (profiles/fp64_peaks_r01.json)"
+            return float(json.load(f)["fp64_tflops_peak_used"]), "round-1 file profiles/fp64_peaks_r01.json (cuBLAS DGEMM 8192^3)"
     except Exception:
         return 37.0, "fallback: nominal B200 FP64 (no measured DGEMM file)"
+
+
+def measure_dgemm_peak(torch, sustained_s=3.0):
+    """The FP64 roofline denominator, measured in THIS run: cuBLAS DGEMM 8192^3 through torch.matmul(float64), CUDA events
+    on torch's current stream.  burst = best of 10 single GEMMs; sustained = back-to-back GEMMs for `sustained_s` seconds."""
+    n = 8192
+    a = torch.rand((n, n), dtype=torch.float64, device="cuda"); b = torch.rand((n, n), dtype=torch.float64, device="cuda")
+    c = torch.empty((n, n), dtype=torch.float64, device="cuda")
+    flop = 2.0 * n ** 3
+    for _ in range(3):
+        torch.matmul(a, b, out=c)
+    torch.cuda.synchronize()
+    best = 0.0
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, b, out=c); e1.record(); torch.cuda.synchronize()
+        best = max(best, flop / (e0.elapsed_time(e1) * 1e-3) * 1e-12)
+    per = flop / (best * 1e12)
+    reps = max(4, int(sustained_s / per))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        torch.matmul(a, b, out=c)
+    e1.record(); torch.cuda.synchronize()
+    sus = flop * reps / (e0.elapsed_time(e1) * 1e-3) * 1e-12
+    del a, b, c
+    torch.cuda.empty_cache()
+    return {"burst_tflops": best, "sustained_tflops": sus, "sustained_reps": reps,
+            "how": "cuBLAS DGEMM 8192^3 via torch.matmul(float64), CUDA events, in this run"}
 
 
 def make_problem():
@@ -128,14 +158,24 @@ def run_reference(args):
         cpu_score_once(post, Xs, best)
     dt = (time.perf_counter() - t0) / args.steps
     val = CPU_SAMPLE_M / dt
+    # mode A beside it: what BOSS.jl's maximizers actually do - one candidate per call (grid.jl:52-53)
+    t1 = time.perf_counter(); k = 0
+    while time.perf_counter() - t1 < 3.0 and k < 2000:
+        cpu_score_once(post, Xs[:, k % CPU_SAMPLE_M][:, None], best); k += 1
+    mode_a = k / (time.perf_counter() - t1)
     cb = {"value": val, "unit": "candidates/s", "cores": cpu_threads(), "kind": "port",
           "sample": f"each step = one {CPU_SAMPLE_M}-candidate batched tile (mode B, level-3 BLAS, all host threads) of the "
-                    f"2 Mi-candidate per-GPU workload; oracle port - the Julia reference cannot run in this image"}
+                    f"2 Mi-candidate per-GPU workload; oracle port - the Julia reference cannot run in this image",
+          "one_candidate_per_call_value": mode_a,
+          "note": "mode B (batched matrix API) is the best case for the CPU; mode A is the access pattern BOSS.jl ships"}
     print(file=args.out, flush=True, *[json.dumps({
         "impl": "reference", "metric": "EI candidate evals/sec (n=2048,d=8)", "value": val, "unit": "candidates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.gpus), "cpu_baseline": cb,
+        "config": dict(workload_config(args.gpus), candidates_per_step=CPU_SAMPLE_M,
+                       reference_sample="one 8192-candidate tile per step (a bounded sample of the 2 Mi-candidate share; "
+                                        "throughput is per candidate, so the sample size does not change it)"),
+        "cpu_baseline": cb,
         "e2e": {"value": val, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})])
 
 
@@ -226,6 +266,7 @@ def run_gpu(args):
     Xs_host = torch.empty((M, X_DIM), dtype=torch.float64, pin_memory=True)
     Xs_host.copy_(Xs_dev)
     Xs_np = Xs_host.numpy().T                                 # d x M view, no copy (pinned)
+    Xs_pageable = np.array(Xs_host.numpy(), copy=True).T      # ordinary pageable memory: what a Julia Matrix{Float64} is
 
     # loglik workload: S hyper-parameter vectors per GPU
     from tests.util_problems import make_hyper_samples
@@ -260,6 +301,10 @@ def run_gpu(args):
 
     def step_e2e():
         acq, bv, bi = _lib.ei_score([gp], 1, 1, Xs_np, [1.0], best, None, want_acq=False)
+        return reduce_pairs(bv, bi)
+
+    def step_e2e_pageable():
+        acq, bv, bi = _lib.ei_score([gp], 1, 1, Xs_pageable, [1.0], best, None, want_acq=False)
         return reduce_pairs(bv, bi)
 
     def step_loglik():
@@ -307,6 +352,7 @@ def run_gpu(args):
     xcov_ms, xcov_cnt = _lib.last_kernel_ms(1)
     _lib.set_timing(False)
     ms_e2e, _, res_e2e = timed(step_e2e, args.steps, args.warmup)
+    ms_e2e_pg, _, res_e2e_pg = timed(step_e2e_pageable, max(2, args.steps // 2), 3)
     ms_ll, launches_ll, _ = timed(step_loglik, max(2, args.steps // 2), 3)   # 4 concurrent sub-batch streams
     _lib.set_timing(True)                                                     # per-kernel-class events: one stream
     ms_ll_serial, _, _ = timed(step_loglik, 2, 3)
@@ -314,9 +360,24 @@ def run_gpu(args):
     _lib.set_timing(False)
     ms_llg, launches_llg, _ = timed(step_loglik_grad, max(2, args.steps // 2), 3)
     clocks = sampler.stop() if sampler else None
+    try:
+        dg = measure_dgemm_peak(torch)          # every rank (keeps the ranks in step); rank 0 reports
+    except Exception as e:                      # noqa: BLE001
+        dg = {"error": repr(e)}
+    cfgs = None
+    if not args.no_configs:
+        # per-GPU shares of BASELINE configs C3 / C4 / C5 (device-resident, oracle parity spot checks inside); at N > 1
+        # every rank runs its share and the times are the max over ranks
+        from tools import bench_configs
+        cfgs = bench_configs.run_all(torch, _lib, lib_stream, steps=3, dist=dist if world > 1 else None, world=world,
+                                     peak_tflops=dg.get("burst_tflops"))
 
     if rank == 0:
-        peak, peak_src = fp64_peak()
+        if "burst_tflops" in dg:
+            peak, peak_src = dg["burst_tflops"], ("cuBLAS DGEMM 8192^3 measured in this run (burst = best of 10; the "
+                                                  "sustained figure is in roofline.dgemm)")
+        else:
+            peak, peak_src = fp64_peak_static()
         per_launch_cands = M / max(trmm_cnt, 1)
         achieved = F_CAND * per_launch_cands / (trmm_ms / max(trmm_cnt, 1) * 1e-3) * 1e-12
         ll_val = S * world / (ms_ll * 1e-3)
@@ -326,7 +387,13 @@ def run_gpu(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(world),
             "e2e": {"value": M * world / (ms_e2e * 1e-3), "unit": "candidates/s",
-                    "h2d_bytes_per_step": M * X_DIM * 8, "d2h_bytes_per_step": 24, "ms_per_step": ms_e2e},
+                    "h2d_bytes_per_step": M * X_DIM * 8, "d2h_bytes_per_step": 24, "ms_per_step": ms_e2e,
+                    "host_memory": "pinned",
+                    "pageable": {"value": M * world / (ms_e2e_pg * 1e-3), "ms_per_step": ms_e2e_pg,
+                                 "what": "the same call with the candidates in ordinary pageable memory (a Julia "
+                                         "Matrix{Float64}): the library stages them through two pinned slots on a copy "
+                                         "stream while the previous chunk computes",
+                                 "argmax_index": res_e2e_pg[1]}},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "score_trmm_kernel (FP64 DMMA.8x8x4)", "achieved": achieved,
@@ -334,7 +401,19 @@ def run_gpu(args):
                          "peak_source": peak_src, "launches_timed": trmm_cnt, "avg_launch_ms": trmm_ms / max(trmm_cnt, 1),
                          "flop_per_candidate": F_CAND, "candidates_per_launch": per_launch_cands,
                          "xcov_ms_per_step": xcov_ms, "trmm_ms_per_step": trmm_ms,
-                         "whole_step_frac": F_CAND * M / (ms_step * 1e-3) * 1e-12 / peak},
+                         "whole_step_frac": F_CAND * M / (ms_step * 1e-3) * 1e-12 / peak,
+                         "dgemm": dg, "dgemm_round1_file": fp64_peak_static()[0],
+                         # the second headline metric and the per-config numbers, repeated here because only the contract's
+                         # keys of this line are carried into the driver's summary
+                         "loglik": {"evals_per_s": ll_val, "ms_per_step": ms_ll,
+                                    "frac_of_peak": F_LL * S / (ms_ll * 1e-3) * 1e-12 / peak},
+                         "loglik_grad": {"evals_per_s": S * world / (ms_llg * 1e-3),
+                                         "frac_of_peak": F_LLG * S / (ms_llg * 1e-3) * 1e-12 / peak},
+                         "configs": [{k: c[k] for k in c if k in ("config", "kernel", "frac_of_dgemm_peak",
+                                                                  "frac_of_dgemm_peak_value_grad", "ms_per_step",
+                                                                  "loglik_evals_per_s", "candidates_per_s",
+                                                                  "on_device_multistart_frac", "n_gpus")}
+                                     for c in (cfgs or [])]},
             "loglik": {"metric": "GP loglik evals/sec (n=2048,d=8)", "value": ll_val, "unit": "evals/s",
                        "samples_per_gpu_per_step": S, "ms_per_step": ms_ll, "flop_per_eval": F_LL,
                        "achieved_tflops_per_gpu": F_LL * S / (ms_ll * 1e-3) * 1e-12,
@@ -354,10 +433,8 @@ def run_gpu(args):
                 out["roofline"]["traffic"] = json.load(f)["dram_bytes_per_launch"]
         except Exception:
             pass
-        if world == 1 and not args.no_configs:
-            # per-GPU shares of BASELINE configs C3 / C4 / C5 (device-resident, oracle parity spot checks inside)
-            from tools import bench_configs
-            out["configs"] = bench_configs.run_all(torch, _lib, lib_stream, steps=3)
+        if cfgs is not None:
+            out["configs"] = cfgs
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline()
         print(json.dumps(out), file=args.out, flush=True)
