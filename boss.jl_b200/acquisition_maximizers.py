@@ -90,58 +90,67 @@ def _rand_in_domain(am: SamplingAM, domain: Domain):
 
 
 def batched_lbfgs_maximize(value_and_grad, starts, lb, ub, iters=60, history=8, discrete=None):
-    """Maximise f over the box [lb, ub] from every column of `starts` simultaneously.
-    value_and_grad(X: d x S) -> (f: S, g: d x S).  Returns X (d x S), f (S)."""
+    """Maximise f over the box [lb, ub] from every column of `starts` simultaneously (projected L-BFGS with Armijo
+    backtracking).  value_and_grad(X: d x S) -> (f: S, g: d x S).  Returns X (d x S), f (S).
+
+    Host twin of the device-resident driver (csrc/multistart.cuh, boss_ei_maximize_multistart): every start is its own
+    state machine - own history ring, own step counter, own termination - and one ROUND advances every unfinished
+    start by exactly one function evaluation (all their trial points in one batched call).  A start is finished after
+    `iters` accepted steps, when an accepted step no longer moves it, or when 12 step sizes in a row were rejected."""
     X = np.clip(np.array(starts, dtype=np.float64, copy=True), lb[:, None], ub[:, None])
     d, S = X.shape
     f, g = value_and_grad(X)
     f = np.where(np.isfinite(f), f, -np.inf)
-    s_hist, y_hist = [], []
+    g = np.array(g, dtype=np.float64, copy=True)
+    H = max(1, min(history, 15))
+    Sh = np.zeros((H, d, S)); Yh = np.zeros((H, d, S))       # per-start rings, oldest first in rows [0, hist_len)
+    hist_len = np.zeros(S, dtype=int)
+    state = np.zeros(S, dtype=int) if iters > 0 else np.full(S, 2)          # 0 needs a direction, 1 line search, 2 finished
+    steps = np.zeros(S, dtype=int); trials = np.zeros(S, dtype=int)
+    t = np.ones(S); dirn = np.zeros((d, S))
     step0 = 0.1 * np.max(ub - lb)
-    for it in range(iters):
-        # two-loop recursion, vectorised over starts (ascent direction)
-        q = g.copy()
-        alphas = []
-        for s_k, y_k in zip(reversed(s_hist), reversed(y_hist)):
-            rho = 1.0 / np.maximum(np.sum(s_k * y_k, axis=0), 1e-300)
-            a = rho * np.sum(s_k * q, axis=0)
-            q = q - a * y_k
-            alphas.append((a, rho))
-        if s_hist:
-            gamma = np.sum(s_hist[-1] * y_hist[-1], axis=0) / np.maximum(np.sum(y_hist[-1] ** 2, axis=0), 1e-300)
-            q = q * np.where(np.isfinite(gamma) & (gamma > 0), gamma, 1.0)
-        else:
-            q = q * (step0 / np.maximum(np.linalg.norm(g, axis=0), 1e-300))
-        for (a, rho), s_k, y_k in zip(reversed(alphas), s_hist, y_hist):
-            b = rho * np.sum(y_k * q, axis=0)
-            q = q + s_k * (a - b)
-        dirn = q
-        bad = np.sum(dirn * g, axis=0) <= 0                  # not an ascent direction -> steepest ascent
-        dirn[:, bad] = g[:, bad] * (step0 / np.maximum(np.linalg.norm(g[:, bad], axis=0), 1e-300))
-        t = np.ones(S)
-        Xn, fn, gn = X, f, g
-        done = np.zeros(S, dtype=bool)
-        for _ in range(12):                                   # backtracking, all starts per trial in one call
-            Xt = np.clip(X + dirn * t, lb[:, None], ub[:, None])
-            ft, gt = value_and_grad(Xt)
-            ft = np.where(np.isfinite(ft), ft, -np.inf)
-            ok = (ft >= f + 1e-4 * np.sum(g * (Xt - X), axis=0)) & ~done
-            Xn = np.where(ok, Xt, Xn); fn = np.where(ok, ft, fn); gn = np.where(ok, gt, gn)
-            done |= ok
-            if done.all():
-                break
-            t = np.where(done, t, t * 0.5)
-        sk, yk = Xn - X, -(gn - g)                            # curvature pairs for maximisation (minimise -f)
-        valid = np.sum(sk * yk, axis=0) > 1e-16
-        sk[:, ~valid] = 0.0; yk[:, ~valid] = 0.0
-        if valid.any():
-            s_hist.append(sk); y_hist.append(yk)
-            if len(s_hist) > history:
-                s_hist.pop(0); y_hist.pop(0)
-        moved = np.max(np.abs(Xn - X)) if S else 0.0
-        X, f, g = Xn, fn, gn
-        if moved < 1e-10:
+    for _ in range(2 * iters + 12 if iters > 0 else 0):
+        act = np.flatnonzero(state != 2)
+        if act.size == 0:
             break
+        for m in np.flatnonzero(state == 0):                  # two-loop recursion on the start's own history
+            q = g[:, m].copy()
+            hl = hist_len[m]
+            al, rh = np.zeros(hl), np.zeros(hl)
+            for k in range(hl - 1, -1, -1):
+                rh[k] = 1.0 / max(Sh[k, :, m] @ Yh[k, :, m], 1e-300)
+                al[k] = rh[k] * (Sh[k, :, m] @ q)
+                q -= al[k] * Yh[k, :, m]
+            sd = step0 / max(np.linalg.norm(g[:, m]), 1e-300)
+            if hl > 0:
+                gamma = (Sh[hl - 1, :, m] @ Yh[hl - 1, :, m]) / max(Yh[hl - 1, :, m] @ Yh[hl - 1, :, m], 1e-300)
+                q *= gamma if (np.isfinite(gamma) and gamma > 0) else 1.0
+            else:
+                q *= sd
+            for k in range(hl):
+                q += Sh[k, :, m] * (al[k] - rh[k] * (Yh[k, :, m] @ q))
+            dirn[:, m] = q if (q @ g[:, m]) > 0 else g[:, m] * sd          # not an ascent direction -> steepest ascent
+            t[m] = 1.0; trials[m] = 0; state[m] = 1
+        Xt = np.clip(X[:, act] + dirn[:, act] * t[act], lb[:, None], ub[:, None])
+        ft, gt = value_and_grad(Xt)
+        ft = np.where(np.isfinite(ft), ft, -np.inf)
+        for c, m in enumerate(act):
+            if ft[c] >= f[m] + 1e-4 * (g[:, m] @ (Xt[:, c] - X[:, m])):
+                sk, yk = Xt[:, c] - X[:, m], -(gt[:, c] - g[:, m])          # curvature pair for maximisation
+                if sk @ yk > 1e-16:
+                    if hist_len[m] == H:
+                        Sh[:-1, :, m] = Sh[1:, :, m]; Yh[:-1, :, m] = Yh[1:, :, m]
+                        hist_len[m] -= 1
+                    Sh[hist_len[m], :, m] = sk; Yh[hist_len[m], :, m] = yk
+                    hist_len[m] += 1
+                moved = np.max(np.abs(sk))
+                X[:, m], f[m], g[:, m] = Xt[:, c], ft[c], gt[:, c]
+                steps[m] += 1
+                state[m] = 2 if (steps[m] >= iters or moved < 1e-10) else 0
+            else:
+                t[m] *= 0.5
+                trials[m] += 1
+                state[m] = 2 if trials[m] >= 12 else 1
     return X, f
 
 

@@ -1750,41 +1750,36 @@ static int multistart_single(const boss_gp *const *slices, int y_dim, int n_samp
   const int RC = H + 1;   // ring capacity: H live pairs + one free slot for the pair being formed
   if (iters < 0) iters = 0;
   const size_t Md = (size_t)M * d;
-  // carve one workspace: X Xt Xn | g gt gn | dirn | Sh Yh | f ft fn t | done | moved, counters
-  const size_t FANCAP = 4;   // compact trial buffers hold up to 4 M points (fan of MS_FAN steps for <= 0.4 M stragglers)
-  const size_t n_aff = prior_mean_affine ? (size_t)y_dim * (d + 1) + FANCAP * ((size_t)M * y_dim + Md * y_dim) : 0;
-  const size_t n_dbl = 3 * Md + 3 * Md + Md + 2 * (size_t)RC * Md + 4 * (size_t)M + n_aff + FANCAP * (2 * Md + M);
-  CUDA_TRY(C().ms_buf.ensure(n_dbl * 8 + (size_t)M * 12 + 64));
+  // carve one workspace: X g dirn | Sh Yh | f t | [affine mean scratch] | Xc gc fc | counters, per-start ints
+  const size_t n_aff = prior_mean_affine ? (size_t)y_dim * (d + 1) + (size_t)M * y_dim + Md * y_dim : 0;
+  const size_t n_dbl = 3 * Md + 2 * (size_t)RC * Md + 2 * (size_t)M + n_aff + 2 * Md + M;
+  CUDA_TRY(C().ms_buf.ensure(n_dbl * 8 + (size_t)M * 24 + 64));
   double *base = C().ms_buf.as<double>();
   MsState st{};
   st.d = d;
   st.H = RC;
+  st.iters = iters;
   st.M = M;
   st.X = base;
-  st.Xt = st.X + Md;
-  st.Xn = st.Xt + Md;
-  st.g = st.Xn + Md;
-  st.gt = st.g + Md;
-  st.gn = st.gt + Md;
-  st.dirn = st.gn + Md;
+  st.g = st.X + Md;
+  st.dirn = st.g + Md;
   st.Sh = st.dirn + Md;
   st.Yh = st.Sh + (size_t)RC * Md;
   st.f = st.Yh + (size_t)RC * Md;
-  st.ft = st.f + M;
-  st.fn = st.ft + M;
-  st.t = st.fn + M;
-  double *aff = st.t + M, *pm = aff + (size_t)y_dim * (d + 1), *pmg = pm + FANCAP * (size_t)M * y_dim;
+  st.t = st.f + M;
+  double *aff = st.t + M, *pm = aff + (size_t)y_dim * (d + 1), *pmg = pm + (size_t)M * y_dim;
   if (prior_mean_affine)
     CUDA_TRY(cudaMemcpyAsync(aff, prior_mean_affine, (size_t)y_dim * (d + 1) * 8, cudaMemcpyHostToDevice, C().stream));
   st.Xc = st.t + M + n_aff;
-  st.gc = st.Xc + FANCAP * Md;
-  st.fc = st.gc + FANCAP * Md;
-  st.moved_bits = reinterpret_cast<unsigned long long *>(st.fc + FANCAP * M);
-  st.counters = reinterpret_cast<int *>(st.moved_bits + 1);
-  st.done = st.counters + 4;
-  st.frozen = st.done + M;
-  st.idx = st.frozen + M;
-  CUDA_TRY(cudaMemsetAsync(st.frozen, 0, (size_t)M * 4, C().stream));
+  st.gc = st.Xc + Md;
+  st.fc = st.gc + Md;
+  st.counters = reinterpret_cast<int *>(st.fc + M);
+  st.hist_len = st.counters + 4;
+  st.hist_start = st.hist_len + M;
+  st.trials = st.hist_start + M;
+  st.steps = st.trials + M;
+  st.state = st.steps + M;
+  st.idx = st.state + M;
   double span = 0.0;
   for (int j = 0; j < d; ++j) {
     st.lb[j] = lb[j];
@@ -1824,56 +1819,31 @@ static int multistart_single(const boss_gp *const *slices, int y_dim, int n_samp
     return score_core(a);
   };
 
-  CUDA_TRY(cudaMemcpyAsync(st.Xt, starts, Md * 8, cudaMemcpyHostToDevice, C().stream));
-  ms_init_kernel<<<nbm, 128, 0, C().stream>>>(st, st.Xt);
+  // the pageable `starts` go through the synchronous copy path: the workspace is free (stream idle) at this point
+  CUDA_TRY(cudaMemcpyAsync(st.Xc, starts, Md * 8, cudaMemcpyHostToDevice, C().stream));
+  CUDA_TRY(cudaStreamSynchronize(C().stream));
+  ms_init_kernel<<<nbm, 128, 0, C().stream>>>(st, st.Xc);
+  ++C().launches;
   int rc = eval(st.X, M, st.f, st.g, false, nullptr, nullptr);
   if (rc) return rc;
   ms_sanitize_kernel<<<nbm, 128, 0, C().stream>>>(st.f, M);
-  int hist_len = 0, hist_start = 0;
-  for (int it = 0; it < iters; ++it) {
-    ms_direction_kernel<<<nbm, 128, 0, C().stream>>>(st, hist_len, hist_start);
-    for (int trial = 0; trial < 12; ++trial) {
-      // only the starts that have not yet accepted a step are evaluated again (compacted batch)
-      CUDA_TRY(cudaMemsetAsync(st.counters, 0, 16, C().stream));
-      ms_compact_kernel<<<nbm, 128, 0, C().stream>>>(st);
-      int count = 0;
-      CUDA_TRY(cudaMemcpyAsync(&count, st.counters, 4, cudaMemcpyDeviceToHost, C().stream));
-      CUDA_TRY(cudaStreamSynchronize(C().stream));
-      ++C().launches;
-      if (count == 0) break;
-      if (trial >= 2 && (size_t)count * MS_FAN <= FANCAP * (size_t)M) {
-        // few stragglers left: all remaining step sizes in one batch instead of up to 10 tiny sequential ones
-        ms_fan_kernel<<<(count * MS_FAN + 127) / 128, 128, 0, C().stream>>>(st, count);
-        rc = eval(st.Xc, (long long)count * MS_FAN, st.fc, st.gc, false, nullptr, nullptr);
-        if (rc) return rc;
-        ms_accept_fan_kernel<<<(count + 127) / 128, 128, 0, C().stream>>>(st, count);
-        C().launches += 2;
-        break;
-      }
-      rc = eval(st.Xc, count, st.fc, st.gc, false, nullptr, nullptr);
-      if (rc) return rc;
-      ms_accept_kernel<<<(count + 127) / 128, 128, 0, C().stream>>>(st, count);
-      ++C().launches;
-    }
-    ms_freeze_kernel<<<nbm, 128, 0, C().stream>>>(st);
-    CUDA_TRY(cudaMemsetAsync(st.moved_bits, 0, 8 + 16, C().stream));
-    ms_update_kernel<<<nbm, 128, 0, C().stream>>>(st, (hist_start + hist_len) % RC);   // always a free slot
-    C().launches += 3;
-    struct {
-      unsigned long long moved;
-      int cnt[4];
-    } hs;
-    CUDA_TRY(cudaMemcpyAsync(&hs, st.moved_bits, 24, cudaMemcpyDeviceToHost, C().stream));
+  ++C().launches;
+  // rounds: every unfinished start advances by one function evaluation.  A start needs `iters` accepted steps plus its
+  // rejected trials; the budget below lets a start reject every other trial on average before it is cut off.
+  const int max_rounds = iters > 0 ? 2 * iters + MS_MAX_TRIALS : 0;
+  int active = iters > 0 ? (int)M : 0;
+  for (int round = 0; round < max_rounds && active > 0; ++round) {
+    CUDA_TRY(cudaMemsetAsync(st.counters, 0, 16, C().stream));
+    ms_propose_kernel<<<nbm, 128, 0, C().stream>>>(st);
+    rc = eval(st.Xc, active, st.fc, st.gc, false, nullptr, nullptr);   // `active` = the compact list's length
+    if (rc) return rc;
+    ms_advance_kernel<<<(active + 127) / 128, 128, 0, C().stream>>>(st, active);
+    C().launches += 2;
+    int hc[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(hc, st.counters, 8, cudaMemcpyDeviceToHost, C().stream));
     CUDA_TRY(cudaStreamSynchronize(C().stream));
-    if (hs.cnt[1]) {   // at least one start produced a valid pair: commit the slot
-      if (hist_len == H)
-        hist_start = (hist_start + 1) % RC;   // drop the oldest pair
-      else
-        ++hist_len;
-    }
-    double moved;
-    std::memcpy(&moved, &hs.moved, 8);
-    if (moved < 1e-10) break;
+    if (hc[0] != active) return fail(BOSS_ERR_STATE, "boss_ei_maximize_multistart: internal batch-length mismatch");
+    active = hc[1];
   }
   // final rounding of discrete dimensions and re-evaluation (optimization.jl:116-117), argmax over the starts
   const unsigned long long disc = mask_bits(discrete_mask, d);

@@ -31,7 +31,8 @@ struct WtvIt {
   __device__ __forceinline__ bool tile_end() const { return kt == ktiles - 1; }
   __device__ __forceinline__ int tile() const { return i; }
   // the first 8 k-tiles of row block i are the diagonal block W_ii^T: upper triangular (gemm_core.cuh, has_tri_stages)
-  __device__ __forceinline__ int tri_mode() const { return kt < (i + 1) * KT_PER_BLOCK ? 2 : 0; }
+  static constexpr int kTriMode = 2;
+  __device__ __forceinline__ bool tri_diag() const { return kt < (i + 1) * KT_PER_BLOCK; }
   __device__ __forceinline__ int tri_g() const { return kt - i * KT_PER_BLOCK; }
   __device__ __forceinline__ void next() {
     if (kt == ktiles - 1) {

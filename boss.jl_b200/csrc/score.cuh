@@ -62,7 +62,8 @@ struct ScoreIt {
   __device__ __forceinline__ bool tile_end() const { return kt == (i + 1) * KT_PER_BLOCK - 1; }
   __device__ __forceinline__ int tile() const { return i; }
   // the last 8 k-tiles of row block i are the diagonal block W_ii: lower triangular (gemm_core.cuh, has_tri_stages)
-  __device__ __forceinline__ int tri_mode() const { return kt >= i * KT_PER_BLOCK ? 1 : 0; }
+  static constexpr int kTriMode = 1;
+  __device__ __forceinline__ bool tri_diag() const { return kt >= i * KT_PER_BLOCK; }
   __device__ __forceinline__ int tri_g() const { return kt - i * KT_PER_BLOCK; }
   __device__ __forceinline__ void next() {
     if (kt == (i + 1) * KT_PER_BLOCK - 1) {
