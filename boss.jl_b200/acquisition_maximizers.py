@@ -96,7 +96,8 @@ def batched_lbfgs_maximize(value_and_grad, starts, lb, ub, iters=60, history=8, 
     Host twin of the device-resident driver (csrc/multistart.cuh, boss_ei_maximize_multistart): every start is its own
     state machine - own history ring, own step counter, own termination - and one ROUND advances every unfinished
     start by exactly one function evaluation (all their trial points in one batched call).  A start is finished after
-    `iters` accepted steps, when an accepted step no longer moves it, or when 12 step sizes in a row were rejected."""
+    `iters` accepted steps, when an accepted step no longer moves it, or when 12 step sizes in a row were rejected along
+    the projected gradient (after 12 rejections along an L-BFGS direction the history is dropped first)."""
     X = np.clip(np.array(starts, dtype=np.float64, copy=True), lb[:, None], ub[:, None])
     d, S = X.shape
     f, g = value_and_grad(X)
@@ -114,14 +115,16 @@ def batched_lbfgs_maximize(value_and_grad, starts, lb, ub, iters=60, history=8, 
         if act.size == 0:
             break
         for m in np.flatnonzero(state == 0):                  # two-loop recursion on the start's own history
-            q = g[:, m].copy()
+            bound = ((X[:, m] <= lb) & (g[:, m] < 0)) | ((X[:, m] >= ub) & (g[:, m] > 0))
+            pg = np.where(bound, 0.0, g[:, m])                 # projected gradient
+            q = pg.copy()
             hl = hist_len[m]
             al, rh = np.zeros(hl), np.zeros(hl)
             for k in range(hl - 1, -1, -1):
                 rh[k] = 1.0 / max(Sh[k, :, m] @ Yh[k, :, m], 1e-300)
                 al[k] = rh[k] * (Sh[k, :, m] @ q)
                 q -= al[k] * Yh[k, :, m]
-            sd = step0 / max(np.linalg.norm(g[:, m]), 1e-300)
+            sd = step0 / max(np.linalg.norm(pg), 1e-300)
             if hl > 0:
                 gamma = (Sh[hl - 1, :, m] @ Yh[hl - 1, :, m]) / max(Yh[hl - 1, :, m] @ Yh[hl - 1, :, m], 1e-300)
                 q *= gamma if (np.isfinite(gamma) and gamma > 0) else 1.0
@@ -129,7 +132,8 @@ def batched_lbfgs_maximize(value_and_grad, starts, lb, ub, iters=60, history=8, 
                 q *= sd
             for k in range(hl):
                 q += Sh[k, :, m] * (al[k] - rh[k] * (Yh[k, :, m] @ q))
-            dirn[:, m] = q if (q @ g[:, m]) > 0 else g[:, m] * sd          # not an ascent direction -> steepest ascent
+            q[bound] = 0.0                                     # stay on the active bounds
+            dirn[:, m] = q if (q @ pg) > 0 else pg * sd        # not an ascent direction -> projected steepest ascent
             t[m] = 1.0; trials[m] = 0; state[m] = 1
         Xt = np.clip(X[:, act] + dirn[:, act] * t[act], lb[:, None], ub[:, None])
         ft, gt = value_and_grad(Xt)
@@ -150,7 +154,10 @@ def batched_lbfgs_maximize(value_and_grad, starts, lb, ub, iters=60, history=8, 
             else:
                 t[m] *= 0.5
                 trials[m] += 1
-                state[m] = 2 if trials[m] >= 12 else 1
+                state[m] = 1
+                if trials[m] >= 12:        # drop the history and retry along the projected gradient; finished if that fails too
+                    state[m] = 0 if hist_len[m] > 0 else 2
+                    hist_len[m] = 0
     return X, f
 
 

@@ -62,8 +62,12 @@ __global__ void ms_propose_kernel(MsState st) {
     const int hist_len = st.hist_len[m], hist_start = st.hist_start[m];
     double q[MS_MAXD], gl[MS_MAXD], al[MS_MAXH], rh[MS_MAXH];
     double gnorm2 = 0.0;
+    unsigned bound = 0;   // coordinates that sit on a bound with the gradient pointing out of the box
     for (int j = 0; j < d; ++j) {
-      gl[j] = st.g[m * d + j];
+      const double x = st.X[m * d + j], gj = st.g[m * d + j];
+      const bool out = (x <= st.lb[j] && gj < 0.0) || (x >= st.ub[j] && gj > 0.0);
+      bound |= out ? (1u << j) : 0u;
+      gl[j] = out ? 0.0 : gj;            // projected gradient
       q[j] = gl[j];
       gnorm2 = fma(gl[j], gl[j], gnorm2);
     }
@@ -100,7 +104,10 @@ __global__ void ms_propose_kernel(MsState st) {
       for (int j = 0; j < d; ++j) q[j] = fma(st.Sh[o + j], al[k] - b, q[j]);
     }
     double dg = 0.0;
-    for (int j = 0; j < d; ++j) dg = fma(q[j], gl[j], dg);
+    for (int j = 0; j < d; ++j) {
+      if ((bound >> j) & 1u) q[j] = 0.0;             // stay on the active bounds
+      dg = fma(q[j], gl[j], dg);
+    }
     const bool bad = !(dg > 0.0);                    // not an ascent direction -> steepest ascent
     for (int j = 0; j < d; ++j) st.dirn[m * d + j] = bad ? gl[j] * sd : q[j];
     st.t[m] = 1.0;
@@ -115,8 +122,9 @@ __global__ void ms_propose_kernel(MsState st) {
 }
 
 // Armijo test of this round's trial points.  Accepted: curvature pair into the start's own ring, move, count the
-// step; finished after `iters` steps or when the step no longer moves the point.  Rejected: halve the step;
-// finished (no acceptable step exists any more) after MS_MAX_TRIALS step sizes.
+// step; finished after `iters` steps or when the step no longer moves the point.  Rejected: halve the step; after
+// MS_MAX_TRIALS step sizes the history is dropped and the search restarts along the projected gradient, and a start
+// whose projected-gradient search fails as well is finished (no acceptable step exists any more).
 __global__ void ms_advance_kernel(MsState st, int count) {
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= count) return;
@@ -158,7 +166,14 @@ __global__ void ms_advance_kernel(MsState st, int count) {
     state = (steps >= st.iters || mv < 1e-10) ? 2 : 0;
   } else {
     st.t[m] *= 0.5;
-    state = (++st.trials[m] >= MS_MAX_TRIALS) ? 2 : 1;
+    state = 1;
+    if (++st.trials[m] >= MS_MAX_TRIALS) {
+      // no step size along this direction is acceptable: with curvature history, forget it and retry along the
+      // projected gradient; a failed steepest-ascent search means the start cannot improve any more
+      state = st.hist_len[m] > 0 ? 0 : 2;
+      st.hist_len[m] = 0;
+      st.hist_start[m] = 0;
+    }
   }
   st.state[m] = state;
   if (state != 2) atomicAdd(&st.counters[1], 1);
