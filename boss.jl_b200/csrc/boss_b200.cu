@@ -23,6 +23,7 @@
 
 #include "../../include/boss_b200.h"
 #include "cholesky.cuh"
+#include "chol_matrix.cuh"
 #include "score.cuh"
 #include "grad.cuh"
 #include "append.cuh"
@@ -295,6 +296,9 @@ int set_kernel_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(wtv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(potrf_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(chol_matrix_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, CM_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(chol_matrix_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CM_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(chol_matrix_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CM_SMEM_BYTES));
   C().attrs_done = true;
   return 0;
 }
@@ -2135,7 +2139,50 @@ static int loglik_core(const double *X, int d, int n, const double *Ymm, int64_t
   // factorisation, forward solve) and partially filled last waves overlap with another group's GEMM launches.
   cudaStream_t main_stream = C().stream;
   const size_t winv_stride = (size_t)nblk * TM * TM;
-  for (long long s0 = 0; s0 < S && !small; s0 += Sb) {
+  // n_pad <= 512, value only: one persistent CTA takes a whole matrix through the factorisation (chol_matrix.cuh)
+  const bool per_matrix = !small && !need_w && nblk <= CM_MAX_NBLK && !unfused_diag() && getenv("BOSS_NO_PER_MATRIX") == nullptr;
+  for (long long s0 = 0; s0 < S && per_matrix; s0 += Sb) {
+    const int sb = (int)std::min<long long>(Sb, S - s0);
+    CUDA_TRY(cudaMemsetAsync(status, 0, (size_t)sb * 4, C().stream));
+    CmParams cp{};
+    cp.S = sb;
+    PotrfParams &pp = cp.pp;
+    pp.L = C().chol_L.as<double>();
+    pp.L_stride = mat;
+    pp.nblk = nblk;
+    pp.ktiles = ktiles;
+    pp.logdet_blk = logdet_blk;
+    pp.status = status;
+    pp.fwd_ymm = dY + (ldy ? (size_t)s0 * ldy : 0);
+    pp.fwd_ldy = ldy;
+    pp.fwd_n = n;
+    pp.n_pad = n_pad;
+    pp.fwd_w = misc + owv;
+    pp.fwd_ssq = misc + ossq;
+    pp.gen_X = dX;
+    pp.gen_d = d;
+    pp.gen_dp = dp;
+    pp.gen_n = n;
+    pp.gen_kid = kernel_id;
+    pp.gen_ls = dls + (size_t)s0 * d;
+    pp.gen_amp = damp + s0;
+    pp.gen_noise = dnoise + s0;
+    pp.gen_disc = disc;
+    pp.store_L = 0;
+    {
+      Timed t(2);
+      const unsigned grid = (unsigned)std::min<long long>(sb, 2 * 148);
+      if (kernel_id == 0)
+        chol_matrix_kernel<0><<<grid, 256, CM_SMEM_BYTES, C().stream>>>(cp);
+      else if (kernel_id == 1)
+        chol_matrix_kernel<1><<<grid, 256, CM_SMEM_BYTES, C().stream>>>(cp);
+      else
+        chol_matrix_kernel<2><<<grid, 256, CM_SMEM_BYTES, C().stream>>>(cp);
+    }
+    loglik_finish_kernel<<<(sb + 127) / 128, 128, 0, C().stream>>>(logdet_blk, pp.fwd_ssq, status, nblk, n, sb, dll + s0);
+    C().launches += 2;
+  }
+  for (long long s0 = 0; s0 < S && !small && !per_matrix; s0 += Sb) {
     const int sb = (int)std::min<long long>(Sb, S - s0);
     int want_groups = 4;
     if (const char *e = getenv("BOSS_LL_GROUPS")) want_groups = std::max(1, std::min(LL_GROUPS, atoi(e)));

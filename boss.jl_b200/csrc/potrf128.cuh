@@ -149,8 +149,11 @@ __device__ __forceinline__ void pf_syrk_batch(double (&acc)[17][2], const double
 // FUSED = false: the diagonal tile is read from global memory (posterior fit, right-looking steps).
 // FUSED = true : the CTA generates K_jj, subtracts the SYRK of row block j of L (streamed through a 6-stage TMA ring
 //                that lives in the tile store before it is needed) and carries the forward substitution's r_j.
-template <bool FUSED>
-__device__ __forceinline__ void potrf_tile_body(const PotrfParams &p) {
+// s_mat: matrix of the batch; jc: block column (p.j for the stand-alone kernels).  LOCAL_ONLY (fused, persistent per-matrix kernel of chol_matrix.cuh): Winv_jj stays in
+// the tile store for the caller's panel solves and is not written to global memory; the function then returns with
+// the CTA synchronised.
+template <bool FUSED, bool LOCAL_ONLY = false>
+__device__ __forceinline__ void potrf_tile_body(const PotrfParams &p, const int s_mat, const int jc) {
   extern __shared__ __align__(16) double sm[];
   double *T = sm;                          // [136][64] packed lower tiles: A -> L -> W
   double *tmp = sm + PT_TILES * 64;        // [64][64] as 8x8 tiles (row-major tile grid, 8 tiles per row)
@@ -158,8 +161,8 @@ __device__ __forceinline__ void potrf_tile_body(const PotrfParams &p) {
   double *lg = dinv + 128;                 // [128] log L_kk
   int *flag = reinterpret_cast<int *>(lg + 128);
   double *fv = lg + 128 + 8;               // [128] delta_j - r_j, then [8] warp partials of |w_j|^2
-  const int s_mat = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  double *blk = p.L + (size_t)s_mat * p.L_stride + ((size_t)p.j * p.ktiles + (size_t)p.j * KT_PER_BLOCK) * TILE_ELEMS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double *blk = p.L + (size_t)s_mat * p.L_stride + ((size_t)jc * p.ktiles + (size_t)jc * KT_PER_BLOCK) * TILE_ELEMS;
 
   if (tid == 0) *flag = 0;
   if constexpr (!FUSED) {
@@ -191,7 +194,7 @@ __device__ __forceinline__ void potrf_tile_body(const PotrfParams &p) {
     double acc[17][2];
 #pragma unroll
     for (int t = 0; t < 17; ++t) acc[t][0] = acc[t][1] = 0.0;
-    if (p.j > 0) {
+    if (jc > 0) {
       // ---- SYRK of the diagonal tile: both operands are row block j of L, so a stage is ONE 16 KB macro-tile ----
       uint64_t *full = bars, *empty = bars + PF_RING_STAGES;
       if (tid < 2 * PF_RING_STAGES) {
@@ -202,8 +205,8 @@ __device__ __forceinline__ void potrf_tile_body(const PotrfParams &p) {
         mbar_fence_init();
       }
       __syncthreads();
-      const double *src = p.L + (size_t)s_mat * p.L_stride + (size_t)p.j * p.ktiles * TILE_ELEMS;
-      const int nk = p.j * KT_PER_BLOCK;
+      const double *src = p.L + (size_t)s_mat * p.L_stride + (size_t)jc * p.ktiles * TILE_ELEMS;
+      const int nk = jc * KT_PER_BLOCK;
       int issued = 0;
       auto try_issue = [&](bool blocking) -> bool {
         const int slot = issued % PF_RING_STAGES;
@@ -279,7 +282,7 @@ __device__ __forceinline__ void potrf_tile_body(const PotrfParams &p) {
     }
     __syncthreads();   // every warp is through the ring: the tile store and tmp are free
     // ---- scaled (and rounded) training inputs of this block into tmp, then K_jj - acc into the tile store ----
-    const int dp = p.gen_dp, row0 = p.j * 128;
+    const int dp = p.gen_dp, row0 = jc * 128;
     for (int e = tid; e < 128 * dp; e += 256) {
       const int rr = e / dp, i = e - rr * dp, gi = row0 + rr;
       double v = 0.0;
@@ -434,7 +437,7 @@ __device__ __forceinline__ void potrf_tile_body(const PotrfParams &p) {
     if (*flag && p.status[s_mat] == 0) p.status[s_mat] = 1;
     double ld = 0.0;
     for (int k = 0; k < 128; ++k) ld += lg[k];
-    p.logdet_blk[(size_t)s_mat * p.nblk + p.j] = ld;
+    p.logdet_blk[(size_t)s_mat * p.nblk + jc] = ld;
   }
 
   // ---- inverse, level 0: 8x8 diagonal tiles, one column per thread (threads 0..127) -> tmp, then back ----
@@ -547,9 +550,10 @@ __device__ __forceinline__ void potrf_tile_body(const PotrfParams &p) {
   }
 
   // ---- Winv_jj -> global (and, for a posterior fit, into W(j,j) and transposed into WT(j,j)) ----
-  double *wi = p.Winv + (size_t)s_mat * p.Winv_stride + (size_t)p.j * (TM * TM);
-  double *wfull = p.W ? p.W + (size_t)s_mat * p.W_stride + ((size_t)p.j * p.ktiles + (size_t)p.j * KT_PER_BLOCK) * TILE_ELEMS : nullptr;
-  double *wtfull = p.WT ? p.WT + (size_t)s_mat * p.W_stride + ((size_t)p.j * p.ktiles + (size_t)p.j * KT_PER_BLOCK) * TILE_ELEMS : nullptr;
+  double *wi = p.Winv + (size_t)s_mat * p.Winv_stride + (size_t)jc * (TM * TM);
+  double *wfull = p.W ? p.W + (size_t)s_mat * p.W_stride + ((size_t)jc * p.ktiles + (size_t)jc * KT_PER_BLOCK) * TILE_ELEMS : nullptr;
+  double *wtfull = p.WT ? p.WT + (size_t)s_mat * p.W_stride + ((size_t)jc * p.ktiles + (size_t)jc * KT_PER_BLOCK) * TILE_ELEMS : nullptr;
+  if constexpr (!LOCAL_ONLY)
   for (int e = 2 * tid; e < TM * TM; e += 512) {   // 16 B per lane, a micro-tile per warp pass
     const int kt = e >> 11, micro = (e >> 6) & 31, w = e & 63;
     const int I = micro >> 1, J = (kt << 1) + (micro & 1);
@@ -568,13 +572,13 @@ __device__ __forceinline__ void potrf_tile_body(const PotrfParams &p) {
   // ---- forward substitution step of the log-likelihood: w_j = Winv_jj (delta_j - r_j), |w_j|^2 ----
   if (p.fwd_w) {
     if (tid < 128) {
-      const int row = p.j * 128 + tid;
+      const int row = jc * 128 + tid;
       const double dl = (row < p.fwd_n) ? p.fwd_ymm[(size_t)s_mat * p.fwd_ldy + row] : 0.0;
       double rj;
       if constexpr (FUSED)
         rj = (fv + 136 + 16 + EXPTAB_N + 32)[tid];
       else
-        rj = p.j > 0 ? p.fwd_r[(size_t)s_mat * p.n_pad + row] : 0.0;
+        rj = jc > 0 ? p.fwd_r[(size_t)s_mat * p.n_pad + row] : 0.0;
       fv[tid] = dl - rj;
     }
     __syncthreads();
@@ -593,7 +597,7 @@ __device__ __forceinline__ void potrf_tile_body(const PotrfParams &p) {
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
       acc += __shfl_xor_sync(0xffffffffu, acc, 2);
       if (c4 == 0) {
-        p.fwd_w[(size_t)s_mat * p.n_pad + p.j * 128 + I * 8 + (lane >> 2)] = acc;
+        p.fwd_w[(size_t)s_mat * p.n_pad + jc * 128 + I * 8 + (lane >> 2)] = acc;
         sq = fma(acc, acc, sq);
       }
     }
@@ -605,12 +609,13 @@ __device__ __forceinline__ void potrf_tile_body(const PotrfParams &p) {
     if (tid == 0) {
       double t = 0.0;
       for (int q = 0; q < 8; ++q) t += fv[128 + q];
-      p.fwd_ssq[(size_t)s_mat * p.nblk + p.j] = t;
+      p.fwd_ssq[(size_t)s_mat * p.nblk + jc] = t;
     }
   }
+  if constexpr (LOCAL_ONLY) __syncthreads();
 }
 
-__global__ void __launch_bounds__(256, 2) potrf_tile_kernel(PotrfParams p) { potrf_tile_body<false>(p); }
-__global__ void __launch_bounds__(256, 2) potrf_fused_kernel(PotrfParams p) { potrf_tile_body<true>(p); }
+__global__ void __launch_bounds__(256, 2) potrf_tile_kernel(PotrfParams p) { potrf_tile_body<false>(p, blockIdx.x, p.j); }
+__global__ void __launch_bounds__(256, 2) potrf_fused_kernel(PotrfParams p) { potrf_tile_body<true>(p, blockIdx.x, p.j); }
 
 }  // namespace boss
