@@ -35,36 +35,29 @@ constexpr int CM_SMEM_BYTES = PF_SMEM_BYTES;
 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-// A small TMA ring whose stages hold one or two bulk copies; barriers are re-initialised at the start of every job
-// (the previous job ended with a CTA-wide barrier, so no wait is pending on them).
+// A small TMA ring whose stages hold one or two bulk copies.  Each ring shape owns its barriers (initialised once at
+// kernel start) and carries the absolute index of its next stage from job to job, so the phases just keep counting.
 template <int NST>
 struct CmRing {
   double *base;
   uint64_t *full, *empty;
-  int stage_elems, issued;
-  __device__ __forceinline__ void init(double *b, uint64_t *bars, int se) {
+  int stage_elems, pos0, issued;   // pos0: absolute index of this job's stage 0; issued: stages issued in this job
+  __device__ __forceinline__ void begin(double *b, uint64_t *bars, int se, int pos) {
     base = b;
     full = bars;
     empty = bars + NST;
     stage_elems = se;
+    pos0 = pos;
     issued = 0;
-    const int tid = threadIdx.x;
-    if (tid < 2 * NST) {
-      if (tid < NST)
-        mbar_init(smem_u32(&full[tid]), 1);
-      else
-        mbar_init(smem_u32(&empty[tid - NST]), 8);
-      mbar_fence_init();
-    }
     fence_proxy_async();   // generic-proxy accesses of the ring area (tile store / scratch) precede the bulk copies
     __syncthreads();
   }
   // thread 0: issue stage `issued` = (srcA, bytesA) [+ (srcB, bytesB) behind it]
   __device__ __forceinline__ bool try_issue(const double *srcA, uint32_t bytesA, const double *srcB, uint32_t bytesB, bool blocking) {
-    const int slot = issued % NST;
-    if (issued >= NST) {
+    const int ai = pos0 + issued, slot = ai % NST;
+    if (ai >= NST) {
       const uint32_t eb = smem_u32(&empty[slot]);
-      const uint32_t par = (uint32_t)((issued / NST - 1) & 1);
+      const uint32_t par = (uint32_t)((ai / NST - 1) & 1);
       if (blocking)
         mbar_wait(eb, par);
       else if (!mbar_try_wait(eb, par))
@@ -79,13 +72,19 @@ struct CmRing {
     return true;
   }
   __device__ __forceinline__ const double *wait(int g) const {
-    mbar_wait(smem_u32(&full[g % NST]), (uint32_t)((g / NST) & 1));
-    return base + (size_t)(g % NST) * stage_elems;
+    const int ai = pos0 + g;
+    mbar_wait(smem_u32(&full[ai % NST]), (uint32_t)((ai / NST) & 1));
+    return base + (size_t)(ai % NST) * stage_elems;
   }
   __device__ __forceinline__ void release(int g) const {
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) mbar_arrive(smem_u32(&empty[g % NST]));
+    if ((threadIdx.x & 31) == 0) mbar_arrive(smem_u32(&empty[(pos0 + g) % NST]));
   }
+};
+
+// running stage counters of the three rings of a CTA (uniform across its threads)
+struct CmPos {
+  int d, u, s;
 };
 
 struct CmParams {
@@ -96,7 +95,7 @@ struct CmParams {
 // ---- U(i, j, h): half tile h (columns 64h .. 64h+63) of T_ij = K_ij - sum_{k<j} L_ik L_jk^T  ->  global block (i, j) ----
 template <int KID>
 __device__ __forceinline__ void cm_update_job(const PotrfParams &p, const int s_mat, const int i, const int j, const int h,
-                                              double *sm, uint64_t *bars, const double *etab, const double *invl,
+                                              double *sm, uint64_t *bars, int &pos, const double *etab, const double *invl,
                                               const double a2) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp >> 1, wn = warp & 1;
   double *Lm = p.L + (size_t)s_mat * p.L_stride;
@@ -108,7 +107,8 @@ __device__ __forceinline__ void cm_update_job(const PotrfParams &p, const int s_
   const int nk = j * KT_PER_BLOCK;
   if (nk > 0) {
     CmRing<CM_U_STAGES> rg;
-    rg.init(sm, bars, CM_U_STAGE_ELEMS);
+    rg.begin(sm, bars + 12, CM_U_STAGE_ELEMS, pos);
+    pos += nk;
     const double *srcA = Lm + (size_t)i * p.ktiles * TILE_ELEMS;                            // row block i, k-tiles 0..
     const double *srcB = Lm + (size_t)j * p.ktiles * TILE_ELEMS + (size_t)h * (TILE_ELEMS / 2);   // rows 64h.. of row block j
     auto feed = [&](int g) {
@@ -213,7 +213,7 @@ __device__ __forceinline__ void cm_solve_step(double (&acc)[4][4][2], const doub
 //      packed lower-triangular tile store in shared memory; T_ij streams through a 2-stage ring in tmp.  Half 1 must run
 //      before half 0 (it still needs the T values of columns 0..63). ----
 __device__ __forceinline__ void cm_solve_job(const PotrfParams &p, const int s_mat, const int i, const int j, const int h,
-                                             double *sm, uint64_t *bars) {
+                                             double *sm, uint64_t *bars, int &pos) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp >> 1, wn = warp & 1;
   double *blk = p.L + (size_t)s_mat * p.L_stride + ((size_t)i * p.ktiles + (size_t)j * KT_PER_BLOCK) * TILE_ELEMS;
   const double *T = sm;
@@ -224,7 +224,8 @@ __device__ __forceinline__ void cm_solve_job(const PotrfParams &p, const int s_m
     for (int fn = 0; fn < 4; ++fn) acc[fm][fn][0] = acc[fm][fn][1] = 0.0;
   const int nk = 4 * (h + 1);   // k-tiles 0 .. 4(h+1)-1: Winv rows 64h.. have no entries beyond column 64h+63
   CmRing<CM_S_STAGES> rg;
-  rg.init(sm + PT_TILES * 64, bars, TILE_ELEMS);
+  rg.begin(sm + PT_TILES * 64, bars + 12 + 2 * CM_U_STAGES, TILE_ELEMS, pos);
+  pos += nk;
   auto feed = [&](int g) {
     while (rg.issued < nk && rg.issued < g + CM_S_STAGES) {
       if (!rg.try_issue(blk + (size_t)rg.issued * TILE_ELEMS, TILE_BYTES, nullptr, 0, rg.issued <= g)) break;
@@ -265,10 +266,10 @@ __device__ __forceinline__ void cm_solve_job(const PotrfParams &p, const int s_m
 }
 
 template <int KID>
-__device__ __forceinline__ void cm_matrix(const PotrfParams &pp, const int s_mat, double *sm) {
+__device__ __forceinline__ void cm_matrix(const PotrfParams &pp, const int s_mat, double *sm, CmPos &pos) {
   double *fv = sm + PT_TILES * 64 + PT_TMP_ELEMS + 128 + 128 + 8;
   uint64_t *bars = reinterpret_cast<uint64_t *>(fv + 136);
-  double *etab = fv + 136 + 16, *invl = etab + EXPTAB_N;
+  double *etab = fv + 136 + PF_BAR_SLOTS, *invl = etab + EXPTAB_N;
   const int nblk = pp.nblk, tid = threadIdx.x;
   // per-matrix constants of the kernel-value generation (the diagonal step rewrites the same values)
   exptab_init(etab);
@@ -283,20 +284,32 @@ __device__ __forceinline__ void cm_matrix(const PotrfParams &pp, const int s_mat
   for (int j = 0; j < nblk; ++j) {
     // T_ij for the rows below the diagonal block (for j = 0 this is just K_i0): independent of the diagonal step
 #pragma unroll 1
-    for (int ih = 2 * (j + 1); ih < 2 * nblk; ++ih) cm_update_job<KID>(pp, s_mat, ih >> 1, j, ih & 1, sm, bars, etab, invl, a2);
+    for (int ih = 2 * (j + 1); ih < 2 * nblk; ++ih) cm_update_job<KID>(pp, s_mat, ih >> 1, j, ih & 1, sm, bars, pos.u, etab, invl, a2);
     fence_proxy_async();   // the tile store was written through the generic proxy; the SYRK ring reuses it
     __syncthreads();
-    potrf_tile_body<true, true>(pp, s_mat, j);     // ends with a CTA-wide barrier; Winv_jj is in the tile store
+    potrf_tile_body<true, true>(pp, s_mat, j, &pos.d);     // ends with a CTA-wide barrier; Winv_jj is in the tile store
 #pragma unroll 1
-    for (int ih = 2 * (j + 1); ih < 2 * nblk; ++ih) cm_solve_job(pp, s_mat, ih >> 1, j, 1 - (ih & 1), sm, bars);   // half 1 first
+    for (int ih = 2 * (j + 1); ih < 2 * nblk; ++ih) cm_solve_job(pp, s_mat, ih >> 1, j, 1 - (ih & 1), sm, bars, pos.s);   // half 1 first
   }
 }
 
 template <int KID>
 __global__ void __launch_bounds__(256, 2) chol_matrix_kernel(const __grid_constant__ CmParams p) {
   extern __shared__ __align__(16) double sm[];
+  {
+    // all rings' barriers, once: SYRK ring full[6] empty[6] | update ring full[4] empty[4] | solve ring full[2] empty[2]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + PT_TILES * 64 + PT_TMP_ELEMS + 128 + 128 + 8 + 136);
+    const int t = threadIdx.x;
+    if (t < PF_BAR_SLOTS) {
+      const bool is_full = t < 6 || (t >= 12 && t < 16) || (t >= 20 && t < 22);
+      mbar_init(smem_u32(&bars[t]), is_full ? 1u : 8u);
+      mbar_fence_init();
+    }
+    __syncthreads();
+  }
+  CmPos pos{0, 0, 0};
   for (int s = blockIdx.x; s < (int)p.S; s += gridDim.x) {
-    cm_matrix<KID>(p.pp, s, sm);
+    cm_matrix<KID>(p.pp, s, sm, pos);
     __syncthreads();
   }
 }

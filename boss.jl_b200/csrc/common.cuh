@@ -15,6 +15,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace boss {
 
@@ -43,6 +44,13 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+// Re-initialise a barrier that already holds a valid mbarrier object (persistent kernels that reuse one set of
+// barriers for rings of different depth): PTX leaves mbarrier.init on a live object undefined -- on B200 the arrival
+// count of the old object survived -- so the object is invalidated first.
+__device__ __forceinline__ void mbar_reinit(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
 __device__ __forceinline__ void mbar_fence_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -63,11 +71,17 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
-// Bounded wait: a lost TMA transaction traps (launch fails with an error) instead of hanging the GPU.
+// Bounded wait: a lost TMA transaction traps (launch fails with an error) instead of hanging the GPU.  A failed
+// try_wait suspends the thread for a few microseconds, so the bound is ~15 s -- far beyond any legitimate wait.
+static __device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
+  printf("boss_b200: mbarrier wait timed out: smem 0x%x parity %u block (%d,%d) thread %d\n", bar, parity, blockIdx.x,
+         blockIdx.y, threadIdx.x);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();
+    if (++spins > (1u << 22)) mbar_timeout(bar, parity);
   }
 }
 // 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (complete_tx::bytes).

@@ -56,9 +56,10 @@ struct PotrfParams {
 constexpr int PT_TILES = 136;                        // 16*17/2 lower micro-tiles
 constexpr int PT_TMP_ELEMS = 64 * 64;                // scratch for the inverse products (one 64x64 block)
 constexpr int PT_SMEM_BYTES = (PT_TILES * 64 + PT_TMP_ELEMS + 128 + 128 + 8 + 128 + 8) * 8;   // 105 600 B -> 2 CTAs / SM
-// the fused kernel adds: 12 mbarriers (16 doubles), the exp table (32), 1/l (32), per-row forward-substitution sums (128)
+// the fused kernel adds: 24 mbarrier slots, the exp table (32), 1/l (32), per-row forward-substitution sums (128)
 constexpr int PF_RING_STAGES = 6;                    // 6 x 16 KB single-tile stages live in the (not yet used) T | tmp area
-constexpr int PF_EXTRA_ELEMS = 16 + EXPTAB_N + 32 + 128;
+constexpr int PF_BAR_SLOTS = 24;                     // mbarrier slots: [0,12) the SYRK ring here, [12,24) the rings of chol_matrix.cuh
+constexpr int PF_EXTRA_ELEMS = PF_BAR_SLOTS + EXPTAB_N + 32 + 128;
 constexpr int PF_SMEM_BYTES = PT_SMEM_BYTES + PF_EXTRA_ELEMS * 8;   // 107 264 B -> still 2 CTAs / SM
 
 // (I, J) of the t-th packed lower micro-tile
@@ -152,8 +153,11 @@ __device__ __forceinline__ void pf_syrk_batch(double (&acc)[17][2], const double
 // s_mat: matrix of the batch; jc: block column (p.j for the stand-alone kernels).  LOCAL_ONLY (fused, persistent per-matrix kernel of chol_matrix.cuh): Winv_jj stays in
 // the tile store for the caller's panel solves and is not written to global memory; the function then returns with
 // the CTA synchronised.
+// ring_pos (LOCAL_ONLY): stages the SYRK ring has carried so far in this kernel; the barriers are initialised once per
+// kernel and their phases simply keep counting (re-initialising a used mbarrier did not take effect on B200, with or
+// without mbarrier.inval: the old arrival count survived).
 template <bool FUSED, bool LOCAL_ONLY = false>
-__device__ __forceinline__ void potrf_tile_body(const PotrfParams &p, const int s_mat, const int jc) {
+__device__ __forceinline__ void potrf_tile_body(const PotrfParams &p, const int s_mat, const int jc, int *ring_pos = nullptr) {
   extern __shared__ __align__(16) double sm[];
   double *T = sm;                          // [136][64] packed lower tiles: A -> L -> W
   double *tmp = sm + PT_TILES * 64;        // [64][64] as 8x8 tiles (row-major tile grid, 8 tiles per row)
@@ -178,7 +182,7 @@ __device__ __forceinline__ void potrf_tile_body(const PotrfParams &p, const int 
     for (int k = 0; k < PT_TILES / 8; ++k) *reinterpret_cast<double2 *>(T + (warp + 8 * k) * 64 + 2 * lane) = buf[k];
   } else {
     uint64_t *bars = reinterpret_cast<uint64_t *>(fv + 136);          // full[6], empty[6]
-    double *etab = fv + 136 + 16;
+    double *etab = fv + 136 + PF_BAR_SLOTS;
     double *invl = etab + EXPTAB_N;
     double *rsum = invl + 32;                                         // [128] r_j = sum_{k<j} L_jk w_k
     exptab_init(etab);
@@ -197,22 +201,24 @@ __device__ __forceinline__ void potrf_tile_body(const PotrfParams &p, const int 
     if (jc > 0) {
       // ---- SYRK of the diagonal tile: both operands are row block j of L, so a stage is ONE 16 KB macro-tile ----
       uint64_t *full = bars, *empty = bars + PF_RING_STAGES;
-      if (tid < 2 * PF_RING_STAGES) {
-        if (tid < PF_RING_STAGES)
-          mbar_init(smem_u32(&full[tid]), 1);
-        else
-          mbar_init(smem_u32(&empty[tid - PF_RING_STAGES]), 8);
-        mbar_fence_init();
+      int pos0 = 0;   // absolute index of this job's first stage
+      if constexpr (LOCAL_ONLY) {
+        pos0 = *ring_pos;   // persistent kernel: barriers were initialised at kernel start, phases keep counting
+      } else {
+        if (tid < 2 * PF_RING_STAGES) {
+          mbar_init(smem_u32(&bars[tid]), tid < PF_RING_STAGES ? 1u : 8u);
+          mbar_fence_init();
+        }
+        __syncthreads();
       }
-      __syncthreads();
       const double *src = p.L + (size_t)s_mat * p.L_stride + (size_t)jc * p.ktiles * TILE_ELEMS;
       const int nk = jc * KT_PER_BLOCK;
       int issued = 0;
       auto try_issue = [&](bool blocking) -> bool {
-        const int slot = issued % PF_RING_STAGES;
-        if (issued >= PF_RING_STAGES) {
+        const int ai = pos0 + issued, slot = ai % PF_RING_STAGES;
+        if (ai >= PF_RING_STAGES) {
           const uint32_t eb = smem_u32(&empty[slot]);
-          const uint32_t par = (uint32_t)((issued / PF_RING_STAGES - 1) & 1);
+          const uint32_t par = (uint32_t)((ai / PF_RING_STAGES - 1) & 1);
           if (blocking)
             mbar_wait(eb, par);
           else if (!mbar_try_wait(eb, par))
@@ -232,13 +238,13 @@ __device__ __forceinline__ void potrf_tile_body(const PotrfParams &p, const int 
       const double *wv = fwd ? p.fwd_w + (size_t)s_mat * p.n_pad + c4 : nullptr;
       double r0 = 0.0, r1 = 0.0;
       for (int g = 0; g < nk; ++g) {
-        const int slot = g % PF_RING_STAGES;
+        const int slot = (pos0 + g) % PF_RING_STAGES;
         if (tid == 0) {
           while (issued < nk && issued < g + PF_RING_STAGES) {
             if (!try_issue(issued <= g)) break;
           }
         }
-        mbar_wait(smem_u32(&full[slot]), (uint32_t)((g / PF_RING_STAGES) & 1));
+        mbar_wait(smem_u32(&full[slot]), (uint32_t)(((pos0 + g) / PF_RING_STAGES) & 1));
         const double *st = sm + (size_t)slot * TILE_ELEMS;
 #pragma unroll
         for (int mc = 0; mc < 2; ++mc) {
@@ -267,6 +273,7 @@ __device__ __forceinline__ void potrf_tile_body(const PotrfParams &p, const int 
           }
         }
       }
+      if constexpr (LOCAL_ONLY) *ring_pos = pos0 + nk;
       if (fwd) {
         r0 += __shfl_xor_sync(0xffffffffu, r0, 1);
         r0 += __shfl_xor_sync(0xffffffffu, r0, 2);
@@ -576,7 +583,7 @@ __device__ __forceinline__ void potrf_tile_body(const PotrfParams &p, const int 
       const double dl = (row < p.fwd_n) ? p.fwd_ymm[(size_t)s_mat * p.fwd_ldy + row] : 0.0;
       double rj;
       if constexpr (FUSED)
-        rj = (fv + 136 + 16 + EXPTAB_N + 32)[tid];
+        rj = (fv + 136 + PF_BAR_SLOTS + EXPTAB_N + 32)[tid];
       else
         rj = jc > 0 ? p.fwd_r[(size_t)s_mat * p.n_pad + row] : 0.0;
       fv[tid] = dl - rj;
