@@ -1125,11 +1125,11 @@ int score_core(ScoreArgs &a) {
     CUDA_TRY(C().part_gm.ensure((size_t)2 * max_nblk * d * CH * 8));
     CUDA_TRY(C().part_gv.ensure((size_t)2 * max_nblk * d * CH * 8));
   }
-  const int nblk_acq_max = (CH + 255) / 256;
+  const int nblk_acq_max = (CH + 127) / 128;     // block winners: per 256 candidates (acq_kernel) or per 128 (fused epilogue)
   CUDA_TRY(C().blk_val.ensure((size_t)nblk_acq_max * 8));
   CUDA_TRY(C().blk_idx.ensure((size_t)nblk_acq_max * 8));
-  // small: a2[nsl] | lb[d] | ub[d] | best(1) | bidx(1 as int64) | any_fail(int)
-  const size_t sm_n = (size_t)nsl + 2 * d + 4;
+  // small: a2[nsl] | lb[d] | ub[d] | best(1) | bidx(1 as int64) | any_fail(int) | finished-CTA counter (fused epilogue)
+  const size_t sm_n = (size_t)nsl + 2 * d + 5;
   CUDA_TRY(C().small.ensure(sm_n * 8));
   double *small = C().small.as<double>();
   std::vector<double> hs(sm_n, 0.0);
@@ -1147,6 +1147,7 @@ int score_core(ScoreArgs &a) {
   double *d_best = small + nsl + 2 * d;
   long long *d_bidx = reinterpret_cast<long long *>(small + nsl + 2 * d + 1);
   int *d_anyfail = reinterpret_cast<int *>(small + nsl + 2 * d + 2);
+  unsigned int *d_counter = reinterpret_cast<unsigned int *>(small + nsl + 2 * d + 3);
   MixParams mixp{};
   if (a.mix) {   // MC-EI: the eps matrix (y_dim x n_eps) goes to the device once per call
     mixp = *a.mix;
@@ -1286,6 +1287,40 @@ int score_core(ScoreArgs &a) {
       if (a.status_out) st_dev = reinterpret_cast<int *>(dev_out[slot] + out_off_st);
       if (a.grad) grad_dev = reinterpret_cast<double *>(dev_out[slot] + out_off_gr);
     }
+    bool fused_chunk = false;
+    AcqParams ap{};
+    ap.y_dim = a.y_dim;
+    ap.n_samples = a.n_samples;
+    ap.d = d;
+    ap.M = a.M;
+    ap.m0 = m0;
+    ap.in_off = host ? m0 : in_off;     // host mode: the slot arrays start at the chunk's first candidate
+    ap.out_off = host ? m0 : out_off;
+    ap.chunk = ch;
+    ap.chunk_ld = CH;
+    ap.mu = C().muv.as<double>();
+    ap.sumsq = C().sumsq.as<double>();
+    ap.a2 = small;
+    ap.prior_mean = pm_dev;
+    for (int i = 0; i < a.y_dim; ++i) {
+      ap.coefs[i] = a.coefs ? a.coefs[i] : (i == 0 ? 1.0 : 0.0);
+      ap.y_max[i] = a.y_max ? a.y_max[i] : INFINITY;
+    }
+    ap.has_best = a.best != nullptr;
+    ap.best = a.best ? *a.best : 0.0;
+    ap.has_ymax = a.y_max != nullptr;
+    ap.Xs = xs_dev;
+    ap.lb = (a.lb && a.ub) ? small + nsl : nullptr;
+    ap.ub = (a.lb && a.ub) ? small + nsl + d : nullptr;
+    ap.cons_mask = cm_dev;
+    ap.acq = acq_dev;
+    ap.mu_out = mu_dev;
+    ap.var_out = var_dev;
+    ap.status_out = st_dev;
+    ap.any_fail = d_anyfail;
+    ap.blk_val = a.want_argmax ? C().blk_val.as<double>() : nullptr;
+    ap.blk_idx = a.want_argmax ? C().blk_idx.as<long long>() : nullptr;
+    ap.mix = mixp;
     for (int q = 0; q < nsl; ++q) {
       const boss_gp *h = sl[q];
       // Small candidate batches (multi-start optimiser iterations, single-point calls) cannot fill 148 SMs
@@ -1316,8 +1351,13 @@ int score_core(ScoreArgs &a) {
         Timed t(1);
         launch_xcov(h->kernel_id, h->dp, xp, dim3(ncb, nks), C().stream);
       }
-      reduce_rows_kernel<<<(cnt + 255) / 256, 256, 0, C().stream>>>(C().part_mu.as<double>(), 2 * h->nblk, (size_t)CH,
-                                                                 C().muv.as<double>() + (size_t)q * CH, cnt);
+      // One CTA per candidate block walks all of W (large batches) and this is the chunk's last slice: the scoring
+      // kernel finishes the candidates itself (fused epilogue) -- no reduce / acquisition / argmax launches.
+      const bool fuse = nsp == 1 && q == nsl - 1 && getenv("BOSS_UNFUSED_SCORE") == nullptr;
+      fused_chunk = fuse;
+      if (!fuse)
+        reduce_rows_kernel<<<(cnt + 255) / 256, 256, 0, C().stream>>>(C().part_mu.as<double>(), 2 * h->nblk, (size_t)CH,
+                                                                   C().muv.as<double>() + (size_t)q * CH, cnt);
       ScoreParams sp{};
       sp.W = h->W;
       sp.Ks = C().ks.as<double>();
@@ -1326,13 +1366,25 @@ int score_core(ScoreArgs &a) {
       sp.ss_part = C().part_ss.as<double>();
       sp.ld = CH;
       sp.VT = a.grad ? C().vt.as<double>() : nullptr;
+      if (fuse) {
+        sp.fused = 1;
+        sp.ap = ap;
+        sp.mu_part = C().part_mu.as<double>();
+        sp.P = 2 * h->nblk;
+        sp.mu_row = C().muv.as<double>() + (size_t)q * CH;
+        sp.ss_row = C().sumsq.as<double>() + (size_t)q * CH;
+        sp.best = d_best;
+        sp.bidx = d_bidx;
+        sp.counter = d_counter;
+      }
       {
         Timed t(0);
         score_trmm_kernel<<<dim3(ncb, nsp), GEMM_THREADS, GEMM_SMEM_BYTES, C().stream>>>(sp);
       }
-      reduce_rows_kernel<<<(cnt + 255) / 256, 256, 0, C().stream>>>(C().part_ss.as<double>(), 2 * h->nblk, (size_t)CH,
-                                                                 C().sumsq.as<double>() + (size_t)q * CH, cnt);
-      C().launches += 4;
+      if (!fuse)
+        reduce_rows2_kernel<<<(cnt + 255) / 256, 256, 0, C().stream>>>(C().part_ss.as<double>(), 2 * h->nblk, (size_t)CH,
+                                                                    C().sumsq.as<double>() + (size_t)q * CH, cnt);
+      C().launches += fuse ? 2 : 4;
       if (a.grad) {
         WtvParams wp{h->WT, C().vt.as<double>(), C().ut.as<double>(), h->nblk, h->ktiles};
         {
@@ -1367,45 +1419,14 @@ int score_core(ScoreArgs &a) {
         C().launches += 3;
       }
     }
-    AcqParams ap{};
-    ap.y_dim = a.y_dim;
-    ap.n_samples = a.n_samples;
-    ap.d = d;
-    ap.M = a.M;
-    ap.m0 = m0;
-    ap.in_off = host ? m0 : in_off;     // host mode: the slot arrays start at the chunk's first candidate
-    ap.out_off = host ? m0 : out_off;
-    ap.chunk = ch;
-    ap.chunk_ld = CH;
-    ap.mu = C().muv.as<double>();
-    ap.sumsq = C().sumsq.as<double>();
-    ap.a2 = small;
-    ap.prior_mean = pm_dev;
-    for (int i = 0; i < a.y_dim; ++i) {
-      ap.coefs[i] = a.coefs ? a.coefs[i] : (i == 0 ? 1.0 : 0.0);
-      ap.y_max[i] = a.y_max ? a.y_max[i] : INFINITY;
-    }
-    ap.has_best = a.best != nullptr;
-    ap.best = a.best ? *a.best : 0.0;
-    ap.has_ymax = a.y_max != nullptr;
-    ap.Xs = xs_dev;
-    ap.lb = (a.lb && a.ub) ? small + nsl : nullptr;
-    ap.ub = (a.lb && a.ub) ? small + nsl + d : nullptr;
-    ap.cons_mask = cm_dev;
-    ap.acq = acq_dev;
-    ap.mu_out = mu_dev;
-    ap.var_out = var_dev;
-    ap.status_out = st_dev;
-    ap.any_fail = d_anyfail;
-    ap.blk_val = a.want_argmax ? C().blk_val.as<double>() : nullptr;
-    ap.blk_idx = a.want_argmax ? C().blk_idx.as<long long>() : nullptr;
-    ap.mix = mixp;
-    const int nb = (ch + 255) / 256;
-    acq_kernel<<<nb, 256, 0, C().stream>>>(ap);
-    ++C().launches;
-    if (a.want_argmax) {
-      argmax_final_kernel<<<1, 256, 0, C().stream>>>(C().blk_val.as<double>(), C().blk_idx.as<long long>(), nb, d_best, d_bidx);
+    if (!fused_chunk) {
+      const int nb = (ch + 255) / 256;
+      acq_kernel<<<nb, 256, 0, C().stream>>>(ap);
       ++C().launches;
+      if (a.want_argmax) {
+        argmax_final_kernel<<<1, 256, 0, C().stream>>>(C().blk_val.as<double>(), C().blk_idx.as<long long>(), nb, d_best, d_bidx);
+        ++C().launches;
+      }
     }
     if (a.grad) {
       AcqGradParams gp2{ap, C().dmu.as<double>(), C().dvar.as<double>(), pmg_dev, grad_dev};
@@ -2140,7 +2161,9 @@ static int loglik_core(const double *X, int d, int n, const double *Ymm, int64_t
   cudaStream_t main_stream = C().stream;
   const size_t winv_stride = (size_t)nblk * TM * TM;
   // n_pad <= 512, value only: one persistent CTA takes a whole matrix through the factorisation (chol_matrix.cuh)
-  const bool per_matrix = !small && !need_w && nblk <= CM_MAX_NBLK && !unfused_diag() && getenv("BOSS_NO_PER_MATRIX") == nullptr;
+  // Measured (C3, 512 matrices): 2.2 ms vs 1.6 ms for the multi-kernel path -- 28 small jobs per matrix with cold rings and
+  // two-stage solve rings do not keep the tensor pipe fed -- so the path is opt-in (BOSS_PER_MATRIX=1) until it is tuned.
+  const bool per_matrix = !small && !need_w && nblk <= CM_MAX_NBLK && !unfused_diag() && getenv("BOSS_PER_MATRIX") != nullptr;
   for (long long s0 = 0; s0 < S && per_matrix; s0 += Sb) {
     const int sb = (int)std::min<long long>(Sb, S - s0);
     CUDA_TRY(cudaMemsetAsync(status, 0, (size_t)sb * 4, C().stream));

@@ -35,72 +35,6 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(const double *__restri
 }
 
 // ---------------------------------------------------------------------------------------------
-// fused triangular product + column sum of squares:  q[m] = sum_r ( sum_{k<=r} W[r][k] K*[k][m] )^2
-// One CTA owns 128 candidates and walks all row blocks of W; the ring streams W (L2-resident) and the
-// CTA's K*^T block (re-read once per row block, triangular k-range).
-// ---------------------------------------------------------------------------------------------
-struct ScoreParams {
-  const double *W;    // P-layout n_pad x n_pad lower-triangular inverse factor
-  const double *Ks;   // chunk scratch
-  int nblk, ktiles;
-  double *ss_part;    // [2*nblk][ld] per-(row block, warp-row half) partial sums of squares
-  int ld;
-  double *VT;         // optional chunk scratch (P-layout, rows = candidates): V = W K* stored transposed (gradient mode)
-};
-
-// Row blocks of a triangular operand are dealt to the `ns` CTAs of a candidate block in zig-zag order
-// (split y gets y, 2ns-1-y, 2ns+y, 4ns-1-y, ...), which balances the triangular work; ns = 1 is the plain walk.
-__device__ __forceinline__ int zigzag_row(int j, int y, int ns2) { return (j >> 1) * ns2 + ((j & 1) ? ns2 - 1 - y : y); }
-
-struct ScoreIt {
-  const double *w;       // W (lower triangular): row block i uses k-tiles 0 .. 8(i+1)-1
-  const double *ks;      // first tile of this CTA's K*^T block
-  int j, i, kt, nblk, ktiles, y, ns2;
-  __device__ __forceinline__ bool valid() const { return i < nblk; }
-  __device__ __forceinline__ const double *A() const { return w + ((size_t)i * ktiles + kt) * TILE_ELEMS; }
-  __device__ __forceinline__ const double *B() const { return ks + (size_t)kt * TILE_ELEMS; }
-  __device__ __forceinline__ bool tile_end() const { return kt == (i + 1) * KT_PER_BLOCK - 1; }
-  __device__ __forceinline__ int tile() const { return i; }
-  // the last 8 k-tiles of row block i are the diagonal block W_ii: lower triangular (gemm_core.cuh, has_tri_stages)
-  static constexpr int kTriMode = 1;
-  __device__ __forceinline__ bool tri_diag() const { return kt >= i * KT_PER_BLOCK; }
-  __device__ __forceinline__ int tri_g() const { return kt - i * KT_PER_BLOCK; }
-  __device__ __forceinline__ void next() {
-    if (kt == (i + 1) * KT_PER_BLOCK - 1) {
-      ++j;
-      i = zigzag_row(j, y, ns2);
-      kt = 0;
-    } else {
-      ++kt;
-    }
-  }
-};
-
-// grid = (candidate blocks, ns row-block splits).  Each finished 128x128 tile of V = W K* contributes one
-// partial column sum of squares per (row block, warp-row half); reduce_rows_kernel adds them in ascending order.
-__global__ void __launch_bounds__(GEMM_THREADS, 1) score_trmm_kernel(ScoreParams p) {
-  const int cb = blockIdx.x, y = blockIdx.y, ns2 = 2 * gridDim.y;
-  ScoreIt it{p.W, p.Ks + (size_t)cb * p.ktiles * TILE_ELEMS, 0, zigzag_row(0, y, ns2), 0, p.nblk, p.ktiles, y, ns2};
-  double *vt = p.VT ? p.VT + (size_t)cb * p.ktiles * TILE_ELEMS : nullptr;
-  gemm_pipeline(it, it, [&](int tile, const double(&acc)[8][4][2], const FragCoord &fc) {
-    if (vt) store_block(vt + (size_t)tile * KT_PER_BLOCK * TILE_ELEMS, true, 1.0, nullptr, acc, fc);
-    double *dst = p.ss_part + (size_t)(2 * tile + fc.wm) * p.ld + (size_t)cb * 128 + 32 * fc.wn;
-#pragma unroll
-    for (int fn = 0; fn < 4; ++fn)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        double v = 0.0;
-#pragma unroll
-        for (int fm = 0; fm < 8; ++fm) v = fma(acc[fm][fn][e], acc[fm][fn][e], v);
-        v += __shfl_xor_sync(0xffffffffu, v, 4);
-        v += __shfl_xor_sync(0xffffffffu, v, 8);
-        v += __shfl_xor_sync(0xffffffffu, v, 16);
-        if (fc.lane < 4) dst[8 * fn + 2 * fc.lane + e] = v;
-      }
-  });
-}
-
-// ---------------------------------------------------------------------------------------------
 // elementwise acquisition stage + block argmax
 // ---------------------------------------------------------------------------------------------
 constexpr int MAX_YDIM = 16;
@@ -182,15 +116,11 @@ __device__ __forceinline__ double norm_cdf(double z) { return 0.5 * erfc(-z * 0.
 __device__ __forceinline__ double norm_pdf(double z) { return exp(-0.5 * z * z) * 0.3989422804014327; }
 
 
-__global__ void __launch_bounds__(256) acq_kernel(AcqParams p) {
-  __shared__ double sv[256];
-  __shared__ long long si[256];
-  const int tid = threadIdx.x;
-  const int c = blockIdx.x * 256 + tid;
-  const long long m = p.m0 + c;
-  double result = -INFINITY;
-  bool active = (c < p.chunk) && (m < p.M);
-  if (active) {
+// The acquisition value of candidate c of the chunk (global index m): slices x BI samples -> EI x PoF, guards.
+// Writes the optional per-candidate outputs.  Shared by acq_kernel and the fused epilogue of score_trmm_kernel.
+__device__ __forceinline__ double acq_candidate(const AcqParams &p, const int c, const long long m) {
+  double result;
+  {
     double accum = 0.0;
     bool failed = false;
     for (int s = 0; s < p.n_samples; ++s) {
@@ -265,6 +195,17 @@ __global__ void __launch_bounds__(256) acq_kernel(AcqParams p) {
     if (p.cons_mask && p.cons_mask[m - p.in_off] == 0) result = 0.0;
     if (p.acq) p.acq[m - p.out_off] = result;
   }
+  return result;
+}
+
+__global__ void __launch_bounds__(256) acq_kernel(AcqParams p) {
+  __shared__ double sv[256];
+  __shared__ long long si[256];
+  const int tid = threadIdx.x;
+  const int c = blockIdx.x * 256 + tid;
+  const long long m = p.m0 + c;
+  const bool active = (c < p.chunk) && (m < p.M);
+  const double result = active ? acq_candidate(p, c, m) : -INFINITY;
   if (p.blk_val == nullptr) return;
   // block argmax with Julia semantics (first maximal, NaN maximal); inactive lanes carry idx = LLONG_MAX
   sv[tid] = result;
@@ -321,6 +262,181 @@ __global__ void argmax_final_kernel(const double *blk_val, const long long *blk_
       *best = sv[0];
       *bidx = si[0];
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused triangular product + column sum of squares:  q[m] = sum_r ( sum_{k<=r} W[r][k] K*[k][m] )^2
+// One CTA owns 128 candidates and walks all row blocks of W; the ring streams W (L2-resident) and the
+// CTA's K*^T block (re-read once per row block, triangular k-range).
+// ---------------------------------------------------------------------------------------------
+struct ScoreParams {
+  const double *W;    // P-layout n_pad x n_pad lower-triangular inverse factor
+  const double *Ks;   // chunk scratch
+  int nblk, ktiles;
+  double *ss_part;    // [2*nblk][ld] per-(row block, warp-row half) partial sums of squares
+  int ld;
+  double *VT;         // optional chunk scratch (P-layout, rows = candidates): V = W K* stored transposed (gradient mode)
+  // fused epilogue (one CTA walks ALL row blocks of its candidate block, last slice of the chunk): the column sums
+  // of squares stay in registers, and the CTA finishes its 128 candidates itself -- mean, variance, EI x PoF, guards,
+  // block argmax -- and the last CTA of the launch folds the block winners into the running (value, index) pair.
+  int fused;
+  AcqParams ap;             // ap.mu / ap.sumsq rows of the other slices were written by earlier launches
+  const double *mu_part;    // xcov's partials for this slice, [P][ld]
+  int P;
+  double *mu_row, *ss_row;  // this slice's rows of ap.mu / ap.sumsq
+  double *best;             // running winner of the call (device)
+  long long *bidx;
+  unsigned int *counter;    // CTAs of this launch that have finished (reset by the last one)
+};
+
+// Row blocks of a triangular operand are dealt to the `ns` CTAs of a candidate block in zig-zag order
+// (split y gets y, 2ns-1-y, 2ns+y, 4ns-1-y, ...), which balances the triangular work; ns = 1 is the plain walk.
+__device__ __forceinline__ int zigzag_row(int j, int y, int ns2) { return (j >> 1) * ns2 + ((j & 1) ? ns2 - 1 - y : y); }
+
+struct ScoreIt {
+  const double *w;       // W (lower triangular): row block i uses k-tiles 0 .. 8(i+1)-1
+  const double *ks;      // first tile of this CTA's K*^T block
+  int j, i, kt, nblk, ktiles, y, ns2;
+  __device__ __forceinline__ bool valid() const { return i < nblk; }
+  __device__ __forceinline__ const double *A() const { return w + ((size_t)i * ktiles + kt) * TILE_ELEMS; }
+  __device__ __forceinline__ const double *B() const { return ks + (size_t)kt * TILE_ELEMS; }
+  __device__ __forceinline__ bool tile_end() const { return kt == (i + 1) * KT_PER_BLOCK - 1; }
+  __device__ __forceinline__ int tile() const { return i; }
+  // the last 8 k-tiles of row block i are the diagonal block W_ii: lower triangular (gemm_core.cuh, has_tri_stages)
+  static constexpr int kTriMode = 1;
+  __device__ __forceinline__ bool tri_diag() const { return kt >= i * KT_PER_BLOCK; }
+  __device__ __forceinline__ int tri_g() const { return kt - i * KT_PER_BLOCK; }
+  __device__ __forceinline__ void next() {
+    if (kt == (i + 1) * KT_PER_BLOCK - 1) {
+      ++j;
+      i = zigzag_row(j, y, ns2);
+      kt = 0;
+    } else {
+      ++kt;
+    }
+  }
+};
+
+// out[c] = (sum of the even rows of `in`, ascending) + (sum of the odd rows, ascending): the order in which the
+// fused epilogue of score_trmm_kernel adds its per-warp-row running sums, so both paths give the same bits.
+__global__ void __launch_bounds__(256) reduce_rows2_kernel(const double *__restrict__ in, int P, size_t ld,
+                                                           double *__restrict__ out, int count) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= count) return;
+  double a0 = 0.0, a1 = 0.0;
+  for (int q = 0; q < P; q += 2) {
+    a0 += in[(size_t)q * ld + c];
+    a1 += in[(size_t)(q + 1) * ld + c];
+  }
+  out[c] = a0 + a1;
+}
+
+// Julia-order argmax of (v, i) pairs over the 256 threads of a CTA (i == LLONG_MAX: no candidate); result in sv[0], si[0].
+__device__ __forceinline__ void block_argmax_256(double *sv, long long *si, double v, long long i) {
+  const int tid = threadIdx.x;
+  sv[tid] = v;
+  si[tid] = i;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) {
+      const long long i2 = si[tid + o];
+      if (i2 != 0x7fffffffffffffffLL && (si[tid] == 0x7fffffffffffffffLL || acq_better(sv[tid + o], i2, sv[tid], si[tid]))) {
+        sv[tid] = sv[tid + o];
+        si[tid] = i2;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// grid = (candidate blocks, ns row-block splits).  Each finished 128x128 tile of V = W K* contributes one
+// partial column sum of squares per (row block, warp-row half); reduce_rows2_kernel adds them (unfused path).
+__global__ void __launch_bounds__(GEMM_THREADS, 1) score_trmm_kernel(const __grid_constant__ ScoreParams p) {
+  const int cb = blockIdx.x, y = blockIdx.y, ns2 = 2 * gridDim.y;
+  ScoreIt it{p.W, p.Ks + (size_t)cb * p.ktiles * TILE_ELEMS, 0, zigzag_row(0, y, ns2), 0, p.nblk, p.ktiles, y, ns2};
+  double *vt = p.VT ? p.VT + (size_t)cb * p.ktiles * TILE_ELEMS : nullptr;
+  double ssacc[4][2];   // fused: running column sums of squares of this warp's rows (valid in every lane)
+#pragma unroll
+  for (int fn = 0; fn < 4; ++fn) ssacc[fn][0] = ssacc[fn][1] = 0.0;
+  gemm_pipeline(it, it, [&](int tile, const double(&acc)[8][4][2], const FragCoord &fc) {
+    if (vt) store_block(vt + (size_t)tile * KT_PER_BLOCK * TILE_ELEMS, true, 1.0, nullptr, acc, fc);
+    double *dst = p.ss_part + (size_t)(2 * tile + fc.wm) * p.ld + (size_t)cb * 128 + 32 * fc.wn;
+#pragma unroll
+    for (int fn = 0; fn < 4; ++fn)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        double v = 0.0;
+#pragma unroll
+        for (int fm = 0; fm < 8; ++fm) v = fma(acc[fm][fn][e], acc[fm][fn][e], v);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if (p.fused)
+          ssacc[fn][e] += v;
+        else if (fc.lane < 4)
+          dst[8 * fn + 2 * fc.lane + e] = v;
+      }
+  });
+  if (!p.fused) return;
+  // ---- fused epilogue: this CTA owns candidates cb*128 .. +127 of the chunk ----
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  double *scr = reinterpret_cast<double *>(smem_raw);                 // [2][128] per-warp-row sums, then argmax scratch
+  long long *sidx = reinterpret_cast<long long *>(smem_raw + 4096);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp >> 2, wn = warp & 3;
+  __syncthreads();   // every warp is through the ring
+  if (lane < 4) {
+#pragma unroll
+    for (int fn = 0; fn < 4; ++fn)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) scr[wm * 128 + 32 * wn + 8 * fn + 2 * lane + e] = ssacc[fn][e];
+  }
+  __syncthreads();
+  double result = -INFINITY;
+  long long ridx = 0x7fffffffffffffffLL;
+  if (tid < 128) {
+    const int c = cb * 128 + tid;
+    const double ss = scr[tid] + scr[128 + tid];
+    double mu = 0.0;
+    for (int q = 0; q < p.P; ++q) mu += p.mu_part[(size_t)q * p.ld + c];
+    p.ss_row[c] = ss;
+    p.mu_row[c] = mu;
+    const long long m = p.ap.m0 + c;
+    if (c < p.ap.chunk && m < p.ap.M) {
+      result = acq_candidate(p.ap, c, m);
+      ridx = m;
+    }
+  }
+  __syncthreads();   // scr is reused by the argmax
+  if (p.ap.blk_val == nullptr) return;
+  block_argmax_256(scr, sidx, result, ridx);
+  __shared__ unsigned int s_last;
+  if (tid == 0) {
+    p.ap.blk_val[cb] = scr[0];
+    p.ap.blk_idx[cb] = sidx[0];
+    __threadfence();
+    s_last = atomicAdd(p.counter, 1u) == gridDim.x - 1 ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  // last CTA of the launch: fold the block winners (fixed order) into the call's running winner
+  __threadfence();
+  double v = 0.0;
+  long long ix = 0x7fffffffffffffffLL;
+  for (int b = tid; b < (int)gridDim.x; b += 256) {
+    const long long i2 = p.ap.blk_idx[b];
+    if (i2 != 0x7fffffffffffffffLL && (ix == 0x7fffffffffffffffLL || acq_better(p.ap.blk_val[b], i2, v, ix))) {
+      v = p.ap.blk_val[b];
+      ix = i2;
+    }
+  }
+  block_argmax_256(scr, sidx, v, ix);
+  if (tid == 0) {
+    if (sidx[0] != 0x7fffffffffffffffLL && (*p.bidx < 0 || acq_better(scr[0], sidx[0], *p.best, *p.bidx))) {
+      *p.best = scr[0];
+      *p.bidx = sidx[0];
+    }
+    *p.counter = 0u;
   }
 }
 
