@@ -73,15 +73,25 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
 }
 // Bounded wait: a lost TMA transaction traps (launch fails with an error) instead of hanging the GPU.  A failed
 // try_wait suspends the thread for a few microseconds, so the bound is ~15 s -- far beyond any legitimate wait.
+// -DBOSS_DEBUG_MBAR additionally prints which barrier timed out; it is off by default because the (never taken) call
+// inside every wait loop cost the tensor-core mainloops 3 % (register allocation around the call site).
+#ifdef BOSS_DEBUG_MBAR
 static __device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
   printf("boss_b200: mbarrier wait timed out: smem 0x%x parity %u block (%d,%d) thread %d\n", bar, parity, blockIdx.x,
          blockIdx.y, threadIdx.x);
   __trap();
 }
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 22)) mbar_timeout(bar, parity);
+    if (++spins > (1u << 22)) {
+#ifdef BOSS_DEBUG_MBAR
+      mbar_timeout(bar, parity);
+#else
+      __trap();
+#endif
+    }
   }
 }
 // 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (complete_tx::bytes).

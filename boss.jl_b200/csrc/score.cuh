@@ -356,9 +356,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) score_trmm_kernel(const __gri
   const int cb = blockIdx.x, y = blockIdx.y, ns2 = 2 * gridDim.y;
   ScoreIt it{p.W, p.Ks + (size_t)cb * p.ktiles * TILE_ELEMS, 0, zigzag_row(0, y, ns2), 0, p.nblk, p.ktiles, y, ns2};
   double *vt = p.VT ? p.VT + (size_t)cb * p.ktiles * TILE_ELEMS : nullptr;
-  double ssacc[4][2];   // fused: running column sums of squares of this warp's rows (valid in every lane)
+  // fused: running column sums of squares per warp row, in the 4 KB scratch behind the ring ([2][128]; every slot is
+  // owned by one lane, so no synchronisation is needed until the end) -- eight more live registers per thread in the
+  // mainloop cost 3 % of its throughput
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  double *ssrun = reinterpret_cast<double *>(smem_raw + GEMM_RING_BYTES);
+  if (p.fused && (threadIdx.x & 31) < 4) {
+    const int w_ = threadIdx.x >> 5, l_ = threadIdx.x & 31;
 #pragma unroll
-  for (int fn = 0; fn < 4; ++fn) ssacc[fn][0] = ssacc[fn][1] = 0.0;
+    for (int fn = 0; fn < 4; ++fn) ssrun[(w_ >> 2) * 128 + 32 * (w_ & 3) + 8 * fn + 2 * l_] = ssrun[(w_ >> 2) * 128 + 32 * (w_ & 3) + 8 * fn + 2 * l_ + 1] = 0.0;
+  }
   gemm_pipeline(it, it, [&](int tile, const double(&acc)[8][4][2], const FragCoord &fc) {
     if (vt) store_block(vt + (size_t)tile * KT_PER_BLOCK * TILE_ELEMS, true, 1.0, nullptr, acc, fc);
     double *dst = p.ss_part + (size_t)(2 * tile + fc.wm) * p.ld + (size_t)cb * 128 + 32 * fc.wn;
@@ -372,33 +379,34 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) score_trmm_kernel(const __gri
         v += __shfl_xor_sync(0xffffffffu, v, 4);
         v += __shfl_xor_sync(0xffffffffu, v, 8);
         v += __shfl_xor_sync(0xffffffffu, v, 16);
-        if (p.fused)
-          ssacc[fn][e] += v;
-        else if (fc.lane < 4)
-          dst[8 * fn + 2 * fc.lane + e] = v;
+        if (fc.lane < 4) {
+          if (p.fused)
+            ssrun[fc.wm * 128 + 32 * fc.wn + 8 * fn + 2 * fc.lane + e] += v;
+          else
+            dst[8 * fn + 2 * fc.lane + e] = v;
+        }
       }
   });
   if (!p.fused) return;
   // ---- fused epilogue: this CTA owns candidates cb*128 .. +127 of the chunk ----
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  double *scr = reinterpret_cast<double *>(smem_raw);                 // [2][128] per-warp-row sums, then argmax scratch
+  double *scr = reinterpret_cast<double *>(smem_raw);                 // argmax scratch (the ring is idle now)
   long long *sidx = reinterpret_cast<long long *>(smem_raw + 4096);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp >> 2, wn = warp & 3;
-  __syncthreads();   // every warp is through the ring
-  if (lane < 4) {
-#pragma unroll
-    for (int fn = 0; fn < 4; ++fn)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) scr[wm * 128 + 32 * wn + 8 * fn + 2 * lane + e] = ssacc[fn][e];
-  }
+  const int tid = threadIdx.x;
+  __syncthreads();   // every warp is through the ring and has added its last tile to ssrun
+  // xcov's partial means of these 128 candidates: one coalesced sweep into the (idle) ring, summed in order below --
+  // P dependent global loads per thread would hold the SM (and its tensor pipe) for tens of microseconds
+  double *mup = reinterpret_cast<double *>(smem_raw + 8192);           // [P][128], P <= 2 * 64
+  const int Pm = p.P < 128 ? p.P : 128;
+  for (int e = tid; e < Pm * 128; e += GEMM_THREADS) mup[e] = p.mu_part[(size_t)(e >> 7) * p.ld + cb * 128 + (e & 127)];
   __syncthreads();
   double result = -INFINITY;
   long long ridx = 0x7fffffffffffffffLL;
   if (tid < 128) {
     const int c = cb * 128 + tid;
-    const double ss = scr[tid] + scr[128 + tid];
+    const double ss = ssrun[tid] + ssrun[128 + tid];
     double mu = 0.0;
-    for (int q = 0; q < p.P; ++q) mu += p.mu_part[(size_t)q * p.ld + c];
+    for (int q = 0; q < Pm; ++q) mu += mup[q * 128 + tid];
+    for (int q = Pm; q < p.P; ++q) mu += p.mu_part[(size_t)q * p.ld + c];
     p.ss_row[c] = ss;
     p.mu_row[c] = mu;
     const long long m = p.ap.m0 + c;
