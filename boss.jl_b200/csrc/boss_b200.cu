@@ -26,6 +26,7 @@
 #include "chol_matrix.cuh"
 #include "score.cuh"
 #include "grad.cuh"
+#include "score_narrow.cuh"
 #include "append.cuh"
 #include "multistart.cuh"
 
@@ -255,7 +256,8 @@ unsigned long long mask_bits(const uint8_t *mask, int d) {
 
 // Number of zig-zag row-block splits per candidate block for the triangular products (score_trmm / wtv):
 // minimise waves x (largest per-CTA share of the nblk(nblk+1)/2 block-steps + ~1 block-step of pipeline fill).
-int pick_row_splits(int ncb, int nblk) {
+int pick_row_splits(int ncb, int nblk, double *cost = nullptr) {
+  if (cost) *cost = ((ncb + 147) / 148) * (nblk * (nblk + 1) / 2 + 1.0);
   if (ncb >= 4 * 148 || nblk < 2) return 1;
   double best_t = 1e300;
   int best = 1;
@@ -277,6 +279,7 @@ int pick_row_splits(int ncb, int nblk) {
       best = ns;
     }
   }
+  if (cost) *cost = best_t;
   return best;
 }
 
@@ -294,6 +297,8 @@ int set_kernel_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(trtri_row_rl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(score_trmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(wtv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(score_narrow_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, NW_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(score_narrow_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, NW_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(potrf_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(chol_matrix_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, CM_SMEM_BYTES));
@@ -1328,7 +1333,14 @@ int score_core(ScoreArgs &a) {
       // several CTAs.  Partial sums are kept per chunk / per row block, so results do not depend on the split.
       const int want = (16 * 148 + ncb - 1) / ncb;   // >= 16 CTAs per SM in flight over the launch (4 waves of 4)
       const int nks = std::max(1, std::min(h->nblk, want));            // xcov / grad: splits over training chunks
-      const int nsp = pick_row_splits(ncb, h->nblk);                   // trmm / wtv: zig-zag row-block splits
+      double cost_w = 0.0, cost_n = 0.0;
+      const int nsp = pick_row_splits(ncb, h->nblk, &cost_w);          // trmm / wtv: zig-zag row-block splits
+      // Small batches: 32-candidate CTAs (score_narrow.cuh) do a quarter of the tensor work per stage of W; worth it
+      // when the wide launch cannot fill the GPU (cost = waves x longest per-CTA share, in block-steps; a narrow stage
+      // takes ~0.3 of a wide one).  Same bits either way.
+      const int ncb32 = (ch + NW_NB - 1) / NW_NB;
+      const int nsp32 = pick_row_splits(ncb32, h->nblk, &cost_n);
+      const bool narrow = 0.32 * cost_n < cost_w && getenv("BOSS_NO_NARROW") == nullptr;
       const int cnt = ncb * 128;
       XcovParams xp{};
       xp.Xs = xs_dev;
@@ -1353,7 +1365,7 @@ int score_core(ScoreArgs &a) {
       }
       // One CTA per candidate block walks all of W (large batches) and this is the chunk's last slice: the scoring
       // kernel finishes the candidates itself (fused epilogue) -- no reduce / acquisition / argmax launches.
-      const bool fuse = nsp == 1 && q == nsl - 1 && getenv("BOSS_UNFUSED_SCORE") == nullptr;
+      const bool fuse = nsp == 1 && !narrow && q == nsl - 1 && getenv("BOSS_UNFUSED_SCORE") == nullptr;
       fused_chunk = fuse;
       if (!fuse)
         reduce_rows_kernel<<<(cnt + 255) / 256, 256, 0, C().stream>>>(C().part_mu.as<double>(), 2 * h->nblk, (size_t)CH,
@@ -1377,7 +1389,12 @@ int score_core(ScoreArgs &a) {
         sp.bidx = d_bidx;
         sp.counter = d_counter;
       }
-      {
+      if (narrow) {
+        NarrowParams np{h->W, C().ks.as<double>(), h->nblk, h->ktiles, C().part_ss.as<double>(), CH,
+                        a.grad ? C().vt.as<double>() : nullptr};
+        Timed t(0);
+        score_narrow_kernel<0><<<dim3(ncb32, nsp32), 256, NW_SMEM_BYTES, C().stream>>>(np);
+      } else {
         Timed t(0);
         score_trmm_kernel<<<dim3(ncb, nsp), GEMM_THREADS, GEMM_SMEM_BYTES, C().stream>>>(sp);
       }
@@ -1387,7 +1404,11 @@ int score_core(ScoreArgs &a) {
       C().launches += fuse ? 2 : 4;
       if (a.grad) {
         WtvParams wp{h->WT, C().vt.as<double>(), C().ut.as<double>(), h->nblk, h->ktiles};
-        {
+        if (narrow) {
+          NarrowParams np{h->WT, C().vt.as<double>(), h->nblk, h->ktiles, nullptr, CH, C().ut.as<double>()};
+          Timed t(0);
+          score_narrow_kernel<1><<<dim3(ncb32, nsp32), 256, NW_SMEM_BYTES, C().stream>>>(np);
+        } else {
           Timed t(0);
           wtv_kernel<<<dim3(ncb, nsp), GEMM_THREADS, GEMM_SMEM_BYTES, C().stream>>>(wp);
         }
@@ -1857,7 +1878,9 @@ static int multistart_single(const boss_gp *const *slices, int y_dim, int n_samp
   // rejected trials; the budget below lets a start reject every other trial on average before it is cut off.
   const int max_rounds = iters > 0 ? 2 * iters + MS_MAX_TRIALS : 0;
   int active = iters > 0 ? (int)M : 0;
+  const bool trace = getenv("BOSS_MS_TRACE") != nullptr;   // one line per round on stderr: round, batch size
   for (int round = 0; round < max_rounds && active > 0; ++round) {
+    if (trace) fprintf(stderr, "boss multistart: round %d active %d\n", round, active);
     CUDA_TRY(cudaMemsetAsync(st.counters, 0, 16, C().stream));
     ms_propose_kernel<<<nbm, 128, 0, C().stream>>>(st);
     rc = eval(st.Xc, active, st.fc, st.gc, false, nullptr, nullptr);   // `active` = the compact list's length

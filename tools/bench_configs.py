@@ -163,6 +163,7 @@ def run_c4(torch, _lib, O, stream, args):
     gerr = float(np.max(np.abs(g_dev[:, :k][:, m] - g_ref[:, m]) / gscale)) if m.any() else 0.0
     # the whole multi-start solve, device resident: 50 lock-step L-BFGS iterations over all starts
     aff = np.zeros((1, d + 1)); aff[0, 0] = theta[1]; aff[0, 1] = theta[0]
+    _lib.ei_maximize_multistart([gp], 1, 1, starts, [1.0], best, None, lb, ub, iters=50, prior_mean_affine=aff)   # grows workspaces
     t0 = time.perf_counter()
     Xo, fo, bx, bv, bi, evals = _lib.ei_maximize_multistart([gp], 1, 1, starts, [1.0], best, None, lb, ub, iters=50,
                                                             prior_mean_affine=aff)
