@@ -2266,7 +2266,11 @@ static int loglik_core(const double *X, int d, int n, const double *Ymm, int64_t
       bk.K = Lg;
       bk.K_stride = mat;
       bk.status = stg;
-      const bool fuse_diag = !unfused_diag();
+      // Fused diagonal step (K_jj generated on chip + SYRK + potrf in one 2-CTA/SM kernel) for small matrices, where the
+      // three short launches and the tile's HBM trip dominate (C3, n = 512: 1.61 -> 1.55 ms); for long k-ranges the
+      // dedicated SYRK kernel (5-stage ring, 218 registers) runs its DMMAs at 75 % of the SM's rate against 51 % for the
+      // 128-register fused one (11.8 vs 17.5 us per 128-block of k at n = 2048), so larger matrices keep the separate steps.
+      const bool fuse_diag = !unfused_diag() && nblk <= 6;
       bk.skip_diag = fuse_diag ? 1 : 0;     // the diagonal tiles are generated inside potrf_fused_kernel
       if (!(fuse_diag && nblk == 1)) {
         Timed t(1);
