@@ -7,7 +7,7 @@ Layout:
   meaning and error behaviour) on top of the C ABI.
 """
 from . import _lib  # noqa: F401  (raises loudly when the CUDA library has not been built)
-from .types import (BIParams, BossOptions, BossProblem, Dirac, Domain, ExperimentData, FixedParams, LinFitness,  # noqa: F401
+from .types import (BIParams, BossOptions, BossProblem, Dirac, Domain, ExperimentData, ExprFitness, FixedParams, LinFitness,  # noqa: F401
                     LogNormal, MAPParams, NonlinFitness, Product, Uniform, generate_LHC, in_bounds, in_domain,
                     mvlognormal)
 from .gaussian_process import (DiscreteKernel, GaussianProcess, GaussianProcessParams, GaussianProcessPosterior,  # noqa: F401
@@ -18,7 +18,7 @@ from .acquisition import (Acquisition, ExpectedImprovement, best_so_far, constru
                           construct_safe_acquisition)
 from .acquisition_maximizers import (GridAM, OptimizationAM, SampleOptAM, SamplingAM, SequentialBatchAM,  # noqa: F401
                                      batched_lbfgs_maximize, maximize_acquisition)
-from .model_fitters import OptimizationMAP, SamplingMAP, estimate_parameters, model_loglike  # noqa: F401
+from .model_fitters import OptimizationMAP, SampleOptMAP, SamplingMAP, estimate_parameters, model_loglike  # noqa: F401
 from .bo import IterLimit, bo  # noqa: F401
 from . import parallel  # noqa: F401
 

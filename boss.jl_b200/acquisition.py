@@ -10,7 +10,7 @@ import numpy as np
 
 from . import _lib
 from .posterior import model_posterior
-from .types import BossOptions, BossProblem, LinFitness, cons_mask
+from .types import BossOptions, BossProblem, ExprFitness, LinFitness, cons_mask
 
 _erfc = np.vectorize(math.erfc, otypes=[np.float64])
 
@@ -78,6 +78,7 @@ class Acquisition:
         # (expected_improvement.jl:104-111) is finished on the host.
         self.fitness = ei.fitness
         self.nonlin = not isinstance(ei.fitness, LinFitness)
+        self.expr = ei.fitness if isinstance(ei.fitness, ExprFitness) else None    # device MC-EI (boss_mcei_score)
         if self.nonlin:
             count = ei.eps_samples if len(self.posts) == 1 else len(self.posts)   # ϵ_sample_count, :115-116
             self.eps = sample_eps(self.y_dim, count) if eps is None else np.asarray(eps, dtype=np.float64)
@@ -106,9 +107,16 @@ class Acquisition:
             pass
         return np.array([float(self.fitness(pred[:, k])) for k in range(P)])
 
-    def _mc_acq(self, X):
+    def _mc_acq(self, X, want_argmax=False):
         """construct_ei for a NonlinFitness (expected_improvement.jl:68-90, :104-111)."""
         M = X.shape[1]
+        if self.expr is not None:     # expression-set fitness: the whole Monte-Carlo EI runs on the device
+            lb, ub, cm = self._guards(X)
+            e = self.expr
+            acq, bv, bi = _lib.mcei_score(self.slices, self.y_dim, len(self.posts), X, e.kind_id, self.eps, self.best,
+                                          self.y_max, c0=e.c0, c=e.c, q=e.q, t=e.t, lb=lb, ub=ub, cons_mask=cm,
+                                          prior_mean_s=self._prior_mean(X), want_acq=not want_argmax)
+            return (int(bi), float(bv)) if want_argmax else acq
         pm = self._prior_mean(X)
         acc = np.zeros(M)
         failed = np.zeros(M, dtype=bool)
@@ -167,6 +175,8 @@ class Acquisition:
         """-> (index, value) with Julia argmax semantics, one fused launch sequence (no score vector round trip)."""
         X = np.asarray(X, dtype=np.float64)
         if self.nonlin:
+            if self.expr is not None:
+                return self._mc_acq(X, want_argmax=True)
             acq = self._mc_acq(X)
             bi = julia_argmax(acq)
             return int(bi), float(acq[bi])

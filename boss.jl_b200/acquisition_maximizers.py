@@ -89,7 +89,7 @@ def _rand_in_domain(am: SamplingAM, domain: Domain):
     return None
 
 
-def batched_lbfgs_maximize(value_and_grad, starts, lb, ub, iters=60, history=8, discrete=None):
+def batched_lbfgs_maximize(value_and_grad, starts, lb, ub, iters=60, history=8, discrete=None, publish_active=None):
     """Maximise f over the box [lb, ub] from every column of `starts` simultaneously (projected L-BFGS with Armijo
     backtracking).  value_and_grad(X: d x S) -> (f: S, g: d x S).  Returns X (d x S), f (S).
 
@@ -100,6 +100,8 @@ def batched_lbfgs_maximize(value_and_grad, starts, lb, ub, iters=60, history=8, 
     the projected gradient (after 12 rejections along an L-BFGS direction the history is dropped first)."""
     X = np.clip(np.array(starts, dtype=np.float64, copy=True), lb[:, None], ub[:, None])
     d, S = X.shape
+    if publish_active is not None:           # callers whose closure needs to know which starts a batch belongs to
+        publish_active.active = np.arange(S)
     f, g = value_and_grad(X)
     f = np.where(np.isfinite(f), f, -np.inf)
     g = np.array(g, dtype=np.float64, copy=True)
@@ -136,6 +138,8 @@ def batched_lbfgs_maximize(value_and_grad, starts, lb, ub, iters=60, history=8, 
             dirn[:, m] = q if (q @ pg) > 0 else pg * sd        # not an ascent direction -> projected steepest ascent
             t[m] = 1.0; trials[m] = 0; state[m] = 1
         Xt = np.clip(X[:, act] + dirn[:, act] * t[act], lb[:, None], ub[:, None])
+        if publish_active is not None:
+            publish_active.active = act
         ft, gt = value_and_grad(Xt)
         ft = np.where(np.isfinite(ft), ft, -np.inf)
         for c, m in enumerate(act):

@@ -5,7 +5,8 @@ from typing import Optional
 
 import numpy as np
 
-from .gaussian_process import GaussianProcessParams, Semiparametric, SemiparametricParams, data_loglike
+from .gaussian_process import (GaussianProcessParams, Semiparametric, SemiparametricParams, data_loglike,
+                               data_loglike_and_grad)
 from .types import BossOptions, BossProblem, MAPParams
 
 
@@ -19,13 +20,32 @@ class SamplingMAP:
 
 
 class OptimizationMAP:
-    """optimization.jl:23-164 with a derivative-free local search: all multistarts advance in lock-step and every
-    iteration evaluates 2*P+... probes for all starts in one batched log-likelihood call (compass search in log space)."""
+    """optimization.jl:23-164.  All multistarts advance together and every evaluation of all of them is one batched
+    device call.  algorithm:
+      "lbfgs"    gradient-based (the reference's default autodiff = AutoForwardDiff(), optimization.jl:41,153): batched
+                 L-BFGS in log-parameter space on boss_gp_loglik_grad_batch (value + analytic gradient of the data
+                 log-likelihood for all starts at once; the prior term's gradient is a host-side central difference).
+                 GaussianProcess models; a Semiparametric model falls back to "compass".
+      "compass"  derivative-free compass search in log space (what NEWUOA / BOBYQA are used for in the examples)."""
 
-    def __init__(self, multistart: int = 20, iters: int = 40, step0: float = 0.5, seed: Optional[int] = None):
-        self.multistart = multistart
+    def __init__(self, multistart=20, iters: int = 40, step0: float = 0.5, seed: Optional[int] = None,
+                 algorithm: str = "lbfgs"):
+        self.multistart = multistart          # an int, or a list of start params (SampleOptMAP hands its best samples over)
         self.iters = iters
         self.step0 = step0
+        self.algorithm = algorithm
+        self.rng = np.random.default_rng(seed)
+
+
+class SampleOptMAP:
+    """sample_opt.jl:37-48: SamplingMAP (return_all) -> the `multistart` best samples -> OptimizationMAP from them."""
+
+    def __init__(self, samples: int = 200, multistart: int = 20, iters: int = 40, seed: Optional[int] = None,
+                 algorithm: str = "lbfgs"):
+        self.samples = samples
+        self.multistart = multistart
+        self.iters = iters
+        self.algorithm = algorithm
         self.rng = np.random.default_rng(seed)
 
 
@@ -106,8 +126,17 @@ def estimate_parameters(fitter, problem: BossProblem, options: BossOptions = Bos
             return [MAPParams(p, float(v)) for p, v in zip(samples, vals)]
         b = int(np.argmax(vals))                       # first maximum == the reference's strict `v > best_v`
         return MAPParams(samples[b], float(vals[b]))
+    if isinstance(fitter, SampleOptMAP):
+        # sample_opt.jl:41-46: all samples with their log-likelihoods, sorted, the best `multistart` become the starts
+        sm = SamplingMAP(fitter.samples)
+        sm.rng = fitter.rng
+        allp = estimate_parameters(sm, problem, options, return_all=True)
+        order = np.argsort([-p.loglike for p in allp], kind="stable")[: fitter.multistart]
+        om = OptimizationMAP([allp[i].params for i in order], fitter.iters, algorithm=fitter.algorithm)
+        om.rng = fitter.rng
+        return estimate_parameters(om, problem, options, return_all=return_all)
     if isinstance(fitter, OptimizationMAP):
-        starts = [sampler() for _ in range(fitter.multistart)]
+        starts = list(fitter.multistart) if not isinstance(fitter.multistart, int) else [sampler() for _ in range(fitter.multistart)]
         tmpl = starts[0]
         fixed = _dirac_mask(model, tmpl)
         V0 = np.stack([_vectorize(p) for p in starts])             # S x P_all
@@ -132,6 +161,8 @@ def estimate_parameters(fitter, problem: BossProblem, options: BossOptions = Bos
             b = int(np.argmax(f0))
             return MAPParams(starts[b], float(f0[b]))
         _devectorize_rows = lambda rows, owners: [_devec_free(o, v) for v, o in zip(rows, owners)]
+        if fitter.algorithm == "lbfgs" and not isinstance(model, Semiparametric):
+            return _lbfgs_map(fitter, model, data, V, free, tmpl, _devec_free, return_all)
         f = ll(_devectorize_rows(V, range(S)))
         step = np.full(S, fitter.step0)
         for _ in range(fitter.iters):
@@ -158,3 +189,52 @@ def estimate_parameters(fitter, problem: BossProblem, options: BossOptions = Bos
         b = int(np.argmax(f))
         return MAPParams(_devec_free(b, V[b]), float(f[b]))
     raise TypeError(f"unsupported model fitter {type(fitter).__name__}")
+
+
+def _lbfgs_map(fitter, model, data, V, free, tmpl, devec_free, return_all):
+    """Gradient OptimizationMAP: maximise data_loglike + params_loglike over the free log-parameters of all starts with
+    the batched L-BFGS of acquisition_maximizers.batched_lbfgs_maximize.  One value + gradient evaluation of all
+    unfinished starts = one boss_gp_loglik_grad_batch call per output slice."""
+    from .acquisition_maximizers import batched_lbfgs_maximize
+    llg = data_loglike_and_grad(model, data)
+    pll = model.params_loglike()
+    S, P = V.shape
+    off = _offsets(tmpl)
+    owners = {"n": 0}
+
+    def prior_and_grad(p, vfree, s_idx):
+        base = pll(p)
+        g = np.zeros(P)
+        if not np.isfinite(base):
+            return base, g
+        h = 1e-6
+        for k in range(P):                       # O(#params) host work per start: central difference of the prior term
+            vp, vm = vfree.copy(), vfree.copy()
+            vp[k] += h; vm[k] -= h
+            fp, fm = pll(devec_free(s_idx, vp)), pll(devec_free(s_idx, vm))
+            g[k] = (fp - fm) / (2 * h) if np.isfinite(fp) and np.isfinite(fm) else 0.0
+        return base, g
+
+    def value_and_grad(Z):                      # Z: P x m (columns = the unfinished starts, in the order given by `act`)
+        cols = value_and_grad.active
+        plist = [devec_free(s, Z[:, c]) for c, s in enumerate(cols)]
+        ll_d, grads = llg(plist)
+        f = np.empty(len(cols)); G = np.zeros((P, len(cols)))
+        for c, (s, p) in enumerate(zip(cols, plist)):
+            full = np.concatenate([grads[c].lengthscales.ravel(order="F") * p.lengthscales.ravel(order="F"),
+                                   grads[c].amplitudes * p.amplitudes, grads[c].noise_std * p.noise_std])   # d/d log(theta)
+            pr, gpr = prior_and_grad(p, Z[:, c], s)
+            f[c] = ll_d[c] + pr if np.isfinite(pr) else -np.inf
+            G[:, c] = full[free] + gpr
+        return f, G
+
+    # batched_lbfgs_maximize calls value_and_grad on the columns of the unfinished starts; it needs to know which
+    # starts those are (Dirac-pinned entries are rebuilt per start), so the driver publishes the active set
+    lo = np.full(P, -30.0); hi = np.full(P, 30.0)          # log-parameters: an effectively unbounded box
+    X, f = batched_lbfgs_maximize(value_and_grad, V.T.copy(), lo, hi, iters=fitter.iters, publish_active=value_and_grad)
+    if np.all(np.isneginf(f)):
+        raise RuntimeError("All optimization runs failed!")
+    if return_all:
+        return [MAPParams(devec_free(i, X[:, i]), float(f[i])) for i in range(S) if np.isfinite(f[i])]
+    b = int(np.argmax(f))
+    return MAPParams(devec_free(b, X[:, b]), float(f[b]))

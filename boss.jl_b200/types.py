@@ -85,6 +85,37 @@ class NonlinFitness:
         return self.fitness(y)
 
 
+class ExprFitness(NonlinFitness):
+    """A NonlinFitness from the small expression set the device can evaluate (include/boss_b200.h, boss_mcei_score):
+         kind "affine"     f(y) = c0 + c . y
+              "quadratic"  f(y) = c0 + c . y + sum_i q_i (y_i - t_i)^2
+              "max"/"min"  f(y) = c0 + max/min over {i : c_i != 0} of (c_i y_i + t_i)
+    It is an ordinary fitness closure on the host (so best_so_far etc. work unchanged); ExpectedImprovement with it runs
+    the Monte-Carlo EI of expected_improvement.jl:104-111 on the device instead of finishing it on the host."""
+    KINDS = {"affine": 1, "quadratic": 2, "max": 3, "min": 4}
+
+    def __init__(self, kind: str, c, c0: float = 0.0, q=None, t=None):
+        self.kind = kind
+        self.kind_id = self.KINDS[kind]
+        self.c = np.asarray(c, dtype=np.float64)
+        self.c0 = float(c0)
+        self.q = np.zeros_like(self.c) if q is None else np.asarray(q, dtype=np.float64)
+        self.t = np.zeros_like(self.c) if t is None else np.asarray(t, dtype=np.float64)
+        super().__init__(self._eval)
+
+    def _eval(self, y):
+        y = np.asarray(y, dtype=np.float64)
+        cy = self.c[:, None] * y if y.ndim == 2 else self.c * y
+        if self.kind_id == 1:
+            return self.c0 + cy.sum(axis=0)
+        if self.kind_id == 2:
+            dv = y - (self.t[:, None] if y.ndim == 2 else self.t)
+            return self.c0 + cy.sum(axis=0) + ((self.q[:, None] if y.ndim == 2 else self.q) * dv * dv).sum(axis=0)
+        live = self.c != 0
+        v = (cy + (self.t[:, None] if y.ndim == 2 else self.t))[live]
+        return self.c0 + (v.max(axis=0) if self.kind_id == 3 else v.min(axis=0))
+
+
 # ---- data (src/data/simple_data.jl) ---------------------------------------------------------------
 class ExperimentData:
     def __init__(self, X, Y):

@@ -213,3 +213,48 @@ def test_nonlin_fitness_mc_ei_matches_oracle_map_and_bi():
     ref = O.mc_ei_acquisition(posts, Xs, fit_scalar, eps3, best, prob.y_max, *prob.domain.bounds, cons_mask=cm)
     got = acq_bi(Xs)
     assert np.all(np.abs(got - ref) <= 1e-9 * np.maximum(np.abs(ref), 1e-300))
+
+
+def test_expr_fitness_runs_mc_ei_on_the_device_and_matches_the_host_closure_path():
+    """ExprFitness = a NonlinFitness from the device's expression set: ExpectedImprovement with it evaluates the
+    Monte-Carlo EI (expected_improvement.jl:104-111) inside boss_mcei_score; the same fitness wrapped as an opaque
+    NonlinFitness closure goes through the host finish -- both must agree, and agree with the oracle."""
+    f = lambda x: np.array([np.sin(x[0]) + 0.1 * x[1], np.cos(x[0]) - 0.05 * x[1]])
+    Xs = np.random.default_rng(11).random((2, 300)) * 11.0 - 0.5
+    eps = np.random.default_rng(12).standard_normal((2, 64))
+    for ef in (B.ExprFitness("quadratic", [1.0, 0.3], c0=0.1, q=[0.0, -0.5], t=[0.0, 0.2]),
+               B.ExprFitness("min", [1.0, 2.0], t=[0.0, 0.5]), B.ExprFitness("affine", [0.7, -0.2], c0=1.0)):
+        prob = _problem(y_max=[np.inf, 0.6], cons=lambda x: [x[0] + x[1] - 1.0], seed=6, f=f)
+        prob.acquisition = B.ExpectedImprovement(ef, eps_samples=64)
+        prob.params = B.estimate_parameters(B.SamplingMAP(32, seed=3), prob)
+        acq_dev = B.construct_acquisition(prob, eps=eps)
+        assert acq_dev.expr is not None
+        prob2 = _problem(y_max=[np.inf, 0.6], cons=lambda x: [x[0] + x[1] - 1.0], seed=6, f=f)
+        prob2.acquisition = B.ExpectedImprovement(B.NonlinFitness(lambda y, ef=ef: ef(y)), eps_samples=64)
+        prob2.params = prob.params
+        acq_host = B.construct_acquisition(prob2, eps=eps)
+        assert acq_host.expr is None
+        a, b = acq_dev(Xs), acq_host(Xs)
+        assert np.any(b > 0)
+        assert np.max(np.abs(a - b)) <= 1e-9 * np.max(np.abs(b))
+        k, v = acq_dev.argmax(Xs)
+        assert k == int(np.argmax(a)) and v == a[k]
+
+
+def test_gradient_optimization_map_and_sample_opt_map():
+    """OptimizationMAP with the analytic hyper-parameter gradient (boss_gp_loglik_grad_batch; the reference's default
+    autodiff path, optimization.jl:41,153) and SampleOptMAP (sample_opt.jl:37-48): both must reach at least the
+    log-likelihood of the best of their starts, and the gradient search must match or beat the compass search."""
+    prob = _problem(seed=8, n=40)
+    ll = B.model_loglike(prob.model, prob.data)
+    samp = B.estimate_parameters(B.SamplingMAP(64, seed=21), prob)
+    grad = B.estimate_parameters(B.OptimizationMAP(multistart=12, iters=30, seed=21, algorithm="lbfgs"), prob)
+    comp = B.estimate_parameters(B.OptimizationMAP(multistart=12, iters=30, seed=21, algorithm="compass"), prob)
+    so = B.estimate_parameters(B.SampleOptMAP(samples=64, multistart=6, iters=30, seed=21), prob)
+    for r in (grad, comp, so):
+        assert abs(ll(r.params) - r.loglike) <= 1e-8 * abs(r.loglike)          # reported value is the value at the point
+        assert np.all(r.params.noise_std == 0.1)                                 # Dirac-pinned noise stays exact
+    assert so.loglike >= samp.loglike - 1e-9                                     # starts from the best samples
+    assert grad.loglike >= comp.loglike - 0.05 * abs(comp.loglike)
+    allr = B.estimate_parameters(B.OptimizationMAP(multistart=5, iters=5, seed=3), prob, return_all=True)
+    assert 1 <= len(allr) <= 5
