@@ -78,6 +78,8 @@ EXPORTS = {
     "boss_dbg_gemm_nt": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     "boss_dbg_factors": (C.c_int, [_vp, _vp, _vp, _vp]),
     "boss_dbg_kernel_fn": (C.c_int, [C.c_int, _vp, C.c_int, _vp]),
+    "boss_dbg_check_redzones": (C.c_int64, [_i64p]),
+    "boss_dbg_redzone_selftest": (C.c_int64, []),
 }
 for _name, (_res, _args) in EXPORTS.items():
     _f = getattr(lib, _name)          # AttributeError here = header and library disagree
@@ -525,3 +527,10 @@ def dbg_factors(gp: GP):
     al = np.empty(n)
     _check(lib.boss_dbg_factors(gp.handle, _ptr(L), _ptr(W), _ptr(al)), "boss_dbg_factors")
     return L, W, al
+
+
+def dbg_check_redzones():
+    """(overwritten guard bytes, allocations scanned); (-1, 0) unless the process runs with BOSS_DEBUG_REDZONE=1."""
+    n = C.c_int64(0)
+    bad = lib.boss_dbg_check_redzones(C.byref(n))
+    return int(bad), int(n.value)

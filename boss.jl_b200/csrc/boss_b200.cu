@@ -39,25 +39,71 @@ struct boss_gp;
 // ---------------------------------------------------------------------------------------------
 namespace {
 
+// Red zones (BOSS_DEBUG_REDZONE=1; the home-grown stand-in for compute-sanitizer memcheck, which is closed on the
+// build pool): every device allocation of the library is then made exactly as large as requested (no growth slack)
+// and bracketed by two RZ_BYTES guard bands filled with 0xA5; boss_dbg_check_redzones() scans all live guard bands
+// on the device and returns the number of bytes a kernel has overwritten.  Off by default: zero cost.
+constexpr size_t RZ_BYTES = 64 << 10;
+struct RzEntry {
+  char *base;
+  size_t bytes;   // user bytes (rounded up to 256)
+  int device;
+};
+std::mutex g_rz_mu;
+std::map<void *, RzEntry> g_rz;      // user pointer -> allocation
+inline bool redzones_on() {
+  static const bool on = getenv("BOSS_DEBUG_REDZONE") != nullptr;
+  return on;
+}
+cudaError_t dev_malloc(void **out, size_t bytes) {
+  if (!redzones_on()) return cudaMalloc(out, bytes);
+  const size_t user = (bytes + 255) & ~(size_t)255;
+  char *base = nullptr;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&base), user + 2 * RZ_BYTES);
+  if (e != cudaSuccess) return e;
+  cudaMemset(base, 0xA5, RZ_BYTES);
+  // the bytes between the requested size and the 256-byte rounding belong to the upper guard band as well
+  cudaMemset(base + RZ_BYTES + bytes, 0xA5, user - bytes + RZ_BYTES);
+  int dev = -1;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(g_rz_mu);
+  g_rz[base + RZ_BYTES] = RzEntry{base, bytes, dev};
+  *out = base + RZ_BYTES;
+  return cudaSuccess;
+}
+cudaError_t dev_free(void *p) {
+  if (!p) return cudaSuccess;
+  if (redzones_on()) {
+    std::lock_guard<std::mutex> lk(g_rz_mu);
+    auto it = g_rz.find(p);
+    if (it != g_rz.end()) {
+      void *base = it->second.base;
+      g_rz.erase(it);
+      return cudaFree(base);
+    }
+  }
+  return cudaFree(p);
+}
+
 struct DevBuf {
   void *p = nullptr;
   size_t cap = 0;
   cudaError_t ensure(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
+    if (p) dev_free(p);
     p = nullptr;
     cap = 0;
-    size_t want = bytes + bytes / 8;
-    cudaError_t e = cudaMalloc(&p, want);
+    size_t want = redzones_on() ? bytes : bytes + bytes / 8;
+    cudaError_t e = dev_malloc(&p, want);
     if (e != cudaSuccess) {
-      e = cudaMalloc(&p, bytes);
+      e = dev_malloc(&p, bytes);
       want = bytes;
     }
     if (e == cudaSuccess) cap = want;
     return e;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) dev_free(p);
     p = nullptr;
     cap = 0;
   }
@@ -149,16 +195,16 @@ cudaError_t pool_alloc(double **out, size_t bytes) {
     return cudaSuccess;
   }
   void *p = nullptr;
-  cudaError_t e = cudaMalloc(&p, bytes);
+  cudaError_t e = dev_malloc(&p, bytes);
   if (e != cudaSuccess && !C().pool.empty()) {   // out of memory: drop the pooled buffers and retry
     for (auto &kv : C().pool) {
-      cudaFree(kv.second);
+      dev_free(kv.second);
       C().pool_sizes.erase(kv.second);
     }
     C().pool.clear();
     C().pool_bytes = 0;
     cudaGetLastError();
-    e = cudaMalloc(&p, bytes);
+    e = dev_malloc(&p, bytes);
   }
   if (e == cudaSuccess) {
     C().pool_sizes[p] = bytes;
@@ -171,14 +217,14 @@ void pool_free(void *p) {
   auto it = C().pool_sizes.find(p);
   if (it == C().pool_sizes.end() || C().pool_bytes + it->second > POOL_CAP || C().device < 0) {
     if (it != C().pool_sizes.end()) C().pool_sizes.erase(it);
-    cudaFree(p);
+    dev_free(p);
     return;
   }
   C().pool.emplace(it->second, p);
   C().pool_bytes += it->second;
 }
 void pool_release_all() {
-  for (auto &kv : C().pool) cudaFree(kv.second);
+  for (auto &kv : C().pool) dev_free(kv.second);
   C().pool.clear();
   C().pool_sizes.clear();
   C().pool_bytes = 0;
@@ -283,6 +329,12 @@ int pick_row_splits(int ncb, int nblk, double *cost = nullptr) {
   return best;
 }
 
+// cost model of the quarter-row kernels (score_narrow.cuh) in pick_row_splits' unit (one 128-block step of the wide
+// kernel on one SM, 17 us): per row block of the longest CTA's chain, per (32-candidate block x block step) of tensor
+// work spread over the GPU, fixed cost of the extra reduction launch.  Calibrated on the B200 (tools/bench_small_batch.py).
+constexpr long long MS_FAN_BATCH = 256;   // capacity of a multi-start round's batch once the step-size fan is on
+constexpr double NQ_COST_CHAIN = 0.085, NQ_COST_WORK = 0.0023, NQ_COST_FIXED = 0.15;
+
 // dynamic shared-memory opt-in is per device: once per context
 int set_kernel_attrs() {
   if (C().attrs_done) return 0;
@@ -299,6 +351,8 @@ int set_kernel_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(wtv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(score_narrow_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, NW_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(score_narrow_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, NW_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(score_quarter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, NQ_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(score_quarter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, NQ_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(potrf_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(chol_matrix_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, CM_SMEM_BYTES));
@@ -1121,6 +1175,9 @@ int score_core(ScoreArgs &a) {
   const int max_nblk = max_npad / TM;
   CUDA_TRY(C().part_mu.ensure((size_t)2 * max_nblk * CH * 8));
   CUDA_TRY(C().part_ss.ensure((size_t)2 * max_nblk * CH * 8));
+  // tiny batches keep V^T even without gradients: the quarter-row kernels reduce the variance from the stored tile
+  const bool have_vt = a.grad || CH <= 2048;
+  if (have_vt && !a.grad) CUDA_TRY(C().vt.ensure((size_t)CH * max_npad * 8));
   if (a.grad) {
     if (d > 32) return fail(BOSS_ERR_ARG, "score: gradients need x_dim <= 32");
     CUDA_TRY(C().vt.ensure((size_t)CH * max_npad * 8));
@@ -1148,7 +1205,9 @@ int score_core(ScoreArgs &a) {
   long long neg1 = -1;
   std::memcpy(&hs[nsl + 2 * d + 1], &neg1, 8);
   CUDA_TRY(cudaMemcpyAsync(small, hs.data(), sm_n * 8, cudaMemcpyHostToDevice, C().stream));
-  CUDA_TRY(cudaStreamSynchronize(C().stream));   // hs is a stack temporary (pageable)
+  // hs is pageable: the runtime has staged these few bytes when the call returns and hs lives until the end of this
+  // function, so the rounds of the multi-start driver (internal calls) do not pay a stream round trip here
+  if (!a.internal) CUDA_TRY(cudaStreamSynchronize(C().stream));
   double *d_best = small + nsl + 2 * d;
   long long *d_bidx = reinterpret_cast<long long *>(small + nsl + 2 * d + 1);
   int *d_anyfail = reinterpret_cast<int *>(small + nsl + 2 * d + 2);
@@ -1340,7 +1399,17 @@ int score_core(ScoreArgs &a) {
       // takes ~0.3 of a wide one).  Same bits either way.
       const int ncb32 = (ch + NW_NB - 1) / NW_NB;
       const int nsp32 = pick_row_splits(ncb32, h->nblk, &cost_n);
-      const bool narrow = 0.32 * cost_n < cost_w && getenv("BOSS_NO_NARROW") == nullptr;
+      bool narrow = 0.32 * cost_n < cost_w && getenv("BOSS_NO_NARROW") == nullptr;
+      // Tiny batches: quarter-row-block CTAs (4 nblk per 32 candidates, 4 to an SM).  Cost in the same unit: the
+      // longest CTA's latency-bound walk over 8 nblk short stages, or the launch's tensor work spread over the SMs.
+      const double cost_q = std::max(NQ_COST_CHAIN * h->nblk, NQ_COST_WORK * ncb32 * (h->nblk * (h->nblk + 1) / 2)) + NQ_COST_FIXED;
+      bool quarter = have_vt && cost_q < std::min(cost_w, narrow ? 0.32 * cost_n : cost_w) && h->nblk >= 2;
+      if (const char *e = getenv("BOSS_SCORE_PATH")) {   // A/B switch: wide | narrow | quarter
+        if (!strcmp(e, "wide")) narrow = quarter = false;
+        if (!strcmp(e, "narrow")) narrow = true, quarter = false;
+        if (!strcmp(e, "quarter") && have_vt) quarter = true;
+      }
+      if (quarter) narrow = false;
       const int cnt = ncb * 128;
       XcovParams xp{};
       xp.Xs = xs_dev;
@@ -1365,7 +1434,7 @@ int score_core(ScoreArgs &a) {
       }
       // One CTA per candidate block walks all of W (large batches) and this is the chunk's last slice: the scoring
       // kernel finishes the candidates itself (fused epilogue) -- no reduce / acquisition / argmax launches.
-      const bool fuse = nsp == 1 && !narrow && q == nsl - 1 && getenv("BOSS_UNFUSED_SCORE") == nullptr;
+      const bool fuse = nsp == 1 && !narrow && !quarter && q == nsl - 1 && getenv("BOSS_UNFUSED_SCORE") == nullptr;
       fused_chunk = fuse;
       if (!fuse)
         reduce_rows_kernel<<<(cnt + 255) / 256, 256, 0, C().stream>>>(C().part_mu.as<double>(), 2 * h->nblk, (size_t)CH,
@@ -1389,7 +1458,13 @@ int score_core(ScoreArgs &a) {
         sp.bidx = d_bidx;
         sp.counter = d_counter;
       }
-      if (narrow) {
+      if (quarter) {
+        NarrowParams np{h->W, C().ks.as<double>(), h->nblk, h->ktiles, nullptr, CH, C().vt.as<double>()};
+        Timed t(0);
+        score_quarter_kernel<0><<<dim3(ncb32, 4 * h->nblk), NQ_THREADS, NQ_SMEM_BYTES, C().stream>>>(np);
+        quarter_sumsq_kernel<<<dim3(ncb32, h->nblk), 256, 0, C().stream>>>(C().vt.as<double>(), h->ktiles,
+                                                                         C().part_ss.as<double>(), CH);
+      } else if (narrow) {
         NarrowParams np{h->W, C().ks.as<double>(), h->nblk, h->ktiles, C().part_ss.as<double>(), CH,
                         a.grad ? C().vt.as<double>() : nullptr};
         Timed t(0);
@@ -1401,10 +1476,14 @@ int score_core(ScoreArgs &a) {
       if (!fuse)
         reduce_rows2_kernel<<<(cnt + 255) / 256, 256, 0, C().stream>>>(C().part_ss.as<double>(), 2 * h->nblk, (size_t)CH,
                                                                     C().sumsq.as<double>() + (size_t)q * CH, cnt);
-      C().launches += fuse ? 2 : 4;
+      C().launches += fuse ? 2 : quarter ? 5 : 4;
       if (a.grad) {
         WtvParams wp{h->WT, C().vt.as<double>(), C().ut.as<double>(), h->nblk, h->ktiles};
-        if (narrow) {
+        if (quarter) {
+          NarrowParams np{h->WT, C().vt.as<double>(), h->nblk, h->ktiles, nullptr, CH, C().ut.as<double>()};
+          Timed t(0);
+          score_quarter_kernel<1><<<dim3(ncb32, 4 * h->nblk), NQ_THREADS, NQ_SMEM_BYTES, C().stream>>>(np);
+        } else if (narrow) {
           NarrowParams np{h->WT, C().vt.as<double>(), h->nblk, h->ktiles, nullptr, CH, C().ut.as<double>()};
           Timed t(0);
           score_narrow_kernel<1><<<dim3(ncb32, nsp32), 256, NW_SMEM_BYTES, C().stream>>>(np);
@@ -1478,6 +1557,10 @@ int score_core(ScoreArgs &a) {
   if (host && prev_m0 >= 0) {
     int rc = drain_out(prev_m0, prev_ch, (cidx - 1) & 1);
     if (rc) return rc;
+  }
+  if (a.internal && !a.want_argmax && !C().timing) {   // a round of the multi-start driver: it synchronises itself
+    a.any_fail = 0;
+    return 0;
   }
   double *hres = reinterpret_cast<double *>(hs.data());   // reuse: 3 doubles
   CUDA_TRY(cudaMemcpyAsync(hres, d_best, 24, cudaMemcpyDeviceToHost, C().stream));
@@ -1796,10 +1879,13 @@ static int multistart_single(const boss_gp *const *slices, int y_dim, int n_samp
   const int RC = H + 1;   // ring capacity: H live pairs + one free slot for the pair being formed
   if (iters < 0) iters = 0;
   const size_t Md = (size_t)M * d;
+  // the compact batch of a round holds `fan` trial points per unfinished start: up to MS_FAN_BATCH points once the
+  // step-size fan is on (few starts left), never more than M points before that
+  const size_t cap = (size_t)std::max<long long>(M, MS_FAN_BATCH), capd = cap * d;
   // carve one workspace: X g dirn | Sh Yh | f t | [affine mean scratch] | Xc gc fc | counters, per-start ints
-  const size_t n_aff = prior_mean_affine ? (size_t)y_dim * (d + 1) + (size_t)M * y_dim + Md * y_dim : 0;
-  const size_t n_dbl = 3 * Md + 2 * (size_t)RC * Md + 2 * (size_t)M + n_aff + 2 * Md + M;
-  CUDA_TRY(C().ms_buf.ensure(n_dbl * 8 + (size_t)M * 24 + 64));
+  const size_t n_aff = prior_mean_affine ? (size_t)y_dim * (d + 1) + cap * y_dim + capd * y_dim : 0;
+  const size_t n_dbl = 3 * Md + 2 * (size_t)RC * Md + 2 * (size_t)M + n_aff + 2 * capd + cap;
+  CUDA_TRY(C().ms_buf.ensure(n_dbl * 8 + (size_t)M * 20 + cap * 4 + 64));
   double *base = C().ms_buf.as<double>();
   MsState st{};
   st.d = d;
@@ -1813,19 +1899,20 @@ static int multistart_single(const boss_gp *const *slices, int y_dim, int n_samp
   st.Yh = st.Sh + (size_t)RC * Md;
   st.f = st.Yh + (size_t)RC * Md;
   st.t = st.f + M;
-  double *aff = st.t + M, *pm = aff + (size_t)y_dim * (d + 1), *pmg = pm + (size_t)M * y_dim;
+  double *aff = st.t + M, *pm = aff + (size_t)y_dim * (d + 1), *pmg = pm + cap * y_dim;
   if (prior_mean_affine)
     CUDA_TRY(cudaMemcpyAsync(aff, prior_mean_affine, (size_t)y_dim * (d + 1) * 8, cudaMemcpyHostToDevice, C().stream));
   st.Xc = st.t + M + n_aff;
-  st.gc = st.Xc + Md;
-  st.fc = st.gc + Md;
-  st.counters = reinterpret_cast<int *>(st.fc + M);
+  st.gc = st.Xc + capd;
+  st.fc = st.gc + capd;
+  st.counters = reinterpret_cast<int *>(st.fc + cap);
   st.hist_len = st.counters + 4;
   st.hist_start = st.hist_len + M;
   st.trials = st.hist_start + M;
   st.steps = st.trials + M;
   st.state = st.steps + M;
-  st.idx = st.state + M;
+  st.idx = st.state + M;    // [cap]
+  st.fan = 1;
   double span = 0.0;
   for (int j = 0; j < d; ++j) {
     st.lb[j] = lb[j];
@@ -1879,20 +1966,30 @@ static int multistart_single(const boss_gp *const *slices, int y_dim, int n_samp
   const int max_rounds = iters > 0 ? 2 * iters + MS_MAX_TRIALS : 0;
   int active = iters > 0 ? (int)M : 0;
   const bool trace = getenv("BOSS_MS_TRACE") != nullptr;   // one line per round on stderr: round, batch size
+  const bool use_fan = getenv("BOSS_MS_NO_FAN") == nullptr;
+  CUDA_TRY(cudaMemsetAsync(st.counters, 0, 16, C().stream));
+  int hc[3] = {0, 0, 0};
   for (int round = 0; round < max_rounds && active > 0; ++round) {
-    if (trace) fprintf(stderr, "boss multistart: round %d active %d\n", round, active);
-    CUDA_TRY(cudaMemsetAsync(st.counters, 0, 16, C().stream));
+    // Step-size fan: below ~64 points a pass over W costs the same whatever the batch holds (the DMMA accumulation
+    // chain of the last row block bounds it), so the next few backtracking trials are evaluated speculatively.
+    int fan = 1;
+    if (use_fan) fan = active <= 10 ? 6 : active <= 21 ? 3 : active <= 128 ? 2 : 1;
+    fan = (int)std::max<size_t>(1, std::min<size_t>(fan, cap / (size_t)active));
+    st.fan = fan;
+    if (trace) fprintf(stderr, "boss multistart: round %d active %d fan %d\n", round, active, fan);
+    CUDA_TRY(cudaMemsetAsync(st.counters, 0, 8, C().stream));
     ms_propose_kernel<<<nbm, 128, 0, C().stream>>>(st);
-    rc = eval(st.Xc, active, st.fc, st.gc, false, nullptr, nullptr);   // `active` = the compact list's length
+    rc = eval(st.Xc, (long long)active * fan, st.fc, st.gc, false, nullptr, nullptr);   // the compact list's length
     if (rc) return rc;
     ms_advance_kernel<<<(active + 127) / 128, 128, 0, C().stream>>>(st, active);
     C().launches += 2;
-    int hc[2] = {0, 0};
-    CUDA_TRY(cudaMemcpyAsync(hc, st.counters, 8, cudaMemcpyDeviceToHost, C().stream));
+    CUDA_TRY(cudaMemcpyAsync(hc, st.counters, 12, cudaMemcpyDeviceToHost, C().stream));
     CUDA_TRY(cudaStreamSynchronize(C().stream));
-    if (hc[0] != active) return fail(BOSS_ERR_STATE, "boss_ei_maximize_multistart: internal batch-length mismatch");
+    if (hc[0] != active * fan) return fail(BOSS_ERR_STATE, "boss_ei_maximize_multistart: internal batch-length mismatch");
     active = hc[1];
   }
+  // what one-trial-per-round backtracking evaluates (same trajectory): first + trial + final evaluations
+  const long long sequential_evals = 2 * M + hc[2];
   // final rounding of discrete dimensions and re-evaluation (optimization.jl:116-117), argmax over the starts
   const unsigned long long disc = mask_bits(discrete_mask, d);
   if (disc) ms_round_kernel<<<(unsigned)((Md + 255) / 256), 256, 0, C().stream>>>(st.X, M, d, disc);
@@ -1906,7 +2003,12 @@ static int multistart_single(const boss_gp *const *slices, int y_dim, int n_samp
   CUDA_TRY(cudaStreamSynchronize(C().stream));
   if (best_val) *best_val = bv;
   if (best_idx) *best_idx = bi;
-  if (evals_out) *evals_out = (int)((evaluated + M - 1) / M);   // work in units of full-batch evaluations
+  // work in units of full-batch evaluations: the evaluations of the sequential search; the speculative extra trials
+  // of the fan (evaluated - sequential_evals of them) are reported through BOSS_MS_TRACE only
+  if (trace)
+    fprintf(stderr, "boss multistart: evaluated %lld points, %lld of them needed by the sequential search\n", evaluated,
+            sequential_evals);
+  if (evals_out) *evals_out = (int)((sequential_evals + M - 1) / M);
   return 0;
 }
 
@@ -2587,6 +2689,55 @@ int boss_dbg_kernel_fn(int which, const double *t, int n, double *out) {
   cudaFree(dt);
   cudaFree(dout);
   return 0;
+}
+
+__global__ void rz_scan_kernel(const unsigned char *p, size_t nbytes, unsigned long long *bad) {
+  unsigned long long c = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nbytes; i += (size_t)gridDim.x * blockDim.x)
+    c += p[i] != 0xA5;
+  if (c) atomicAdd(bad, c);
+}
+// Scans the guard bands of every live device allocation of the calling thread's device (BOSS_DEBUG_REDZONE=1).
+// Returns the number of overwritten guard bytes (0 = clean), -1 when red zones are off; *n_allocs = allocations scanned.
+int64_t boss_dbg_check_redzones(int64_t *n_allocs) {
+  if (n_allocs) *n_allocs = 0;
+  if (!redzones_on()) return -1;
+  REQUIRE_INIT();
+  CUDA_TRY(cudaDeviceSynchronize());
+  unsigned long long *bad = nullptr;
+  CUDA_TRY(cudaMalloc(&bad, 8));
+  CUDA_TRY(cudaMemset(bad, 0, 8));
+  int64_t cnt = 0;
+  {
+    std::lock_guard<std::mutex> lk(g_rz_mu);
+    for (auto &kv : g_rz) {
+      const RzEntry &e = kv.second;
+      if (e.device != C().device) continue;
+      const size_t user = (e.bytes + 255) & ~(size_t)255;
+      rz_scan_kernel<<<64, 256>>>(reinterpret_cast<const unsigned char *>(e.base), RZ_BYTES, bad);
+      rz_scan_kernel<<<64, 256>>>(reinterpret_cast<const unsigned char *>(e.base) + RZ_BYTES + e.bytes, user - e.bytes + RZ_BYTES, bad);
+      ++cnt;
+    }
+  }
+  unsigned long long h = 0;
+  CUDA_TRY(cudaMemcpy(&h, bad, 8, cudaMemcpyDeviceToHost));
+  cudaFree(bad);
+  if (n_allocs) *n_allocs = cnt;
+  return (int64_t)h;
+}
+
+// Negative control of the red-zone check: one byte written just past a fresh 1000-byte allocation and one just before
+// it must be reported (returns the number of guard bytes found overwritten: 2), and nothing after the buffer is freed.
+int64_t boss_dbg_redzone_selftest(void) {
+  if (!redzones_on()) return -1;
+  void *p = nullptr;
+  if (dev_malloc(&p, 1000) != cudaSuccess) return -2;
+  const int64_t before = boss_dbg_check_redzones(nullptr);
+  cudaMemset(static_cast<char *>(p) + 1000, 0, 1);
+  cudaMemset(static_cast<char *>(p) - 1, 0, 1);
+  const int64_t after = boss_dbg_check_redzones(nullptr);
+  dev_free(p);
+  return after - before;
 }
 
 int boss_dbg_factors(const boss_gp *gp, double *L, double *W, double *alpha) {

@@ -71,6 +71,20 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
+// Truly non-blocking probe (mbarrier.try_wait may suspend the thread up to a system time limit before it reports
+// failure -- harmless in the long stages of the 128-wide mainloops, ruinous for a producer that shares its warp with
+// consumers of 150-cycle stages).
+__device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
 // Bounded wait: a lost TMA transaction traps (launch fails with an error) instead of hanging the GPU.  A failed
 // try_wait suspends the thread for a few microseconds, so the bound is ~15 s -- far beyond any legitimate wait.
 // -DBOSS_DEBUG_MBAR additionally prints which barrier timed out; it is off by default because the (never taken) call
@@ -92,6 +106,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       __trap();
 #endif
     }
+  }
+}
+// Spinning wait on test_wait (no suspension): for short pipeline stages, where the wake-up latency of a suspended
+// try_wait is of the order of the stage itself.  Same bound as mbar_wait.
+__device__ __forceinline__ void mbar_spin_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_test_wait(bar, parity)) {
+    if (++spins > (1u << 28)) __trap();
   }
 }
 // 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (complete_tx::bytes).

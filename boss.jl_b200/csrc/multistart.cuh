@@ -30,10 +30,12 @@ struct MsState {
   double *Sh, *Yh;           // [H][M][d] curvature pairs, one ring per start
   int *hist_len, *hist_start, *trials, *steps;   // [M] each
   int *state;                // [M] 0 = needs a direction, 1 = in a line search, 2 = finished
-  int *idx;                  // [M] compact list: idx[slot] = start
+  int *idx;                  // [cap] compact list: idx[slot] = start
+  int fan;                   // trial points per unfinished start in this round (speculative step-size fan, see below)
   double lb[MS_MAXD], ub[MS_MAXD];
   double step0;
-  int *counters;             // [0] length of this round's compact list, [1] starts still unfinished after the round
+  int *counters;             // [0] length of this round's compact list, [1] starts still unfinished after the round,
+                             // [2] running total of the evaluations a one-trial-per-round search would have made
 };
 
 __device__ __forceinline__ double ms_clip(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -52,8 +54,13 @@ __global__ void ms_sanitize_kernel(double *f, long long M) {
   if (m < M && !isfinite(f[m])) f[m] = -INFINITY;
 }
 
-// Every unfinished start contributes one trial point to this round's batch.  A start that has just accepted a step
-// (or has not moved yet) first gets its L-BFGS ascent direction from its own history (two-loop recursion).
+// Every unfinished start contributes `fan` trial points to this round's batch: the step sizes t, t/2, ... its
+// backtracking search would try one after the other.  fan = 1 is plain one-evaluation-per-round backtracking; once few
+// starts are left a pass over W costs the same for 1 or 64 points (it is bound by the length of the DMMA accumulation
+// chain), so the next step sizes ride along and a start that has to backtrack does not spend another round on it.  The
+// trials are examined in order and the first acceptable one wins, so the trajectory is exactly the sequential one.
+// A start that has just accepted a step (or has not moved yet) first gets its L-BFGS ascent direction from its own
+// history (two-loop recursion).
 __global__ void ms_propose_kernel(MsState st) {
   const long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (m >= st.M || st.state[m] == 2) return;
@@ -114,11 +121,13 @@ __global__ void ms_propose_kernel(MsState st) {
     st.trials[m] = 0;
     st.state[m] = 1;
   }
-  const int slot = atomicAdd(&st.counters[0], 1);    // the order of the batch does not matter: scores are per point
-  st.idx[slot] = (int)m;
-  const double t = st.t[m];
-  for (int j = 0; j < d; ++j)
-    st.Xc[(size_t)slot * d + j] = ms_clip(fma(st.dirn[m * d + j], t, st.X[m * d + j]), st.lb[j], st.ub[j]);
+  const int slot0 = atomicAdd(&st.counters[0], st.fan);   // the order of the batch does not matter: scores are per point
+  double t = st.t[m];
+  for (int k = 0; k < st.fan; ++k, t *= 0.5) {            // slots beyond the start's remaining trials are ignored later
+    st.idx[slot0 + k] = (int)m;
+    for (int j = 0; j < d; ++j)
+      st.Xc[(size_t)(slot0 + k) * d + j] = ms_clip(fma(st.dirn[m * d + j], t, st.X[m * d + j]), st.lb[j], st.ub[j]);
+  }
 }
 
 // Armijo test of this round's trial points.  Accepted: curvature pair into the start's own ring, move, count the
@@ -126,47 +135,51 @@ __global__ void ms_propose_kernel(MsState st) {
 // MS_MAX_TRIALS step sizes the history is dropped and the search restarts along the projected gradient, and a start
 // whose projected-gradient search fails as well is finished (no acceptable step exists any more).
 __global__ void ms_advance_kernel(MsState st, int count) {
-  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot >= count) return;
-  const long long m = st.idx[slot];
+  const int grp = blockIdx.x * blockDim.x + threadIdx.x;   // one thread per start of the round = per group of `fan` slots
+  if (grp >= count) return;
+  const long long m = st.idx[grp * st.fan];
   const int d = st.d;
-  double ft = st.fc[slot];
-  if (!isfinite(ft)) ft = -INFINITY;
-  double slope = 0.0;
-  for (int j = 0; j < d; ++j) slope = fma(st.g[m * d + j], st.Xc[(size_t)slot * d + j] - st.X[m * d + j], slope);
-  int state;
-  if (ft >= st.f[m] + 1e-4 * slope) {
-    double sy = 0.0, mv = 0.0;
-    for (int j = 0; j < d; ++j) {
-      const double s = st.Xc[(size_t)slot * d + j] - st.X[m * d + j], y = -(st.gc[(size_t)slot * d + j] - st.g[m * d + j]);
-      sy = fma(s, y, sy);
-      mv = fmax(mv, fabs(s));
-    }
-    if (sy > 1e-16) {   // a safely positive curvature pair: push it (dropping the oldest when the ring is full)
-      int hl = st.hist_len[m], hs = st.hist_start[m];
-      const int ring = (hs + hl) % st.H;
-      const size_t o = ((size_t)ring * st.M + m) * d;
+  const int nk = min(st.fan, MS_MAX_TRIALS - st.trials[m]);   // trials the sequential search would still make
+  int state = 1, used = nk;
+  for (int k = 0; k < nk; ++k) {
+    const size_t slot = (size_t)grp * st.fan + k;
+    double ft = st.fc[slot];
+    if (!isfinite(ft)) ft = -INFINITY;
+    double slope = 0.0;
+    for (int j = 0; j < d; ++j) slope = fma(st.g[m * d + j], st.Xc[slot * d + j] - st.X[m * d + j], slope);
+    if (ft >= st.f[m] + 1e-4 * slope) {
+      double sy = 0.0, mv = 0.0;
       for (int j = 0; j < d; ++j) {
-        st.Sh[o + j] = st.Xc[(size_t)slot * d + j] - st.X[m * d + j];
-        st.Yh[o + j] = -(st.gc[(size_t)slot * d + j] - st.g[m * d + j]);
+        const double s = st.Xc[slot * d + j] - st.X[m * d + j], y = -(st.gc[slot * d + j] - st.g[m * d + j]);
+        sy = fma(s, y, sy);
+        mv = fmax(mv, fabs(s));
       }
-      if (hl == st.H - 1)
-        hs = (hs + 1) % st.H;
-      else
-        ++hl;
-      st.hist_len[m] = hl;
-      st.hist_start[m] = hs;
+      if (sy > 1e-16) {   // a safely positive curvature pair: push it (dropping the oldest when the ring is full)
+        int hl = st.hist_len[m], hs = st.hist_start[m];
+        const int ring = (hs + hl) % st.H;
+        const size_t o = ((size_t)ring * st.M + m) * d;
+        for (int j = 0; j < d; ++j) {
+          st.Sh[o + j] = st.Xc[slot * d + j] - st.X[m * d + j];
+          st.Yh[o + j] = -(st.gc[slot * d + j] - st.g[m * d + j]);
+        }
+        if (hl == st.H - 1)
+          hs = (hs + 1) % st.H;
+        else
+          ++hl;
+        st.hist_len[m] = hl;
+        st.hist_start[m] = hs;
+      }
+      for (int j = 0; j < d; ++j) {
+        st.X[m * d + j] = st.Xc[slot * d + j];
+        st.g[m * d + j] = st.gc[slot * d + j];
+      }
+      st.f[m] = ft;
+      const int steps = ++st.steps[m];
+      state = (steps >= st.iters || mv < 1e-10) ? 2 : 0;
+      used = k + 1;
+      break;
     }
-    for (int j = 0; j < d; ++j) {
-      st.X[m * d + j] = st.Xc[(size_t)slot * d + j];
-      st.g[m * d + j] = st.gc[(size_t)slot * d + j];
-    }
-    st.f[m] = ft;
-    const int steps = ++st.steps[m];
-    state = (steps >= st.iters || mv < 1e-10) ? 2 : 0;
-  } else {
     st.t[m] *= 0.5;
-    state = 1;
     if (++st.trials[m] >= MS_MAX_TRIALS) {
       // no step size along this direction is acceptable: with curvature history, forget it and retry along the
       // projected gradient; a failed steepest-ascent search means the start cannot improve any more
@@ -175,6 +188,7 @@ __global__ void ms_advance_kernel(MsState st, int count) {
       st.hist_start[m] = 0;
     }
   }
+  atomicAdd(&st.counters[2], used);   // evaluations the sequential search would have made (the rest was speculation)
   st.state[m] = state;
   if (state != 2) atomicAdd(&st.counters[1], 1);
 }

@@ -175,4 +175,146 @@ __global__ void __launch_bounds__(256, 1) score_narrow_kernel(const __grid_const
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Quarter-row-block CTAs for TINY batches (a handful of unfinished multi-start runs, the reference's one-x-per-call
+// access pattern).  With one 32-candidate block the kernels above expose only nblk CTAs and the longest of them walks
+// all 8 nblk stages of the last row block alone: 218 us at n = 4096 whatever the batch holds.  Here a CTA owns 32 rows
+// (4 row slabs) of one row block x 32 candidates (warp = 1 slab x 2 candidate slabs), 4 nblk CTAs per candidate block,
+// launched longest first; the structurally dead head / tail k-tiles of a quarter are not even loaded.
+// What bounds such a CTA is the rate at which ONE SM can pull its operands, and that is set by the number of
+// requests, not bytes (measured, tools/bulk_copy_rate.cu -> profiles/r02_bulk_copy_rate.json): a TMA / mbarrier ring
+// stage costs ~310 ns + 15 ns per 4 KB bulk copy whatever the ring depth or the source (L2 or HBM) -- 24 GB/s per SM
+// with 8 KB stages, 75 GB/s with 32 KB stages; direct LDG.128 fragment loads four k-tiles ahead in registers reach
+// ~28 GB/s (both tried here: 0.53 and 0.43 us per k-tile).  So a stage carries NQ_KT = 8 k-tiles (16 bulk copies of
+// 4 KB, 64 KB), issued by a dedicated producer warp, 3 stages in flight.
+// Accumulation order inside a fragment is unchanged (k ascending, same fragments skipped), V^T is always stored, and
+// quarter_sumsq_kernel replays the wide kernel's reduction over the stored tile -- THE SAME BITS again (DMMA.8x8x4
+// itself accumulates k ascending like an FMA chain: tools/dmma_order_test.cu, profiles/r02_dmma_order.json).
+// ---------------------------------------------------------------------------------------------
+constexpr int NQ_KT = 8;                                     // k-tiles per ring stage
+constexpr int NQ_STAGES = 3;
+constexpr int NQ_QELEMS = TILE_ELEMS / 4;                    // 512 doubles: 4 row slabs of W, or a 32-candidate slice
+constexpr int NQ_STAGE_ELEMS = 2 * NQ_QELEMS * NQ_KT;        // 64 KB: [k-tile][A quarter | B slice]
+constexpr int NQ_SMEM_BYTES = NQ_STAGES * NQ_STAGE_ELEMS * 8 + 2 * NQ_STAGES * 8;
+constexpr int NQ_THREADS = 288;                              // 8 consumer warps + 1 producer warp
+
+// grid = (32-candidate blocks, 4 nblk): blockIdx.y = 4 * (rank of the row block, longest k-range first) + quarter
+template <int MODE>
+__global__ void __launch_bounds__(NQ_THREADS, 1) score_quarter_kernel(const __grid_constant__ NarrowParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  double *ring = reinterpret_cast<double *>(smem_raw);
+  uint64_t *full = reinterpret_cast<uint64_t *>(ring + NQ_STAGES * NQ_STAGE_ELEMS), *empty = full + NQ_STAGES;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int cb32 = blockIdx.x, cb = cb32 >> 2, sub = cb32 & 3, qd = blockIdx.y & 3;
+  const int i = MODE == 0 ? p.nblk - 1 - (int)(blockIdx.y >> 2) : (int)(blockIdx.y >> 2);
+  // live k-tiles of the quarter: lower block (MODE 0) slab R sees k micro-steps kk <= R, R <= 4 qd + 3;
+  // upper block (MODE 1) slab R sees kk >= R, R >= 4 qd
+  const int kt0 = MODE == 0 ? 0 : i * KT_PER_BLOCK + 2 * qd;
+  const int kt1 = MODE == 0 ? i * KT_PER_BLOCK + 2 * qd + 2 : p.ktiles;
+  const int nk = kt1 - kt0, nst = (nk + NQ_KT - 1) / NQ_KT;
+  if (tid < 2 * NQ_STAGES) {
+    mbar_init(smem_u32(tid < NQ_STAGES ? &full[tid] : &empty[tid - NQ_STAGES]), tid < NQ_STAGES ? 1u : 8u);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (w == 8) {   // producer warp: one lane streams the stages, blocking only on the slot it is about to refill
+    if (lane == 0) {
+      const double *Ablk = p.A + ((size_t)i * p.ktiles + kt0) * TILE_ELEMS + (size_t)qd * NQ_QELEMS;
+      const double *Bblk = p.B + ((size_t)cb * p.ktiles + kt0) * TILE_ELEMS + (size_t)sub * NQ_QELEMS;
+      for (int s = 0; s < nst; ++s) {
+        const int slot = s % NQ_STAGES;
+        if (s >= NQ_STAGES) mbar_wait(smem_u32(&empty[slot]), (uint32_t)((s / NQ_STAGES - 1) & 1));
+        const int cnt = min(NQ_KT, nk - s * NQ_KT);
+        const uint32_t bar = smem_u32(&full[slot]);
+        double *dst = ring + (size_t)slot * NQ_STAGE_ELEMS;
+        mbar_arrive_expect_tx(bar, (uint32_t)(cnt * 2 * NQ_QELEMS * 8));
+        for (int t = 0; t < cnt; ++t) {
+          const size_t off = (size_t)(s * NQ_KT + t) * TILE_ELEMS;
+          bulk_g2s(smem_u32(dst + (size_t)t * 2 * NQ_QELEMS), Ablk + off, NQ_QELEMS * 8, bar);
+          bulk_g2s(smem_u32(dst + (size_t)t * 2 * NQ_QELEMS + NQ_QELEMS), Bblk + off, NQ_QELEMS * 8, bar);
+        }
+      }
+    }
+    return;
+  }
+  const int sl = w >> 1, R = 4 * qd + sl, fn0 = 2 * (w & 1);   // this warp: row slab R x candidate slabs fn0, fn0 + 1
+  double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+  for (int s = 0; s < nst; ++s) {
+    const int slot = s % NQ_STAGES;
+    mbar_wait(smem_u32(&full[slot]), (uint32_t)((s / NQ_STAGES) & 1));
+    const int cnt = min(NQ_KT, nk - s * NQ_KT);
+    const double *st = ring + (size_t)slot * NQ_STAGE_ELEMS + 2 * lane + sl * 128;
+    const double *sb = ring + (size_t)slot * NQ_STAGE_ELEMS + 2 * lane + NQ_QELEMS + fn0 * 128;
+    const int dgs = kt0 + s * NQ_KT - i * KT_PER_BLOCK;   // k-tile t of the stage is k-tile dgs + t of the diagonal block (if in 0..7)
+    // fragments of k-tile t + 1 are fetched from shared memory before the DMMA chain of k-tile t starts
+    auto fetch = [&](int t, double2(&f)[6]) {
+      const double *As = st + (size_t)t * 2 * NQ_QELEMS, *Bs = sb + (size_t)t * 2 * NQ_QELEMS;
+      f[0] = lds128(As);
+      f[1] = lds128(As + 64);
+      f[2] = lds128(Bs);
+      f[3] = lds128(Bs + 64);
+      f[4] = lds128(Bs + 128);
+      f[5] = lds128(Bs + 192);
+    };
+    auto mma = [&](int t, const double2(&f)[6]) {
+      const int dg = dgs + t;
+      const bool diag = dg >= 0 && dg < KT_PER_BLOCK;
+#pragma unroll
+      for (int mc = 0; mc < 2; ++mc) {
+        const int kk = 2 * dg + mc;
+        const bool live = !diag || (MODE == 0 ? R >= kk : R <= kk);   // warp-uniform
+        if (live) {
+          dmma884(acc[0][0], acc[0][1], f[mc].x, f[2 + mc].x);
+          dmma884(acc[1][0], acc[1][1], f[mc].x, f[4 + mc].x);
+          dmma884(acc[0][0], acc[0][1], f[mc].y, f[2 + mc].y);
+          dmma884(acc[1][0], acc[1][1], f[mc].y, f[4 + mc].y);
+        }
+      }
+    };
+    double2 f0[6], f1[6];
+    fetch(0, f0);
+#pragma unroll
+    for (int t = 0; t < NQ_KT; t += 2) {
+      if (t < cnt) {
+        if (t + 1 < cnt) fetch(t + 1, f1);
+        mma(t, f0);
+      }
+      if (t + 1 < cnt) {
+        if (t + 2 < cnt) fetch(t + 2, f0);
+        mma(t + 1, f1);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&empty[slot]));
+  }
+  // transposed store: rows = candidates (block cb, slabs 4 sub + fn), columns = rows of block i
+  double *ot = p.OT + (size_t)cb * p.ktiles * TILE_ELEMS + (size_t)i * KT_PER_BLOCK * TILE_ELEMS;
+  p_store_cfrag_t(ot, R, 4 * sub + fn0, lane, acc[0][0], acc[0][1]);
+  p_store_cfrag_t(ot, R, 4 * sub + fn0 + 1, lane, acc[1][0], acc[1][1]);
+}
+
+// Column sums of squares of the stored V^T in the wide kernel's order: per row block and slab parity the fma chain over
+// the 8 slabs of the parity at a fixed row-in-slab r, then the 3-level butterfly over r; the partials land in ss_part
+// exactly where score_trmm_kernel / score_narrow_kernel<0> put theirs (reduce_rows2_kernel folds them).
+// grid = (32-candidate blocks, nblk), 256 threads = 32 candidates x 8 rows-in-slab.
+__global__ void __launch_bounds__(256) quarter_sumsq_kernel(const double *__restrict__ VT, int ktiles, double *__restrict__ ss_part,
+                                                            int ld) {
+  const int r = threadIdx.x & 7, c = blockIdx.x * NW_NB + (threadIdx.x >> 3), i = blockIdx.y;
+  const double *base = VT + (size_t)(c >> 7) * ktiles * TILE_ELEMS;
+  const int cc = c & 127;
+#pragma unroll
+  for (int pr = 0; pr < 2; ++pr) {
+    double x[8];
+#pragma unroll
+    for (int fmw = 0; fmw < 8; ++fmw) x[fmw] = base[p_index(cc, i * TM + (2 * fmw + pr) * 8 + r, ktiles)];
+    double v = 0.0;
+#pragma unroll
+    for (int fmw = 0; fmw < 8; ++fmw) v = fma(x[fmw], x[fmw], v);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    if (r == 0) ss_part[(size_t)(2 * i + pr) * ld + c] = v;
+  }
+}
+
 }  // namespace boss

@@ -212,7 +212,9 @@ int boss_ei_value_grad_dev(const boss_gp *const *slices, int y_dim, int n_sample
  *   prior_mean_affine  y_dim x (d + 1) or NULL: slice i has prior mean c_i + b_i . x with [c_i, b_i1..b_id] at
  *                      prior_mean_affine + i*(d+1) (constant means, linear parametric part of a Semiparametric model)
  *   x_out d x M final points, f_out M final values (either may be NULL); best_val == -Inf <=> all runs failed
- *   evals_out  evaluated points / M (backtracking trials only re-evaluate the starts that have not accepted a step)
+ *   evals_out  evaluated points / M of the backtracking searches (a trial only re-evaluates the starts that have not
+ *              accepted a step; once few starts are left the next step sizes of a search are evaluated speculatively
+ *              in the same pass -- same trajectory, fewer passes -- and those extra points are not counted)
  * General prior-mean closures and `cons` constraints are host code and are not supported here: use
  * boss_ei_value_grad per iteration for those. */
 int boss_ei_maximize_multistart(const boss_gp *const *slices, int y_dim, int n_samples, const double *starts, int64_t M,
@@ -271,6 +273,13 @@ int boss_dbg_gemm_nt(const double *A, const double *B, int M, int N, int K, doub
  * Matern52, 5-7 kappa'(r)/r of the same */
 int boss_dbg_kernel_fn(int which, const double *t, int n, double *out);
 int boss_dbg_factors(const boss_gp *gp, double *L, double *W, double *alpha);          /* dense row-major n x n, n   */
+/* BOSS_DEBUG_REDZONE=1 (environment, read at the first allocation): every device allocation is exact-sized and
+ * bracketed by 64 KB guard bands of 0xA5.  Returns the number of guard bytes overwritten so far on the calling
+ * thread's device (0 = clean), -1 when the mode is off; *n_allocs = live allocations scanned.  The pool that builds
+ * this library has compute-sanitizer closed (profiles/r02_compute_sanitizer_closed.txt); this is the bounds check
+ * it recommends instead. */
+int64_t boss_dbg_check_redzones(int64_t *n_allocs);
+int64_t boss_dbg_redzone_selftest(void);   /* negative control: writes 2 guard bytes on purpose, returns how many the scan found */
 
 #ifdef __cplusplus
 }

@@ -2,6 +2,7 @@
 expression sets, pageable-vs-pinned host arrays, caller-stream ordering of the `_dev` entry points, error text per
 thread, handle invalidation by boss_shutdown, and the single-process multi-GPU path (needs >= 2 devices)."""
 import ctypes
+import os
 import threading
 
 import numpy as np
@@ -11,6 +12,7 @@ from oracle import boss_oracle as O
 from tests.util_problems import make_hyper_samples, make_problem, relerr
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -318,4 +320,73 @@ def test_zzz_shutdown_invalidates_live_handles(lib):
     gp = lib.gp_fit(X, Y[0], ls[0], amp[0], ns[0], 2)
     mu, _, _ = lib.gp_predict(gp, X)
     assert np.all(np.isfinite(mu))
+    gp.free()
+
+
+@pytest.mark.gpu
+def test_redzone_guard_bands_stay_clean_over_every_kernel_family():
+    """Stand-in for compute-sanitizer memcheck (closed on the build pool, profiles/r02_compute_sanitizer_closed.txt):
+    tools/sanitizer_subset.py drives every kernel family with exact-sized, guard-banded device allocations
+    (BOSS_DEBUG_REDZONE=1) and checks results against the oracle; no guard byte may change, and the negative control
+    (two bytes written on purpose) must be seen."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, BOSS_DEBUG_REDZONE="1")
+    for extra in ([], ["--tiny"]):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sanitizer_subset.py"), *extra], env=env,
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        j = json.loads(r.stdout.strip().splitlines()[-1])
+        assert j["redzone_bytes_overwritten"] == 0
+        assert j["redzone_allocations_scanned"] >= 10
+        assert j["redzone_selftest_detected"] == 2
+        assert len(j["families"]) >= 10
+
+
+def test_multistart_step_size_fan_keeps_the_sequential_trajectory(lib):
+    """The speculative step-size fan (several backtracking trials of a start evaluated in one pass once few starts
+    are left) must reproduce one-trial-per-round backtracking bit for bit: same end points, values and evaluation
+    count; and the tiny-batch quarter-row kernels must score like the wide ones (BOSS_SCORE_PATH)."""
+    n, d, M = 300, 3, 150
+    X, Y, ls, amp, ns = make_problem(n, d, seed=4100)
+    gp = lib.gp_fit(X, Y[0], ls[0], amp[0], ns[0], 2)
+    best = float(np.quantile(Y[0], 0.8))
+    lb, ub = np.zeros(d), np.ones(d)
+    starts = np.random.default_rng(41).random((d, M))
+    out = {}
+    try:
+        for tag, env in (("fan", {}), ("nofan", {"BOSS_MS_NO_FAN": "1"}), ("wide", {"BOSS_SCORE_PATH": "wide"}),
+                         ("quarter", {"BOSS_SCORE_PATH": "quarter"})):
+            for k in ("BOSS_MS_NO_FAN", "BOSS_SCORE_PATH"):
+                os.environ.pop(k, None)
+            os.environ.update(env)
+            out[tag] = lib.ei_maximize_multistart([gp], 1, 1, starts, [1.0], best, None, lb, ub, iters=25)
+    finally:
+        for k in ("BOSS_MS_NO_FAN", "BOSS_SCORE_PATH"):
+            os.environ.pop(k, None)
+    Xr, fr, bxr, bvr, bir, evr = out["nofan"]
+    for tag in ("fan", "wide", "quarter"):
+        Xo, fo, bxo, bvo, bio, ev = out[tag]
+        assert np.array_equal(Xo, Xr) and np.array_equal(fo, fr), tag
+        assert bio == bir and bvo == bvr and ev == evr, tag
+    gp.free()
+
+
+@pytest.mark.parametrize("n,d", [(200, 2), (1000, 5), (2048, 8)])
+def test_tiny_batches_score_bitwise_like_large_ones(lib, n, d):
+    """1, 5, 33 and 100 candidates (quarter-row / narrow kernels) against the same points inside a 700-point batch
+    (wide kernel): value, x-gradient, mean and variance are bit-identical."""
+    X, Y, ls, amp, ns = make_problem(n, d, seed=4200 + n)
+    gp = lib.gp_fit(X, Y[0], ls[0], amp[0], ns[0], 2)
+    best = float(np.quantile(Y[0], 0.7))
+    lb, ub = np.zeros(d), np.ones(d)
+    Xs = np.random.default_rng(42).random((d, 700))
+    a_all, g_all = lib.ei_value_grad([gp], 1, 1, Xs, [1.0], best, None, lb, ub)
+    mu_all, var_all, _ = lib.gp_predict(gp, Xs)
+    for m in (1, 5, 33, 100):
+        a, g = lib.ei_value_grad([gp], 1, 1, Xs[:, :m], [1.0], best, None, lb, ub)
+        mu, var, _ = lib.gp_predict(gp, Xs[:, :m])
+        assert np.array_equal(a, a_all[:m]) and np.array_equal(g, g_all[:, :m]), m
+        assert np.array_equal(mu, mu_all[:m]) and np.array_equal(var, var_all[:m]), m
     gp.free()

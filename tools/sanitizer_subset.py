@@ -116,10 +116,18 @@ def main():
     f0, _, _ = _lib.ei_score(gps, 2, 1, starts, coefs, best, y_max, lb=lb, ub=ub)
     assert np.all(fo >= f0 - 1e-15)
     done.append("multistart")
+    # guard bands of every live device allocation (BOSS_DEBUG_REDZONE=1): the workspaces are still alive here
+    bad, nalloc = _lib.dbg_check_redzones()
+    assert bad <= 0, f"{bad} guard bytes overwritten"
+    selftest = int(_lib.lib.boss_dbg_redzone_selftest())      # negative control: 2 when the mode is on, -1 when off
+    assert selftest in (2, -1), selftest
     for g in gps + fb + [ga]:
         g.free()
+    nl = _lib.launch_count()
     _lib.shutdown()
-    print(json.dumps({"sanitizer_subset": "ok", "tiny": tiny, "families": done, "launches": None, "seconds": time.time() - t0}))
+    print(json.dumps({"sanitizer_subset": "ok", "tiny": tiny, "families": done, "launches": int(nl),
+                      "redzone_bytes_overwritten": bad, "redzone_allocations_scanned": nalloc, "redzone_selftest_detected": selftest,
+                      "seconds": time.time() - t0}))
 
 
 if __name__ == "__main__":
