@@ -1885,7 +1885,7 @@ static int multistart_single(const boss_gp *const *slices, int y_dim, int n_samp
   // carve one workspace: X g dirn | Sh Yh | f t | [affine mean scratch] | Xc gc fc | counters, per-start ints
   const size_t n_aff = prior_mean_affine ? (size_t)y_dim * (d + 1) + cap * y_dim + capd * y_dim : 0;
   const size_t n_dbl = 3 * Md + 2 * (size_t)RC * Md + 2 * (size_t)M + n_aff + 2 * capd + cap;
-  CUDA_TRY(C().ms_buf.ensure(n_dbl * 8 + (size_t)M * 20 + cap * 4 + 64));
+  CUDA_TRY(C().ms_buf.ensure(n_dbl * 8 + (size_t)M * 24 + cap * 4 + 64));
   double *base = C().ms_buf.as<double>();
   MsState st{};
   st.d = d;
@@ -1911,7 +1911,8 @@ static int multistart_single(const boss_gp *const *slices, int y_dim, int n_samp
   st.trials = st.hist_start + M;
   st.steps = st.trials + M;
   st.state = st.steps + M;
-  st.idx = st.state + M;    // [cap]
+  st.nev = st.state + M;
+  st.idx = st.nev + M;      // [cap]
   st.fan = 1;
   double span = 0.0;
   for (int j = 0; j < d; ++j) {
@@ -1964,6 +1965,7 @@ static int multistart_single(const boss_gp *const *slices, int y_dim, int n_samp
   // rounds: every unfinished start advances by one function evaluation.  A start needs `iters` accepted steps plus its
   // rejected trials; the budget below lets a start reject every other trial on average before it is cut off.
   const int max_rounds = iters > 0 ? 2 * iters + MS_MAX_TRIALS : 0;
+  st.budget = max_rounds;   // enforced per start (ms_advance_kernel); the round loop below then ends by itself
   int active = iters > 0 ? (int)M : 0;
   const bool trace = getenv("BOSS_MS_TRACE") != nullptr;   // one line per round on stderr: round, batch size
   const bool use_fan = getenv("BOSS_MS_NO_FAN") == nullptr;

@@ -29,6 +29,8 @@ struct MsState {
   double *dirn, *t;          // [M][d], [M] search direction and current step size
   double *Sh, *Yh;           // [H][M][d] curvature pairs, one ring per start
   int *hist_len, *hist_start, *trials, *steps;   // [M] each
+  int *nev;                  // [M] evaluations a start has spent (trial points examined); it is cut off at `budget`
+  int budget;                // = 2 iters + MS_MAX_TRIALS: a start may reject every other trial on average
   int *state;                // [M] 0 = needs a direction, 1 = in a line search, 2 = finished
   int *idx;                  // [cap] compact list: idx[slot] = start
   int fan;                   // trial points per unfinished start in this round (speculative step-size fan, see below)
@@ -44,7 +46,7 @@ __global__ void ms_init_kernel(MsState st, const double *starts) {
   const long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (m >= st.M) return;
   for (int j = 0; j < st.d; ++j) st.X[m * st.d + j] = ms_clip(starts[m * st.d + j], st.lb[j], st.ub[j]);
-  st.hist_len[m] = st.hist_start[m] = st.trials[m] = st.steps[m] = 0;
+  st.hist_len[m] = st.hist_start[m] = st.trials[m] = st.steps[m] = st.nev[m] = 0;
   st.state[m] = st.iters > 0 ? 0 : 2;
 }
 
@@ -139,7 +141,10 @@ __global__ void ms_advance_kernel(MsState st, int count) {
   if (grp >= count) return;
   const long long m = st.idx[grp * st.fan];
   const int d = st.d;
-  const int nk = min(st.fan, MS_MAX_TRIALS - st.trials[m]);   // trials the sequential search would still make
+  // trials the sequential search would still make: to the end of this line search, and within the start's budget of
+  // evaluations (the budget is per start, not per round, so a trajectory does not depend on the fan width and therefore
+  // not on which other starts share the batch)
+  const int nk = min(min(st.fan, MS_MAX_TRIALS - st.trials[m]), st.budget - st.nev[m]);
   int state = 1, used = nk;
   for (int k = 0; k < nk; ++k) {
     const size_t slot = (size_t)grp * st.fan + k;
@@ -189,6 +194,7 @@ __global__ void ms_advance_kernel(MsState st, int count) {
     }
   }
   atomicAdd(&st.counters[2], used);   // evaluations the sequential search would have made (the rest was speculation)
+  if ((st.nev[m] += used) >= st.budget) state = 2;   // out of budget: stays at its last accepted point
   st.state[m] = state;
   if (state != 2) atomicAdd(&st.counters[1], 1);
 }

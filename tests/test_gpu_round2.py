@@ -371,6 +371,28 @@ def test_multistart_step_size_fan_keeps_the_sequential_trajectory(lib):
         assert np.array_equal(Xo, Xr) and np.array_equal(fo, fr), tag
         assert bio == bir and bvo == bvr and ev == evr, tag
     gp.free()
+    # a constrained two-output problem with a tight budget (iters = 15: many starts are cut off by their evaluation
+    # budget mid-search): whole batch == shard by shard == without the fan, start by start
+    n, d, M = 300, 4, 1024
+    X, Y, ls, amp, ns = make_problem(n, d, seed=101, y_dim=2)
+    gps = [lib.gp_fit(X, Y[i], ls[i], amp[i], ns[i], 2) for i in range(2)]
+    y_max = np.array([np.inf, float(np.quantile(Y[1], 0.7))])
+    coefs = np.array([1.0, 0.0])
+    best = O.best_so_far(coefs, Y, y_max)
+    starts = np.random.default_rng(102).random((d, M))
+    lb, ub = np.zeros(d), np.ones(d)
+    whole = lib.ei_maximize_multistart(gps, 2, 1, starts, coefs, best, y_max, lb, ub, iters=15)
+    parts = [lib.ei_maximize_multistart(gps, 2, 1, starts[:, k:k + 256], coefs, best, y_max, lb, ub, iters=15) for k in range(0, M, 256)]
+    os.environ["BOSS_MS_NO_FAN"] = "1"
+    try:
+        nofan = lib.ei_maximize_multistart(gps, 2, 1, starts, coefs, best, y_max, lb, ub, iters=15)
+    finally:
+        os.environ.pop("BOSS_MS_NO_FAN", None)
+    assert np.array_equal(whole[1], nofan[1]) and np.array_equal(whole[0], nofan[0])
+    assert np.array_equal(whole[1], np.concatenate([p[1] for p in parts]))
+    assert np.array_equal(whole[0], np.concatenate([p[0] for p in parts], axis=1))
+    for g in gps:
+        g.free()
 
 
 @pytest.mark.parametrize("n,d", [(200, 2), (1000, 5), (2048, 8)])

@@ -36,6 +36,9 @@ def main():
     y = Y[0]
     best = float(np.max(y))
     out = {"what": "single-process multi-GPU through boss_init_multi (host arrays, pageable)", "n_gpus": N}
+    # one sample set for every device count: the N = 1 call evaluates the first 256 samples of the N-device call
+    La, Aa, Na = make_hyper_samples(S1 * N, d, seed=3003)
+    La = np.ascontiguousarray(La)
     for nd in ([1, N] if N > 1 else [1]):
         if nd == 1:
             _lib.init(0)
@@ -44,7 +47,7 @@ def main():
         gp = _lib.gp_fit(X, y, ls[0], float(amp[0]), float(ns[0]), kid)
         M, S = M1 * nd, S1 * nd
         Xs = np.random.default_rng(2002).random((M, d)).T          # d x M view of an M x d pageable array
-        L, A, Nn = make_hyper_samples(S, d, seed=3003)
+        L, A, Nn = np.ascontiguousarray(La[:S]), Aa[:S].copy(), Na[:S].copy()      # ls is S x d (sample-major)
         res = {}
         for name, fn in (("score", lambda: _lib.ei_score([gp], 1, 1, Xs, [1.0], best, None, want_acq=False)),
                          ("loglik", lambda: _lib.loglik_batch(X, y, L, A, Nn, kid))):
