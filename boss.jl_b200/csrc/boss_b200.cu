@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <limits>
 #include <map>
 #include <mutex>
@@ -1978,7 +1979,15 @@ static int multistart_single(const boss_gp *const *slices, int y_dim, int n_samp
     if (use_fan) fan = active <= 10 ? 6 : active <= 21 ? 3 : active <= 128 ? 2 : 1;
     fan = (int)std::max<size_t>(1, std::min<size_t>(fan, cap / (size_t)active));
     st.fan = fan;
-    if (trace) fprintf(stderr, "boss multistart: round %d active %d fan %d\n", round, active, fan);
+    if (trace) {
+      static thread_local double t_prev = 0.0;
+      timespec ts;
+      clock_gettime(CLOCK_MONOTONIC, &ts);
+      const double t_now = ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+      fprintf(stderr, "boss multistart: round %d active %d fan %d prev_round_us %.0f\n", round, active, fan,
+              round ? t_now - t_prev : 0.0);
+      t_prev = t_now;
+    }
     CUDA_TRY(cudaMemsetAsync(st.counters, 0, 8, C().stream));
     ms_propose_kernel<<<nbm, 128, 0, C().stream>>>(st);
     rc = eval(st.Xc, (long long)active * fan, st.fc, st.gc, false, nullptr, nullptr);   // the compact list's length
