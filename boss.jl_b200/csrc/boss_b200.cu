@@ -1437,7 +1437,7 @@ int score_core(ScoreArgs &a) {
       // kernel finishes the candidates itself (fused epilogue) -- no reduce / acquisition / argmax launches.
       const bool fuse = nsp == 1 && !narrow && !quarter && q == nsl - 1 && getenv("BOSS_UNFUSED_SCORE") == nullptr;
       fused_chunk = fuse;
-      if (!fuse)
+      if (!fuse && !quarter)
         reduce_rows_kernel<<<(cnt + 255) / 256, 256, 0, C().stream>>>(C().part_mu.as<double>(), 2 * h->nblk, (size_t)CH,
                                                                    C().muv.as<double>() + (size_t)q * CH, cnt);
       ScoreParams sp{};
@@ -1474,10 +1474,14 @@ int score_core(ScoreArgs &a) {
         Timed t(0);
         score_trmm_kernel<<<dim3(ncb, nsp), GEMM_THREADS, GEMM_SMEM_BYTES, C().stream>>>(sp);
       }
-      if (!fuse)
+      if (quarter)   // mu partials (xcov) and sums of squares (quarter_sumsq) of this slice in one launch
+        reduce_rows_pair_kernel<<<dim3((cnt + 255) / 256, 2), 256, 0, C().stream>>>(
+            C().part_mu.as<double>(), C().part_ss.as<double>(), 2 * h->nblk, (size_t)CH, C().muv.as<double>() + (size_t)q * CH,
+            C().sumsq.as<double>() + (size_t)q * CH, cnt);
+      else if (!fuse)
         reduce_rows2_kernel<<<(cnt + 255) / 256, 256, 0, C().stream>>>(C().part_ss.as<double>(), 2 * h->nblk, (size_t)CH,
                                                                     C().sumsq.as<double>() + (size_t)q * CH, cnt);
-      C().launches += fuse ? 2 : quarter ? 5 : 4;
+      C().launches += fuse ? 2 : 4;
       if (a.grad) {
         WtvParams wp{h->WT, C().vt.as<double>(), C().ut.as<double>(), h->nblk, h->ktiles};
         if (quarter) {

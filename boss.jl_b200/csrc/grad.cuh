@@ -70,12 +70,8 @@ struct GradReduceParams {
 __global__ void __launch_bounds__(256) grad_reduce_kernel(GradReduceParams p) {
   const int c = blockIdx.x * 256 + threadIdx.x, j = blockIdx.y;
   if (c >= p.count) return;
-  double am = 0.0, av = 0.0;
-  for (int q = 0; q < p.P; ++q) {
-    const size_t o = ((size_t)q * p.d + j) * p.chunk_ld + c;
-    am += p.gm_part[o];
-    av += p.gv_part[o];
-  }
+  const size_t o0 = (size_t)j * p.chunk_ld + c, st = (size_t)p.d * p.chunk_ld;
+  const double am = ordered_sum(p.gm_part + o0, st, p.P), av = ordered_sum(p.gv_part + o0, st, p.P);
   const bool disc = (p.disc_bits >> j) & 1ull;
   const double il = p.invl[j];
   p.dmu[(size_t)j * p.chunk_ld + c] = disc ? 0.0 : am * il;

@@ -164,10 +164,13 @@ def run_c4(torch, _lib, O, stream, args):
     # the whole multi-start solve, device resident: 50 lock-step L-BFGS iterations over all starts
     aff = np.zeros((1, d + 1)); aff[0, 0] = theta[1]; aff[0, 1] = theta[0]
     _lib.ei_maximize_multistart([gp], 1, 1, starts, [1.0], best, None, lb, ub, iters=50, prior_mean_affine=aff)   # grows workspaces
-    t0 = time.perf_counter()
-    Xo, fo, bx, bv, bi, evals = _lib.ei_maximize_multistart([gp], 1, 1, starts, [1.0], best, None, lb, ub, iters=50,
-                                                            prior_mean_affine=aff)
-    t_opt = _max_over_ranks(torch, (time.perf_counter() - t0) * 1e3) * 1e-3
+    walls = []
+    for _ in range(3):       # a single host-timed call is exposed to scheduling hiccups of the box: median of three
+        t0 = time.perf_counter()
+        Xo, fo, bx, bv, bi, evals = _lib.ei_maximize_multistart([gp], 1, 1, starts, [1.0], best, None, lb, ub, iters=50,
+                                                                prior_mean_affine=aff)
+        walls.append(time.perf_counter() - t0)
+    t_opt = _max_over_ranks(torch, float(np.median(walls)) * 1e3) * 1e-3
     Fg = 2 * n * n + n * (9 * d + 16)
     Fv = n * n + n * (3 * d + 12)
     out = {"config": "C4", "n": n, "d": d, "starts_per_gpu": M, "ms_per_value_grad_iteration": ms_vg,
@@ -177,6 +180,7 @@ def run_c4(torch, _lib, O, stream, args):
            "ms_per_value_only": ms_v, "frac_of_dgemm_peak_value_only": Fv * M / (ms_v * 1e-3) * 1e-12 / peak(),
            "lockstep_50_iterations_s": 50 * ms_vg * 1e-3,
            "on_device_multistart": {"iters": 50, "batched_value_grad_evals": int(evals), "wall_s": t_opt,
+                                    "wall_s_of_3_calls": [round(w, 6) for w in walls],
                                     "best_value": float(bv), "start_value_max": float(np.max(a_dev)),
                                     "tflops": Fg * M * evals / t_opt * 1e-12,
                                     "frac_of_dgemm_peak": Fg * M * evals / t_opt * 1e-12 / peak()},
