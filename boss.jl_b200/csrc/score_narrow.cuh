@@ -185,22 +185,24 @@ __global__ void __launch_bounds__(256, 1) score_narrow_kernel(const __grid_const
 // requests, not bytes (measured, tools/bulk_copy_rate.cu -> profiles/r02_bulk_copy_rate.json): a TMA / mbarrier ring
 // stage costs ~310 ns + 15 ns per 4 KB bulk copy whatever the ring depth or the source (L2 or HBM) -- 24 GB/s per SM
 // with 8 KB stages, 75 GB/s with 32 KB stages; direct LDG.128 fragment loads four k-tiles ahead in registers reach
-// ~28 GB/s (both tried here: 0.53 and 0.43 us per k-tile).  So a stage carries NQ_KT = 8 k-tiles (16 bulk copies of
-// 4 KB, 64 KB), issued by a dedicated producer warp, 3 stages in flight.
+// ~28 GB/s (both tried here: 0.53 and 0.43 us per k-tile).  So a stage carries NQ_KT = 4 k-tiles (8 bulk copies of
+// 4 KB, 32 KB), issued by a dedicated producer warp, 3 stages in flight, two CTAs per SM.  (8 k-tiles per stage with one
+// CTA per SM is as fast for a single 32-candidate block and 10-15 % slower from 256 candidates on; 2 k-tiles per stage
+// with three CTAs per SM changes nothing: the SM's operand rate saturates.)
 // Accumulation order inside a fragment is unchanged (k ascending, same fragments skipped), V^T is always stored, and
 // quarter_sumsq_kernel replays the wide kernel's reduction over the stored tile -- THE SAME BITS again (DMMA.8x8x4
 // itself accumulates k ascending like an FMA chain: tools/dmma_order_test.cu, profiles/r02_dmma_order.json).
 // ---------------------------------------------------------------------------------------------
-constexpr int NQ_KT = 8;                                     // k-tiles per ring stage
+constexpr int NQ_KT = 4;                                     // k-tiles per ring stage
 constexpr int NQ_STAGES = 3;
 constexpr int NQ_QELEMS = TILE_ELEMS / 4;                    // 512 doubles: 4 row slabs of W, or a 32-candidate slice
-constexpr int NQ_STAGE_ELEMS = 2 * NQ_QELEMS * NQ_KT;        // 64 KB: [k-tile][A quarter | B slice]
+constexpr int NQ_STAGE_ELEMS = 2 * NQ_QELEMS * NQ_KT;        // 32 KB: [k-tile][A quarter | B slice]
 constexpr int NQ_SMEM_BYTES = NQ_STAGES * NQ_STAGE_ELEMS * 8 + 2 * NQ_STAGES * 8;
 constexpr int NQ_THREADS = 288;                              // 8 consumer warps + 1 producer warp
 
 // grid = (32-candidate blocks, 4 nblk): blockIdx.y = 4 * (rank of the row block, longest k-range first) + quarter
 template <int MODE>
-__global__ void __launch_bounds__(NQ_THREADS, 1) score_quarter_kernel(const __grid_constant__ NarrowParams p) {
+__global__ void __launch_bounds__(NQ_THREADS, 2) score_quarter_kernel(const __grid_constant__ NarrowParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   double *ring = reinterpret_cast<double *>(smem_raw);
   uint64_t *full = reinterpret_cast<uint64_t *>(ring + NQ_STAGES * NQ_STAGE_ELEMS), *empty = full + NQ_STAGES;

@@ -412,3 +412,41 @@ def test_tiny_batches_score_bitwise_like_large_ones(lib, n, d):
         assert np.array_equal(a, a_all[:m]) and np.array_equal(g, g_all[:, :m]), m
         assert np.array_equal(mu, mu_all[:m]) and np.array_equal(var, var_all[:m]), m
     gp.free()
+
+
+def test_tiny_batches_bitwise_with_bi_samples_constraints_prior_mean_and_mask(lib):
+    """The same invariance with everything switched on: 3 BI samples x 2 output slices (mixed kernels and sizes of
+    hyper-parameters), y_max constraint, box, cons mask, host-evaluated prior mean and its gradient, MC-EI expression
+    fitness -- 1, 7 and 40 candidates against the same points inside a 900-point batch."""
+    n, d, y_dim, ns_ = 260, 3, 2, 3
+    X, Y, ls, amp, ns = make_problem(n, d, seed=4300, y_dim=y_dim)
+    rng = np.random.default_rng(43)
+    gps = []
+    for s in range(ns_):
+        for i in range(y_dim):
+            gps.append(lib.gp_fit(X, Y[i], ls[i] * (1.0 + 0.2 * s), amp[i] * (1.0 + 0.1 * s), ns[i], 2 if i == 0 else 1))
+    M = 900
+    Xs = rng.random((d, M)) * 1.1 - 0.05                    # a few points outside the box
+    y_max = np.array([np.inf, float(np.quantile(Y[1], 0.6))])
+    coefs = np.array([1.0, 0.3])
+    best = O.best_so_far(coefs, Y, y_max)
+    lb, ub = np.zeros(d), np.ones(d)
+    cm = (rng.random(M) > 0.1).astype(np.uint8)
+    pm = 0.05 * np.vstack([Xs[0], -Xs[1]])                   # (y_dim, M)
+    pmg = np.zeros((y_dim, d, M)); pmg[0, 0] = 0.05; pmg[1, 1] = -0.05
+    a_all, g_all = lib.ei_value_grad(gps, y_dim, ns_, Xs, coefs, best, y_max, lb, ub, cons_mask=cm, prior_mean_s=pm,
+                                     prior_mean_grad_s=pmg)
+    s_all, _, _ = lib.ei_score(gps, y_dim, ns_, Xs, coefs, best, y_max, lb=lb, ub=ub, cons_mask=cm, prior_mean_s=pm)
+    assert np.array_equal(s_all, a_all)
+    eps = rng.standard_normal((y_dim, ns_))
+    mc_all, _, _ = lib.mcei_score(gps, y_dim, ns_, Xs, 2, eps, best, y_max, c=coefs, q=np.array([0.0, -0.2]), t=np.zeros(y_dim),
+                                  lb=lb, ub=ub)
+    for m in (1, 7, 40):
+        a, g = lib.ei_value_grad(gps, y_dim, ns_, Xs[:, :m], coefs, best, y_max, lb, ub, cons_mask=cm[:m],
+                                 prior_mean_s=pm[:, :m], prior_mean_grad_s=pmg[:, :, :m])
+        assert np.array_equal(a, a_all[:m]) and np.array_equal(g, g_all[:, :m]), m
+        mc, _, _ = lib.mcei_score(gps, y_dim, ns_, Xs[:, :m], 2, eps, best, y_max, c=coefs, q=np.array([0.0, -0.2]),
+                                  t=np.zeros(y_dim), lb=lb, ub=ub)
+        assert np.array_equal(mc, mc_all[:m]), m
+    for g_ in gps:
+        g_.free()
