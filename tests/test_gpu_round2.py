@@ -395,7 +395,7 @@ def test_multistart_step_size_fan_keeps_the_sequential_trajectory(lib):
         g.free()
 
 
-@pytest.mark.parametrize("n,d", [(200, 2), (1000, 5), (2048, 8)])
+@pytest.mark.parametrize("n,d", [(100, 1), (129, 32), (200, 2), (1000, 5), (2048, 8)])
 def test_tiny_batches_score_bitwise_like_large_ones(lib, n, d):
     """1, 5, 33 and 100 candidates (quarter-row / narrow kernels) against the same points inside a 700-point batch
     (wide kernel): value, x-gradient, mean and variance are bit-identical."""
@@ -411,6 +411,14 @@ def test_tiny_batches_score_bitwise_like_large_ones(lib, n, d):
         mu, var, _ = lib.gp_predict(gp, Xs[:, :m])
         assert np.array_equal(a, a_all[:m]) and np.array_equal(g, g_all[:, :m]), m
         assert np.array_equal(mu, mu_all[:m]) and np.array_equal(var, var_all[:m]), m
+    # the same after rank-1 appends (factor cache grown in place; n no longer what the handle was fitted with)
+    xn = np.random.default_rng(7).random((d, 3))
+    for k in range(3):
+        assert lib.gp_append(gp, xn[:, k], 0.1 * k)
+    a_all, g_all = lib.ei_value_grad([gp], 1, 1, Xs, [1.0], best, None, lb, ub)
+    for m in (1, 20):
+        a, g = lib.ei_value_grad([gp], 1, 1, Xs[:, :m], [1.0], best, None, lb, ub)
+        assert np.array_equal(a, a_all[:m]) and np.array_equal(g, g_all[:, :m]), m
     gp.free()
 
 
