@@ -352,8 +352,8 @@ int set_kernel_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(wtv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(score_narrow_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, NW_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(score_narrow_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, NW_SMEM_BYTES));
-  CUDA_TRY(cudaFuncSetAttribute(score_quarter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, NQ_SMEM_BYTES));
-  CUDA_TRY(cudaFuncSetAttribute(score_quarter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, NQ_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(score_quarter_kernel<0, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, NQ_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(score_quarter_kernel<1, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, NQ_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(potrf_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(chol_matrix_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, CM_SMEM_BYTES));
@@ -1462,7 +1462,7 @@ int score_core(ScoreArgs &a) {
       if (quarter) {
         NarrowParams np{h->W, C().ks.as<double>(), h->nblk, h->ktiles, nullptr, CH, C().vt.as<double>()};
         Timed t(0);
-        score_quarter_kernel<0><<<dim3(ncb32, 4 * h->nblk), NQ_THREADS, NQ_SMEM_BYTES, C().stream>>>(np);
+        score_quarter_kernel<0, 4, 1><<<dim3(ncb32, 4 * h->nblk), NQ_THREADS, NQ_SMEM_BYTES, C().stream>>>(np);
         quarter_sumsq_kernel<<<dim3(ncb32, h->nblk), 256, 0, C().stream>>>(C().vt.as<double>(), h->ktiles,
                                                                          C().part_ss.as<double>(), CH);
       } else if (narrow) {
@@ -1487,7 +1487,7 @@ int score_core(ScoreArgs &a) {
         if (quarter) {
           NarrowParams np{h->WT, C().vt.as<double>(), h->nblk, h->ktiles, nullptr, CH, C().ut.as<double>()};
           Timed t(0);
-          score_quarter_kernel<1><<<dim3(ncb32, 4 * h->nblk), NQ_THREADS, NQ_SMEM_BYTES, C().stream>>>(np);
+          score_quarter_kernel<1, 4, 1><<<dim3(ncb32, 4 * h->nblk), NQ_THREADS, NQ_SMEM_BYTES, C().stream>>>(np);
         } else if (narrow) {
           NarrowParams np{h->WT, C().vt.as<double>(), h->nblk, h->ktiles, nullptr, CH, C().ut.as<double>()};
           Timed t(0);

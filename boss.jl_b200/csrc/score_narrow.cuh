@@ -193,27 +193,35 @@ __global__ void __launch_bounds__(256, 1) score_narrow_kernel(const __grid_const
 // quarter_sumsq_kernel replays the wide kernel's reduction over the stored tile -- THE SAME BITS again (DMMA.8x8x4
 // itself accumulates k ascending like an FMA chain: tools/dmma_order_test.cu, profiles/r02_dmma_order.json).
 // ---------------------------------------------------------------------------------------------
-constexpr int NQ_KT = 4;                                     // k-tiles per ring stage
+// The kernel is a template over the CTA tile: RS row slabs (of 8 rows) x NC 32-candidate slices.  <4, 1> is the quarter
+// shape above and the only one instantiated: <8, 2> (64 rows x 64 candidates, half the operand bytes per output) was
+// measured and is slower up to 512 candidates (n = 4096, 256 candidates: 519 vs 378 us per value + gradient call) --
+// four times fewer CTAs with a four times longer DMMA chain each balance worse than the bytes they save.
 constexpr int NQ_STAGES = 3;
-constexpr int NQ_QELEMS = TILE_ELEMS / 4;                    // 512 doubles: 4 row slabs of W, or a 32-candidate slice
-constexpr int NQ_STAGE_ELEMS = 2 * NQ_QELEMS * NQ_KT;        // 32 KB: [k-tile][A quarter | B slice]
+constexpr int NQ_STAGE_ELEMS = 4096;                         // 32 KB per stage, whole k-tiles of [A part | B slices]
 constexpr int NQ_SMEM_BYTES = NQ_STAGES * NQ_STAGE_ELEMS * 8 + 2 * NQ_STAGES * 8;
 constexpr int NQ_THREADS = 288;                              // 8 consumer warps + 1 producer warp
 
-// grid = (32-candidate blocks, 4 nblk): blockIdx.y = 4 * (rank of the row block, longest k-range first) + quarter
-template <int MODE>
+// grid = (NC x 32-candidate blocks, (16 / RS) nblk): blockIdx.y = (16 / RS) * (rank of the row block, longest k-range
+// first) + part of the row block
+template <int MODE, int RS, int NC>
 __global__ void __launch_bounds__(NQ_THREADS, 2) score_quarter_kernel(const __grid_constant__ NarrowParams p) {
+  constexpr int PARTS = 16 / RS;                     // CTAs per row block
+  constexpr int A_EL = RS * 128, B_EL = NC * 512;    // doubles per k-tile: RS row slabs of W, NC candidate slices of K*^T
+  constexpr int KT_EL = A_EL + B_EL;
+  constexpr int KT = NQ_STAGE_ELEMS / KT_EL;         // k-tiles per ring stage: 4 (quarter) or 2 (half)
+  constexpr int SW = RS / 4, FW = 2 * NC;            // a warp: SW row slabs x FW candidate slabs
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   double *ring = reinterpret_cast<double *>(smem_raw);
   uint64_t *full = reinterpret_cast<uint64_t *>(ring + NQ_STAGES * NQ_STAGE_ELEMS), *empty = full + NQ_STAGES;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int cb32 = blockIdx.x, cb = cb32 >> 2, sub = cb32 & 3, qd = blockIdx.y & 3;
-  const int i = MODE == 0 ? p.nblk - 1 - (int)(blockIdx.y >> 2) : (int)(blockIdx.y >> 2);
-  // live k-tiles of the quarter: lower block (MODE 0) slab R sees k micro-steps kk <= R, R <= 4 qd + 3;
-  // upper block (MODE 1) slab R sees kk >= R, R >= 4 qd
-  const int kt0 = MODE == 0 ? 0 : i * KT_PER_BLOCK + 2 * qd;
-  const int kt1 = MODE == 0 ? i * KT_PER_BLOCK + 2 * qd + 2 : p.ktiles;
-  const int nk = kt1 - kt0, nst = (nk + NQ_KT - 1) / NQ_KT;
+  const int s32 = blockIdx.x * NC, cb = s32 >> 2, sub = s32 & 3, part = blockIdx.y % PARTS;
+  const int i = MODE == 0 ? p.nblk - 1 - (int)(blockIdx.y / PARTS) : (int)(blockIdx.y / PARTS);
+  // live k-tiles of the part: lower block (MODE 0) slab R sees k micro-steps kk <= R, R < RS (part + 1);
+  // upper block (MODE 1) slab R sees kk >= R, R >= RS part
+  const int kt0 = MODE == 0 ? 0 : i * KT_PER_BLOCK + (RS * part) / 2;
+  const int kt1 = MODE == 0 ? i * KT_PER_BLOCK + (RS * part + RS) / 2 : p.ktiles;
+  const int nk = kt1 - kt0, nst = (nk + KT - 1) / KT;
   if (tid < 2 * NQ_STAGES) {
     mbar_init(smem_u32(tid < NQ_STAGES ? &full[tid] : &empty[tid - NQ_STAGES]), tid < NQ_STAGES ? 1u : 8u);
     mbar_fence_init();
@@ -221,78 +229,99 @@ __global__ void __launch_bounds__(NQ_THREADS, 2) score_quarter_kernel(const __gr
   __syncthreads();
   if (w == 8) {   // producer warp: one lane streams the stages, blocking only on the slot it is about to refill
     if (lane == 0) {
-      const double *Ablk = p.A + ((size_t)i * p.ktiles + kt0) * TILE_ELEMS + (size_t)qd * NQ_QELEMS;
-      const double *Bblk = p.B + ((size_t)cb * p.ktiles + kt0) * TILE_ELEMS + (size_t)sub * NQ_QELEMS;
+      const double *Ablk = p.A + ((size_t)i * p.ktiles + kt0) * TILE_ELEMS + (size_t)part * A_EL;
+      const double *Bblk = p.B + ((size_t)cb * p.ktiles + kt0) * TILE_ELEMS + (size_t)sub * 512;
       for (int s = 0; s < nst; ++s) {
         const int slot = s % NQ_STAGES;
         if (s >= NQ_STAGES) mbar_wait(smem_u32(&empty[slot]), (uint32_t)((s / NQ_STAGES - 1) & 1));
-        const int cnt = min(NQ_KT, nk - s * NQ_KT);
+        const int cnt = min(KT, nk - s * KT);
         const uint32_t bar = smem_u32(&full[slot]);
         double *dst = ring + (size_t)slot * NQ_STAGE_ELEMS;
-        mbar_arrive_expect_tx(bar, (uint32_t)(cnt * 2 * NQ_QELEMS * 8));
+        mbar_arrive_expect_tx(bar, (uint32_t)(cnt * KT_EL * 8));
         for (int t = 0; t < cnt; ++t) {
-          const size_t off = (size_t)(s * NQ_KT + t) * TILE_ELEMS;
-          bulk_g2s(smem_u32(dst + (size_t)t * 2 * NQ_QELEMS), Ablk + off, NQ_QELEMS * 8, bar);
-          bulk_g2s(smem_u32(dst + (size_t)t * 2 * NQ_QELEMS + NQ_QELEMS), Bblk + off, NQ_QELEMS * 8, bar);
+          const size_t off = (size_t)(s * KT + t) * TILE_ELEMS;
+          bulk_g2s(smem_u32(dst + (size_t)t * KT_EL), Ablk + off, A_EL * 8, bar);
+          bulk_g2s(smem_u32(dst + (size_t)t * KT_EL + A_EL), Bblk + off, B_EL * 8, bar);
         }
       }
     }
     return;
   }
-  const int sl = w >> 1, R = 4 * qd + sl, fn0 = 2 * (w & 1);   // this warp: row slab R x candidate slabs fn0, fn0 + 1
-  double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+  const int sl0 = (w >> 1) * SW, R0 = RS * part + sl0, fn0 = FW * (w & 1);   // this warp: slabs R0.. x candidate slabs fn0..
+  double acc[SW][FW][2];
+#pragma unroll
+  for (int a = 0; a < SW; ++a)
+#pragma unroll
+    for (int f = 0; f < FW; ++f) acc[a][f][0] = acc[a][f][1] = 0.0;
   for (int s = 0; s < nst; ++s) {
     const int slot = s % NQ_STAGES;
     mbar_wait(smem_u32(&full[slot]), (uint32_t)((s / NQ_STAGES) & 1));
-    const int cnt = min(NQ_KT, nk - s * NQ_KT);
-    const double *st = ring + (size_t)slot * NQ_STAGE_ELEMS + 2 * lane + sl * 128;
-    const double *sb = ring + (size_t)slot * NQ_STAGE_ELEMS + 2 * lane + NQ_QELEMS + fn0 * 128;
-    const int dgs = kt0 + s * NQ_KT - i * KT_PER_BLOCK;   // k-tile t of the stage is k-tile dgs + t of the diagonal block (if in 0..7)
-    // fragments of k-tile t + 1 are fetched from shared memory before the DMMA chain of k-tile t starts
-    auto fetch = [&](int t, double2(&f)[6]) {
-      const double *As = st + (size_t)t * 2 * NQ_QELEMS, *Bs = sb + (size_t)t * 2 * NQ_QELEMS;
-      f[0] = lds128(As);
-      f[1] = lds128(As + 64);
-      f[2] = lds128(Bs);
-      f[3] = lds128(Bs + 64);
-      f[4] = lds128(Bs + 128);
-      f[5] = lds128(Bs + 192);
+    const int cnt = min(KT, nk - s * KT);
+    const double *st = ring + (size_t)slot * NQ_STAGE_ELEMS + 2 * lane + sl0 * 128;
+    const double *sb = ring + (size_t)slot * NQ_STAGE_ELEMS + 2 * lane + A_EL + fn0 * 128;
+    const int dgs = kt0 + s * KT - i * KT_PER_BLOCK;   // k-tile t of the stage is k-tile dgs + t of the diagonal block (if in 0..7)
+    // fragments: [mc][slab] of W, [mc][candidate slab] of K*^T
+    auto fetch = [&](int t, double2(&fa)[2][SW], double2(&fb)[2][FW]) {
+      const double *As = st + (size_t)t * KT_EL, *Bs = sb + (size_t)t * KT_EL;
+#pragma unroll
+      for (int mc = 0; mc < 2; ++mc) {
+#pragma unroll
+        for (int a = 0; a < SW; ++a) fa[mc][a] = lds128(As + a * 128 + mc * 64);
+#pragma unroll
+        for (int f = 0; f < FW; ++f) fb[mc][f] = lds128(Bs + f * 128 + mc * 64);
+      }
     };
-    auto mma = [&](int t, const double2(&f)[6]) {
+    auto mma = [&](int t, const double2(&fa)[2][SW], const double2(&fb)[2][FW]) {
       const int dg = dgs + t;
       const bool diag = dg >= 0 && dg < KT_PER_BLOCK;
 #pragma unroll
       for (int mc = 0; mc < 2; ++mc) {
         const int kk = 2 * dg + mc;
-        const bool live = !diag || (MODE == 0 ? R >= kk : R <= kk);   // warp-uniform
-        if (live) {
-          dmma884(acc[0][0], acc[0][1], f[mc].x, f[2 + mc].x);
-          dmma884(acc[1][0], acc[1][1], f[mc].x, f[4 + mc].x);
-          dmma884(acc[0][0], acc[0][1], f[mc].y, f[2 + mc].y);
-          dmma884(acc[1][0], acc[1][1], f[mc].y, f[4 + mc].y);
+#pragma unroll
+        for (int a = 0; a < SW; ++a) {
+          const bool live = !diag || (MODE == 0 ? R0 + a >= kk : R0 + a <= kk);   // warp-uniform
+          if (live) {
+#pragma unroll
+            for (int f = 0; f < FW; ++f) dmma884(acc[a][f][0], acc[a][f][1], fa[mc][a].x, fb[mc][f].x);
+#pragma unroll
+            for (int f = 0; f < FW; ++f) dmma884(acc[a][f][0], acc[a][f][1], fa[mc][a].y, fb[mc][f].y);
+          }
         }
       }
     };
-    double2 f0[6], f1[6];
-    fetch(0, f0);
+    if constexpr (SW * FW <= 2) {
+      // quarter shape: the fragments of k-tile t + 1 are fetched before the (short) DMMA chain of k-tile t starts
+      double2 a0[2][SW], b0[2][FW], a1[2][SW], b1[2][FW];
+      fetch(0, a0, b0);
 #pragma unroll
-    for (int t = 0; t < NQ_KT; t += 2) {
-      if (t < cnt) {
-        if (t + 1 < cnt) fetch(t + 1, f1);
-        mma(t, f0);
+      for (int t = 0; t < KT; t += 2) {
+        if (t < cnt) {
+          if (t + 1 < cnt) fetch(t + 1, a1, b1);
+          mma(t, a0, b0);
+        }
+        if (t + 1 < cnt) {
+          if (t + 2 < cnt) fetch(t + 2, a0, b0);
+          mma(t + 1, a1, b1);
+        }
       }
-      if (t + 1 < cnt) {
-        if (t + 2 < cnt) fetch(t + 2, f0);
-        mma(t + 1, f1);
-      }
+    } else {
+      double2 a0[2][SW], b0[2][FW];
+#pragma unroll
+      for (int t = 0; t < KT; ++t)
+        if (t < cnt) {
+          fetch(t, a0, b0);
+          mma(t, a0, b0);
+        }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(&empty[slot]));
   }
   // transposed store: rows = candidates (block cb, slabs 4 sub + fn), columns = rows of block i
   double *ot = p.OT + (size_t)cb * p.ktiles * TILE_ELEMS + (size_t)i * KT_PER_BLOCK * TILE_ELEMS;
-  p_store_cfrag_t(ot, R, 4 * sub + fn0, lane, acc[0][0], acc[0][1]);
-  p_store_cfrag_t(ot, R, 4 * sub + fn0 + 1, lane, acc[1][0], acc[1][1]);
+#pragma unroll
+  for (int a = 0; a < SW; ++a)
+#pragma unroll
+    for (int f = 0; f < FW; ++f) p_store_cfrag_t(ot, R0 + a, 4 * sub + fn0 + f, lane, acc[a][f][0], acc[a][f][1]);
 }
 
 // Column sums of squares of the stored V^T in the wide kernel's order: per row block and slab parity the fma chain over
