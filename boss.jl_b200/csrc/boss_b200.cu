@@ -334,7 +334,7 @@ int pick_row_splits(int ncb, int nblk, double *cost = nullptr) {
 // kernel on one SM, 17 us): per row block of the longest CTA's chain, per (32-candidate block x block step) of tensor
 // work spread over the GPU, fixed cost of the extra reduction launch.  Calibrated on the B200 (tools/bench_small_batch.py).
 constexpr long long MS_FAN_BATCH = 256;   // capacity of a multi-start round's batch once the step-size fan is on
-constexpr double NQ_COST_CHAIN = 0.085, NQ_COST_WORK = 0.0023, NQ_COST_FIXED = 0.15;
+constexpr double NQ_COST_CHAIN = 0.085, NQ_COST_WORK = 0.0019, NQ_COST_FIXED = 0.15;
 
 // dynamic shared-memory opt-in is per device: once per context
 int set_kernel_attrs() {
