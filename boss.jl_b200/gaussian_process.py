@@ -127,6 +127,29 @@ class GaussianProcessPosterior:
     def var(self, x):
         return self.mean_and_var(x)[1]
 
+    def std(self, x):
+        """src/types/model_posterior.jl: std = sqrt(var)"""
+        return np.sqrt(self.var(x))
+
+    def mean_and_std(self, x):
+        mu, var = self.mean_and_var(x)
+        return mu, np.sqrt(var)
+
+    def mean_and_cov(self, X):
+        """gaussian_process.jl:180-184: matrix X (d x M) -> (mu (M,), Sigma (M, M)), diagonal through _clip_var."""
+        X = np.asarray(X, dtype=np.float64)
+        if X.ndim != 2:
+            raise TypeError("cov / mean_and_cov take a matrix of points (the reference defines no vector method)")
+        pm = self.model.mean_at(self.slice_idx, X)
+        mu, cov, rc = _lib.gp_cov(self.gp, X, pm)
+        if rc != 0:
+            raise ValueError("DomainError: The posterior GP predicted a variance below -1e-8.")
+        return mu, cov
+
+    def cov(self, X):
+        """gaussian_process.jl:163-167"""
+        return self.mean_and_cov(X)[1]
+
 
 def model_posterior_slice(model, params, data: ExperimentData, slice_idx: int) -> GaussianProcessPosterior:
     """gaussian_process.jl:133-141 / semiparametric.jl:79-84.  Raises ValueError (PosDefException) if K is not PD."""

@@ -30,6 +30,19 @@ class DefaultModelPosterior:
     def std(self, x):
         return np.sqrt(self.var(x))
 
+    def mean_and_std(self, x):
+        mu, var = self.mean_and_var(x)
+        return mu, np.sqrt(var)
+
+    def mean_and_cov(self, X):
+        """src/posterior.jl:73-78: (mu (y_dim, M), Sigma (M, M, y_dim))"""
+        res = [s.mean_and_cov(X) for s in self.slices]
+        return np.stack([r[0] for r in res]), np.stack([r[1] for r in res], axis=2)
+
+    def cov(self, X):
+        """src/posterior.jl:55-57"""
+        return self.mean_and_cov(X)[1]
+
 
 def model_posterior(problem_or_model, params=None, data=None):
     """model_posterior(problem) | model_posterior(model, params, data); a list of params (BIParams)

@@ -258,3 +258,58 @@ def test_gradient_optimization_map_and_sample_opt_map():
     assert grad.loglike >= comp.loglike - 0.05 * abs(comp.loglike)
     allr = B.estimate_parameters(B.OptimizationMAP(multistart=5, iters=5, seed=3), prob, return_all=True)
     assert 1 <= len(allr) <= 5
+
+
+def test_model_posterior_testset_of_the_reference():
+    """test/unit/test/models/gaussian_process.jl:57-160 ("model_posterior(model, params, data)"), assertion by assertion:
+    two outputs, prior mean x -> [1, 1], data on the diagonal (y = x at 2, 5, 8), noise 1e-4, parameters estimated by
+    SamplingMAP(samples = 200); vector / matrix / single-column-matrix forms of mean, std, var, cov and their mean_and_*
+    pairs agree to 1e-8, the posterior interpolates the data to 0.01, reverts to the prior mean far away, and the
+    variance grows away from the data."""
+    X = np.array([[2.0, 5.0, 8.0], [2.0, 5.0, 8.0]])
+    model = B.GaussianProcess(mean=lambda x: [1.0, 1.0],
+                              amplitude_priors=[B.LogNormal(0.0, 1.0)] * 2,
+                              lengthscale_priors=[B.mvlognormal([1.0, 1.0], [1.0, 1.0])] * 2,
+                              noise_std_priors=[B.Dirac(1e-4)] * 2)
+    problem = B.BossProblem(lambda x: x, B.Domain(([0.0, 0.0], [10.0, 10.0])),
+                            B.ExpectedImprovement(B.LinFitness([1.0, 0.0])), model, B.ExperimentData(X, X.copy()),
+                            y_max=[np.inf, 5.0])
+    problem.params = B.estimate_parameters(B.SamplingMAP(samples=200, seed=5), problem)
+    out = B.model_posterior(problem.model, problem.params, problem.data)
+    x2 = np.array([2.0, 2.0])
+    # vector
+    for f in (out.mean, out.std, out.var):
+        assert np.asarray(f(x2)).shape == (2,)
+    assert np.allclose(out.mean(x2), out.mean_and_std(x2)[0], atol=1e-8)
+    assert np.allclose(out.mean(x2), out.mean_and_var(x2)[0], atol=1e-8)
+    assert np.allclose(out.std(x2), out.mean_and_std(x2)[1], atol=1e-8)
+    assert np.allclose(out.var(x2), out.mean_and_var(x2)[1], atol=1e-8)
+    for v in (2.0, 5.0, 8.0):
+        assert np.allclose(out.mean(np.array([v, v])), [v, v], atol=0.01)
+    assert np.all(out.mean(np.array([1.0, 1.0])) < [2.0, 2.0])
+    assert np.all(out.mean(np.array([4.0, 4.0])) < [5.0, 5.0])
+    assert np.allclose(out.mean(np.array([100.0, 100.0])), [1.0, 1.0], atol=0.01)
+    assert np.all(out.var(x2) <= out.var(np.array([3.0, 3.0])))
+    assert np.all(out.var(np.array([10.0, 10.0])) <= out.var(np.array([11.0, 11.0])))
+    # matrix, and single-element matrix
+    for Xm in (np.array([[1.0, 2.0, 3.0], [1.0, 2.0, 3.0]]), np.array([[1.0], [1.0]])):
+        M = Xm.shape[1]
+        assert out.mean(Xm).shape == (2, M) and out.std(Xm).shape == (2, M) and out.var(Xm).shape == (2, M)
+        assert out.cov(Xm).shape == (M, M, 2)
+        assert np.allclose(out.mean(Xm), out.mean_and_std(Xm)[0], atol=1e-8)
+        assert np.allclose(out.mean(Xm), out.mean_and_var(Xm)[0], atol=1e-8)
+        assert np.allclose(out.mean(Xm), out.mean_and_cov(Xm)[0], atol=1e-8)
+        assert np.allclose(out.std(Xm), out.mean_and_std(Xm)[1], atol=1e-8)
+        assert np.allclose(out.var(Xm), out.mean_and_var(Xm)[1], atol=1e-8)
+        assert np.allclose(out.cov(Xm), out.mean_and_cov(Xm)[1], atol=1e-8)
+        for j in range(M):
+            assert np.allclose(out.mean(Xm)[:, j], out.mean(Xm[:, j]), atol=1e-8)
+            assert np.allclose(out.var(Xm)[:, j], out.var(Xm[:, j]), atol=1e-8)
+            # the diagonal of the covariance is the variance (both clipped by _clip_var)
+            assert np.allclose(out.cov(Xm)[j, j, :], out.var(Xm[:, j]), atol=1e-8)
+    # slices: model_posterior_slice agrees with the stacked posterior (src/posterior.jl:4-5, gaussian_process.jl:133-141)
+    for i in range(2):
+        sl = B.model_posterior_slice(problem.model, problem.params.params if hasattr(problem.params, "params") else problem.params,
+                                     problem.data, i)
+        assert abs(sl.mean(x2) - out.mean(x2)[i]) <= 1e-8 and abs(sl.var(x2) - out.var(x2)[i]) <= 1e-8
+        assert abs(sl.std(x2) - out.std(x2)[i]) <= 1e-8
