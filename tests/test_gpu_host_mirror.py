@@ -313,3 +313,51 @@ def test_model_posterior_testset_of_the_reference():
                                      problem.data, i)
         assert abs(sl.mean(x2) - out.mean(x2)[i]) <= 1e-8 and abs(sl.var(x2) - out.var(x2)[i]) <= 1e-8
         assert abs(sl.std(x2) - out.std(x2)[i]) <= 1e-8
+
+
+def test_loglike_testsets_of_the_reference():
+    """test/unit/test/models/gaussian_process.jl:244-356: the "model_loglike", "data_loglike" and "params_loglike"
+    testsets with the reference's own inputs (3 training points -> the warp-register path; noise_std = 0 included)."""
+    GPP = B.GaussianProcessParams
+    ones22 = np.ones((2, 2))
+    # --- model_loglike(model, data) ---
+    model = B.GaussianProcess(mean=lambda x: [1.0, 1.0], amplitude_priors=[B.LogNormal()] * 2,
+                              lengthscale_priors=[B.mvlognormal([1.0, 1.0], [1.0, 1.0])] * 2,
+                              noise_std_priors=[B.LogNormal()] * 2)
+    X = np.array([[2.0, 5.0, 8.0], [2.0, 5.0, 8.0]])
+    out = B.model_loglike(model, B.ExperimentData(X, X.copy()))
+    assert callable(out)
+    v = out(GPP(ones22, np.array([1.0, 1.0]), np.array([1.0, 1.0])))
+    assert isinstance(v, float) and v < 0.0
+    assert out(GPP(ones22, np.ones(2), np.array([5.0, 5.0]))) > out(GPP(ones22, np.ones(2), np.array([100.0, 100.0])))
+    assert out(GPP(ones22, np.array([5.0, 5.0]), np.ones(2))) > out(GPP(ones22, np.array([100.0, 100.0]), np.ones(2)))
+    assert out(GPP(5.0 * ones22, np.ones(2), np.ones(2))) > out(GPP(100.0 * ones22, np.ones(2), np.ones(2)))
+    # --- data_loglike(model, data) ---
+    model1 = B.GaussianProcess(mean=lambda x: [0.0], amplitude_priors=[B.LogNormal()],
+                               lengthscale_priors=[B.Product([B.Dirac(1.0)])], noise_std_priors=[B.Dirac(0.1)])
+    X1 = np.array([[1.0, 2.0, 3.0]])
+    t_ls = lambda l: GPP(np.array([[l]]), np.array([1.0]), np.array([0.0]))
+    t_amp = lambda a: GPP(np.array([[1.0]]), np.array([a]), np.array([0.0]))
+    t_ns = lambda s: GPP(np.array([[1.0]]), np.array([1.0]), np.array([s]))
+    assert isinstance(B.data_loglike(model1, B.ExperimentData(X1, X1.copy()))(GPP(np.array([[1.0]]), np.array([1.0]), np.array([1.0]))), float)
+    out = B.data_loglike(model1, B.ExperimentData(X1, np.array([[1.0, -1.0, 1.0]])))
+    assert out(t_ls(0.1)) > out(t_ls(1.0)) > out(t_ls(10.0))
+    assert out(t_amp(1.0)) > out(t_amp(0.1))
+    assert out(t_ns(1.0)) > out(t_ns(0.1)) and out(t_ns(1.0)) > out(t_ns(10.0))
+    t_data = lambda Y: B.data_loglike(model1, B.ExperimentData(X1, np.array([Y])))(GPP(np.array([[1.0]]), np.array([1.0]), np.array([0.0])))
+    assert t_data([99.9, 100.0, 100.1]) > t_data([99.0, 100.0, 101.0]) > t_data([90.0, 100.0, 110.0])
+    # the device values are the oracle's (the reference's logpdf(::FiniteGP)) to 1e-8
+    for p in (t_ls(0.1), t_ls(10.0), t_amp(0.1), t_ns(10.0)):
+        ref = O.gp_loglik(X1, np.array([1.0, -1.0, 1.0]), p.lengthscales[:, 0], p.amplitudes[0], p.noise_std[0], O.KERNEL_MATERN52)
+        assert abs(out(p) - ref) <= 1e-8 * abs(ref)
+    # --- params_loglike(model, params) ---
+    m = B.GaussianProcess(lengthscale_priors=[B.mvlognormal([1.0, 1.0], [1.0, 1.0])] * 2, amplitude_priors=[B.LogNormal()] * 2,
+                          noise_std_priors=[B.Dirac(0.1)] * 2)
+    assert isinstance(m.params_loglike()(GPP(ones22, np.array([1.0, 2.0]), np.array([0.1, 0.1]))), float)
+    md = B.GaussianProcess(lengthscale_priors=[B.Product([B.Dirac(1.0), B.Dirac(1.0)])] * 2, amplitude_priors=[B.Dirac(1.0)] * 2,
+                           noise_std_priors=[B.Dirac(0.1)] * 2)
+    pl = md.params_loglike()
+    assert pl(GPP(ones22, np.ones(2), np.array([0.1, 0.1]))) == 0.0
+    assert pl(GPP(np.array([[1.0, 5.0], [1.0, 5.0]]), np.ones(2), np.array([0.1, 0.1]))) == -np.inf
+    assert pl(GPP(ones22, np.array([1.0, 5.0]), np.array([0.1, 0.1]))) == -np.inf
+    assert pl(GPP(ones22, np.ones(2), np.array([0.1, 0.5]))) == -np.inf

@@ -777,3 +777,49 @@ def test_small_n_append_and_multistart_paths_are_repeatable(lib):
         else:
             for k, (a, b) in enumerate(zip(ref, out)):
                 assert np.array_equal(a, b), (rep, k)
+
+
+def test_construct_ei_testset_of_the_reference(lib):
+    """test/unit/test/acquisitions/expected_improvement.jl:43-110 ("construct_ei(fitness, posterior, constraints,
+    eps_samples, best_yet)") on the device.  The reference uses ParametricPosterior(f = identity, noise_std = [1, 1]):
+    mean(x) = x, std = 1.  Here two GP slices whose only training point is far away (posterior = prior, variance
+    a^2 = 1) carry the identity as host-evaluated prior mean.  Single posterior and 4 identical posteriors (the BI
+    average), LinFitness([1, 0]) through boss_ei_score and NonlinFitness(x -> x[1]) through the device MC-EI."""
+    gps = [lib.gp_fit(np.array([[1000.0], [1000.0]]), np.array([0.0]), [1.0, 1.0], 1.0, 0.1, 0) for _ in range(2)]
+    eps = np.array([[0.422498, -1.33921, 0.490985, -0.951167], [-0.289737, 0.162767, -0.499742, 0.892919]])
+    coefs = np.array([1.0, 0.0])
+
+    def make(nonlin, n_post, y_max, best):
+        sl = gps * n_post
+
+        def out(x):
+            Xs = np.array(x, dtype=np.float64)[:, None]
+            pm = Xs.copy()                                    # prior mean = identity: (y_dim, M)
+            if nonlin:
+                a, _, _ = lib.mcei_score(sl, 2, n_post, Xs, 1, eps, best, y_max, c=coefs, prior_mean_s=pm)
+            else:
+                a, _, _ = lib.ei_score(sl, 2, n_post, Xs, coefs, best, y_max, prior_mean_s=pm)
+            return float(a[0])
+        return out
+
+    for nonlin in (False, True):
+        for n_post in (1, 4):
+            out = make(nonlin, n_post, None, None)
+            assert out([1.0, 1.0]) == out([1.0, 1.0]) and out([1.0, 1.0]) == 0.0
+            out = make(nonlin, n_post, np.array([np.inf, 10.0]), None)
+            assert out([1.0, 1.0]) == out([1.0, 1.0]) and out([1.0, 1.0]) > 0.0
+            assert out([5.0, 1.0]) == out([10.0, 1.0]) == out([15.0, 1.0])
+            assert out([1.0, 5.0]) > out([1.0, 10.0]) > out([1.0, 15.0])
+            assert abs(out([1.0, 20.0])) <= 1e-8
+            out = make(nonlin, n_post, None, 10.0)
+            assert out([11.0, 1.0]) == out([11.0, 1.0]) and out([11.0, 1.0]) > 0.0
+            assert out([5.0, 1.0]) < out([10.0, 1.0]) < out([15.0, 1.0])
+            assert abs(out([0.0, 1.0])) <= 1e-8
+            assert out([1.0, 5.0]) == out([1.0, 10.0]) == out([1.0, 15.0])
+            out = make(nonlin, n_post, np.array([np.inf, 10.0]), 10.0)
+            assert out([11.0, 1.0]) == out([11.0, 1.0]) and out([11.0, 1.0]) > 0.0
+            assert out([5.0, 1.0]) < out([10.0, 1.0]) < out([15.0, 1.0])
+            assert out([11.0, 5.0]) > out([11.0, 10.0]) > out([11.0, 15.0])
+            assert abs(out([1.0, 1.0])) <= 1e-8 and abs(out([11.0, 20.0])) <= 1e-8
+    for g in gps:
+        g.free()
