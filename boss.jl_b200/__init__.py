@@ -8,7 +8,7 @@ Layout:
 """
 from . import _lib  # noqa: F401  (raises loudly when the CUDA library has not been built)
 from .types import (BIParams, BossOptions, BossProblem, Dirac, Domain, ExperimentData, ExprFitness, FixedParams, LinFitness,  # noqa: F401
-                    LogNormal, MAPParams, NonlinFitness, Product, Uniform, generate_LHC, in_bounds, in_domain,
+                    LogNormal, MAPParams, NonlinFitness, Normal, Product, Uniform, generate_LHC, in_bounds, in_domain,
                     mvlognormal)
 from .gaussian_process import (DiscreteKernel, GaussianProcess, GaussianProcessParams, GaussianProcessPosterior,  # noqa: F401
                                Matern32Kernel, Matern52Kernel, Parametric, Semiparametric, SemiparametricParams,

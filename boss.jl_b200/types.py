@@ -215,6 +215,19 @@ class LogNormal(Prior):
 
 
 @dataclass
+class Normal(Prior):
+    mu: float = 0.0
+    sigma: float = 1.0
+
+    def rand(self, rng):
+        return float(rng.normal(self.mu, self.sigma))
+
+    def logpdf(self, x):
+        z = (x - self.mu) / self.sigma
+        return -0.5 * z * z - math.log(self.sigma * math.sqrt(2 * math.pi))
+
+
+@dataclass
 class Uniform(Prior):
     lo: float
     hi: float

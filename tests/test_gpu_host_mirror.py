@@ -361,3 +361,37 @@ def test_loglike_testsets_of_the_reference():
     assert pl(GPP(np.array([[1.0, 5.0], [1.0, 5.0]]), np.ones(2), np.array([0.1, 0.1]))) == -np.inf
     assert pl(GPP(ones22, np.array([1.0, 5.0]), np.array([0.1, 0.1]))) == -np.inf
     assert pl(GPP(ones22, np.ones(2), np.array([0.1, 0.5]))) == -np.inf
+
+
+def test_semiparametric_model_posterior_testset_of_the_reference():
+    """test/unit/test/models/semiparametric.jl:1-130: Semiparametric(NonlinearModel + GP residual) on the reference's
+    own problem (theta ~ Normal^4, noise 1e-4, SamplingMAP(samples = 200)); vector / matrix forms agree, the variance
+    grows away from the data, and the GP residual interpolates the data on top of the parametric mean."""
+    X = np.array([[2.0, 5.0, 8.0], [2.0, 5.0, 8.0]])
+    fY = lambda x: np.array([np.sin(x[0]) + np.exp(x[1]), np.cos(x[0]) + np.exp(x[1])])
+    Y = np.stack([fY(X[:, j]) for j in range(3)], axis=1)
+    predict = lambda x, th: np.array([th[0] * np.sin(x[0]) + th[1] * np.exp(x[1]), th[2] * np.cos(x[0]) + th[3] * np.exp(x[1])])
+    model = B.Semiparametric(B.Parametric(predict, [B.Normal()] * 4),
+                             B.GaussianProcess(amplitude_priors=[B.LogNormal()] * 2,
+                                               lengthscale_priors=[B.mvlognormal([1.0, 1.0], [1.0, 1.0])] * 2,
+                                               noise_std_priors=[B.Dirac(1e-4)] * 2))
+    problem = B.BossProblem(lambda x: x, B.Domain(([0.0, 0.0], [10.0, 10.0])), B.ExpectedImprovement(B.LinFitness([1.0, 0.0])),
+                            model, B.ExperimentData(X, Y), y_max=[np.inf, 5.0])
+    problem.params = B.estimate_parameters(B.SamplingMAP(samples=200, seed=6), problem)
+    out = B.model_posterior(problem.model, problem.params, problem.data)
+    x2 = np.array([2.0, 2.0])
+    assert np.asarray(out.mean(x2)).shape == (2,) and np.asarray(out.std(x2)).shape == (2,) and np.asarray(out.var(x2)).shape == (2,)
+    assert np.allclose(out.mean(x2), out.mean_and_std(x2)[0], atol=1e-8) and np.allclose(out.mean(x2), out.mean_and_var(x2)[0], atol=1e-8)
+    assert np.allclose(out.std(x2), out.mean_and_std(x2)[1], atol=1e-8) and np.allclose(out.var(x2), out.mean_and_var(x2)[1], atol=1e-8)
+    assert np.all(out.var(x2) <= out.var(np.array([3.0, 3.0])))
+    assert np.all(out.var(np.array([10.0, 10.0])) <= out.var(np.array([11.0, 11.0])))
+    Xm = np.array([[1.0, 2.0, 3.0], [1.0, 2.0, 3.0]])
+    assert out.mean(Xm).shape == (2, 3) and out.std(Xm).shape == (2, 3) and out.var(Xm).shape == (2, 3) and out.cov(Xm).shape == (3, 3, 2)
+    assert np.allclose(out.mean(Xm), out.mean_and_cov(Xm)[0], atol=1e-8) and np.allclose(out.cov(Xm), out.mean_and_cov(Xm)[1], atol=1e-8)
+    assert np.allclose(out.var(Xm), out.mean_and_var(Xm)[1], atol=1e-8) and np.allclose(out.std(Xm), out.mean_and_std(Xm)[1], atol=1e-8)
+    for j in range(3):
+        assert np.allclose(out.mean(Xm)[:, j], out.mean(Xm[:, j]), atol=1e-8) and np.allclose(out.var(Xm)[:, j], out.var(Xm[:, j]), atol=1e-8)
+    # the data are interpolated (noise 1e-4) whatever theta was drawn: parametric mean + GP residual.  exp(8) = 2981, so
+    # "to 0.01" is relative to the data scale here
+    for j in range(3):
+        assert np.allclose(out.mean(X[:, j]), Y[:, j], atol=0.01 + 1e-5 * np.max(np.abs(Y[:, j])))
