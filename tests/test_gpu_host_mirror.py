@@ -395,3 +395,23 @@ def test_semiparametric_model_posterior_testset_of_the_reference():
     # "to 0.01" is relative to the data scale here
     for j in range(3):
         assert np.allclose(out.mean(X[:, j]), Y[:, j], atol=0.01 + 1e-5 * np.max(np.abs(Y[:, j])))
+
+
+def test_average_mean_testset_of_the_reference():
+    """test/unit/test/posterior.jl: average_mean over BI posteriors (8 hyper-parameter samples -- the reference draws them
+    with TuringBI, out of scope here: 8 prior samples stand in; one boss_gp_fit_batch call per output slice fits them)."""
+    X = np.array([[2.0, 5.0, 8.0], [2.0, 5.0, 8.0]])
+    model = B.GaussianProcess(amplitude_priors=[B.LogNormal()] * 2, lengthscale_priors=[B.mvlognormal([1.0, 1.0], [1.0, 1.0])] * 2,
+                              noise_std_priors=[B.Dirac(1e-4)] * 2)
+    problem = B.BossProblem(lambda x: x, B.Domain(([0.0, 0.0], [10.0, 10.0])), B.ExpectedImprovement(B.LinFitness([1.0, 0.0])),
+                            model, B.ExperimentData(X, X.copy()), y_max=[np.inf, 5.0])
+    sampler = model.params_sampler(np.random.default_rng(12))
+    problem.params = B.BIParams([sampler() for _ in range(8)])
+    posts = B.model_posterior(problem)
+    assert len(posts) == 8
+    for x in (np.array([3.0, 3.0]), np.array([5.0, 5.0])):
+        assert np.allclose(B.average_mean(posts, x), sum(p.mean(x) for p in posts) / len(posts), rtol=1e-12, atol=0)
+    # the batched fit is the one-by-one fit, bit for bit
+    one = B.model_posterior(problem.model, problem.params.samples[3], problem.data)
+    assert np.array_equal(one.mean(np.array([3.0, 3.0])), posts[3].mean(np.array([3.0, 3.0])))
+    assert np.array_equal(one.var(np.array([3.0, 3.0])), posts[3].var(np.array([3.0, 3.0])))
