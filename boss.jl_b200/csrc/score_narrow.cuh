@@ -176,8 +176,9 @@ __global__ void __launch_bounds__(256, 1) score_narrow_kernel(const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------------
-// Quarter-row-block CTAs for TINY batches (a handful of unfinished multi-start runs, the reference's one-x-per-call
-// access pattern).  With one 32-candidate block the kernels above expose only nblk CTAs and the longest of them walks
+// Quarter-row-block CTAs: built for TINY batches (a handful of unfinished multi-start runs, the reference's one-x-per-call
+// access pattern) and, as it turned out, the fastest shape up to a few thousand candidates (its many short CTAs balance
+// better than the row-split wide kernels: 10 % faster up to 8192 candidates at n = 2048; the cost model in score_core decides).  With one 32-candidate block the kernels above expose only nblk CTAs and the longest of them walks
 // all 8 nblk stages of the last row block alone: 218 us at n = 4096 whatever the batch holds.  Here a CTA owns 32 rows
 // (4 row slabs) of one row block x 32 candidates (warp = 1 slab x 2 candidate slabs), 4 nblk CTAs per candidate block,
 // launched longest first; the structurally dead head / tail k-tiles of a quarter are not even loaded.
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(256, 1) score_narrow_kernel(const __grid_const
 // requests, not bytes (measured, tools/bulk_copy_rate.cu -> profiles/r02_bulk_copy_rate.json): a TMA / mbarrier ring
 // stage costs ~310 ns + 15 ns per 4 KB bulk copy whatever the ring depth or the source (L2 or HBM) -- 24 GB/s per SM
 // with 8 KB stages, 75 GB/s with 32 KB stages; direct LDG.128 fragment loads four k-tiles ahead in registers reach
-// ~28 GB/s (both tried here: 0.53 and 0.43 us per k-tile).  So a stage carries NQ_KT = 4 k-tiles (8 bulk copies of
+// ~28 GB/s (both tried here: 0.53 and 0.43 us per k-tile).  So a stage carries 4 k-tiles (8 bulk copies of
 // 4 KB, 32 KB), issued by a dedicated producer warp, 3 stages in flight, two CTAs per SM.  (8 k-tiles per stage with one
 // CTA per SM is as fast for a single 32-candidate block and 10-15 % slower from 256 candidates on; 2 k-tiles per stage
 // with three CTAs per SM changes nothing: the SM's operand rate saturates.)
