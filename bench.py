@@ -363,6 +363,19 @@ def run_gpu(args):
     _lib.set_timing(False)
     ms_llg, launches_llg, _ = timed(step_loglik_grad, max(2, args.steps // 2), 3)
     clocks = sampler.stop() if sampler else None
+    # one candidate per call -- the access pattern of the reference's stock maximizers (acq(x) inside NLopt / Optim,
+    # grid.jl:52-53): host-pointer C-ABI calls, wall time per call (H2D of the point, all kernels, D2H of the result)
+    x1 = np.ascontiguousarray(Xs_pageable[:, :1])
+    single = {}
+    for name, fn in (("value", lambda: _lib.ei_score([gp], 1, 1, x1, [1.0], best, None)),
+                     ("value_grad", lambda: _lib.ei_value_grad([gp], 1, 1, x1, [1.0], best, None))):
+        for _ in range(20):
+            fn()
+        t0 = time.perf_counter()
+        for _ in range(200):
+            fn()
+        single[name + "_call_us"] = (time.perf_counter() - t0) / 200 * 1e6
+    single["value_calls_per_s"] = 1e6 / single["value_call_us"]
     try:
         dg = measure_dgemm_peak(torch)          # every rank (keeps the ranks in step); rank 0 reports
     except Exception as e:                      # noqa: BLE001
@@ -428,6 +441,8 @@ def run_gpu(args):
                             "value": S * world / (ms_llg * 1e-3), "unit": "evals/s", "ms_per_step": ms_llg,
                             "flop_per_eval": F_LLG, "achieved_tflops_per_gpu": F_LLG * S / (ms_llg * 1e-3) * 1e-12,
                             "frac_of_peak": F_LLG * S / (ms_llg * 1e-3) * 1e-12 / peak, "gpu_launches": int(launches_llg)},
+            "single_point": dict(single, what="one candidate per host call through boss_ei_score / boss_ei_value_grad "
+                                              "(n=2048, d=8); cpu_baseline.one_candidate_per_call_value is the CPU port's rate"),
             "fit": {"what": "boss_gp_fit wall time (host call: H2D of X, y; K, Cholesky, W = L^-1, alpha; n=2048, d=8)",
                     "ms_median": float(np.median(fit_ms)), "flop": F_LL + N_TRAIN ** 3 / 3},
             "argmax": {"value": res[0], "index": res[1], "e2e_index": res_e2e[1], "per_rank_pairs": list(last_pairs)},

@@ -14,5 +14,7 @@ print("loglik+grad %.0f evals/s  frac %.3f   fit %.2f ms" % (
 for c in j.get("configs", []):
     print({k: (round(v, 4) if isinstance(v, float) else v) for k, v in c.items()
            if "frac" in k or "ms_per" in k or "relerr" in k or k in ("config", "kernel")})
+if "single_point" in j:
+    print("single point: value %.0f us/call, value+grad %.0f us/call" % (j["single_point"]["value_call_us"], j["single_point"]["value_grad_call_us"]))
 if "cpu_baseline" in j:
     print("cpu", j["cpu_baseline"].get("value"), j["cpu_baseline"].get("cores"))
