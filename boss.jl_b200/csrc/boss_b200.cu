@@ -1207,9 +1207,9 @@ int score_core(ScoreArgs &a) {
   long long neg1 = -1;
   std::memcpy(&hs[nsl + 2 * d + 1], &neg1, 8);
   CUDA_TRY(cudaMemcpyAsync(small, hs.data(), sm_n * 8, cudaMemcpyHostToDevice, C().stream));
-  // hs is pageable: the runtime has staged these few bytes when the call returns and hs lives until the end of this
-  // function, so the rounds of the multi-start driver (internal calls) do not pay a stream round trip here
-  if (!a.internal) CUDA_TRY(cudaStreamSynchronize(C().stream));
+  // hs is pageable: the runtime has copied these few bytes to its staging memory when the call returns (CUDA's
+  // documented behaviour for pageable-to-device cudaMemcpyAsync), and hs lives until the end of this function: no
+  // stream round trip is needed here
   double *d_best = small + nsl + 2 * d;
   long long *d_bidx = reinterpret_cast<long long *>(small + nsl + 2 * d + 1);
   int *d_anyfail = reinterpret_cast<int *>(small + nsl + 2 * d + 2);
