@@ -1560,18 +1560,20 @@ int score_core(ScoreArgs &a) {
     }
   }
   CUDA_TRY(cudaGetLastError());
-  if (host && prev_m0 >= 0) {
-    int rc = drain_out(prev_m0, prev_ch, (cidx - 1) & 1);
-    if (rc) return rc;
-  }
   if (a.internal && !a.want_argmax && !C().timing) {   // a round of the multi-start driver: it synchronises itself
     a.any_fail = 0;
     return 0;
   }
+  // one wait for everything: the (value, index, failure flag) triple is fetched behind the last chunk's outputs, and
+  // the last chunk is handed to the caller after the stream has drained (its event has completed by then)
   double *hres = reinterpret_cast<double *>(hs.data());   // reuse: 3 doubles
   CUDA_TRY(cudaMemcpyAsync(hres, d_best, 24, cudaMemcpyDeviceToHost, C().stream));
   CUDA_TRY(cudaStreamSynchronize(C().stream));
   if (host) CUDA_TRY(cudaStreamSynchronize(cp));
+  if (host && prev_m0 >= 0) {
+    int rc = drain_out(prev_m0, prev_ch, (cidx - 1) & 1);
+    if (rc) return rc;
+  }
   timing_end();
   long long bidx;
   std::memcpy(&bidx, &hres[1], 8);
